@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py -- the headline measurement of BASELINE.json on B200.
+
+Metric: output blocks/s of the ciphertext hot path -- multiply (all-pairs AND of
+T1 x T2 blocks) followed by decrypt of the product -- at Context(1247,16),
+1000 x 1000 -> 1,000,000 output blocks per ciphertext pair (BASELINE.json configs[1]).
+
+A step is one pass over a batch of `pairs` independent ciphertext pairs:
+    [multiply pair 0 .. P-1]  then  [decrypt product 0 .. P-1]
+so every product (160 MB) is written and, P-1 products later, read back: the batch
+(P x 160 MB) is far larger than the 126 MB L2 and both kernels run against HBM.
+
+  value     device-resident operands and outputs, no host traffic in the timed region
+  e2e       the same batch through the public C ABI from pinned HOST operands:
+            csgn_buf_upload x2 -> csgn_mul -> csgn_decrypt_count_async, one D2H of
+            the P counts per step
+  roofline  multiply kernel: 160 B written per output block / CUDA-event time of the
+            multiply phase, against the measured HBM figure of MEASURED_PEAKS.json
+  cpu_baseline  the unmodified reference (oracle/_ref) or the oracle port, 1 thread
+
+N > 1 (torchrun, one process per GPU): weak scaling.  The left operand of every pair
+has 1000*N blocks and is sharded by contiguous block range (csgn_shard_range); the
+right operand is replicated; every rank multiplies and folds its own 1M-block shard
+and the per-pair satisfied-block counts are summed by ONE NCCL all-reduce per step
+(P words) -- decrypt is the parity of the sum.
+
+`--impl reference` times the reference's own CPU implementation (public operator*
+and SecretKey::decrypt) on the host cores, one replica per core.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (N, D, T1, T2, description)
+    "cfg2": (1247, 16, 1000, 1000, "Context(1247,16): 1000x1000 -> 1M output blocks, multiply then decrypt"),
+    "cfg5": (16383, 64, 300, 300, "Context(16383,64): 300x300 -> 90k output blocks, multiply then decrypt"),
+}
+METRIC = "ctxt-mul+decrypt output blocks/s"
+UNIT = "blocks/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--pairs", type=int, default=16, help="independent ciphertext pairs per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def words_per_block(N):
+    return N // 64 + (1 if N % 64 else 0)
+
+
+def seeded_blocks(rng, T, N):
+    L = words_per_block(N)
+    w = rng.integers(0, 2**64, size=(T, L), dtype=np.uint64)
+    rem = N % 64
+    if rem:
+        w[:, L - 1] &= np.uint64((0xFFFFFFFFFFFFFFFF << (64 - rem)) & 0xFFFFFFFFFFFFFFFF)
+    return w.reshape(-1)
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons during the timed region (NVML, ~2 ms period)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = str(e)
+
+    NAMES = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+             0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+             0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.NAMES.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------
+# CPU arms (the only place bench.py touches oracle/)
+# ---------------------------------------------------------------------------
+def cpu_reference_once(N, D, T1, T2, threads, reps):
+    """(kind, mul_s, dec_s) for `threads` replicas of a T1 x T2 multiply + decrypt."""
+    from oracle import pyoracle
+    if pyoracle.ref_available():
+        ref = pyoracle.Ref()
+        m, d, _ = ref.bench_mul_decrypt(N, D, T1, T2, threads=threads, reps=reps, seed=1)
+        return "reference", m, d
+    # the reference build did not travel: time the C restatement (one thread)
+    o = pyoracle.Oracle()
+    rng = np.random.default_rng(1)
+    a, b = seeded_blocks(rng, T1, N), seeded_blocks(rng, T2, N)
+    s = rng.permutation(N)[:D].astype(np.uint64)
+    best_m = best_d = 1e300
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        prod = o.mul(a, b, words_per_block(N))
+        t1 = time.perf_counter()
+        o.decrypt(prod, N, s)
+        t2 = time.perf_counter()
+        best_m, best_d = min(best_m, t1 - t0), min(best_d, t2 - t1)
+    return "port", best_m, best_d
+
+
+def cpu_baseline(N, D, T1, T2):
+    kind, m, d = cpu_reference_once(N, D, T1, T2, threads=1, reps=2)
+    blocks = T1 * T2
+    return {"value": blocks / (m + d), "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": "one %dx%d pair (%d output blocks): public operator* %.3f s + SecretKey::decrypt %.3f s, "
+                      "best of 2, single thread (the reference has no threading)" % (T1, T2, blocks, m, d),
+            "mul_blocks_per_s": blocks / m, "decrypt_blocks_per_s": blocks / d,
+            "host_cores_available": os.cpu_count()}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    N, D, T1, T2, desc = WORKLOADS[args.workload]
+    threads = max(1, os.cpu_count() or 1)
+    # bounded sample: a quarter of the left operand per replica keeps one step near 1 s
+    T1s = max(1, T1 // 4)
+    try:
+        import psutil
+        per_replica = T1s * T2 * (words_per_block(N) * 8 * 4 + N) * 1.2   # v+bitlen twice + unpack scratch
+        threads = max(1, min(threads, int(psutil.virtual_memory().available * 0.6 / per_replica)))
+    except Exception:
+        pass
+    times = []
+    kind = "reference"
+    for i in range(args.warmup + args.steps):
+        kind, m, d = cpu_reference_once(N, D, T1s, T2, threads=threads, reps=1)
+        if i >= args.warmup:
+            times.append(m + d)
+    blocks = threads * T1s * T2
+    total = float(np.sum(times))
+    value = blocks * len(times) / total
+    sample = ("%d replica threads x one %dx%d pair per step (%d output blocks/step), public operator* + "
+              "SecretKey::decrypt; harness-level parallelism, the reference itself is single-threaded"
+              % (threads, T1s, T2, blocks))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": args.workload + ": " + desc, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from csgn_b200 import engine as eng
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    N, D, T1, T2, desc = WORKLOADS[args.workload]
+    L, P = words_per_block(N), args.pairs
+    eng.init(local)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    ctx = eng.Context(N, D)
+
+    # --- synthetic inputs: pinned host copies (e2e) and device copies (value) ---------
+    # Global left operand of pair p has T1*world blocks; this rank owns csgn_shard_range.
+    first, count = eng.shard_range(T1 * world, rank, world)
+    assert count == T1
+    host_a = torch.empty((P, T1 * L), dtype=torch.int64).pin_memory()
+    host_b = torch.empty((P, T2 * L), dtype=torch.int64).pin_memory()
+    key_pos = np.random.default_rng(7).permutation(N)[:D].astype(np.uint64)
+    key = eng.SecretKey(ctx, key_pos)
+    key_mask = np.zeros(L, dtype=np.uint64)
+    for s_ in key_pos:
+        key_mask[int(s_) >> 6] |= np.uint64(1 << (63 - (int(s_) & 63)))
+
+    def planted(rng, T):
+        # raw random blocks almost never satisfy a D=16 key; set the key bits in a few
+        # of them so that the decrypt fold has something to count
+        w = seeded_blocks(rng, T, N).reshape(T, L)
+        rows = rng.choice(T, size=int(rng.integers(20, 60)), replace=False)
+        w[rows] |= key_mask
+        return w.reshape(-1)
+
+    for p in range(P):
+        rng_a = np.random.default_rng([1000 + p, rank])       # this rank's shard of A_p
+        rng_b = np.random.default_rng([2000 + p])             # B_p, identical on every rank
+        host_a[p].numpy().view(np.uint64)[:] = planted(rng_a, T1)
+        host_b[p].numpy().view(np.uint64)[:] = planted(rng_b, T2)
+    dev_a, dev_b = host_a.to(dev), host_b.to(dev)
+    out = torch.empty((P, T1 * T2 * L), dtype=torch.int64, device=dev)
+    counts = torch.zeros(P, dtype=torch.int64, device=dev)
+    host_counts = torch.zeros(P, dtype=torch.int64).pin_memory()
+    va = [eng.Ciphertext.from_tensor(dev_a[p], ctx) for p in range(P)]
+    vb = [eng.Ciphertext.from_tensor(dev_b[p], ctx) for p in range(P)]
+    vo = [eng.Ciphertext.from_tensor(out[p], ctx) for p in range(P)]
+    count_ptrs = [counts.data_ptr() + 8 * p for p in range(P)]
+
+    def step_device(evs=None):
+        if evs:
+            evs[0].record()
+        for p in range(P):
+            va[p].mul_into(vb[p], vo[p])
+        if evs:
+            evs[1].record()
+        for p in range(P):
+            key.count_satisfied_async(vo[p], count_ptrs[p])
+        if evs:
+            evs[2].record()
+        if world > 1:
+            dist.all_reduce(counts)
+        if evs:
+            evs[3].record()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    barrier()
+
+    # sanity (outside the timed region, no oracle): satisfied-block counts are multiplicative
+    ca = [key.count_satisfied(va[p]) for p in range(P)]
+    cb = [key.count_satisfied(vb[p]) for p in range(P)]
+    local_counts = torch.tensor([a * b for a, b in zip(ca, cb)], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(local_counts)
+    if not torch.equal(local_counts, counts):
+        raise SystemExit("bench sanity failed: count(a*b) != count(a)*count(b): %s vs %s" % (counts, local_counts))
+
+    K = args.steps
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    sampler = ClockSampler(local)
+    barrier()
+    launches0 = eng.launch_count()
+    sampler.start()
+    t_wall = time.perf_counter()
+    for k in range(K):
+        step_device(evs[k])
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    launches = eng.launch_count() - launches0
+
+    total_ms = evs[0][0].elapsed_time(evs[K - 1][3])
+    mul_ms = sum(e[0].elapsed_time(e[1]) for e in evs)
+    dec_ms = sum(e[1].elapsed_time(e[2]) for e in evs)
+    ar_ms = sum(e[2].elapsed_time(e[3]) for e in evs)
+    t = torch.tensor([total_ms, mul_ms, dec_ms, ar_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, mul_ms, dec_ms, ar_ms = (float(x) for x in t.tolist())
+
+    blocks_per_step = P * T1 * T2 * world            # whole job
+    value = blocks_per_step * K / (total_ms * 1e-3)
+    bytes_per_block = 8 * L
+    peak, peak_src = measured_peak_gbs()
+    mul_gbs = P * T1 * T2 * bytes_per_block * K / (mul_ms * 1e-3) / 1e9      # per GPU
+    dec_gbs = P * T1 * T2 * bytes_per_block * K / (dec_ms * 1e-3) / 1e9
+
+    # --- e2e: pinned host operands through the public C ABI ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        a_ptrs = [host_a[p].data_ptr() for p in range(P)]
+        b_ptrs = [host_b[p].data_ptr() for p in range(P)]
+
+        def step_e2e():
+            for p in range(P):
+                ha = eng.Ciphertext.from_host_ptr(a_ptrs[p], T1, ctx)      # H2D, async (pinned)
+                hb = eng.Ciphertext.from_host_ptr(b_ptrs[p], T2, ctx)
+                prod = ha * hb                                             # csgn_mul (allocates)
+                key.count_satisfied_async(prod, count_ptrs[p])
+                del ha, hb, prod                                           # stream-ordered frees
+            if world > 1:
+                dist.all_reduce(counts)
+            host_counts.copy_(counts, non_blocking=True)                   # D2H of the result
+            stream.synchronize()
+            return host_counts
+
+        for _ in range(max(3, args.warmup)):
+            step_e2e()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            res = step_e2e()
+        e1.record()
+        barrier()
+        e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        if not torch.equal(res.to(dev), local_counts):
+            raise SystemExit("e2e result differs from the device-resident result")
+        e2e = {"value": blocks_per_step * K / (float(e2e_ms.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(P * (T1 + T2) * L * 8), "d2h_bytes_per_step": int(P * 8),
+               "ms_per_step": float(e2e_ms.item()) / K,
+               "path": "csgn_buf_upload x2 (pinned host) -> csgn_mul -> csgn_decrypt_count_async; one D2H of the "
+                       "P counts per step; per GPU"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": args.workload + ": " + desc, "pairs_per_step": P,
+                       "blocks_per_step": blocks_per_step, "bytes_per_block": bytes_per_block,
+                       "l2": "no flush needed: a step writes then reads %d x %.0f MB of products (>> 126 MB L2), "
+                             "each product is read %d kernels after it was written" % (P, T1 * T2 * L * 8 / 1e6, P),
+                       "sharding": "left operand by block range, right operand replicated, one %d-word NCCL "
+                                   "all-reduce per step" % P if world > 1 else "single GPU",
+                       "inputs": "numpy default_rng raw blocks, pad bits zero, key bits set in 20-60 blocks per operand; "
+                                 "key = default_rng(7).permutation(N)[:D]"},
+            "roofline": {"bound": "hbm", "kernel": "mul_outer_kernel", "achieved": mul_gbs, "peak": peak,
+                         "unit": "GB/s", "frac": mul_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": T1 * T2 * bytes_per_block,
+                         "avg_launch_us": mul_ms * 1e3 / (K * P)},
+            "kernels": {"multiply": {"blocks_per_s_per_gpu": P * T1 * T2 * K / (mul_ms * 1e-3), "gbs": mul_gbs,
+                                     "frac_of_peak": mul_gbs / peak, "avg_launch_us": mul_ms * 1e3 / (K * P)},
+                        "decrypt": {"blocks_per_s_per_gpu": P * T1 * T2 * K / (dec_ms * 1e-3), "gbs": dec_gbs,
+                                    "frac_of_peak": dec_gbs / peak, "avg_launch_us": dec_ms * 1e3 / (K * P)},
+                        "allreduce_ms_per_step": ar_ms / K},
+            "clocks": clocks, "gpu_launches": int(launches), "wall_ms_per_step": 1e3 * t_wall / K,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(N, D, T1, T2)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,108 @@
+"""In-tree build of the native code (nvcc cross-compiles sm_100a without a GPU).
+
+  csgn_b200/lib/libcsgn.so      CUDA kernels + C ABI (include/csgn.h)
+  csgn_b200/lib/libcertFHE.so   the certFHE C++ drop-in classes over that C ABI
+  tests/cpp/bin/*               C++ acceptance / differential executables
+
+Everything is written for sm_100a only.  Built files are git-ignored but travel to
+the GPU box with the gpurun snapshot.
+"""
+import glob
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+CERTFHE = os.path.join(PKG, "certfhe")
+LIBDIR = os.path.join(PKG, "lib")
+INCLUDE = os.path.join(ROOT, "include")
+CPP_TESTS = os.path.join(ROOT, "tests", "cpp")
+
+NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: the CUDA extension cannot be built (there is no CPU fallback)")
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _run(cmd, verbose):
+    if verbose:
+        print("+", " ".join(cmd), flush=True)
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("build step failed: " + " ".join(cmd))
+    if verbose and r.stdout.strip():
+        print(r.stdout)
+
+
+def libcsgn_path():
+    return os.path.join(LIBDIR, "libcsgn.so")
+
+
+def libcertfhe_path():
+    return os.path.join(LIBDIR, "libcertFHE.so")
+
+
+def build_libcsgn(force=False, verbose=False):
+    os.makedirs(LIBDIR, exist_ok=True)
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
+    out = libcsgn_path()
+    if force or _stale(out, deps):
+        _run([_nvcc()] + NVCC_ARCH + NVCC_FLAGS + ["-shared", "-o", out] + srcs, verbose)
+    return out
+
+
+def build_libcertfhe(force=False, verbose=False):
+    srcs = sorted(glob.glob(os.path.join(CERTFHE, "*.cpp")))
+    if not srcs:
+        return None
+    deps = srcs + glob.glob(os.path.join(CERTFHE, "*.h")) + glob.glob(os.path.join(INCLUDE, "*.h")) + [libcsgn_path()]
+    out = libcertfhe_path()
+    if force or _stale(out, deps):
+        _run(["g++", "-O2", "-std=c++11", "-fPIC", "-shared", "-Wall", "-I" + INCLUDE, "-I" + CERTFHE, "-o", out]
+             + srcs + ["-L" + LIBDIR, "-lcsgn", "-Wl,-rpath,$ORIGIN"], verbose)
+    return out
+
+
+def build_cpp_tests(force=False, verbose=False):
+    """C++ executables under tests/cpp: written against the certFHE class API."""
+    outs = []
+    bindir = os.path.join(CPP_TESTS, "bin")
+    srcs = sorted(glob.glob(os.path.join(CPP_TESTS, "*.cpp")))
+    if not srcs or not os.path.exists(libcertfhe_path()):
+        return outs
+    os.makedirs(bindir, exist_ok=True)
+    for src in srcs:
+        out = os.path.join(bindir, os.path.splitext(os.path.basename(src))[0])
+        if force or _stale(out, [src, libcertfhe_path()] + glob.glob(os.path.join(CERTFHE, "*.h"))):
+            _run(["g++", "-O2", "-std=c++11", "-Wall", "-I" + CERTFHE, "-I" + INCLUDE, "-o", out, src,
+                  "-L" + LIBDIR, "-lcertFHE", "-lcsgn", "-Wl,-rpath,$ORIGIN/../../../csgn_b200/lib"], verbose)
+        outs.append(out)
+    return outs
+
+
+def build_all(force=False, verbose=False):
+    build_libcsgn(force, verbose)
+    build_libcertfhe(force, verbose)
+    build_cpp_tests(force, verbose)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose=True)
+    print("built:", libcsgn_path())

@@ -1,0 +1,601 @@
+// capi.cu -- the C ABI of include/csgn.h: device state, buffer handles, and the
+// thin argument checking in front of the kernel launchers.  No CPU compute path
+// exists here: every operation either launches an sm_100a kernel or fails.
+#include "../../include/csgn.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+#define CSGN_VERSION_STRING "csgn-b200 0.1 (sm_100a)"
+
+// ---------------------------------------------------------------------------
+// handles
+// ---------------------------------------------------------------------------
+struct csgn_buf {
+    uint64_t *d = nullptr;     // device words, n_blocks * L valid
+    uint64_t n_blocks = 0;
+    uint32_t L = 0;
+    uint64_t cap_words = 0;    // allocated words (>= n_blocks*L); 0 for views
+    bool owns = true;
+};
+
+struct csgn_key {
+    uint64_t *d_mask = nullptr;  // L words
+    uint64_t N = 0;
+    uint32_t L = 0, D = 0;
+};
+
+struct csgn_perm {
+    uint32_t *d_map = nullptr;   // N entries: (src_word << 6) | right_shift
+    uint64_t N = 0;
+    uint32_t L = 0;
+};
+
+namespace csgn {
+namespace {
+
+struct State {
+    bool inited = false;
+    int device = -1;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    uint64_t *d_scratch = nullptr;   // [0..1] decrypt fold scratch, [2] result, [4..6] checksum
+    uint64_t *h_result = nullptr;    // pinned, 8 words
+};
+State g;
+DeviceProps g_props;
+std::atomic<uint64_t> g_launches{0};
+thread_local std::string t_error;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_error = buf;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    // leave the sticky-error state readable but do not hide it
+    cudaGetLastError();
+    return fail(e == cudaErrorMemoryAllocation ? CSGN_ERR_OUT_OF_MEMORY : CSGN_ERR_CUDA, "%s: %s (%s)", what,
+                cudaGetErrorString(e), cudaGetErrorName(e));
+}
+
+#define CU(call)                                            \
+    do {                                                    \
+        cudaError_t e_ = (call);                            \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+
+#define NEED_INIT()                                                                              \
+    do {                                                                                         \
+        if (!g.inited) return fail(CSGN_ERR_NOT_INITIALIZED, "csgn_init has not been called");   \
+        int cur_ = -1;                                                                           \
+        if (cudaGetDevice(&cur_) != cudaSuccess || cur_ != g.device) CU(cudaSetDevice(g.device)); \
+    } while (0)
+
+int dev_alloc(uint64_t words, uint64_t **out) {
+    *out = nullptr;
+    if (words == 0) return CSGN_OK;
+    void *p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, words * sizeof(uint64_t), g.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync");
+    *out = static_cast<uint64_t *>(p);
+    return CSGN_OK;
+}
+
+void dev_free(void *p) {
+    if (p) cudaFreeAsync(p, g.stream);
+}
+
+int new_buf(uint64_t n_blocks, uint32_t L, uint64_t cap_words, csgn_buf **out) {
+    if (L == 0) return fail(CSGN_ERR_INVALID_ARGUMENT, "words per block must be > 0");
+    if (n_blocks > (UINT64_MAX / 8) / L) return fail(CSGN_ERR_INVALID_ARGUMENT, "block count overflows");
+    csgn_buf *b = new csgn_buf;
+    b->n_blocks = n_blocks;
+    b->L = L;
+    b->cap_words = std::max<uint64_t>(cap_words, n_blocks * L);
+    int rc = dev_alloc(b->cap_words, &b->d);
+    if (rc != CSGN_OK) {
+        delete b;
+        return rc;
+    }
+    *out = b;
+    return CSGN_OK;
+}
+
+}  // namespace
+
+const DeviceProps &device_props() { return g_props; }
+void set_device_props(const DeviceProps &p) { g_props = p; }
+void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+uint64_t launches() { return g_launches.load(std::memory_order_relaxed); }
+
+long env_long(const char *name, long dflt) {
+    const char *s = std::getenv(name);
+    if (!s || !*s) return dflt;
+    char *end = nullptr;
+    long v = std::strtol(s, &end, 10);
+    return (end && *end == 0) ? v : dflt;
+}
+
+}  // namespace csgn
+
+using namespace csgn;
+
+// ---------------------------------------------------------------------------
+// library
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int csgn_init(int device) {
+    if (device < 0) device = (int)env_long("CSGN_DEVICE", env_long("LOCAL_RANK", 0));
+    if (g.inited) {
+        if (g.device == device) return CSGN_OK;
+        return fail(CSGN_ERR_INVALID_ARGUMENT, "already bound to device %d (one process per GPU)", g.device);
+    }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(CSGN_ERR_NO_DEVICE, "no CUDA device visible (%s); this engine has no CPU path",
+                    e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    }
+    if (device >= n) return fail(CSGN_ERR_NO_DEVICE, "device %d requested, %d visible", device, n);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp p;
+    CU(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10)
+        return fail(CSGN_ERR_NO_DEVICE, "device %d is sm_%d%d; the kernels are built for sm_100a (B200) only",
+                    device, p.major, p.minor);
+    DeviceProps dp;
+    dp.device = device;
+    dp.sm_count = p.multiProcessorCount;
+    dp.cc = p.major * 10 + p.minor;
+    dp.smem_optin = p.sharedMemPerBlockOptin;
+    set_device_props(dp);
+
+    CU(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
+    g.stream = g.own_stream;
+    // keep freed blocks in the pool: a*b chains reuse them without going to the driver
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    CU(cudaMalloc(reinterpret_cast<void **>(&g.d_scratch), 8 * sizeof(uint64_t)));
+    CU(cudaMemset(g.d_scratch, 0, 8 * sizeof(uint64_t)));
+    CU(cudaHostAlloc(reinterpret_cast<void **>(&g.h_result), 8 * sizeof(uint64_t), cudaHostAllocDefault));
+    g.device = device;
+    g.inited = true;
+    return CSGN_OK;
+}
+
+int csgn_shutdown(void) {
+    if (!g.inited) return CSGN_OK;
+    cudaSetDevice(g.device);
+    cudaStreamSynchronize(g.stream);
+    cudaFree(g.d_scratch);
+    cudaFreeHost(g.h_result);
+    cudaStreamDestroy(g.own_stream);
+    g = State();
+    return CSGN_OK;
+}
+
+int csgn_is_initialized(void) { return g.inited ? 1 : 0; }
+const char *csgn_last_error(void) { return t_error.c_str(); }
+const char *csgn_version(void) { return CSGN_VERSION_STRING; }
+
+int csgn_device_info(int *sm_count, uint64_t *hbm_total, uint64_t *hbm_free, int *cc) {
+    NEED_INIT();
+    size_t fr = 0, tot = 0;
+    CU(cudaMemGetInfo(&fr, &tot));
+    if (sm_count) *sm_count = device_props().sm_count;
+    if (hbm_total) *hbm_total = tot;
+    if (hbm_free) *hbm_free = fr;
+    if (cc) *cc = device_props().cc;
+    return CSGN_OK;
+}
+
+int csgn_set_stream(void *cuda_stream) {
+    NEED_INIT();
+    g.stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : g.own_stream;
+    return CSGN_OK;
+}
+
+void *csgn_get_stream(void) { return g.inited ? static_cast<void *>(g.stream) : nullptr; }
+
+int csgn_sync(void) {
+    NEED_INIT();
+    CU(cudaStreamSynchronize(g.stream));
+    return CSGN_OK;
+}
+
+uint64_t csgn_launch_count(void) { return launches(); }
+
+uint32_t csgn_words_per_block(uint64_t N) { return (uint32_t)(N / 64 + (N % 64 ? 1 : 0)); }
+
+int csgn_host_alloc(size_t bytes, void **out) {
+    NEED_INIT();
+    if (!out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null output pointer");
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return CSGN_OK;
+}
+
+int csgn_host_free(void *p) {
+    NEED_INIT();
+    if (p) CU(cudaFreeHost(p));
+    return CSGN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// buffers
+// ---------------------------------------------------------------------------
+int csgn_buf_alloc(uint64_t n_blocks, uint32_t L, csgn_buf **out) {
+    NEED_INIT();
+    if (!out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null output handle");
+    return new_buf(n_blocks, L, 0, out);
+}
+
+int csgn_buf_upload(const uint64_t *host_words, uint64_t n_blocks, uint32_t L, csgn_buf **out) {
+    NEED_INIT();
+    if (!out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null output handle");
+    if (n_blocks && !host_words) return fail(CSGN_ERR_INVALID_ARGUMENT, "null host words");
+    csgn_buf *b = nullptr;
+    int rc = new_buf(n_blocks, L, 0, &b);
+    if (rc != CSGN_OK) return rc;
+    if (n_blocks) {
+        cudaError_t e = cudaMemcpyAsync(b->d, host_words, n_blocks * L * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                                        g.stream);
+        if (e != cudaSuccess) {
+            csgn_buf_free(b);
+            return cuda_fail(e, "cudaMemcpyAsync(H2D)");
+        }
+    }
+    *out = b;
+    return CSGN_OK;
+}
+
+int csgn_buf_wrap(void *device_words, uint64_t n_blocks, uint32_t L, csgn_buf **out) {
+    NEED_INIT();
+    if (!out || L == 0) return fail(CSGN_ERR_INVALID_ARGUMENT, "bad view arguments");
+    if (n_blocks && !device_words) return fail(CSGN_ERR_INVALID_ARGUMENT, "null device pointer");
+    if (reinterpret_cast<uintptr_t>(device_words) & 7u)
+        return fail(CSGN_ERR_INVALID_ARGUMENT, "device pointer must be 8-byte aligned");
+    csgn_buf *b = new csgn_buf;
+    b->d = static_cast<uint64_t *>(device_words);
+    b->n_blocks = n_blocks;
+    b->L = L;
+    b->cap_words = 0;
+    b->owns = false;
+    *out = b;
+    return CSGN_OK;
+}
+
+int csgn_buf_clone(const csgn_buf *src, csgn_buf **out) {
+    NEED_INIT();
+    if (!src || !out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
+    csgn_buf *b = nullptr;
+    int rc = new_buf(src->n_blocks, src->L, 0, &b);
+    if (rc != CSGN_OK) return rc;
+    cudaError_t e = launch_concat(src->d, src->n_blocks * src->L, nullptr, 0, b->d, g.stream);
+    if (e != cudaSuccess) {
+        csgn_buf_free(b);
+        return cuda_fail(e, "clone kernel");
+    }
+    *out = b;
+    return CSGN_OK;
+}
+
+int csgn_buf_download_range(const csgn_buf *buf, uint64_t first_block, uint64_t n_blocks, uint64_t *host_words) {
+    NEED_INIT();
+    if (!buf) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
+    if (first_block > buf->n_blocks || n_blocks > buf->n_blocks - first_block)
+        return fail(CSGN_ERR_INVALID_ARGUMENT, "block range [%llu,+%llu) outside %llu blocks",
+                    (unsigned long long)first_block, (unsigned long long)n_blocks, (unsigned long long)buf->n_blocks);
+    if (n_blocks == 0) return CSGN_OK;
+    if (!host_words) return fail(CSGN_ERR_INVALID_ARGUMENT, "null host destination");
+    CU(cudaMemcpyAsync(host_words, buf->d + first_block * buf->L, n_blocks * buf->L * sizeof(uint64_t),
+                       cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    return CSGN_OK;
+}
+
+int csgn_buf_download(const csgn_buf *buf, uint64_t *host_words) {
+    if (!buf) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
+    return csgn_buf_download_range(buf, 0, buf->n_blocks, host_words);
+}
+
+int csgn_buf_free(csgn_buf *buf) {
+    if (!buf) return CSGN_OK;
+    if (g.inited && buf->owns) dev_free(buf->d);
+    delete buf;
+    return CSGN_OK;
+}
+
+uint64_t csgn_buf_blocks(const csgn_buf *buf) { return buf ? buf->n_blocks : 0; }
+uint32_t csgn_buf_words_per_block(const csgn_buf *buf) { return buf ? buf->L : 0; }
+void *csgn_buf_device_ptr(const csgn_buf *buf) { return buf ? buf->d : nullptr; }
+
+// ---------------------------------------------------------------------------
+// K1 multiply
+// ---------------------------------------------------------------------------
+int csgn_mul_into(const csgn_buf *a, const csgn_buf *b, csgn_buf *out) {
+    NEED_INIT();
+    if (!a || !b || !out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
+    if (a->L != b->L || a->L != out->L)
+        return fail(CSGN_ERR_SHAPE_MISMATCH, "words per block differ (%u, %u, %u)", a->L, b->L, out->L);
+    if (b->n_blocks && a->n_blocks > UINT64_MAX / b->n_blocks)
+        return fail(CSGN_ERR_INVALID_ARGUMENT, "product block count overflows");
+    if (out->n_blocks != a->n_blocks * b->n_blocks)
+        return fail(CSGN_ERR_SHAPE_MISMATCH, "output holds %llu blocks, product has %llu",
+                    (unsigned long long)out->n_blocks, (unsigned long long)(a->n_blocks * b->n_blocks));
+    if (out->d == a->d || out->d == b->d) return fail(CSGN_ERR_INVALID_ARGUMENT, "output aliases an operand");
+    cudaError_t e = launch_mul(a->d, a->n_blocks, b->d, b->n_blocks, a->L, out->d, g.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "multiply kernel");
+    return CSGN_OK;
+}
+
+int csgn_mul(const csgn_buf *a, const csgn_buf *b, csgn_buf **out) {
+    NEED_INIT();
+    if (!a || !b || !out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
+    if (a->L != b->L) return fail(CSGN_ERR_SHAPE_MISMATCH, "words per block differ (%u vs %u)", a->L, b->L);
+    if (b->n_blocks && a->n_blocks > UINT64_MAX / b->n_blocks)
+        return fail(CSGN_ERR_INVALID_ARGUMENT, "product block count overflows");
+    csgn_buf *c = nullptr;
+    int rc = new_buf(a->n_blocks * b->n_blocks, a->L, 0, &c);
+    if (rc != CSGN_OK) return rc;
+    rc = csgn_mul_into(a, b, c);
+    if (rc != CSGN_OK) {
+        csgn_buf_free(c);
+        return rc;
+    }
+    *out = c;
+    return CSGN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K2 add
+// ---------------------------------------------------------------------------
+int csgn_concat(const csgn_buf *a, const csgn_buf *b, csgn_buf **out) {
+    NEED_INIT();
+    if (!a || !b || !out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
+    if (a->L != b->L) return fail(CSGN_ERR_SHAPE_MISMATCH, "words per block differ (%u vs %u)", a->L, b->L);
+    csgn_buf *c = nullptr;
+    int rc = new_buf(a->n_blocks + b->n_blocks, a->L, 0, &c);
+    if (rc != CSGN_OK) return rc;
+    cudaError_t e = launch_concat(a->d, a->n_blocks * a->L, b->d, b->n_blocks * b->L, c->d, g.stream);
+    if (e != cudaSuccess) {
+        csgn_buf_free(c);
+        return cuda_fail(e, "concat kernel");
+    }
+    *out = c;
+    return CSGN_OK;
+}
+
+int csgn_append(csgn_buf *a, const csgn_buf *b) {
+    NEED_INIT();
+    if (!a || !b) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
+    if (!a->owns) return fail(CSGN_ERR_INVALID_ARGUMENT, "cannot grow a non-owning view");
+    if (a->L != b->L) return fail(CSGN_ERR_SHAPE_MISMATCH, "words per block differ (%u vs %u)", a->L, b->L);
+    const uint64_t na = a->n_blocks * a->L, nb = b->n_blocks * b->L;
+    if (nb == 0) return CSGN_OK;
+    if (na + nb <= a->cap_words) {
+        // b == a is fine: source [0,na) and destination [na,2na) do not overlap
+        cudaError_t e = launch_concat(a->d, na, b->d, nb, a->d, g.stream);
+        if (e != cudaSuccess) return cuda_fail(e, "append kernel");
+    } else {
+        const uint64_t cap = std::max<uint64_t>(na + nb, 2 * a->cap_words);
+        uint64_t *nd = nullptr;
+        int rc = dev_alloc(cap, &nd);
+        if (rc != CSGN_OK && cap > na + nb) rc = dev_alloc(na + nb, &nd);  // no room to double
+        if (rc != CSGN_OK) return rc;
+        cudaError_t e = launch_concat(a->d, na, b->d, nb, nd, g.stream);
+        if (e != cudaSuccess) {
+            dev_free(nd);
+            return cuda_fail(e, "append kernel");
+        }
+        dev_free(a->d);  // stream-ordered: the copy above still reads it safely
+        a->d = nd;
+        a->cap_words = cap;
+    }
+    a->n_blocks += b->n_blocks;
+    return CSGN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K3 decrypt
+// ---------------------------------------------------------------------------
+int csgn_key_create(uint64_t N, const uint64_t *positions, uint32_t D, csgn_key **out) {
+    NEED_INIT();
+    if (!out || N == 0) return fail(CSGN_ERR_INVALID_ARGUMENT, "bad key arguments");
+    if (D && !positions) return fail(CSGN_ERR_INVALID_ARGUMENT, "null positions");
+    const uint32_t L = csgn_words_per_block(N);
+    std::vector<uint64_t> mask(L, 0);
+    for (uint32_t i = 0; i < D; ++i) {
+        if (positions[i] >= N)
+            return fail(CSGN_ERR_INVALID_ARGUMENT, "secret position %llu outside [0,%llu)",
+                        (unsigned long long)positions[i], (unsigned long long)N);
+        mask[positions[i] >> 6] |= 1ull << (63u - (positions[i] & 63u));
+    }
+    csgn_key *k = new csgn_key;
+    k->N = N;
+    k->L = L;
+    k->D = D;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&k->d_mask), (size_t)L * sizeof(uint64_t));
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(k->d_mask, mask.data(), (size_t)L * sizeof(uint64_t), cudaMemcpyHostToDevice, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);  // `mask` dies with this frame
+    std::fill(mask.begin(), mask.end(), 0);
+    if (e != cudaSuccess) {
+        if (k->d_mask) cudaFree(k->d_mask);
+        delete k;
+        return cuda_fail(e, "key upload");
+    }
+    *out = k;
+    return CSGN_OK;
+}
+
+int csgn_key_free(csgn_key *key) {
+    if (!key) return CSGN_OK;
+    if (g.inited && key->d_mask) {
+        cudaMemsetAsync(key->d_mask, 0, (size_t)key->L * sizeof(uint64_t), g.stream);  // zeroise, as the reference's dtor does
+        cudaStreamSynchronize(g.stream);
+        cudaFree(key->d_mask);
+    }
+    delete key;
+    return CSGN_OK;
+}
+
+int csgn_decrypt_count_async(const csgn_buf *c, const csgn_key *key, uint64_t *device_count) {
+    NEED_INIT();
+    if (!c || !key || !device_count) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
+    if (c->L != key->L)
+        return fail(CSGN_ERR_SHAPE_MISMATCH, "ciphertext has %u words per block, key expects %u", c->L, key->L);
+    cudaError_t e = launch_decrypt_count(c->d, c->n_blocks, c->L, key->d_mask, g.d_scratch, device_count, g.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "decrypt kernel");
+    return CSGN_OK;
+}
+
+int csgn_decrypt_count(const csgn_buf *c, const csgn_key *key, uint64_t *count) {
+    if (!count) return fail(CSGN_ERR_INVALID_ARGUMENT, "null output");
+    int rc = csgn_decrypt_count_async(c, key, g.d_scratch + 2);
+    if (rc != CSGN_OK) return rc;
+    CU(cudaMemcpyAsync(g.h_result, g.d_scratch + 2, sizeof(uint64_t), cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    *count = g.h_result[0];
+    return CSGN_OK;
+}
+
+int csgn_decrypt(const csgn_buf *c, const csgn_key *key, uint8_t *bit) {
+    if (!bit) return fail(CSGN_ERR_INVALID_ARGUMENT, "null output");
+    uint64_t count = 0;
+    int rc = csgn_decrypt_count(c, key, &count);
+    if (rc != CSGN_OK) return rc;
+    *bit = (uint8_t)(count & 1u);
+    return CSGN_OK;
+}
+
+int csgn_decrypt_positions(const csgn_buf *c, uint64_t N, const uint64_t *positions, uint32_t D, uint8_t *bit) {
+    csgn_key *k = nullptr;
+    int rc = csgn_key_create(N, positions, D, &k);
+    if (rc != CSGN_OK) return rc;
+    rc = csgn_decrypt(c, k, bit);
+    csgn_key_free(k);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// K4 permute
+// ---------------------------------------------------------------------------
+int csgn_perm_create(uint64_t N, const uint64_t *perm, csgn_perm **out) {
+    NEED_INIT();
+    if (!out || !perm || N == 0) return fail(CSGN_ERR_INVALID_ARGUMENT, "bad permutation arguments");
+    if (N >= (1ull << 32)) return fail(CSGN_ERR_INVALID_ARGUMENT, "N too large for the source map");
+    std::vector<uint32_t> map(N);
+    std::vector<uint8_t> seen(N, 0);
+    for (uint64_t i = 0; i < N; ++i) {
+        const uint64_t p = perm[i];
+        if (p >= N || seen[p])
+            return fail(CSGN_ERR_INVALID_ARGUMENT, "not a permutation of [0,%llu): entry %llu = %llu",
+                        (unsigned long long)N, (unsigned long long)i, (unsigned long long)p);
+        seen[p] = 1;
+        map[i] = (uint32_t)(((p >> 6) << 6) | (63u - (p & 63u)));
+    }
+    csgn_perm *h = new csgn_perm;
+    h->N = N;
+    h->L = csgn_words_per_block(N);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&h->d_map), (size_t)N * sizeof(uint32_t));
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(h->d_map, map.data(), (size_t)N * sizeof(uint32_t), cudaMemcpyHostToDevice, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) {
+        if (h->d_map) cudaFree(h->d_map);
+        delete h;
+        return cuda_fail(e, "permutation upload");
+    }
+    *out = h;
+    return CSGN_OK;
+}
+
+int csgn_perm_free(csgn_perm *perm) {
+    if (!perm) return CSGN_OK;
+    if (g.inited && perm->d_map) {
+        cudaStreamSynchronize(g.stream);
+        cudaFree(perm->d_map);
+    }
+    delete perm;
+    return CSGN_OK;
+}
+
+int csgn_permute_into(const csgn_buf *c, const csgn_perm *perm, csgn_buf *out) {
+    NEED_INIT();
+    if (!c || !perm || !out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
+    if (c->L != perm->L || out->L != perm->L)
+        return fail(CSGN_ERR_SHAPE_MISMATCH, "words per block: ciphertext %u, output %u, permutation %u", c->L,
+                    out->L, perm->L);
+    if (out->n_blocks > c->n_blocks)
+        return fail(CSGN_ERR_SHAPE_MISMATCH, "output holds more blocks than the input");
+    if (out->d == c->d) return fail(CSGN_ERR_INVALID_ARGUMENT, "permute cannot run in place");
+    cudaError_t e = launch_permute(c->d, out->n_blocks, c->L, (uint32_t)perm->N, perm->d_map, out->d, g.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "permute kernel");
+    return CSGN_OK;
+}
+
+int csgn_permute(const csgn_buf *c, const csgn_perm *perm, int strict_ref_truncate, csgn_buf **out) {
+    NEED_INIT();
+    if (!c || !perm || !out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
+    if (c->n_blocks == 0) return fail(CSGN_ERR_INVALID_ARGUMENT, "cannot permute an empty ciphertext");
+    csgn_buf *r = nullptr;
+    int rc = new_buf(strict_ref_truncate ? 1 : c->n_blocks, c->L, 0, &r);
+    if (rc != CSGN_OK) return rc;
+    rc = csgn_permute_into(c, perm, r);
+    if (rc != CSGN_OK) {
+        csgn_buf_free(r);
+        return rc;
+    }
+    *out = r;
+    return CSGN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// checksum, sharding
+// ---------------------------------------------------------------------------
+int csgn_buf_checksum(const csgn_buf *buf, uint64_t *xor_out, uint64_t *sum_out, uint64_t *wsum_out) {
+    NEED_INIT();
+    if (!buf) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
+    uint64_t *acc = g.d_scratch + 4;
+    CU(cudaMemsetAsync(acc, 0, 3 * sizeof(uint64_t), g.stream));
+    cudaError_t e = launch_checksum(buf->d, buf->n_blocks * buf->L, acc, g.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "checksum kernel");
+    CU(cudaMemcpyAsync(g.h_result + 4, acc, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    if (xor_out) *xor_out = g.h_result[4];
+    if (sum_out) *sum_out = g.h_result[5];
+    if (wsum_out) *wsum_out = g.h_result[6];
+    return CSGN_OK;
+}
+
+int csgn_shard_range(uint64_t n_blocks, int rank, int world, uint64_t *first, uint64_t *count) {
+    if (world < 1 || rank < 0 || rank >= world || !first || !count)
+        return fail(CSGN_ERR_INVALID_ARGUMENT, "bad shard arguments (rank %d of %d)", rank, world);
+    const uint64_t base = n_blocks / (uint64_t)world, extra = n_blocks % (uint64_t)world;
+    const uint64_t r = (uint64_t)rank;
+    *first = r * base + std::min<uint64_t>(r, extra);
+    *count = base + (r < extra ? 1 : 0);
+    return CSGN_OK;
+}
+
+}  // extern "C"

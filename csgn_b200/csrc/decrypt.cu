@@ -1,0 +1,180 @@
+// decrypt.cu -- K3, the decrypt fold.
+//
+//   count = #{ blocks k : for every word w, (v[k*L+w] & M[w]) == M[w] }
+//   decrypt = count & 1                       (reference src/SecretKey.cpp:126-140)
+//
+// M is the secret key as a position mask (bit 63-(s&63) of word s>>6 per secret
+// position s).  The reference first unpacks every bit to one byte
+// (src/SecretKey.cpp:113-124) and then ANDs the D selected bytes; testing the packed
+// words against the mask is the same predicate.
+//
+// Roofline: HBM READ bandwidth, 8*L bytes per block, one bit out.
+//
+// Shape of the kernel.  The ciphertext is read as one flat stream of 16-byte units
+// (L4 = L/2 per block), fully coalesced: a warp owns a chunk of 32 consecutive blocks
+// = 32*L4 units and walks it in L4 steps of 32 lanes x 16 bytes.  A lane marks its
+// unit "failing" when a key bit inside it is 0; __ballot_sync turns each step into
+// 32 bits of a per-chunk fail string kept in shared memory.  Block b of the chunk is
+// satisfied iff bits [b*L4, (b+1)*L4) of that string are all clear -- lane b checks
+// exactly that, so the per-block AND across lanes needs no shuffles, whatever L4 is.
+// The loads of a chunk are independent (unrolled, up to 10 x 16 B in flight per
+// lane).  Counts fold lane -> warp -> CTA -> one atomicAdd per CTA; the last CTA to
+// finish publishes the total and re-arms the scratch words, so a decrypt is ONE launch.
+#include "kernels.cuh"
+
+#include <algorithm>
+
+namespace csgn {
+namespace {
+
+constexpr int kDecThreads = 256;
+constexpr int kDecWarps = kDecThreads / 32;
+constexpr uint32_t kDecMaxL4 = 512;   // mask x2 + fail strings stay within 32 KB of shared memory
+
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) { return __ldcs(p); }
+
+__device__ __forceinline__ bool unit_fails(const uint4 v, const uint4 m) {
+    // some key bit inside this 16-byte unit is zero
+    return (((~v.x) & m.x) | ((~v.y) & m.y) | ((~v.z) & m.z) | ((~v.w) & m.w)) != 0u;
+}
+
+// Publish the CTA's count; the last CTA writes the grand total and resets scratch.
+__device__ __forceinline__ void fold_and_publish(uint64_t lane_count, uint64_t *scratch, uint64_t *count_out) {
+    __shared__ uint64_t s_warp[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) lane_count += __shfl_xor_sync(0xffffffffu, lane_count, off);
+    if (lane == 0) s_warp[warp] = lane_count;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t cta = 0;
+        const int nw = (blockDim.x + 31) >> 5;
+        for (int w = 0; w < nw; ++w) cta += s_warp[w];
+        if (cta) atomicAdd(reinterpret_cast<unsigned long long *>(scratch), (unsigned long long)cta);
+        __threadfence();
+        const unsigned long long ticket = atomicAdd(reinterpret_cast<unsigned long long *>(scratch + 1), 1ull);
+        if (ticket == (unsigned long long)gridDim.x - 1) {
+            __threadfence();
+            *count_out = atomicExch(reinterpret_cast<unsigned long long *>(scratch), 0ull);
+            scratch[1] = 0;
+        }
+    }
+}
+
+// L4C > 0: units per block known at compile time (fully unrolled walk); 0: runtime.
+template <int L4C, int UNROLL>
+__global__ void __launch_bounds__(kDecThreads)
+decrypt_count_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint32_t L4rt,
+                     const uint4 *__restrict__ M4, uint64_t *scratch, uint64_t *count_out) {
+    extern __shared__ uint4 smem[];
+    const uint32_t L4 = L4C ? (uint32_t)L4C : L4rt;
+    uint4 *sM2 = smem;                                               // mask, twice over
+    uint32_t *sF = reinterpret_cast<uint32_t *>(smem + 2 * L4);      // fail strings
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < 2 * L4; i += blockDim.x) sM2[i] = M4[i < L4 ? i : i - L4];
+    __syncthreads();
+
+    uint32_t *sFw = sF + warp * L4;
+    const uint4 *mk = sM2 + (lane % L4);
+    const uint32_t step = 32u % L4;          // advance of the unit-in-block index per walk step
+    const uint64_t n_units = T * L4;
+    const uint64_t n_chunks = (T + 31) >> 5;
+    uint64_t my_count = 0;
+
+    for (uint64_t chunk = (uint64_t)blockIdx.x * kDecWarps + warp; chunk < n_chunks;
+         chunk += (uint64_t)gridDim.x * kDecWarps) {
+        const uint64_t q_lane = chunk * 32u * L4 + lane;
+        uint32_t koff = 0;                   // (32*r) % L4
+        for (uint32_t r = 0; r < L4; r += UNROLL) {
+            uint4 v[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const uint64_t q = q_lane + 32u * (r + u);
+                v[u] = (r + u < L4 && q < n_units) ? ld_stream(V4 + q) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if (r + u < L4) {            // warp-uniform
+                    const bool f = unit_fails(v[u], mk[koff]);
+                    const uint32_t bal = __ballot_sync(0xffffffffu, f);
+                    if (lane == 0) sFw[r + u] = bal;
+                    koff += step;
+                    if (koff >= L4) koff -= L4;
+                }
+            }
+        }
+        __syncwarp();
+        // lane b <-> block b of the chunk: bits [b*L4, b*L4+L4) of the fail string
+        const uint64_t blk = chunk * 32u + lane;
+        const uint32_t lo = lane * L4, hi = lo + L4;
+        uint32_t any = 0;
+        for (uint32_t w = lo >> 5; w <= (hi - 1) >> 5; ++w) {
+            const uint32_t first = max(lo, w << 5) - (w << 5);
+            const uint32_t last = min(hi, (w + 1) << 5) - (w << 5);   // exclusive, 1..32
+            const uint32_t m = (last - first == 32u) ? 0xffffffffu : (((1u << (last - first)) - 1u) << first);
+            any |= sFw[w] & m;
+        }
+        my_count += (blk < T && any == 0u) ? 1u : 0u;
+        __syncwarp();                        // before the next chunk overwrites sFw
+    }
+    fold_and_publish(my_count, scratch, count_out);
+}
+
+// Any L (odd, or too long for the fail string), any alignment: one warp per block.
+__global__ void __launch_bounds__(kDecThreads)
+decrypt_count_generic_kernel(const uint64_t *__restrict__ V, const uint64_t T, const uint32_t L,
+                             const uint64_t *__restrict__ M, uint64_t *scratch, uint64_t *count_out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    uint64_t my_count = 0;
+    for (uint64_t blk = warp_global; blk < T; blk += n_warps) {
+        const uint64_t *row = V + blk * L;
+        bool f = false;
+        for (uint32_t w = lane; w < L; w += 32) {
+            const uint64_t m = __ldg(M + w);
+            f |= ((~__ldcs(row + w)) & m) != 0ull;
+        }
+        const bool bad = __any_sync(0xffffffffu, f);
+        if (lane == 0 && !bad) ++my_count;
+    }
+    fold_and_publish(my_count, scratch, count_out);
+}
+
+template <int L4C, int UNROLL>
+cudaError_t launch_fast(const uint64_t *v, uint64_t T, uint32_t L4, const uint64_t *mask, uint64_t *scratch,
+                        uint64_t *count_out, uint32_t grid, cudaStream_t stream) {
+    const size_t smem = (size_t)2 * L4 * sizeof(uint4) + (size_t)kDecWarps * L4 * sizeof(uint32_t);
+    decrypt_count_kernel<L4C, UNROLL><<<grid, kDecThreads, smem, stream>>>(
+        reinterpret_cast<const uint4 *>(v), T, L4, reinterpret_cast<const uint4 *>(mask), scratch, count_out);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_decrypt_count(const uint64_t *v, uint64_t T, uint32_t L, const uint64_t *mask,
+                                 uint64_t *scratch, uint64_t *count_out, cudaStream_t stream) {
+    if (T == 0 || L == 0) return cudaMemsetAsync(count_out, 0, sizeof(uint64_t), stream);
+    const DeviceProps &dp = device_props();
+    const uint64_t ctas_per_sm = (uint64_t)env_long("CSGN_DEC_CTAS_PER_SM", 8);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(mask)) & 15u) == 0;
+    const uint32_t L4 = L / 2;
+    cudaError_t err;
+    if ((L & 1u) || !aligned || L4 > kDecMaxL4 || env_long("CSGN_DEC_GENERIC", 0)) {
+        const uint64_t want = (T + kDecWarps - 1) / kDecWarps;
+        const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, dp.sm_count * ctas_per_sm));
+        decrypt_count_generic_kernel<<<grid, kDecThreads, 0, stream>>>(v, T, L, mask, scratch, count_out);
+        err = cudaGetLastError();
+    } else {
+        const uint64_t n_chunks = (T + 31) / 32;
+        const uint64_t want = (n_chunks + kDecWarps - 1) / kDecWarps;
+        const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, dp.sm_count * ctas_per_sm));
+        if (L4 == 10) err = launch_fast<10, 10>(v, T, L4, mask, scratch, count_out, grid, stream);       // N=1247
+        else if (L4 == 128) err = launch_fast<128, 8>(v, T, L4, mask, scratch, count_out, grid, stream); // N=16383
+        else err = launch_fast<0, 4>(v, T, L4, mask, scratch, count_out, grid, stream);
+    }
+    count_launch();
+    return err;
+}
+
+}  // namespace csgn

@@ -1,0 +1,49 @@
+// kernels.cuh -- internal launch interface between the C ABI (capi.cu) and the
+// sm_100a kernels.  Device pointers + sizes + stream; every launcher returns the
+// cudaError_t of the launch and bumps the library's launch counter.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace csgn {
+
+struct DeviceProps {
+    int device = -1;
+    int sm_count = 148;
+    int cc = 100;
+    size_t smem_optin = 227 * 1024;
+};
+const DeviceProps &device_props();
+void set_device_props(const DeviceProps &p);
+void count_launch(unsigned n = 1);
+uint64_t launches();
+
+// Integer environment knob (tuning sweeps only); `dflt` when unset or malformed.
+long env_long(const char *name, long dflt);
+
+// K1  out[(i*T2+j)*L+k] = a[i*L+k] & b[j*L+k]        (reference src/Ciphertext.cpp:153-163)
+cudaError_t launch_mul(const uint64_t *a, uint64_t T1, const uint64_t *b, uint64_t T2, uint32_t L,
+                       uint64_t *out, cudaStream_t stream);
+
+// K2  out = a || b                                     (reference src/Ciphertext.cpp:107-122)
+// Either source may be null/empty; out may alias a (append in place) when a == out.
+cudaError_t launch_concat(const uint64_t *a, uint64_t n_words_a, const uint64_t *b, uint64_t n_words_b,
+                          uint64_t *out, cudaStream_t stream);
+
+// K3  count of blocks with all_w((v[w] & M[w]) == M[w]) (reference src/SecretKey.cpp:126-140)
+// `scratch` is two zero-initialised uint64 (running count, CTA ticket) that the kernel
+// leaves zeroed again; the total is written to *count_out (device memory).
+cudaError_t launch_decrypt_count(const uint64_t *v, uint64_t T, uint32_t L, const uint64_t *mask,
+                                 uint64_t *scratch, uint64_t *count_out, cudaStream_t stream);
+
+// K4  out_bit[i] = in_bit[perm[i]] for every block     (reference src/Ciphertext.cpp:24-69)
+// src_map[i] = (perm[i]>>6)<<6 | (63 - (perm[i]&63)): source word and right-shift.
+cudaError_t launch_permute(const uint64_t *in, uint64_t T, uint32_t L, uint32_t N, const uint32_t *src_map,
+                           uint64_t *out, cudaStream_t stream);
+
+// xor / wrapping sum / sum(w[i]*(2i+1)) of n_words words, accumulated into acc[0..2]
+// (device, must be zeroed by the caller).
+cudaError_t launch_checksum(const uint64_t *v, uint64_t n_words, uint64_t *acc, cudaStream_t stream);
+
+}  // namespace csgn

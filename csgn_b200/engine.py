@@ -1,0 +1,281 @@
+"""Python host layer over the C ABI -- used by tests, bench.py and torch.distributed
+launches.  It mirrors the names of the reference's interface for this path
+(Context / Ciphertext + * / SecretKey.decrypt / applyPermutation), but holds no
+arithmetic of its own: every operation is one call into libcsgn.so.
+
+The product for C++ users is csgn_b200/certfhe (libcertFHE.so); this module is the
+same boundary seen from Python.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _native
+from ._native import CsgnError, check  # noqa: F401
+
+_vp = ctypes.c_void_p
+
+
+def _lib():
+    return _native.load()
+
+
+def init(device=-1):
+    """csgn_init: bind this process to one GPU (LOCAL_RANK by default)."""
+    check(_lib().csgn_init(int(device)))
+
+
+def shutdown():
+    check(_lib().csgn_shutdown())
+
+
+def is_initialized():
+    return bool(_lib().csgn_is_initialized())
+
+
+def sync():
+    check(_lib().csgn_sync())
+
+
+def launch_count():
+    return int(_lib().csgn_launch_count())
+
+
+def set_stream(cuda_stream_ptr):
+    """Enqueue on an external stream (e.g. torch.cuda.current_stream().cuda_stream); 0/None = own."""
+    check(_lib().csgn_set_stream(_vp(cuda_stream_ptr or 0)))
+
+
+def device_info():
+    sm, cc = ctypes.c_int(), ctypes.c_int()
+    tot, fr = ctypes.c_uint64(), ctypes.c_uint64()
+    check(_lib().csgn_device_info(ctypes.byref(sm), ctypes.byref(tot), ctypes.byref(fr), ctypes.byref(cc)))
+    return {"sm_count": sm.value, "hbm_total": tot.value, "hbm_free": fr.value, "cc": cc.value}
+
+
+def words_per_block(N):
+    return int(_lib().csgn_words_per_block(int(N)))
+
+
+def shard_range(n_blocks, rank, world):
+    first, count = ctypes.c_uint64(), ctypes.c_uint64()
+    check(_lib().csgn_shard_range(int(n_blocks), int(rank), int(world), ctypes.byref(first), ctypes.byref(count)))
+    return first.value, count.value
+
+
+class Context:
+    """Context(N, D): reference src/Context.cpp:20-29."""
+
+    def __init__(self, N, D):
+        self.N, self.D = int(N), int(D)
+        self.S = self.N // (2 * self.D)
+        self.L = words_per_block(self.N)
+
+    def getN(self):
+        return self.N
+
+    def getD(self):
+        return self.D
+
+    def getS(self):
+        return self.S
+
+    def getDefaultN(self):
+        return self.L
+
+
+def _host_words(a):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.uint64).reshape(-1))
+    return a
+
+
+class Ciphertext:
+    """Device-resident ciphertext: n_blocks blocks of ctx.L words behind a csgn_buf."""
+
+    def __init__(self, handle, ctx, keepalive=None):
+        self._h = handle
+        self.ctx = ctx
+        self._keepalive = keepalive  # e.g. the torch tensor a view was built over
+
+    # -- construction -----------------------------------------------------
+    @classmethod
+    def from_host(cls, words, ctx):
+        """Ciphertext(V, Bitlen, len, ctx) with the canonical Bitlen (src/Ciphertext.cpp:344-358)."""
+        w = _host_words(words)
+        if w.size % ctx.L:
+            raise ValueError("len must be a multiple of the %d words per block" % ctx.L)
+        h = _vp()
+        check(_lib().csgn_buf_upload(w.ctypes.data_as(_vp), w.size // ctx.L, ctx.L, ctypes.byref(h)))
+        sync()  # `w` may be a temporary; the copy is asynchronous
+        return cls(h, ctx)
+
+    @classmethod
+    def from_host_ptr(cls, host_ptr, n_blocks, ctx):
+        """Asynchronous upload from caller-managed (ideally pinned) host memory."""
+        h = _vp()
+        check(_lib().csgn_buf_upload(_vp(host_ptr), int(n_blocks), ctx.L, ctypes.byref(h)))
+        return cls(h, ctx)
+
+    @classmethod
+    def empty(cls, n_blocks, ctx):
+        h = _vp()
+        check(_lib().csgn_buf_alloc(int(n_blocks), ctx.L, ctypes.byref(h)))
+        return cls(h, ctx)
+
+    @classmethod
+    def view(cls, device_ptr, n_blocks, ctx, keepalive=None):
+        h = _vp()
+        check(_lib().csgn_buf_wrap(_vp(device_ptr), int(n_blocks), ctx.L, ctypes.byref(h)))
+        return cls(h, ctx, keepalive)
+
+    @classmethod
+    def from_tensor(cls, t, ctx):
+        """View over a torch int64/uint64 CUDA tensor of n_blocks*L words (no copy)."""
+        assert t.is_cuda and t.is_contiguous() and t.element_size() == 8
+        return cls.view(t.data_ptr(), t.numel() // ctx.L, ctx, keepalive=t)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib().csgn_buf_free(h)
+            except Exception:
+                pass
+
+    # -- accessors ----------------------------------------------------------
+    @property
+    def n_blocks(self):
+        return int(_lib().csgn_buf_blocks(self._h))
+
+    def getLen(self):
+        """Length in 64-bit words, as the reference reports it (src/Ciphertext.cpp:417-420)."""
+        return self.n_blocks * self.ctx.L
+
+    def device_ptr(self):
+        return _lib().csgn_buf_device_ptr(self._h) or 0
+
+    def getValues(self):
+        out = np.empty(self.getLen(), dtype=np.uint64)
+        check(_lib().csgn_buf_download(self._h, out.ctypes.data_as(_vp)))
+        return out
+
+    def download_range(self, first_block, n_blocks):
+        out = np.empty(n_blocks * self.ctx.L, dtype=np.uint64)
+        check(_lib().csgn_buf_download_range(self._h, int(first_block), int(n_blocks), out.ctypes.data_as(_vp)))
+        return out
+
+    def getBitlen(self):
+        """The reference's side array, synthesised: [64]*(L-1)+[N%64 or 64] per block."""
+        L, rem = self.ctx.L, self.ctx.N % 64
+        one = np.full(L, 64, dtype=np.uint64)
+        if rem:
+            one[L - 1] = rem
+        return np.tile(one, self.n_blocks)
+
+    def size(self):
+        """Bytes, by the reference's formula (src/Ciphertext.cpp:91-101)."""
+        return 32 + 16 * self.getLen()
+
+    def checksum(self):
+        x, s, h = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        check(_lib().csgn_buf_checksum(self._h, ctypes.byref(x), ctypes.byref(s), ctypes.byref(h)))
+        return x.value, s.value, h.value
+
+    def clone(self):
+        h = _vp()
+        check(_lib().csgn_buf_clone(self._h, ctypes.byref(h)))
+        return Ciphertext(h, self.ctx)
+
+    # -- the hot path ---------------------------------------------------------
+    def __mul__(self, other):
+        h = _vp()
+        check(_lib().csgn_mul(self._h, other._h, ctypes.byref(h)))
+        return Ciphertext(h, self.ctx)
+
+    def mul_into(self, other, out):
+        check(_lib().csgn_mul_into(self._h, other._h, out._h))
+        return out
+
+    def __imul__(self, other):
+        h = _vp()
+        check(_lib().csgn_mul(self._h, other._h, ctypes.byref(h)))
+        old, self._h = self._h, h
+        _lib().csgn_buf_free(old)
+        return self
+
+    def __add__(self, other):
+        h = _vp()
+        check(_lib().csgn_concat(self._h, other._h, ctypes.byref(h)))
+        return Ciphertext(h, self.ctx)
+
+    def __iadd__(self, other):
+        check(_lib().csgn_append(self._h, other._h))
+        return self
+
+    def applyPermutation(self, perm, strict_ref_truncate=False):
+        h = _vp()
+        check(_lib().csgn_permute(self._h, perm._h, 1 if strict_ref_truncate else 0, ctypes.byref(h)))
+        return Ciphertext(h, self.ctx)
+
+    def permute_into(self, perm, out):
+        check(_lib().csgn_permute_into(self._h, perm._h, out._h))
+        return out
+
+
+class SecretKey:
+    """Secret positions held as a device position mask (csgn_key)."""
+
+    def __init__(self, ctx, positions):
+        self.ctx = ctx
+        self.s = _host_words(positions)
+        self._h = _vp()
+        check(_lib().csgn_key_create(ctx.N, self.s.ctypes.data_as(_vp), self.s.size, ctypes.byref(self._h)))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib().csgn_key_free(h)
+            except Exception:
+                pass
+
+    def decrypt(self, ct):
+        bit = ctypes.c_uint8()
+        check(_lib().csgn_decrypt(ct._h, self._h, ctypes.byref(bit)))
+        return int(bit.value)
+
+    def count_satisfied(self, ct):
+        c = ctypes.c_uint64()
+        check(_lib().csgn_decrypt_count(ct._h, self._h, ctypes.byref(c)))
+        return int(c.value)
+
+    def count_satisfied_async(self, ct, device_count_ptr):
+        check(_lib().csgn_decrypt_count_async(ct._h, self._h, _vp(device_count_ptr)))
+
+    def size(self):
+        return 16 + 8 * int(self.s.size)
+
+
+class Permutation:
+    """Permutation of [0,N) held as a device bit-source map (csgn_perm)."""
+
+    def __init__(self, ctx, perm):
+        self.ctx = ctx
+        self.p = _host_words(perm)
+        self._h = _vp()
+        check(_lib().csgn_perm_create(ctx.N, self.p.ctypes.data_as(_vp), ctypes.byref(self._h)))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib().csgn_perm_free(h)
+            except Exception:
+                pass
+
+
+def decrypt_positions(ct, ctx, positions):
+    s = _host_words(positions)
+    bit = ctypes.c_uint8()
+    check(_lib().csgn_decrypt_positions(ct._h, ctx.N, s.ctypes.data_as(_vp), s.size, ctypes.byref(bit)))
+    return int(bit.value)

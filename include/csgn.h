@@ -1,0 +1,156 @@
+/*
+ * csgn.h -- C ABI of the B200-native CSGN / certFHE ciphertext evaluation engine.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types.
+ * It sits exactly on the raw-pointer seam the reference already has -- the private
+ * member functions of Ciphertext / SecretKey that take `uint64_t*` + lengths
+ * (reference src/Ciphertext.h:34,43,58 and src/SecretKey.h:47,60).  The certFHE C++
+ * classes of this repository (csgn_b200/certfhe/) call nothing else; a maintainer
+ * of the reference would bind the same entry points from src/Ciphertext.cpp and
+ * src/SecretKey.cpp (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every function returns CSGN_OK (0) or a negative csgn_status; the message of
+ *     the last failure on the calling thread is csgn_last_error();
+ *   - there is no CPU fallback: without a usable sm_100 device every call fails;
+ *   - a "block" is one N-bit ciphertext unit stored as L = ceil(N/64) uint64 words,
+ *     bits MSB-first (position p -> word p>>6, bit 63-(p&63)); a ciphertext is a
+ *     dense array of n_blocks*L words; the reference's `bitlen` side array is the
+ *     fixed pattern [64]*(L-1)+[N%64] and is never materialised on the device;
+ *   - `csgn_buf` handles own device memory, are created and freed only here, and
+ *     belong to the process' bound device (one process per GPU);
+ *   - work is enqueued on one stream (csgn_set_stream); calls that return data to
+ *     the host (download, decrypt) synchronise that stream, the others do not.
+ */
+#ifndef CSGN_H_
+#define CSGN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum csgn_status {
+    CSGN_OK = 0,
+    CSGN_ERR_NOT_INITIALIZED = -1,
+    CSGN_ERR_INVALID_ARGUMENT = -2,
+    CSGN_ERR_CUDA = -3,
+    CSGN_ERR_NO_DEVICE = -4,
+    CSGN_ERR_SHAPE_MISMATCH = -5,
+    CSGN_ERR_OUT_OF_MEMORY = -6
+} csgn_status;
+
+typedef struct csgn_buf csgn_buf;   /* device-resident ciphertext words            */
+typedef struct csgn_key csgn_key;   /* secret positions as a device position mask  */
+typedef struct csgn_perm csgn_perm; /* permutation as a device bit-source map      */
+
+/* ---- library ------------------------------------------------------------- */
+
+/* One-time initialisation; the CUDA half of Library::initializeLibrary
+ * (src/Helpers.cpp:8-12).  Binds the process to `device` (-1: LOCAL_RANK env or 0),
+ * creates the work stream and the memory pool.  Idempotent for the same device. */
+int csgn_init(int device);
+int csgn_shutdown(void);
+int csgn_is_initialized(void);
+const char *csgn_last_error(void);
+const char *csgn_version(void);
+/* SM count, total/free HBM bytes, compute capability (major*10+minor). */
+int csgn_device_info(int *sm_count, uint64_t *hbm_total, uint64_t *hbm_free, int *cc);
+/* Use an external cudaStream_t (e.g. torch's current stream); NULL restores the
+ * library's own stream. */
+int csgn_set_stream(void *cuda_stream);
+void *csgn_get_stream(void);
+int csgn_sync(void);
+/* Kernels launched by this library since csgn_init (for bench.py's gpu_launches). */
+uint64_t csgn_launch_count(void);
+
+/* Block geometry of Context(N,D): src/Context.cpp:20-29. */
+uint32_t csgn_words_per_block(uint64_t N);
+
+/* Pinned host staging memory for uploads/downloads that should overlap compute. */
+int csgn_host_alloc(size_t bytes, void **out);
+int csgn_host_free(void *p);
+
+/* ---- ciphertext buffers (storage behind certFHE::Ciphertext, src/Ciphertext.h:17-21) */
+
+/* Deep-copies n_blocks*L host words to the device: the Ciphertext(V,Bitlen,len,ctx)
+ * constructor / setValues (src/Ciphertext.cpp:344-358, :392-403). */
+int csgn_buf_upload(const uint64_t *host_words, uint64_t n_blocks, uint32_t L, csgn_buf **out);
+/* Uninitialised device storage for n_blocks blocks. */
+int csgn_buf_alloc(uint64_t n_blocks, uint32_t L, csgn_buf **out);
+/* Non-owning view over caller-owned device memory (e.g. a torch tensor). */
+int csgn_buf_wrap(void *device_words, uint64_t n_blocks, uint32_t L, csgn_buf **out);
+/* Device-to-device deep copy: the copy constructor / operator= (src/Ciphertext.cpp:306-363). */
+int csgn_buf_clone(const csgn_buf *src, csgn_buf **out);
+/* getValues() (src/Ciphertext.cpp:422-425): all words, or a block range, to the host. */
+int csgn_buf_download(const csgn_buf *buf, uint64_t *host_words);
+int csgn_buf_download_range(const csgn_buf *buf, uint64_t first_block, uint64_t n_blocks,
+                            uint64_t *host_words);
+int csgn_buf_free(csgn_buf *buf);
+uint64_t csgn_buf_blocks(const csgn_buf *buf);
+uint32_t csgn_buf_words_per_block(const csgn_buf *buf);
+void *csgn_buf_device_ptr(const csgn_buf *buf);
+
+/* ---- the hot path -------------------------------------------------------- */
+
+/* Ciphertext::multiply (src/Ciphertext.cpp:133-179, :124-131):
+ *   out[(i*T2+j)*L+k] = a[i*L+k] & b[j*L+k],  T1*T2 blocks, i-major.
+ * csgn_mul allocates the result; csgn_mul_into writes into a buffer of exactly
+ * T1*T2 blocks (a view from csgn_buf_wrap included). */
+int csgn_mul(const csgn_buf *a, const csgn_buf *b, csgn_buf **out);
+int csgn_mul_into(const csgn_buf *a, const csgn_buf *b, csgn_buf *out);
+
+/* Ciphertext::add / operator+ (src/Ciphertext.cpp:107-122, :204-229): out = a || b. */
+int csgn_concat(const csgn_buf *a, const csgn_buf *b, csgn_buf **out);
+/* operator+= (src/Ciphertext.cpp:249-281): a = a || b, growing a's storage
+ * geometrically so that a chain of += copies each block O(1) times. */
+int csgn_append(csgn_buf *a, const csgn_buf *b);
+
+/* Secret key as the per-word position mask M[s>>6] |= 1<<(63-(s&63)); the block
+ * predicate of SecretKey::decrypt (src/SecretKey.cpp:131-137) is all_w((v&M)==M). */
+int csgn_key_create(uint64_t N, const uint64_t *positions, uint32_t D, csgn_key **out);
+int csgn_key_free(csgn_key *key);
+
+/* SecretKey::decrypt (src/SecretKey.cpp:104-147, :208-224): XOR over blocks of the
+ * AND of the D secret bits.  *bit receives 0/1.  An empty buffer decrypts to 0. */
+int csgn_decrypt(const csgn_buf *c, const csgn_key *key, uint8_t *bit);
+/* Number of blocks whose secret bits are all one (decrypt = count & 1).  This is
+ * the per-shard partial a multi-GPU decrypt all-reduces (sum, then & 1). */
+int csgn_decrypt_count(const csgn_buf *c, const csgn_key *key, uint64_t *count);
+/* Same, asynchronous: the count is written to a device uint64 (caller-owned, e.g.
+ * the tensor handed to the NCCL all-reduce); no host synchronisation. */
+int csgn_decrypt_count_async(const csgn_buf *c, const csgn_key *key, uint64_t *device_count);
+/* One-shot convenience without a key handle. */
+int csgn_decrypt_positions(const csgn_buf *c, uint64_t N, const uint64_t *positions, uint32_t D,
+                           uint8_t *bit);
+
+/* Permutation as a device source map: out_bit[i] = in_bit[perm[i]], i < N
+ * (src/Ciphertext.cpp:33-34).  Fails unless perm is a bijection of [0,N). */
+int csgn_perm_create(uint64_t N, const uint64_t *perm, csgn_perm **out);
+int csgn_perm_free(csgn_perm *perm);
+/* Ciphertext::applyPermutation (src/Ciphertext.cpp:7-89).  strict_ref_truncate = 0
+ * permutes every block (Dec_{pi(k)}(pi(c)) = Dec_k(c) for multi-block c);
+ * strict_ref_truncate = 1 reproduces the reference exactly: the result is block 0
+ * permuted, one block long (src/Ciphertext.cpp:33-40). Pad bits of the last word
+ * come out zero. */
+int csgn_permute(const csgn_buf *c, const csgn_perm *perm, int strict_ref_truncate, csgn_buf **out);
+int csgn_permute_into(const csgn_buf *c, const csgn_perm *perm, csgn_buf *out);
+
+/* Three order-insensitive/-sensitive folds of all words of a buffer, computed on the
+ * device (xor, wrapping sum, and sum of word*(2*index+1) mod 2^64) -- lets tests
+ * compare products that are too large to download. */
+int csgn_buf_checksum(const csgn_buf *buf, uint64_t *xor_out, uint64_t *sum_out, uint64_t *wsum_out);
+
+/* ---- sharding helpers (one process per GPU) ------------------------------- */
+
+/* Contiguous range of the LEFT operand's blocks owned by `rank` of `world`:
+ * rank g multiplies a[first..first+count) by the replicated right operand and owns
+ * output blocks [first*T2, (first+count)*T2) -- globally i-major like the reference. */
+int csgn_shard_range(uint64_t n_blocks, int rank, int world, uint64_t *first, uint64_t *count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSGN_H_ */

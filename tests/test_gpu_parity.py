@@ -1,0 +1,383 @@
+"""GPU: the CUDA path, called through the C ABI, against the oracle -- bit-exact.
+
+Small and medium sizes compare every output word with oracle/csgn_oracle.c on the
+same seeded inputs and with the golden fixtures generated from the unmodified
+reference; BASELINE.json's full sizes are checked through size-independent
+properties (streamed checksums, multiplicativity of the satisfied-block count,
+chunk identities, permute/decrypt round trips)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import sha, unhex
+from oracle.pyoracle import pad_mask, random_blocks, random_key, srand, words_per_block
+
+pytestmark = pytest.mark.gpu
+
+
+def _ct(engine, words, N, D=16):
+    return engine.Ciphertext.from_host(words, engine.Context(N, D))
+
+
+class _Env:
+    """Temporarily set tuning knobs (read by the launchers on every call)."""
+
+    def __init__(self, **kv):
+        self.kv = {k: str(v) for k, v in kv.items()}
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        os.environ.update(self.kv)
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+# ---------------------------------------------------------------------------
+# K1 multiply
+# ---------------------------------------------------------------------------
+MUL_SHAPES = [(1, 1), (1, 7), (7, 1), (2, 2), (37, 53), (300, 200), (1000, 3), (3, 1000), (129, 65)]
+
+
+@pytest.mark.parametrize("N", [1247, 16383, 65, 191, 63, 2048, 4097, 33000, 70000])
+def test_mul_matches_oracle(engine, oracle, N):
+    L = words_per_block(N)
+    rng = np.random.default_rng(N)
+    shapes = MUL_SHAPES if L <= 64 else [(1, 1), (1, 5), (5, 1), (9, 14), (40, 33)]
+    for T1, T2 in shapes:
+        a, b = random_blocks(rng, T1, N), random_blocks(rng, T2, N)
+        got = (_ct(engine, a, N) * _ct(engine, b, N)).getValues()
+        assert got.size == T1 * T2 * L
+        assert np.array_equal(got, oracle.mul(a, b, L)), (N, T1, T2)
+
+
+@pytest.mark.parametrize("knobs", [dict(CSGN_MUL_U=1), dict(CSGN_MUL_U=2, CSGN_MUL_R=1), dict(CSGN_MUL_U=8, CSGN_MUL_R=5),
+                                   dict(CSGN_MUL_U=4, CSGN_MUL_R=64, CSGN_MUL_GRID=3), dict(CSGN_MUL_TPB=160),
+                                   dict(CSGN_MUL_TPB=512, CSGN_MUL_U=8), dict(CSGN_MUL_GENERIC=1)])
+def test_mul_every_kernel_variant(engine, oracle, knobs):
+    rng = np.random.default_rng(99)
+    for N in (1247, 16383):
+        L = words_per_block(N)
+        for T1, T2 in ((61, 97), (5, 700), (200, 1)):
+            if N == 16383:
+                T1, T2 = max(1, T1 // 4), max(1, T2 // 4)
+            a, b = random_blocks(rng, T1, N), random_blocks(rng, T2, N)
+            with _Env(**knobs):
+                got = (_ct(engine, a, N) * _ct(engine, b, N)).getValues()
+            assert np.array_equal(got, oracle.mul(a, b, L)), (knobs, N, T1, T2)
+
+
+def test_mul_inplace_and_chain(engine, oracle):
+    N, L = 1247, 20
+    rng = np.random.default_rng(3)
+    a, b, c = (random_blocks(rng, t, N) for t in (6, 5, 4))
+    x = _ct(engine, a, N)
+    x *= _ct(engine, b, N)
+    x *= _ct(engine, c, N)
+    want = oracle.mul(oracle.mul(a, b, L), c, L)
+    assert x.n_blocks == 120 and np.array_equal(x.getValues(), want)
+    # bitlen is the canonical pattern the reference propagates (src/Ciphertext.cpp:165-176)
+    assert np.array_equal(x.getBitlen(), oracle.canonical_bitlen(N, 120))
+    assert x.size() == 32 + 16 * 120 * L
+
+
+def test_mul_error_behaviour(engine):
+    a = _ct(engine, np.zeros(20, dtype=np.uint64), 1247)
+    b = _ct(engine, np.zeros(256, dtype=np.uint64), 16383, 64)
+    with pytest.raises(engine.CsgnError) as e:
+        a * b
+    assert e.value.code == -5
+    out = engine.Ciphertext.empty(3, engine.Context(1247, 16))
+    with pytest.raises(engine.CsgnError):
+        a.mul_into(a, out)
+
+
+# ---------------------------------------------------------------------------
+# golden fixtures from the unmodified reference
+# ---------------------------------------------------------------------------
+def test_golden_cases_end_to_end(engine, golden):
+    for c in golden["cases"]:
+        N, D, L = c["N"], c["D"], c["L"]
+        ctx = engine.Context(N, D)
+        key = engine.SecretKey(ctx, c["key"])
+        a = engine.Ciphertext.from_host(unhex(c["enc_a"]), ctx)
+        b = engine.Ciphertext.from_host(unhex(c["enc_b"]), ctx)
+        prod, summ = a * b, a + b
+        pv, sv = prod.getValues(), summ.getValues()
+        assert pv.size == c["mul_len"] and sha(pv) == c["mul_sha256"]
+        assert sha(prod.getBitlen()) == c["mul_bitlen_sha256"]
+        assert sv.size == c["add_len"] and sha(sv) == c["add_sha256"]
+        assert sha(summ.getBitlen()) == c["add_bitlen_sha256"]
+        assert key.decrypt(a) == c["dec_a"] and key.decrypt(b) == c["dec_b"]
+        assert key.decrypt(prod) == c["dec_mul"] and key.decrypt(summ) == c["dec_add"]
+        assert a.size() == 32 + 16 * a.getLen() and key.size() == c["sk_size"]
+        # permutation: regenerate from the fixture's seed when the full list is not stored
+        if "perm" in c:
+            perm = np.array(c["perm"], dtype=np.uint64)
+        else:
+            from oracle.pyoracle import Oracle
+            srand(c["seed"] + 2)
+            perm = Oracle().perm_generate(N)
+            assert sha(perm) == c["perm_sha256"]
+        p = engine.Permutation(ctx, perm)
+        strict = a.applyPermutation(p, strict_ref_truncate=True)
+        assert strict.getLen() == c["permute_strict_len"]
+        assert np.array_equal(strict.getValues(), unhex(c["permute_strict"]))
+        allb = a.applyPermutation(p)
+        assert sha(allb.getValues()) == c["permute_each_block_sha256"]
+        pkey = engine.SecretKey(ctx, c["permuted_key"])
+        assert pkey.decrypt(allb) == c["dec_permuted"]
+
+
+def test_golden_raw_cases(engine, golden):
+    for c in golden["raw_cases"]:
+        N, L = c["N"], c["L"]
+        rng = np.random.default_rng(c["seed"])
+        a = rng.integers(0, 2**64, size=(c["T1"], L), dtype=np.uint64)
+        b = rng.integers(0, 2**64, size=(c["T2"], L), dtype=np.uint64)
+        a[:, L - 1] &= pad_mask(N)
+        b[:, L - 1] &= pad_mask(N)
+        key_pos = rng.permutation(N)[:c["D"]].astype(np.uint64)
+        ctx = engine.Context(N, c["D"])
+        prod = engine.Ciphertext.from_host(a, ctx) * engine.Ciphertext.from_host(b, ctx)
+        assert sha(prod.getValues()) == c["mul_sha256"]
+        key = engine.SecretKey(ctx, key_pos)
+        assert key.decrypt(prod) == c["dec_mul"]
+        assert engine.decrypt_positions(prod, ctx, key_pos) == c["dec_mul"]
+
+
+# ---------------------------------------------------------------------------
+# K3 decrypt
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("N,D", [(1247, 1), (1247, 3), (1247, 16), (16383, 2), (16383, 64), (65, 1), (191, 2),
+                                 (63, 2), (2048, 3), (4097, 2), (33000, 2), (70000, 1)])
+def test_decrypt_count_matches_oracle(engine, oracle, N, D):
+    rng = np.random.default_rng(N * 7 + D)
+    L = words_per_block(N)
+    sizes = [0, 1, 2, 31, 32, 33, 255, 256, 257, 1000, 4099] if L <= 64 else [0, 1, 31, 33, 300]
+    ctx = engine.Context(N, D)
+    for T in sizes:
+        v = random_blocks(rng, T, N)
+        s = random_key(rng, N, D)
+        rng.shuffle(s)
+        key = engine.SecretKey(ctx, s)
+        ct = engine.Ciphertext.from_host(v, ctx)
+        assert key.count_satisfied(ct) == oracle.count_satisfied(v, N, s), (N, D, T)
+        assert key.decrypt(ct) == oracle.decrypt(v, N, s)
+    with _Env(CSGN_DEC_GENERIC=1):
+        v = random_blocks(rng, 777, N)
+        s = random_key(rng, N, D)
+        assert engine.SecretKey(ctx, s).count_satisfied(engine.Ciphertext.from_host(v, ctx)) == oracle.count_satisfied(v, N, s)
+
+
+def test_decrypt_real_ciphertexts(engine, oracle):
+    # fresh encryptions by the oracle's reference-order encrypt; D = 16 and 64
+    for N, D, n in ((1247, 16, 200), (16383, 64, 12)):
+        rng = np.random.default_rng(N)
+        s = rng.permutation(N)[:D].astype(np.uint64)
+        bits = rng.integers(0, 2, size=n)
+        srand(5)
+        enc = np.concatenate([oracle.encrypt(int(x), N, D, s) for x in bits])
+        ctx = engine.Context(N, D)
+        key = engine.SecretKey(ctx, s)
+        ct = engine.Ciphertext.from_host(enc, ctx)
+        assert key.count_satisfied(ct) == int(bits.sum())
+        assert key.decrypt(ct) == int(bits.sum() & 1) == oracle.decrypt(enc, N, s)
+        sq = ct * ct
+        assert key.count_satisfied(sq) == int(bits.sum()) ** 2
+        # a wrong key position flips blocks off
+        s2 = s.copy()
+        s2[0] = (s2[0] + 1) % N if ((s2[0] + 1) % N) not in s else s2[0]
+        assert engine.SecretKey(ctx, s2).count_satisfied(ct) == oracle.count_satisfied(enc, N, s2)
+
+
+def test_key_rejects_out_of_range_position(engine):
+    with pytest.raises(engine.CsgnError):
+        engine.SecretKey(engine.Context(1247, 2), [5, 1247])
+
+
+# ---------------------------------------------------------------------------
+# K2 add
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("N", [1247, 191, 63, 16383])
+def test_add_and_append(engine, oracle, N):
+    rng = np.random.default_rng(N + 1)
+    L = words_per_block(N)
+    for T1, T2 in ((1, 1), (3, 5), (1000, 1), (1, 1000), (257, 255)):
+        if L > 64:
+            T1, T2 = min(T1, 40), min(T2, 40)
+        a, b = random_blocks(rng, T1, N), random_blocks(rng, T2, N)
+        ca, cb = _ct(engine, a, N), _ct(engine, b, N)
+        assert np.array_equal((ca + cb).getValues(), oracle.concat(a, b))
+        ca += cb
+        assert np.array_equal(ca.getValues(), oracle.concat(a, b))
+    # a chain of += (geometric growth) and a self-append
+    acc = _ct(engine, random_blocks(rng, 1, N), N)
+    want = acc.getValues()
+    for i in range(12):
+        piece = random_blocks(rng, 1 + i % 3, N)
+        acc += _ct(engine, piece, N)
+        want = oracle.concat(want, piece)
+    acc += acc
+    want = oracle.concat(want, want)
+    assert np.array_equal(acc.getValues(), want)
+    assert np.array_equal(acc.getBitlen(), oracle.canonical_bitlen(N, want.size // L))
+
+
+# ---------------------------------------------------------------------------
+# K4 permute
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("N", [1247, 16383, 65, 191, 63, 2048, 4097])
+def test_permute_matches_oracle(engine, oracle, N):
+    rng = np.random.default_rng(N + 2)
+    L = words_per_block(N)
+    ctx = engine.Context(N, 4)
+    perm = rng.permutation(N).astype(np.uint64)
+    p = engine.Permutation(ctx, perm)
+    for T in ([1, 2, 31, 33, 100, 1025] if L <= 64 else [1, 3, 70]):
+        v = random_blocks(rng, T, N)
+        ct = engine.Ciphertext.from_host(v, ctx)
+        allb = ct.applyPermutation(p).getValues()
+        assert np.array_equal(allb, oracle.permute_all(v, N, perm)), (N, T)
+        assert not np.any(allb.reshape(T, L)[:, -1] & ~pad_mask(N))      # pad bits stay zero
+        strict = ct.applyPermutation(p, strict_ref_truncate=True).getValues()
+        assert np.array_equal(strict, oracle.permute_block(v[:L], N, perm))
+    # Dec_{pi(k)}(pi(c)) = Dec_k(c)
+    s = random_key(rng, N, 2)
+    v = random_blocks(rng, 500 if L <= 64 else 40, N)
+    ct = engine.Ciphertext.from_host(v, ctx)
+    k1 = engine.SecretKey(ctx, s)
+    k2 = engine.SecretKey(ctx, oracle.key_permute(N, s, perm))
+    assert k1.count_satisfied(ct) == k2.count_satisfied(ct.applyPermutation(p))
+    # identity and inverse round trip
+    ident = engine.Permutation(ctx, np.arange(N, dtype=np.uint64))
+    assert np.array_equal(ct.applyPermutation(ident).getValues(), v)
+    inv = engine.Permutation(ctx, oracle.perm_inverse(perm))
+    assert np.array_equal(ct.applyPermutation(p).applyPermutation(inv).getValues(), v)
+
+
+def test_permutation_must_be_a_bijection(engine):
+    ctx = engine.Context(65, 2)
+    bad = np.arange(65, dtype=np.uint64)
+    bad[3] = 4
+    with pytest.raises(engine.CsgnError):
+        engine.Permutation(ctx, bad)
+
+
+# ---------------------------------------------------------------------------
+# BASELINE.json configs at full size: size-independent properties
+# ---------------------------------------------------------------------------
+def _full_size_properties(engine, oracle, N, D_small, T1, T2, seed):
+    L = words_per_block(N)
+    rng = np.random.default_rng(seed)
+    a, b = random_blocks(rng, T1, N), random_blocks(rng, T2, N)
+    ctx = engine.Context(N, D_small)
+    ca, cb = engine.Ciphertext.from_host(a, ctx), engine.Ciphertext.from_host(b, ctx)
+    prod = ca * cb
+    assert prod.n_blocks == T1 * T2
+    # (1) streamed checksum of the whole product (xor, sum, index-weighted sum)
+    assert prod.checksum() == oracle.mul_checksum(a, b, L)
+    # (2) sampled rows, bit-exact (i-major layout: row i = blocks [i*T2, (i+1)*T2))
+    for i in sorted({0, T1 - 1, T1 // 2, int(rng.integers(0, T1))}):
+        assert np.array_equal(prod.download_range(i * T2, T2), oracle.mul(a[i * L:(i + 1) * L], b, L))
+    # (3) chunk identity: (A1||A2)*B = (A1*B)||(A2*B)
+    h = T1 // 3
+    part = engine.Ciphertext.from_host(a[:h * L], ctx) * cb
+    assert part.checksum() == oracle.mul_checksum(a[:h * L], b, L)
+    assert np.array_equal(part.download_range(h * T2 - 1, 1), prod.download_range(h * T2 - 1, 1))
+    # (4) decrypt: the satisfied-block count is multiplicative, decrypt is its parity
+    s = random_key(rng, N, D_small)
+    key = engine.SecretKey(ctx, s)
+    na, nb = oracle.count_satisfied(a, N, s), oracle.count_satisfied(b, N, s)
+    assert key.count_satisfied(ca) == na and key.count_satisfied(cb) == nb
+    assert key.count_satisfied(prod) == na * nb
+    assert key.decrypt(prod) == (na & 1) & (nb & 1)
+    return prod, ctx, s, na * nb
+
+
+def test_config2_1000x1000_full_size(engine, oracle):
+    """Context(1247,16): two 1,000-block ciphertexts -> 1M output blocks, then decrypt."""
+    prod, ctx, s, count = _full_size_properties(engine, oracle, 1247, 2, 1000, 1000, 1)
+    # config 3: a random Permutation applied to the 1M-block product
+    srand(3)
+    perm = oracle.perm_generate(1247)
+    p = engine.Permutation(ctx, perm)
+    permuted = prod.applyPermutation(p)
+    assert permuted.n_blocks == prod.n_blocks
+    k2 = engine.SecretKey(ctx, oracle.key_permute(1247, s, perm))
+    assert k2.count_satisfied(permuted) == count
+    sample = prod.download_range(123456, 64)
+    assert np.array_equal(permuted.download_range(123456, 64), oracle.permute_all(sample, 1247, perm))
+    assert np.array_equal(prod.applyPermutation(p, strict_ref_truncate=True).getValues(),
+                          oracle.permute_block(prod.download_range(0, 1), 1247, perm))
+    # with the real D=16 on raw random blocks nothing is satisfied: decrypt is 0
+    key16 = engine.SecretKey(engine.Context(1247, 16), random_key(np.random.default_rng(8), 1247, 16))
+    assert key16.decrypt(prod) == 0
+
+
+def test_config5_large_parameters(engine, oracle):
+    """Context(16383,64): L = 256 words per block."""
+    _full_size_properties(engine, oracle, 16383, 2, 300, 300, 5)
+
+
+def test_product_larger_than_l2_4GB(engine, oracle):
+    """5000 x 5000 blocks = 25M blocks = 4 GB: the HBM-sized point of SURVEY 8d."""
+    _full_size_properties(engine, oracle, 1247, 2, 5000, 5000, 7)
+
+
+def test_chain_to_1e7_blocks(engine, oracle):
+    """(a*b)*d with 100-, 100- and 1000-block operands: the config-4 shape, 10^7 blocks."""
+    N, L = 1247, 20
+    rng = np.random.default_rng(4)
+    a, b, d = random_blocks(rng, 100, N), random_blocks(rng, 100, N), random_blocks(rng, 1000, N)
+    ctx = engine.Context(N, 1)
+    ab = oracle.mul(a, b, L)
+    x = engine.Ciphertext.from_host(a, ctx)
+    x *= engine.Ciphertext.from_host(b, ctx)
+    x *= engine.Ciphertext.from_host(d, ctx)
+    assert x.n_blocks == 10**7
+    assert x.checksum() == oracle.mul_checksum(ab, d, L)
+    s = random_key(rng, N, 1)
+    key = engine.SecretKey(ctx, s)
+    want = oracle.count_satisfied(a, N, s) * oracle.count_satisfied(b, N, s) * oracle.count_satisfied(d, N, s)
+    assert key.count_satisfied(x) == want and key.decrypt(x) == want & 1
+
+
+# ---------------------------------------------------------------------------
+# interop: caller-owned device memory and an external stream
+# ---------------------------------------------------------------------------
+def test_torch_views_and_stream(engine, oracle):
+    import torch
+    N, L = 1247, 20
+    rng = np.random.default_rng(17)
+    a, b = random_blocks(rng, 50, N), random_blocks(rng, 70, N)
+    ctx = engine.Context(N, 2)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ta = torch.from_numpy(a.view(np.int64)).to(dev)
+    tb = torch.from_numpy(b.view(np.int64)).to(dev)
+    tout = torch.empty(50 * 70 * L, dtype=torch.int64, device=dev)
+    tcount = torch.zeros(1, dtype=torch.int64, device=dev)
+    stream = torch.cuda.Stream()
+    stream.wait_stream(torch.cuda.current_stream())
+    engine.set_stream(stream.cuda_stream)
+    try:
+        va, vb, vo = (engine.Ciphertext.from_tensor(t, ctx) for t in (ta, tb, tout))
+        va.mul_into(vb, vo)
+        s = random_key(rng, N, 2)
+        key = engine.SecretKey(ctx, s)
+        key.count_satisfied_async(vo, tcount.data_ptr())
+        stream.synchronize()
+    finally:
+        engine.set_stream(None)
+    want = oracle.mul(a, b, L)
+    assert np.array_equal(tout.cpu().numpy().view(np.uint64), want)
+    assert int(tcount.item()) == oracle.count_satisfied(want, N, s)
+    before = engine.launch_count()
+    va.mul_into(vb, vo)
+    engine.sync()
+    assert engine.launch_count() == before + 1
