@@ -222,7 +222,10 @@ def run_ours(args):
     N, D, T1, T2, desc = WORKLOADS[args.workload]
     L, P = words_per_block(N), args.pairs
     eng.init(local)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: handle 0 would mean "the library's own stream" to csgn_set_stream,
+    # and torch.cuda.Event only sees the stream it is recorded on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     ctx = eng.Context(N, D)
 
@@ -310,8 +313,9 @@ def run_ours(args):
     launches = eng.launch_count() - launches0
 
     total_ms = evs[0][0].elapsed_time(evs[K - 1][3])
-    mul_ms = sum(e[0].elapsed_time(e[1]) for e in evs)
-    dec_ms = sum(e[1].elapsed_time(e[2]) for e in evs)
+    mul_steps = [e[0].elapsed_time(e[1]) for e in evs]
+    dec_steps = [e[1].elapsed_time(e[2]) for e in evs]
+    mul_ms, dec_ms = sum(mul_steps), sum(dec_steps)
     ar_ms = sum(e[2].elapsed_time(e[3]) for e in evs)
     t = torch.tensor([total_ms, mul_ms, dec_ms, ar_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -382,9 +386,13 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": T1 * T2 * bytes_per_block,
                          "avg_launch_us": mul_ms * 1e3 / (K * P)},
             "kernels": {"multiply": {"blocks_per_s_per_gpu": P * T1 * T2 * K / (mul_ms * 1e-3), "gbs": mul_gbs,
-                                     "frac_of_peak": mul_gbs / peak, "avg_launch_us": mul_ms * 1e3 / (K * P)},
+                                     "frac_of_peak": mul_gbs / peak, "avg_launch_us": mul_ms * 1e3 / (K * P),
+                                     "min_step_launch_us": min(mul_steps) * 1e3 / P,
+                                     "median_step_launch_us": float(np.median(mul_steps)) * 1e3 / P},
                         "decrypt": {"blocks_per_s_per_gpu": P * T1 * T2 * K / (dec_ms * 1e-3), "gbs": dec_gbs,
-                                    "frac_of_peak": dec_gbs / peak, "avg_launch_us": dec_ms * 1e3 / (K * P)},
+                                    "frac_of_peak": dec_gbs / peak, "avg_launch_us": dec_ms * 1e3 / (K * P),
+                                    "min_step_launch_us": min(dec_steps) * 1e3 / P,
+                                    "median_step_launch_us": float(np.median(dec_steps)) * 1e3 / P},
                         "allreduce_ms_per_step": ar_ms / K},
             "clocks": clocks, "gpu_launches": int(launches), "wall_ms_per_step": 1e3 * t_wall / K,
         }

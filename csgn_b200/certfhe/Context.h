@@ -1,0 +1,3 @@
+// Context.h -- forwarding header: the reference ships one header per class
+// (src/Context.h); here all of them are declared in certFHE.h.
+#include "certFHE.h"

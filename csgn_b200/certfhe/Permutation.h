@@ -1,0 +1,3 @@
+// Permutation.h -- forwarding header: the reference ships one header per class
+// (src/Permutation.h); here all of them are declared in certFHE.h.
+#include "certFHE.h"

@@ -1,0 +1,3 @@
+// Plaintext.h -- forwarding header: the reference ships one header per class
+// (src/Plaintext.h); here all of them are declared in certFHE.h.
+#include "certFHE.h"

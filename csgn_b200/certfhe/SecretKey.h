@@ -1,0 +1,3 @@
+// SecretKey.h -- forwarding header: the reference ships one header per class
+// (src/SecretKey.h); here all of them are declared in certFHE.h.
+#include "certFHE.h"

@@ -1,0 +1,3 @@
+// Timer.h -- forwarding header: the reference ships one header per class
+// (src/Timer.h); here all of them are declared in certFHE.h.
+#include "certFHE.h"

@@ -1,0 +1,231 @@
+// certFHE.h -- the certFHE C++ API, re-implemented over the B200 engine.
+//
+// Source-level drop-in for the reference's umbrella header (reference src/certFHE.h:1-11
+// and the nine class headers it pulls in): same namespace, class names, public member
+// signatures and stream operators, so that programs written against the reference --
+// its tests/*.cpp and the README example -- compile unchanged and link against this
+// repository's libcertFHE.so.
+//
+// What is different underneath:
+//   * a Ciphertext's blocks live in GPU memory behind a csgn_buf handle
+//     (include/csgn.h); + += * *= decrypt applyPermutation are one C-ABI call each
+//     into hand-written sm_100a kernels.  There is no CPU evaluation path.
+//   * getValues()/getBitlen() hand out a lazily materialised host mirror (the
+//     reference hands out its internal arrays: src/Ciphertext.h:92-102);
+//   * the `bitlen` side array is never stored: it is always [64]*(L-1)+[N%64]
+//     per block (src/SecretKey.cpp:171-173, propagated by src/Ciphertext.cpp:165-176);
+//   * defects of the reference that are undefined behaviour there are defined here
+//     (operator= keeps the context, N%64==0 works, 64-bit indices) -- DESIGN.md lists them.
+// Key generation, encryption and Permutation generation stay on the host and consume
+// glibc rand() in exactly the reference's call order, so seeded runs agree bit for bit.
+#ifndef CSGN_CERTFHE_API_H_
+#define CSGN_CERTFHE_API_H_
+
+#include "utils.h"
+
+#include <stdexcept>
+
+struct csgn_buf;
+struct csgn_key;
+struct csgn_perm;
+
+namespace certFHE {
+
+// Raised where the reference would run into undefined behaviour or where the GPU
+// engine reports a failure.  The reference has no error channel at all; an uncaught
+// Error terminates with its message, which is the loud failure we want.
+class Error : public std::runtime_error {
+public:
+    explicit Error(const std::string &what) : std::runtime_error(what) {}
+};
+
+// ---- Library / Helper (reference src/Helpers.h:14-43) -----------------------------
+class Library {
+    Library() {}
+
+public:
+    // Seeds rand() with the wall clock (src/Helpers.cpp:8-12) and brings up the GPU
+    // engine (csgn_init).  Throws Error when no B200 is usable.
+    static void initializeLibrary();
+
+    // Extensions (not in the reference).
+    // applyPermutation on a multi-block ciphertext: false (default) permutes every
+    // block; true reproduces the reference exactly, whose result is block 0 permuted
+    // and one block long (src/Ciphertext.cpp:33-40).  Also set by CSGN_STRICT_REF_PERMUTE=1.
+    static void setStrictReferencePermutation(bool strict);
+    static bool getStrictReferencePermutation();
+    // Block until every enqueued GPU operation has finished (for timing).
+    static void synchronize();
+};
+
+class Helper {
+    Helper() {}
+
+public:
+    static bool exists(const uint64_t *v, const uint64_t len, const uint64_t value);
+    static void deletePointer(void *pointer, bool isArray);
+};
+
+// ---- Context (reference src/Context.h:15-73) ----------------------------------------
+class Context {
+    uint64_t N, D, S, defaultLen;
+
+public:
+    Context() = delete;
+    Context(const Context &context);
+    Context(const uint64_t pN, const uint64_t pD);
+    virtual ~Context();
+    Context &operator=(const Context &context);
+    friend ostream &operator<<(ostream &out, const Context &c);
+
+    uint64_t getN() const;
+    uint64_t getD() const;
+    uint64_t getS() const;
+    uint64_t getDefaultN() const;  // words per block
+    void setN(uint64_t n);
+    void setD(uint64_t d);
+};
+
+// ---- Plaintext (reference src/Plaintext.h:14-46) --------------------------------------
+class Plaintext {
+    unsigned char value;
+
+public:
+    Plaintext();
+    Plaintext(const int value);
+    virtual ~Plaintext();
+    unsigned char getValue() const;
+    void setValue(unsigned char value);
+    friend ostream &operator<<(ostream &out, const Plaintext &c);
+};
+
+// ---- Permutation (reference src/Permutation.h:15-90) ----------------------------------
+class Permutation {
+    uint64_t *permutation;
+    uint64_t length;
+    mutable csgn_perm *device_map;  // bit-source map on the GPU, built on first use
+
+    void drop_device_map() const;
+
+public:
+    Permutation();
+    Permutation(const uint64_t *perm, const uint64_t len);
+    Permutation(const Context &context);  // random, N entries
+    Permutation(const uint64_t len);      // random, rand() order of src/Permutation.cpp:139-157
+    Permutation(const Permutation &perm);
+    virtual ~Permutation();
+
+    uint64_t getLength() const;
+    void setLength(uint64_t len);
+    void setPermutation(uint64_t *perm, uint64_t len);
+    uint64_t *getPermutation() const;  // internal array: do not delete
+
+    friend ostream &operator<<(ostream &out, const Permutation &c);
+    Permutation &operator=(const Permutation &perm);
+    Permutation getInverse();
+    Permutation operator+(const Permutation &permB) const;  // (this o permB)[i] = this[permB[i]]
+    Permutation &operator+=(const Permutation &permB);
+
+    // engine side
+    csgn_perm *deviceMap(uint64_t N) const;
+};
+
+// ---- Ciphertext (reference src/Ciphertext.h:15-144) -----------------------------------
+class Ciphertext {
+    csgn_buf *dev;             // device-resident blocks (null while empty or staged)
+    Context *certFHEcontext;   // context of encryption (null for a default-constructed object)
+    mutable uint64_t *host_v;  // host mirror of the words / host staging before upload
+    mutable uint64_t *host_bitlen;
+    mutable uint64_t host_len; // length of the mirrors, in words
+    mutable bool host_v_valid;
+    bool staged;               // words exist only in host_v (no context yet / not uploadable)
+
+    void invalidate_mirror() const;
+    void release();
+    void upload_staged();
+    friend class SecretKey;
+
+public:
+    Ciphertext();
+    Ciphertext(const uint64_t *V, const uint64_t *Bitlen, const uint64_t len, const Context &context);
+    Ciphertext(const Ciphertext &ctxt);
+    Ciphertext(Ciphertext &&ctxt) noexcept;
+    virtual ~Ciphertext();
+
+    void setValues(const uint64_t *V, const uint64_t length);
+    void setBitlen(const uint64_t *Bitlen, const uint64_t length);
+    void setContext(const Context &context);
+    uint64_t getLen() const;  // in 64-bit words, as the reference counts
+    Context getContext() const;
+    uint64_t *getValues() const;  // host mirror: do not delete; refreshed after every mutation
+    uint64_t *getBitlen() const;  // host mirror of the synthesised pattern: do not delete
+
+    friend ostream &operator<<(ostream &out, const Ciphertext &c);
+
+    Ciphertext operator+(const Ciphertext &c) const;
+    Ciphertext &operator+=(const Ciphertext &c);
+    Ciphertext operator*(const Ciphertext &c) const;
+    Ciphertext &operator*=(const Ciphertext &c);
+    Ciphertext &operator=(const Ciphertext &c);
+    Ciphertext &operator=(Ciphertext &&c) noexcept;
+
+    void applyPermutation_inplace(const Permutation &permutation);
+    Ciphertext applyPermutation(const Permutation &permutation);
+    long size();
+
+    // engine side (extensions)
+    uint64_t getBlocks() const;            // number of N-bit blocks
+    const csgn_buf *deviceBuffer() const;  // uploads staged words first
+};
+
+// ---- SecretKey (reference src/SecretKey.h:18-147) ---------------------------------------
+class SecretKey {
+    uint64_t *s;  // secret positions in [0, N)
+    long length;
+    Context *certFHEContext;
+    mutable csgn_key *device_key;  // position mask on the GPU, built on first decrypt
+
+    void drop_device_key() const;
+    uint64_t *encrypt(unsigned char bit, uint64_t n, uint64_t d, uint64_t *s);
+
+public:
+    SecretKey() = delete;
+    SecretKey(const Context &context);
+    SecretKey(const SecretKey &secKey);
+    virtual ~SecretKey();
+
+    Ciphertext encrypt(Plaintext &plaintext);
+    Plaintext decrypt(Ciphertext &ciphertext);
+    void applyPermutation_inplace(const Permutation &permutation);
+    SecretKey applyPermutation(const Permutation &permutation);
+
+    friend ostream &operator<<(ostream &out, const SecretKey &c);
+    SecretKey &operator=(const SecretKey &secKey);
+
+    uint64_t getLength() const;
+    uint64_t *getKey() const;  // internal array: do not delete
+    void setKey(uint64_t *s, uint64_t len);
+    long size();
+};
+
+// ---- Timer (reference src/Timer.h:13-74) -------------------------------------------------
+class Timer {
+    string name;
+    std::chrono::duration<double> chronometer;
+    std::chrono::high_resolution_clock::time_point start_fingerprint;
+    std::chrono::high_resolution_clock::time_point stop_fingerprint;
+
+public:
+    Timer(string name = "Default timer");
+    virtual ~Timer();
+    void start();
+    double stop();          // milliseconds
+    void reset();
+    double stopAndPrint();
+    void print();
+    double getValue();
+};
+
+}  // namespace certFHE
+
+#endif  // CSGN_CERTFHE_API_H_

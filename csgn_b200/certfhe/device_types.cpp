@@ -1,0 +1,502 @@
+// device_types.cpp -- Ciphertext and SecretKey of the certFHE API over the GPU engine.
+//
+// Ciphertext owns a csgn_buf (device words) instead of the reference's two host arrays
+// (src/Ciphertext.h:17-21).  Each evaluation operator is ONE call into the C ABI:
+//   operator+ / +=   -> csgn_concat / csgn_append     (src/Ciphertext.cpp:204-229, :249-281)
+//   operator* / *=   -> csgn_mul                      (src/Ciphertext.cpp:231-247, :283-304)
+//   applyPermutation -> csgn_permute                  (src/Ciphertext.cpp:7-89)
+//   SecretKey::decrypt -> csgn_decrypt                (src/SecretKey.cpp:208-224)
+// Encryption and key handling stay on the host and replay the reference's rand() order.
+#include "certFHE.h"
+#include "engine_glue.h"
+
+#include <ctime>
+#include <utility>
+
+namespace certFHE {
+
+namespace glue {
+
+void check(int status, const char *what) {
+    if (status != CSGN_OK) throw Error(string(what) + ": " + csgn_last_error());
+}
+
+void ensure_engine() {
+    if (!csgn_is_initialized()) check(csgn_init(-1), "csgn_init");
+}
+
+}  // namespace glue
+
+namespace {
+
+// canonical valid-bit count of word i of a ciphertext (src/SecretKey.cpp:171-173)
+inline uint64_t canonical_bits(uint64_t i, uint64_t L, uint64_t rem) {
+    return ((i % L) + 1 == L && rem) ? rem : 64;
+}
+
+void require_canonical_bitlen(const uint64_t *bitlen, uint64_t len, const Context &ctx) {
+    const uint64_t L = ctx.getDefaultN(), rem = ctx.getN() % 64;
+    for (uint64_t i = 0; i < len; ++i)
+        if (bitlen[i] != canonical_bits(i, L, rem))
+            throw Error("Ciphertext: bitlen[" + to_string(i) + "] = " + to_string(bitlen[i]) +
+                        " is not the canonical pattern for N = " + to_string(ctx.getN()) +
+                        " (the reference would mis-index such an object, src/SecretKey.cpp:133)");
+}
+
+uint64_t *copy_words(const uint64_t *src, uint64_t n) {
+    uint64_t *p = new uint64_t[n ? n : 1];
+    if (n) memcpy(p, src, n * sizeof(uint64_t));
+    return p;
+}
+
+}  // namespace
+
+// =========================================================================================
+// Ciphertext
+// =========================================================================================
+Ciphertext::Ciphertext()
+    : dev(nullptr), certFHEcontext(nullptr), host_v(nullptr), host_bitlen(nullptr), host_len(0),
+      host_v_valid(false), staged(false) {}
+
+Ciphertext::Ciphertext(const uint64_t *V, const uint64_t *Bitlen, const uint64_t len, const Context &context)
+    : Ciphertext() {
+    // reference src/Ciphertext.cpp:344-358: deep copy of the caller's arrays
+    certFHEcontext = new Context(context);
+    const uint64_t L = context.getDefaultN();
+    if (L == 0 || len % L != 0)
+        throw Error("Ciphertext: len = " + to_string(len) + " is not a multiple of the " + to_string(L) +
+                    " words per block");
+    if (Bitlen) require_canonical_bitlen(Bitlen, len, context);
+    glue::ensure_engine();
+    glue::check(csgn_buf_upload(V, len / L, (uint32_t)L, &dev), "csgn_buf_upload");
+    glue::check(csgn_sync(), "csgn_sync");  // the caller may free V right after the constructor
+}
+
+Ciphertext::Ciphertext(const Ciphertext &o) : Ciphertext() {
+    if (o.certFHEcontext) certFHEcontext = new Context(*o.certFHEcontext);
+    if (o.staged) {
+        host_v = copy_words(o.host_v, o.host_len);
+        if (o.host_bitlen) host_bitlen = copy_words(o.host_bitlen, o.host_len);
+        host_len = o.host_len;
+        host_v_valid = true;
+        staged = true;
+    } else if (o.dev) {
+        glue::check(csgn_buf_clone(o.dev, &dev), "csgn_buf_clone");
+    }
+}
+
+Ciphertext::Ciphertext(Ciphertext &&o) noexcept
+    : dev(o.dev), certFHEcontext(o.certFHEcontext), host_v(o.host_v), host_bitlen(o.host_bitlen),
+      host_len(o.host_len), host_v_valid(o.host_v_valid), staged(o.staged) {
+    o.dev = nullptr;
+    o.certFHEcontext = nullptr;
+    o.host_v = o.host_bitlen = nullptr;
+    o.host_len = 0;
+    o.host_v_valid = o.staged = false;
+}
+
+Ciphertext::~Ciphertext() {
+    release();
+    delete certFHEcontext;
+    certFHEcontext = nullptr;
+}
+
+void Ciphertext::invalidate_mirror() const {
+    delete[] host_v;
+    delete[] host_bitlen;
+    host_v = host_bitlen = nullptr;
+    host_len = 0;
+    host_v_valid = false;
+}
+
+void Ciphertext::release() {
+    if (dev) csgn_buf_free(dev);
+    dev = nullptr;
+    invalidate_mirror();
+    staged = false;
+}
+
+void Ciphertext::upload_staged() {
+    if (!staged) return;
+    if (!certFHEcontext) throw Error("Ciphertext: values were set but no Context (call setContext first)");
+    const uint64_t L = certFHEcontext->getDefaultN();
+    if (L == 0 || host_len % L != 0)
+        throw Error("Ciphertext: len = " + to_string(host_len) + " is not a multiple of the " + to_string(L) +
+                    " words per block");
+    if (host_bitlen) require_canonical_bitlen(host_bitlen, host_len, *certFHEcontext);
+    glue::ensure_engine();
+    glue::check(csgn_buf_upload(host_v, host_len / L, (uint32_t)L, &dev), "csgn_buf_upload");
+    glue::check(csgn_sync(), "csgn_sync");
+    staged = false;  // host_v stays behind as a valid mirror
+    host_v_valid = true;
+}
+
+void Ciphertext::setValues(const uint64_t *V, const uint64_t length) {
+    // reference src/Ciphertext.cpp:392-403: replaces v and len; bitlen is left alone
+    uint64_t *fresh = copy_words(V, length);
+    uint64_t *keep_bitlen = (host_bitlen && host_len == length && staged) ? host_bitlen : nullptr;
+    if (keep_bitlen) host_bitlen = nullptr;
+    release();
+    host_v = fresh;
+    host_bitlen = keep_bitlen;
+    host_len = length;
+    host_v_valid = true;
+    staged = true;
+    if (certFHEcontext && certFHEcontext->getDefaultN() && length % certFHEcontext->getDefaultN() == 0) upload_staged();
+}
+
+void Ciphertext::setBitlen(const uint64_t *Bitlen, const uint64_t length) {
+    // reference src/Ciphertext.cpp:405-415.  Only the canonical pattern is representable.
+    if (certFHEcontext) {
+        require_canonical_bitlen(Bitlen, length, *certFHEcontext);
+        if (length != getLen())
+            throw Error("Ciphertext::setBitlen: length " + to_string(length) + " differs from the " +
+                        to_string(getLen()) + " words held");
+        return;
+    }
+    // no context yet: remember it, it is checked when the words go to the device
+    uint64_t *fresh = copy_words(Bitlen, length);
+    delete[] host_bitlen;
+    host_bitlen = fresh;
+    if (!staged) {
+        staged = true;
+        host_len = length;
+        delete[] host_v;
+        host_v = new uint64_t[length ? length : 1]();
+        host_v_valid = true;
+    }
+}
+
+void Ciphertext::setContext(const Context &context) {
+    Context *fresh = new Context(context);
+    delete certFHEcontext;
+    certFHEcontext = fresh;
+    if (staged && fresh->getDefaultN() && host_len % fresh->getDefaultN() == 0) upload_staged();
+}
+
+uint64_t Ciphertext::getBlocks() const {
+    if (staged) {
+        const uint64_t L = certFHEcontext ? certFHEcontext->getDefaultN() : 0;
+        return L ? host_len / L : 0;
+    }
+    return dev ? csgn_buf_blocks(dev) : 0;
+}
+
+uint64_t Ciphertext::getLen() const {
+    if (staged) return host_len;
+    return dev ? csgn_buf_blocks(dev) * csgn_buf_words_per_block(dev) : 0;
+}
+
+Context Ciphertext::getContext() const {
+    if (!certFHEcontext) throw Error("Ciphertext::getContext: this ciphertext has no Context");
+    return *certFHEcontext;
+}
+
+const csgn_buf *Ciphertext::deviceBuffer() const {
+    const_cast<Ciphertext *>(this)->upload_staged();
+    return dev;
+}
+
+uint64_t *Ciphertext::getValues() const {
+    if (staged) return host_v;
+    if (!dev) return nullptr;
+    const uint64_t len = getLen();
+    if (!host_v_valid || host_len != len) {
+        delete[] host_v;
+        host_v = new uint64_t[len ? len : 1];
+        if (host_len != len) {
+            delete[] host_bitlen;
+            host_bitlen = nullptr;
+        }
+        host_len = len;
+        glue::check(csgn_buf_download(dev, host_v), "csgn_buf_download");
+        host_v_valid = true;
+    }
+    return host_v;
+}
+
+uint64_t *Ciphertext::getBitlen() const {
+    if (staged && !certFHEcontext) return host_bitlen;
+    const uint64_t len = getLen();
+    if (!len || !certFHEcontext) return nullptr;
+    if (!host_bitlen || host_len != len) {
+        if (host_len != len && !staged) {  // the word mirror is for another length
+            delete[] host_v;
+            host_v = nullptr;
+            host_v_valid = false;
+        }
+        delete[] host_bitlen;
+        host_bitlen = new uint64_t[len];
+        host_len = len;
+        const uint64_t L = certFHEcontext->getDefaultN(), rem = certFHEcontext->getN() % 64;
+        for (uint64_t i = 0; i < len; ++i) host_bitlen[i] = canonical_bits(i, L, rem);
+    }
+    return host_bitlen;
+}
+
+ostream &operator<<(ostream &out, const Ciphertext &c) {
+    // reference src/Ciphertext.cpp:185-202: the valid bits of every word, MSB first
+    const uint64_t *v = c.getValues();
+    const uint64_t *bl = c.getBitlen();
+    const uint64_t len = c.getLen();
+    for (uint64_t i = 0; i < len; ++i)
+        for (uint64_t k = 0; k < (bl ? bl[i] : 64); ++k) out << ((v[i] >> (63 - k)) & 1ull);
+    out << endl;
+    return out;
+}
+
+long Ciphertext::size() {
+    // reference src/Ciphertext.cpp:91-101: three pointers, one length, two arrays of len words
+    return (long)(sizeof(void *) * 3 + sizeof(uint64_t) + getLen() * 2 * sizeof(uint64_t));
+}
+
+Ciphertext &Ciphertext::operator=(const Ciphertext &c) {
+    // the reference frees the context here and never restores it (src/Ciphertext.cpp:306-329);
+    // this is a complete deep copy
+    if (this == &c) return *this;
+    Ciphertext tmp(c);
+    *this = std::move(tmp);
+    return *this;
+}
+
+Ciphertext &Ciphertext::operator=(Ciphertext &&o) noexcept {
+    if (this == &o) return *this;
+    release();
+    delete certFHEcontext;
+    dev = o.dev;
+    certFHEcontext = o.certFHEcontext;
+    host_v = o.host_v;
+    host_bitlen = o.host_bitlen;
+    host_len = o.host_len;
+    host_v_valid = o.host_v_valid;
+    staged = o.staged;
+    o.dev = nullptr;
+    o.certFHEcontext = nullptr;
+    o.host_v = o.host_bitlen = nullptr;
+    o.host_len = 0;
+    o.host_v_valid = o.staged = false;
+    return *this;
+}
+
+Ciphertext Ciphertext::operator+(const Ciphertext &c) const {
+    const csgn_buf *a = deviceBuffer(), *b = c.deviceBuffer();
+    Ciphertext out;
+    const Context *ctx = certFHEcontext ? certFHEcontext : c.certFHEcontext;
+    if (ctx) out.certFHEcontext = new Context(*ctx);
+    if (a && b) glue::check(csgn_concat(a, b, &out.dev), "csgn_concat");
+    else if (a || b) glue::check(csgn_buf_clone(a ? a : b, &out.dev), "csgn_buf_clone");
+    return out;
+}
+
+Ciphertext &Ciphertext::operator+=(const Ciphertext &c) {
+    const csgn_buf *b = c.deviceBuffer();
+    upload_staged();
+    if (!b) return *this;
+    if (!certFHEcontext && c.certFHEcontext) certFHEcontext = new Context(*c.certFHEcontext);
+    if (!dev) glue::check(csgn_buf_clone(b, &dev), "csgn_buf_clone");
+    else glue::check(csgn_append(dev, b), "csgn_append");
+    invalidate_mirror();
+    return *this;
+}
+
+Ciphertext Ciphertext::operator*(const Ciphertext &c) const {
+    const csgn_buf *a = deviceBuffer(), *b = c.deviceBuffer();
+    if (!a || !b) throw Error("Ciphertext::operator*: empty operand");
+    Ciphertext out;
+    // the reference multiplies in the LEFT operand's context (src/Ciphertext.cpp:239)
+    if (certFHEcontext) out.certFHEcontext = new Context(*certFHEcontext);
+    glue::check(csgn_mul(a, b, &out.dev), "csgn_mul");
+    return out;
+}
+
+Ciphertext &Ciphertext::operator*=(const Ciphertext &c) {
+    const csgn_buf *a = deviceBuffer(), *b = c.deviceBuffer();
+    if (!a || !b) throw Error("Ciphertext::operator*=: empty operand");
+    csgn_buf *prod = nullptr;
+    glue::check(csgn_mul(a, b, &prod), "csgn_mul");
+    csgn_buf_free(dev);  // stream-ordered: the multiply still reads it safely (also when &c == this)
+    dev = prod;
+    invalidate_mirror();
+    return *this;
+}
+
+void Ciphertext::applyPermutation_inplace(const Permutation &permutation) {
+    const csgn_buf *a = deviceBuffer();
+    if (!a || !certFHEcontext) throw Error("Ciphertext::applyPermutation: empty ciphertext or no Context");
+    csgn_buf *out = nullptr;
+    glue::check(csgn_permute(a, permutation.deviceMap(certFHEcontext->getN()),
+                             Library::getStrictReferencePermutation() ? 1 : 0, &out),
+                "csgn_permute");
+    csgn_buf_free(dev);
+    dev = out;
+    invalidate_mirror();
+}
+
+Ciphertext Ciphertext::applyPermutation(const Permutation &permutation) {
+    const csgn_buf *a = deviceBuffer();
+    if (!a || !certFHEcontext) throw Error("Ciphertext::applyPermutation: empty ciphertext or no Context");
+    Ciphertext out;
+    out.certFHEcontext = new Context(*certFHEcontext);
+    glue::check(csgn_permute(a, permutation.deviceMap(certFHEcontext->getN()),
+                             Library::getStrictReferencePermutation() ? 1 : 0, &out.dev),
+                "csgn_permute");
+    return out;
+}
+
+// =========================================================================================
+// SecretKey
+// =========================================================================================
+SecretKey::SecretKey(const Context &context) : s(nullptr), length(0), certFHEContext(nullptr), device_key(nullptr) {
+    // reference src/SecretKey.cpp:308-337: reseed from the clock, then rejection-sample D
+    // distinct positions.  The reference compares against slots it has not written yet
+    // (uninitialised reads); the slots start at an impossible value here instead.
+    srand(time(NULL));
+    certFHEContext = new Context(context);
+    const uint64_t d = context.getD(), n = context.getN();
+    s = new uint64_t[d ? d : 1];
+    length = (long)d;
+    for (uint64_t i = 0; i < d; ++i) s[i] = (uint64_t)-1;
+    if (d > n) throw Error("SecretKey: D = " + to_string(d) + " secret positions do not fit in N = " + to_string(n));
+    uint64_t count = 0;
+    while (count < d) {
+        const uint64_t t = (uint64_t)rand() % n;
+        if (Helper::exists(s, d, t)) continue;
+        s[count++] = t;
+    }
+}
+
+SecretKey::SecretKey(const SecretKey &k) : s(nullptr), length(0), certFHEContext(nullptr), device_key(nullptr) {
+    certFHEContext = new Context(*k.certFHEContext);
+    length = k.length < 0 ? 0 : k.length;
+    s = copy_words(k.s, (uint64_t)length);
+}
+
+SecretKey::~SecretKey() {
+    drop_device_key();
+    // the reference zeroises the positions before freeing them (src/SecretKey.cpp:356-357)
+    for (long i = 0; i < length; ++i) ((volatile uint64_t *)s)[i] = 0;
+    delete[] s;
+    s = nullptr;
+    length = -1;
+    delete certFHEContext;
+    certFHEContext = nullptr;
+}
+
+void SecretKey::drop_device_key() const {
+    if (device_key) {
+        csgn_key_free(device_key);  // zeroises the device mask
+        device_key = nullptr;
+    }
+}
+
+SecretKey &SecretKey::operator=(const SecretKey &k) {
+    if (this == &k) return *this;
+    drop_device_key();
+    uint64_t *fresh = copy_words(k.s, (uint64_t)(k.length < 0 ? 0 : k.length));
+    for (long i = 0; i < length; ++i) ((volatile uint64_t *)s)[i] = 0;
+    delete[] s;
+    s = fresh;
+    length = k.length < 0 ? 0 : k.length;
+    *certFHEContext = *k.certFHEContext;
+    return *this;
+}
+
+ostream &operator<<(ostream &out, const SecretKey &c) {
+    // reference src/SecretKey.cpp:22-29
+    for (uint64_t i = 0; i < c.getLength(); ++i) out << c.getKey()[i] << " ";
+    out << endl;
+    return out;
+}
+
+uint64_t SecretKey::getLength() const { return (uint64_t)length; }
+uint64_t *SecretKey::getKey() const { return s; }
+
+void SecretKey::setKey(uint64_t *key, uint64_t len) {
+    drop_device_key();
+    uint64_t *fresh = copy_words(key, len);
+    delete[] s;
+    s = fresh;
+    length = (long)len;
+}
+
+long SecretKey::size() {
+    // reference src/SecretKey.cpp:269-276
+    return (long)(sizeof(void *) + sizeof(long) + sizeof(uint64_t) * (uint64_t)length);
+}
+
+uint64_t *SecretKey::encrypt(unsigned char bit, uint64_t n, uint64_t d, uint64_t *key) {
+    // One value (0/1) per position, drawn in the reference's order (src/SecretKey.cpp:35-80).
+    uint64_t *res = new uint64_t[n ? n : 1];
+    if (bit & 0x01) {
+        // Enc(1): secret positions are 1, one rand() for every other position, in index order
+        for (uint64_t i = 0; i < n; ++i) res[i] = Helper::exists(key, d, i) ? 1 : (uint64_t)(rand() % 2);
+        return res;
+    }
+    // Enc(0): pick the secret position that may break the all-ones pattern, randomise the
+    // rest, and force a zero there only if every other secret position came out 1
+    const uint64_t hole = key[(uint64_t)rand() % d];
+    uint64_t others = 0;
+    bool seen = false;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (i == hole) continue;
+        res[i] = (uint64_t)(rand() % 2);
+        if (Helper::exists(key, d, i)) {
+            others = seen ? (others & res[i]) : res[i];
+            seen = true;
+        }
+    }
+    res[hole] = (others == 1) ? 0 : (uint64_t)(rand() % 2);
+    return res;
+}
+
+Ciphertext SecretKey::encrypt(Plaintext &plaintext) {
+    // reference src/SecretKey.cpp:153-206: per-bit values, then MSB-first packing
+    const uint64_t n = certFHEContext->getN(), d = certFHEContext->getD();
+    const uint64_t L = certFHEContext->getDefaultN();
+    if ((uint64_t)length < d) throw Error("SecretKey::encrypt: the key holds fewer positions than D");
+    uint64_t *bits = encrypt(plaintext.getValue(), n, d, s);
+    uint64_t *words = new uint64_t[L ? L : 1]();
+    for (uint64_t p = 0; p < n; ++p) words[p >> 6] |= (bits[p] & 1ull) << (63 - (p & 63));
+    delete[] bits;
+    Ciphertext c(words, nullptr, L, *certFHEContext);
+    delete[] words;
+    return c;
+}
+
+Plaintext SecretKey::decrypt(Ciphertext &ciphertext) {
+    const csgn_buf *buf = ciphertext.deviceBuffer();
+    if (!buf) return Plaintext(0);
+    if (!device_key) {
+        glue::ensure_engine();
+        glue::check(csgn_key_create(certFHEContext->getN(), s, (uint32_t)length, &device_key), "csgn_key_create");
+    }
+    uint8_t bit = 0;
+    glue::check(csgn_decrypt(buf, device_key, &bit), "csgn_decrypt");
+    return Plaintext(bit);
+}
+
+void SecretKey::applyPermutation_inplace(const Permutation &permutation) {
+    // reference src/SecretKey.cpp:226-259: new key = ascending { i : perm[i] is a secret position }
+    const uint64_t n = certFHEContext->getN();
+    if (permutation.getLength() != n)
+        throw Error("SecretKey::applyPermutation: permutation length differs from N");
+    const uint64_t *perm = permutation.getPermutation();
+    vector<unsigned char> secret(n, 0);
+    for (long i = 0; i < length; ++i) secret[s[i]] = 1;
+    uint64_t *fresh = new uint64_t[length > 0 ? length : 1];
+    long out = 0;
+    for (uint64_t i = 0; i < n && out < length; ++i)
+        if (secret[perm[i]]) fresh[out++] = i;
+    drop_device_key();
+    for (long i = 0; i < length; ++i) ((volatile uint64_t *)s)[i] = 0;
+    delete[] s;
+    s = fresh;
+}
+
+SecretKey SecretKey::applyPermutation(const Permutation &permutation) {
+    SecretKey k(*this);
+    k.applyPermutation_inplace(permutation);
+    return k;
+}
+
+}  // namespace certFHE

@@ -62,8 +62,8 @@ __device__ __forceinline__ void fold_and_publish(uint64_t lane_count, uint64_t *
 }
 
 // L4C > 0: units per block known at compile time (fully unrolled walk); 0: runtime.
-template <int L4C, int UNROLL>
-__global__ void __launch_bounds__(kDecThreads)
+template <int L4C, int UNROLL, int MINB>
+__global__ void __launch_bounds__(kDecThreads, MINB)
 decrypt_count_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint32_t L4rt,
                      const uint4 *__restrict__ M4, uint64_t *scratch, uint64_t *count_out) {
     extern __shared__ uint4 smem[];
@@ -81,20 +81,29 @@ decrypt_count_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint3
     const uint64_t n_chunks = (T + 31) >> 5;
     uint64_t my_count = 0;
 
+    // persistent warps sweep the stream together: round k covers chunks [k*W, (k+1)*W)
     for (uint64_t chunk = (uint64_t)blockIdx.x * kDecWarps + warp; chunk < n_chunks;
          chunk += (uint64_t)gridDim.x * kDecWarps) {
-        const uint64_t q_lane = chunk * 32u * L4 + lane;
-        uint32_t koff = 0;                   // (32*r) % L4
+        const uint4 *src = V4 + (chunk * 32u * L4 + lane);
+        const bool full = (chunk + 1) * 32u <= T;    // warp-uniform: no per-load bounds in the common case
+        uint32_t koff = 0;                           // (32*r) % L4
         for (uint32_t r = 0; r < L4; r += UNROLL) {
             uint4 v[UNROLL];
+            if (full) {
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const uint64_t q = q_lane + 32u * (r + u);
-                v[u] = (r + u < L4 && q < n_units) ? ld_stream(V4 + q) : make_uint4(0u, 0u, 0u, 0u);
+                for (int u = 0; u < UNROLL; ++u)
+                    if ((L4C && L4C % UNROLL == 0) || r + u < L4) v[u] = ld_stream(src + 32u * (r + u));
+            } else {
+                const uint64_t q_lane = chunk * 32u * L4 + lane;
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    const uint64_t q = q_lane + 32u * (r + u);
+                    v[u] = (r + u < L4 && q < n_units) ? ld_stream(V4 + q) : make_uint4(0u, 0u, 0u, 0u);
+                }
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
-                if (r + u < L4) {            // warp-uniform
+                if ((L4C && L4C % UNROLL == 0) || r + u < L4) {   // warp-uniform
                     const bool f = unit_fails(v[u], mk[koff]);
                     const uint32_t bal = __ballot_sync(0xffffffffu, f);
                     if (lane == 0) sFw[r + u] = bal;
@@ -120,6 +129,42 @@ decrypt_count_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint3
     fold_and_publish(my_count, scratch, count_out);
 }
 
+// L4 a multiple of 32 (e.g. N=16383: L4=128): a block is UPL = L4/32 coalesced warp
+// loads; one warp folds BPI blocks per iteration (BPI*UPL independent 16-byte loads in
+// flight per lane) and votes once per block.
+template <int UPL, int BPI>
+__global__ void __launch_bounds__(kDecThreads, 4)
+decrypt_count_wide_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint4 *__restrict__ M4,
+                          uint64_t *scratch, uint64_t *count_out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint4 m[UPL];
+#pragma unroll
+    for (int u = 0; u < UPL; ++u) m[u] = __ldg(M4 + 32 * u + lane);
+    const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t n_groups = (T + BPI - 1) / BPI;
+    uint64_t my_count = 0;
+    for (uint64_t grp = warp_global; grp < n_groups; grp += n_warps) {
+        uint4 v[BPI][UPL];
+#pragma unroll
+        for (int b = 0; b < BPI; ++b) {
+            const uint64_t blk = grp * BPI + b;
+            const uint4 *row = V4 + blk * (32u * UPL) + lane;
+#pragma unroll
+            for (int u = 0; u < UPL; ++u) v[b][u] = (blk < T) ? ld_stream(row + 32 * u) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int b = 0; b < BPI; ++b) {
+            bool f = false;
+#pragma unroll
+            for (int u = 0; u < UPL; ++u) f |= unit_fails(v[b][u], m[u]);
+            const bool bad = __any_sync(0xffffffffu, f);
+            if (lane == 0 && !bad && grp * BPI + b < T) ++my_count;
+        }
+    }
+    fold_and_publish(my_count, scratch, count_out);
+}
+
 // Any L (odd, or too long for the fail string), any alignment: one warp per block.
 __global__ void __launch_bounds__(kDecThreads)
 decrypt_count_generic_kernel(const uint64_t *__restrict__ V, const uint64_t T, const uint32_t L,
@@ -141,12 +186,36 @@ decrypt_count_generic_kernel(const uint64_t *__restrict__ V, const uint64_t T, c
     fold_and_publish(my_count, scratch, count_out);
 }
 
-template <int L4C, int UNROLL>
+// Persistent grid: exactly the CTAs that are resident at once (a partial second wave
+// costs far more than it balances), never more than there is work for.
+template <typename Kernel>
+uint32_t resident_grid(Kernel kernel, size_t smem, uint64_t work_ctas) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kDecThreads, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    per_sm = (int)std::min<long>(per_sm, env_long("CSGN_DEC_CTAS_PER_SM", per_sm));
+    const uint64_t cap = (uint64_t)device_props().sm_count * (uint64_t)std::max(per_sm, 1);
+    return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(work_ctas, cap));
+}
+
+template <int L4C, int UNROLL, int MINB>
 cudaError_t launch_fast(const uint64_t *v, uint64_t T, uint32_t L4, const uint64_t *mask, uint64_t *scratch,
-                        uint64_t *count_out, uint32_t grid, cudaStream_t stream) {
+                        uint64_t *count_out, cudaStream_t stream) {
+    const uint64_t n_chunks = (T + 31) / 32;
     const size_t smem = (size_t)2 * L4 * sizeof(uint4) + (size_t)kDecWarps * L4 * sizeof(uint32_t);
-    decrypt_count_kernel<L4C, UNROLL><<<grid, kDecThreads, smem, stream>>>(
+    const uint32_t grid = resident_grid(decrypt_count_kernel<L4C, UNROLL, MINB>, smem, (n_chunks + kDecWarps - 1) / kDecWarps);
+    decrypt_count_kernel<L4C, UNROLL, MINB><<<grid, kDecThreads, smem, stream>>>(
         reinterpret_cast<const uint4 *>(v), T, L4, reinterpret_cast<const uint4 *>(mask), scratch, count_out);
+    return cudaGetLastError();
+}
+
+template <int UPL, int BPI>
+cudaError_t launch_wide(const uint64_t *v, uint64_t T, const uint64_t *mask, uint64_t *scratch,
+                        uint64_t *count_out, cudaStream_t stream) {
+    const uint64_t n_groups = (T + BPI - 1) / BPI;
+    const uint32_t grid = resident_grid(decrypt_count_wide_kernel<UPL, BPI>, 0, (n_groups + kDecWarps - 1) / kDecWarps);
+    decrypt_count_wide_kernel<UPL, BPI><<<grid, kDecThreads, 0, stream>>>(
+        reinterpret_cast<const uint4 *>(v), T, reinterpret_cast<const uint4 *>(mask), scratch, count_out);
     return cudaGetLastError();
 }
 
@@ -157,6 +226,7 @@ cudaError_t launch_decrypt_count(const uint64_t *v, uint64_t T, uint32_t L, cons
     if (T == 0 || L == 0) return cudaMemsetAsync(count_out, 0, sizeof(uint64_t), stream);
     const DeviceProps &dp = device_props();
     const uint64_t ctas_per_sm = (uint64_t)env_long("CSGN_DEC_CTAS_PER_SM", 8);
+    const long wide = env_long("CSGN_DEC_WIDE", 1);
     const bool aligned = ((reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(mask)) & 15u) == 0;
     const uint32_t L4 = L / 2;
     cudaError_t err;
@@ -166,12 +236,17 @@ cudaError_t launch_decrypt_count(const uint64_t *v, uint64_t T, uint32_t L, cons
         decrypt_count_generic_kernel<<<grid, kDecThreads, 0, stream>>>(v, T, L, mask, scratch, count_out);
         err = cudaGetLastError();
     } else {
-        const uint64_t n_chunks = (T + 31) / 32;
-        const uint64_t want = (n_chunks + kDecWarps - 1) / kDecWarps;
-        const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, dp.sm_count * ctas_per_sm));
-        if (L4 == 10) err = launch_fast<10, 10>(v, T, L4, mask, scratch, count_out, grid, stream);       // N=1247
-        else if (L4 == 128) err = launch_fast<128, 8>(v, T, L4, mask, scratch, count_out, grid, stream); // N=16383
-        else err = launch_fast<0, 4>(v, T, L4, mask, scratch, count_out, grid, stream);
+        const long variant = env_long("CSGN_DEC_VARIANT", 0);
+        if (L4 == 10 && variant == 1) err = launch_fast<10, 10, 4>(v, T, L4, mask, scratch, count_out, stream);
+        else if (L4 == 10 && variant == 2) err = launch_fast<10, 5, 5>(v, T, L4, mask, scratch, count_out, stream);
+        else if (L4 == 10 && variant == 3) err = launch_fast<10, 5, 6>(v, T, L4, mask, scratch, count_out, stream);
+        else if (L4 == 10 && variant == 4) err = launch_fast<10, 2, 8>(v, T, L4, mask, scratch, count_out, stream);
+        else if (L4 == 10) err = launch_fast<10, 10, 3>(v, T, L4, mask, scratch, count_out, stream);     // N=1247
+        else if (L4 == 128 && wide) err = launch_wide<4, 2>(v, T, mask, scratch, count_out, stream);  // N=16383
+        else if (L4 == 64 && wide) err = launch_wide<2, 4>(v, T, mask, scratch, count_out, stream);
+        else if (L4 == 32 && wide) err = launch_wide<1, 8>(v, T, mask, scratch, count_out, stream);
+        else if (L4 == 128) err = launch_fast<128, 8, 3>(v, T, L4, mask, scratch, count_out, stream);
+        else err = launch_fast<0, 4, 4>(v, T, L4, mask, scratch, count_out, stream);
     }
     count_launch();
     return err;

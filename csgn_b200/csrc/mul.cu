@@ -31,7 +31,16 @@ __device__ __forceinline__ uint4 and4(const uint4 a, const uint4 b) {
     return make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w);
 }
 
-template <int U>
+// Store flavours (tuning): 0 = st.global.cs (evict-first), 1 = default write-back,
+// 2 = st.global.wt (write-through).
+template <int MODE>
+__device__ __forceinline__ void st_out(uint4 *p, const uint4 v) {
+    if (MODE == 0) __stcs(p, v);
+    else if (MODE == 1) *p = v;
+    else __stwt(p, v);
+}
+
+template <int U, int MODE>
 __global__ void __launch_bounds__(kMulMaxThreads)
 mul_outer_kernel(const uint4 *__restrict__ A4, const uint4 *__restrict__ B4, uint4 *__restrict__ out4,
                  const uint32_t L4, const uint64_t T1, const uint64_t Q, const uint32_t R,
@@ -66,7 +75,7 @@ mul_outer_kernel(const uint4 *__restrict__ A4, const uint4 *__restrict__ B4, uin
             for (uint32_t r = 0; r < nrows; ++r, o += Q, sa += L4) {
                 const uint4 a = *sa;
 #pragma unroll
-                for (int u = 0; u < U; ++u) __stcs(o + (uint64_t)u * tpb, and4(a, b[u]));
+                for (int u = 0; u < U; ++u) st_out<MODE>(o + (uint64_t)u * tpb, and4(a, b[u]));
             }
         } else {
             // ragged last column tile: per-unit bounds, loop-invariant predicates
@@ -77,7 +86,7 @@ mul_outer_kernel(const uint4 *__restrict__ A4, const uint4 *__restrict__ B4, uin
                 const uint4 a = *sa;
 #pragma unroll
                 for (int u = 0; u < U; ++u)
-                    if (live[u]) __stcs(o + (uint64_t)u * tpb, and4(a, b[u]));
+                    if (live[u]) st_out<MODE>(o + (uint64_t)u * tpb, and4(a, b[u]));
             }
         }
     }
@@ -97,9 +106,9 @@ mul_outer_generic_kernel(const uint64_t *__restrict__ A, const uint64_t *__restr
     }
 }
 
-template <int U>
-cudaError_t launch_v4(const uint64_t *a, uint64_t T1, const uint64_t *b, uint64_t T2, uint32_t L4,
-                      uint64_t *out, uint32_t tpb, uint32_t R, uint64_t grid_cap, cudaStream_t stream) {
+template <int U, int MODE>
+cudaError_t launch_v4m(const uint64_t *a, uint64_t T1, const uint64_t *b, uint64_t T2, uint32_t L4,
+                       uint64_t *out, uint32_t tpb, uint32_t R, uint64_t grid_cap, cudaStream_t stream) {
     const uint64_t Q = T2 * L4;
     const uint64_t tile_q = (uint64_t)tpb * U;
     const uint64_t n_col_tiles = (Q + tile_q - 1) / tile_q;
@@ -107,10 +116,20 @@ cudaError_t launch_v4(const uint64_t *a, uint64_t T1, const uint64_t *b, uint64_
     const uint64_t n_items = n_col_tiles * n_chunks;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, grid_cap);
     const size_t smem = (size_t)R * L4 * sizeof(uint4);
-    mul_outer_kernel<U><<<grid, tpb, smem, stream>>>(
+    mul_outer_kernel<U, MODE><<<grid, tpb, smem, stream>>>(
         reinterpret_cast<const uint4 *>(a), reinterpret_cast<const uint4 *>(b),
         reinterpret_cast<uint4 *>(out), L4, T1, Q, R, (uint32_t)n_col_tiles, n_items);
     return cudaGetLastError();
+}
+
+template <int U>
+cudaError_t launch_v4(const uint64_t *a, uint64_t T1, const uint64_t *b, uint64_t T2, uint32_t L4,
+                      uint64_t *out, uint32_t tpb, uint32_t R, uint64_t grid_cap, cudaStream_t stream) {
+    switch (env_long("CSGN_MUL_STORE", 0)) {
+        case 1: return launch_v4m<U, 1>(a, T1, b, T2, L4, out, tpb, R, grid_cap, stream);
+        case 2: return launch_v4m<U, 2>(a, T1, b, T2, L4, out, tpb, R, grid_cap, stream);
+        default: return launch_v4m<U, 0>(a, T1, b, T2, L4, out, tpb, R, grid_cap, stream);
+    }
 }
 
 // Largest CTA size <= cap that is a multiple of L4, preferring whole warps.
@@ -143,18 +162,25 @@ cudaError_t launch_mul(const uint64_t *a, uint64_t T1, const uint64_t *b, uint64
     }
 
     const uint64_t Q = T2 * L4;
-    uint32_t tpb = pick_tpb(L4, (uint32_t)env_long("CSGN_MUL_TPB", 384));
+    // Tuned on B200 (tools/sweep.py, profiles/): many small work items balance best, but
+    // an item must keep R >= 3 rows per load of its b tile or the L2 re-reads show;
+    // products of a GiB and more prefer wider tiles and even more items.
+    const bool huge = T1 * Q >= (1ull << 26);     // >= 1 GiB of output
+    uint32_t tpb = pick_tpb(L4, (uint32_t)env_long("CSGN_MUL_TPB", 512));
     if (tpb == 0) tpb = L4;
-    // Units of b per thread: as many as the row can feed, up to the tuned maximum.
-    int U = (int)env_long("CSGN_MUL_U", 4);
-    U = U >= 8 ? 8 : U >= 4 ? 4 : U >= 2 ? 2 : 1;
-    while (U > 1 && (uint64_t)tpb * U > std::max<uint64_t>(Q, tpb)) U >>= 1;
-    const uint64_t n_col_tiles = (Q + (uint64_t)tpb * U - 1) / ((uint64_t)tpb * U);
-    // Rows per item: enough items to balance every SM, few enough re-reads of b.
     const uint32_t r_max = std::max<uint32_t>(1, std::min<uint32_t>(64, kMulMaxSmem / (L4 * 16)));
-    const uint64_t target_items = (uint64_t)dp.sm_count * (uint64_t)env_long("CSGN_MUL_ITEMS_PER_SM", 8);
-    uint64_t R = (T1 * n_col_tiles + target_items - 1) / target_items;
-    R = std::max<uint64_t>(1, std::min<uint64_t>(R, r_max));
+    const uint64_t target_items =
+        (uint64_t)dp.sm_count * (uint64_t)env_long("CSGN_MUL_ITEMS_PER_SM", huge ? 128 : 32);
+    int U = (int)env_long("CSGN_MUL_U", huge ? 4 : 2);
+    U = U >= 8 ? 8 : U >= 4 ? 4 : U >= 2 ? 2 : 1;
+    uint64_t R = 1;
+    for (;; U >>= 1) {
+        // units of b per thread: no wider than the row can feed
+        while (U > 1 && (uint64_t)tpb * U > std::max<uint64_t>(Q, tpb)) U >>= 1;
+        const uint64_t n_col_tiles = (Q + (uint64_t)tpb * U - 1) / ((uint64_t)tpb * U);
+        R = (T1 * n_col_tiles + target_items - 1) / target_items;
+        if (R >= 3 || U == 1 || env_long("CSGN_MUL_U", 0) > 0) break;
+    }
     R = (uint64_t)env_long("CSGN_MUL_R", (long)R);
     R = std::max<uint64_t>(1, std::min<uint64_t>(R, std::min<uint64_t>(r_max, T1)));
     const uint64_t grid_cap = (uint64_t)env_long("CSGN_MUL_GRID", 1 << 30);

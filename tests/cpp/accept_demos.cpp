@@ -1,0 +1,177 @@
+// accept_demos.cpp -- acceptance run of the certFHE API on the GPU engine.
+//
+// Walks the same three user journeys as the reference's demo programs
+// (reference tests/basic_operations.cpp, tests/permutations.cpp, tests/timings.cpp)
+// but, unlike them, ASSERTS the outcome: every decrypted bit, the size() figures the
+// timing demo prints (352 / 672 / 352 / 144 bytes), and the scheme's homomorphic
+// identities on random circuits.  Exit status 0 = all good.
+#include "certFHE.h"
+
+#include <sstream>
+
+using namespace certFHE;
+
+static int failures = 0;
+#define EXPECT(cond)                                                            \
+    do {                                                                        \
+        if (!(cond)) {                                                          \
+            std::cerr << "FAILED " << __FILE__ << ":" << __LINE__ << "  " #cond << std::endl; \
+            ++failures;                                                         \
+        }                                                                       \
+    } while (0)
+
+static void basic_operations() {
+    Context context(1247, 16);
+    SecretKey seckey(context);
+    Plaintext p1(1), p0(0);
+    Ciphertext c1 = seckey.encrypt(p1);
+    Ciphertext c0 = seckey.encrypt(p0);
+    Ciphertext added, multiplied;
+    added = c1 + c0;
+    multiplied = c1 * c0;
+    Plaintext dec_addition = seckey.decrypt(added);
+    Plaintext dec_multiplied = seckey.decrypt(multiplied);
+    std::cout << "Dec ( Enc (1) + Enc (0) ) = " << dec_addition << std::endl;
+    std::cout << "Dec ( Enc (1) * Enc (0) ) = " << dec_multiplied << std::endl;
+    EXPECT(dec_addition.getValue() == 1);
+    EXPECT(dec_multiplied.getValue() == 0);
+    // an assigned-into object keeps a usable context (the reference loses it here)
+    Ciphertext again = added * multiplied;
+    EXPECT(seckey.decrypt(again).getValue() == 0);
+    EXPECT(again.getLen() == 2 * 1 * context.getDefaultN());
+}
+
+static void permutations() {
+    Context context(1247, 16);
+    SecretKey seckey(context);
+    Plaintext p1(1);
+    Ciphertext c1 = seckey.encrypt(p1);
+    Permutation permutation(context);
+    SecretKey permutedSecretKey = seckey.applyPermutation(permutation);
+    Ciphertext permutedCiphertext = c1.applyPermutation(permutation);
+    Plaintext decrypted = permutedSecretKey.decrypt(permutedCiphertext);
+    std::cout << " Dec ( Enc ( 1 ) ) = " << decrypted << endl;
+    EXPECT(decrypted.getValue() == 1);
+    Permutation inversePermutation = permutation.getInverse();
+    Permutation identityPermutation;
+    identityPermutation = permutation + inversePermutation;
+    EXPECT(identityPermutation.getLength() == 1247);
+    for (uint64_t i = 0; i < identityPermutation.getLength(); ++i) EXPECT(identityPermutation.getPermutation()[i] == i);
+    // and back again with the inverse
+    Ciphertext back = permutedCiphertext.applyPermutation(inversePermutation);
+    EXPECT(memcmp(back.getValues(), c1.getValues(), c1.getLen() * 8) == 0);
+    Permutation mismatched(7);
+    EXPECT((permutation + mismatched).getLength() == 0);  // soft failure, as in the reference
+}
+
+static void timings_and_sizes() {
+    Context context(1247, 16);
+    std::ostringstream os;
+    os << context;
+    EXPECT(os.str() == "N= 1247\nD= 16\nS= 38\n");
+    Timer t1("Key generation ");
+    t1.start();
+    SecretKey seckey(context);
+    EXPECT(t1.stopAndPrint() >= 0.0);
+    Plaintext p1(1);
+    Ciphertext c1 = seckey.encrypt(p1);
+    Ciphertext added, multiplicated;
+    added = c1 + c1;
+    multiplicated = c1 * c1;
+    std::cout << "Secret key size: " << seckey.size() << " bytes" << endl;
+    std::cout << "Fresh ciphertext size: " << c1.size() << " bytes" << endl;
+    std::cout << "After multiplication ciphertext size: " << multiplicated.size() << " bytes" << endl;
+    std::cout << "After addition ciphertext size: " << added.size() << " bytes" << endl;
+    EXPECT(seckey.size() == 144);
+    EXPECT(c1.size() == 352);
+    EXPECT(multiplicated.size() == 352);
+    EXPECT(added.size() == 672);
+    EXPECT(seckey.decrypt(added).getValue() == 0);          // 1 xor 1
+    EXPECT(seckey.decrypt(multiplicated).getValue() == 1);  // 1 and 1
+}
+
+// Random depth-2 circuits: Dec(sum_i a_i * sum_j b_j + c) == (xor a) & (xor b) ^ c
+static void random_circuits(uint64_t N, uint64_t D, unsigned seed, int rounds) {
+    Context context(N, D);
+    SecretKey seckey(context);
+    srand(seed);
+    for (int r = 0; r < rounds; ++r) {
+        int na = 1 + rand() % 9, nb = 1 + rand() % 9;
+        int xa = 0, xb = 0;
+        Ciphertext A, B;
+        for (int i = 0; i < na; ++i) {
+            Plaintext p(rand() % 2);
+            xa ^= p.getValue();
+            Ciphertext e = seckey.encrypt(p);
+            if (i == 0) A = e; else A += e;
+        }
+        for (int j = 0; j < nb; ++j) {
+            Plaintext p(rand() % 2);
+            xb ^= p.getValue();
+            Ciphertext e = seckey.encrypt(p);
+            if (j == 0) B = e; else B = B + e;
+        }
+        Plaintext pc(rand() % 2);
+        Ciphertext C = seckey.encrypt(pc);
+        Ciphertext prod = A * B;
+        EXPECT(prod.getLen() == (uint64_t)na * nb * context.getDefaultN());
+        Ciphertext circuit = prod + C;
+        EXPECT(seckey.decrypt(A).getValue() == xa);
+        EXPECT(seckey.decrypt(B).getValue() == xb);
+        EXPECT(seckey.decrypt(prod).getValue() == (xa & xb));
+        EXPECT(seckey.decrypt(circuit).getValue() == ((xa & xb) ^ pc.getValue()));
+        A *= B;
+        EXPECT(memcmp(A.getValues(), prod.getValues(), prod.getLen() * 8) == 0);
+        // every word of the canonical bitlen pattern
+        const uint64_t *bl = prod.getBitlen();
+        const uint64_t L = context.getDefaultN(), rem = N % 64;
+        for (uint64_t i = 0; i < prod.getLen(); ++i) EXPECT(bl[i] == (((i % L) + 1 == L && rem) ? rem : 64));
+        // a permuted multi-block product still decrypts under the permuted key
+        Permutation pi(context);
+        SecretKey pk = seckey.applyPermutation(pi);
+        Ciphertext pprod = prod.applyPermutation(pi);
+        EXPECT(pprod.getLen() == prod.getLen());
+        EXPECT(pk.decrypt(pprod).getValue() == (xa & xb));
+    }
+}
+
+static void misuse_is_loud() {
+    Context context(1247, 16);
+    uint64_t words[20] = {0}, bitlen[20];
+    for (int i = 0; i < 20; ++i) bitlen[i] = 64;  // last word should be 31
+    bool threw = false;
+    try { Ciphertext bad(words, bitlen, 20, context); } catch (const Error &) { threw = true; }
+    EXPECT(threw);
+    threw = false;
+    try { Ciphertext bad(words, nullptr, 19, context); } catch (const Error &) { threw = true; }
+    EXPECT(threw);
+    // staged construction through the setters, in the order the reference allows
+    bitlen[19] = 31;
+    Ciphertext staged;
+    staged.setValues(words, 20);
+    staged.setBitlen(bitlen, 20);
+    staged.setContext(context);
+    EXPECT(staged.getLen() == 20);
+    EXPECT(staged.getBitlen()[19] == 31 && staged.getValues()[0] == 0);
+    Ciphertext empty;
+    EXPECT(empty.getLen() == 0 && empty.getValues() == nullptr);
+}
+
+int main() {
+    std::cout << "Initializing certFHE library................OK" << endl;
+    Library::initializeLibrary();
+    basic_operations();
+    permutations();
+    timings_and_sizes();
+    random_circuits(1247, 16, 1, 6);
+    random_circuits(16383, 64, 2, 2);
+    random_circuits(191, 5, 3, 4);   // odd number of words per block
+    random_circuits(128, 4, 4, 4);   // N % 64 == 0 (the reference overflows its arrays here)
+    misuse_is_loud();
+    if (failures) {
+        std::cerr << failures << " expectation(s) failed" << endl;
+        return 1;
+    }
+    std::cout << "accept_demos: all expectations hold" << endl;
+    return 0;
+}

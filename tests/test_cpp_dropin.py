@@ -1,0 +1,108 @@
+"""The certFHE C++ drop-in (csgn_b200/certfhe -> libcertFHE.so).
+
+CPU: the library exists in-tree, exports the reference's public class API and resolves
+the C ABI it sits on.  GPU: the acceptance program, the one-process differential run
+against the unmodified reference, and the reference's own demo programs compiled
+UNMODIFIED against our headers all run on the B200."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from csgn_b200 import build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "cpp", "bin")
+DEMOS = os.path.join(ROOT, "build", "dropin", "bin")
+
+
+def _run(path, timeout=600):
+    return subprocess.run([path], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
+
+
+def test_libcertfhe_exports_the_reference_api():
+    path = build.libcertfhe_path()
+    assert os.path.exists(path), "run `python -m csgn_b200.build`"
+    syms = subprocess.run(["nm", "-DC", "--defined-only", path], stdout=subprocess.PIPE, text=True).stdout
+    wanted = [
+        "certFHE::Library::initializeLibrary()",
+        "certFHE::Context::Context(unsigned long, unsigned long)",
+        "certFHE::Context::getDefaultN() const",
+        "certFHE::Plaintext::Plaintext(int)",
+        "certFHE::SecretKey::SecretKey(certFHE::Context const&)",
+        "certFHE::SecretKey::encrypt(certFHE::Plaintext&)",
+        "certFHE::SecretKey::decrypt(certFHE::Ciphertext&)",
+        "certFHE::SecretKey::applyPermutation(certFHE::Permutation const&)",
+        "certFHE::SecretKey::setKey(unsigned long*, unsigned long)",
+        "certFHE::Ciphertext::Ciphertext(unsigned long const*, unsigned long const*, unsigned long, certFHE::Context const&)",
+        "certFHE::Ciphertext::operator+(certFHE::Ciphertext const&) const",
+        "certFHE::Ciphertext::operator+=(certFHE::Ciphertext const&)",
+        "certFHE::Ciphertext::operator*(certFHE::Ciphertext const&) const",
+        "certFHE::Ciphertext::operator*=(certFHE::Ciphertext const&)",
+        "certFHE::Ciphertext::operator=(certFHE::Ciphertext const&)",
+        "certFHE::Ciphertext::applyPermutation(certFHE::Permutation const&)",
+        "certFHE::Ciphertext::applyPermutation_inplace(certFHE::Permutation const&)",
+        "certFHE::Ciphertext::getValues() const",
+        "certFHE::Ciphertext::getBitlen() const",
+        "certFHE::Ciphertext::size()",
+        "certFHE::Permutation::Permutation(certFHE::Context const&)",
+        "certFHE::Permutation::getInverse()",
+        "certFHE::Permutation::operator+(certFHE::Permutation const&) const",
+        "certFHE::operator<<(std::ostream&, certFHE::Ciphertext const&)",
+        "certFHE::Timer::stopAndPrint()",
+        "certFHE::Helper::exists(unsigned long const*, unsigned long, unsigned long)",
+    ]
+    for w in wanted:
+        assert w in syms, w
+    # it computes nothing itself: the evaluation entry points are undefined here and come from libcsgn
+    undef = subprocess.run(["nm", "-D", "--undefined-only", path], stdout=subprocess.PIPE, text=True).stdout
+    for f in ("csgn_mul", "csgn_concat", "csgn_append", "csgn_decrypt", "csgn_permute", "csgn_buf_upload"):
+        assert re.search(r"\bU %s\b" % f, undef), f
+    ldd = subprocess.run(["ldd", path], stdout=subprocess.PIPE, text=True).stdout
+    assert "libcsgn.so" in ldd and "not found" not in ldd
+
+
+def test_cpp_test_programs_are_built():
+    assert os.path.exists(os.path.join(BIN, "accept_demos"))
+
+
+@pytest.mark.gpu
+def test_acceptance_program():
+    r = _run(os.path.join(BIN, "accept_demos"))
+    assert r.returncode == 0, r.stdout[-4000:]
+    out = r.stdout
+    assert "Dec ( Enc (1) + Enc (0) ) = 1" in out
+    assert "Dec ( Enc (1) * Enc (0) ) = 0" in out
+    assert " Dec ( Enc ( 1 ) ) = 1" in out
+    assert "Fresh ciphertext size: 352 bytes" in out and "After addition ciphertext size: 672 bytes" in out
+    assert "Secret key size: 144 bytes" in out
+
+
+@pytest.mark.gpu
+def test_differential_against_the_unmodified_reference():
+    exe = os.path.join(BIN, "diff_vs_reference")
+    if not os.path.exists(exe) or not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libcertfhe_ref.so")):
+        pytest.skip("diff_vs_reference is built only where /root/reference was present")
+    r = _run(exe, timeout=1200)
+    assert r.returncode == 0, r.stdout[-4000:]
+    assert "identical to the reference on every observable" in r.stdout
+    assert "config2 N=1247 1000x1000 -> 1000000 blocks" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("demo,lines", [
+    ("tester_basic_operations", ["Dec ( Enc (1) + Enc (0) ) = 1", "Dec ( Enc (1) * Enc (0) ) = 0"]),
+    ("tester_permutations", [" Dec ( Enc ( 1 ) ) = 1"]),
+    ("tester_timings", ["N= 1247", "D= 16", "S= 38", "Security(lambda)= 120", "Secret key size: 144 bytes",
+                        "Fresh ciphertext size: 352 bytes", "After multiplication ciphertext size: 352 bytes",
+                        "After addition ciphertext size: 672 bytes"]),
+])
+def test_unmodified_reference_demos_run_on_the_dropin(demo, lines):
+    exe = os.path.join(DEMOS, demo)
+    if not os.path.exists(exe):
+        pytest.skip("reference demos are compiled only where /root/reference was present")
+    r = _run(exe)
+    assert r.returncode == 0, r.stdout[-4000:]
+    for line in lines:
+        assert line in r.stdout, (line, r.stdout[-2000:])
