@@ -81,6 +81,9 @@ def load(build_if_missing=True):
     if _lib is not None:
         return _lib
     path = _build.libcsgn_path()
+    override = os.environ.get("CSGN_LIBRARY")      # A/B runs of two builds on one GPU box
+    if override:
+        path, build_if_missing = override, False
     if build_if_missing:
         try:
             _build.build_libcsgn()

@@ -31,6 +31,7 @@ struct csgn_buf {
 
 struct csgn_key {
     uint64_t *d_mask = nullptr;  // L words
+    std::vector<uint64_t> h_mask;  // the same, host side (small masks ride in kernel parameters)
     uint64_t N = 0;
     uint32_t L = 0, D = 0;
 };
@@ -438,6 +439,7 @@ int csgn_key_create(uint64_t N, const uint64_t *positions, uint32_t D, csgn_key 
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(k->d_mask, mask.data(), (size_t)L * sizeof(uint64_t), cudaMemcpyHostToDevice, g.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);  // `mask` dies with this frame
+    if (e == cudaSuccess) k->h_mask = mask;
     std::fill(mask.begin(), mask.end(), 0);
     if (e != cudaSuccess) {
         if (k->d_mask) cudaFree(k->d_mask);
@@ -455,6 +457,7 @@ int csgn_key_free(csgn_key *key) {
         cudaStreamSynchronize(g.stream);
         cudaFree(key->d_mask);
     }
+    std::fill(key->h_mask.begin(), key->h_mask.end(), 0);
     delete key;
     return CSGN_OK;
 }
@@ -464,7 +467,9 @@ int csgn_decrypt_count_async(const csgn_buf *c, const csgn_key *key, uint64_t *d
     if (!c || !key || !device_count) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
     if (c->L != key->L)
         return fail(CSGN_ERR_SHAPE_MISMATCH, "ciphertext has %u words per block, key expects %u", c->L, key->L);
-    cudaError_t e = launch_decrypt_count(c->d, c->n_blocks, c->L, key->d_mask, g.d_scratch, device_count, g.stream);
+    cudaError_t e = launch_decrypt_count(c->d, c->n_blocks, c->L, key->d_mask,
+                                         key->h_mask.empty() ? nullptr : key->h_mask.data(), g.d_scratch, device_count,
+                                         g.stream);
     if (e != cudaSuccess) return cuda_fail(e, "decrypt kernel");
     return CSGN_OK;
 }

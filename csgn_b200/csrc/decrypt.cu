@@ -23,6 +23,7 @@
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <cstring>
 
 namespace csgn {
 namespace {
@@ -61,17 +62,30 @@ __device__ __forceinline__ void fold_and_publish(uint64_t lane_count, uint64_t *
     }
 }
 
+// The key mask of a small block travels in the kernel parameters: after a multiply has
+// streamed through L2 a 160-byte mask in global memory is a DRAM miss at the head of
+// every CTA, while the parameter bank is always hot.
+constexpr int kParamMaskUnits = 16;  // up to 32 words per block (N <= 2048)
+struct ParamMask {
+    uint4 u[kParamMaskUnits];
+};
+
 // L4C > 0: units per block known at compile time (fully unrolled walk); 0: runtime.
 template <int L4C, int UNROLL, int MINB>
 __global__ void __launch_bounds__(kDecThreads, MINB)
 decrypt_count_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint32_t L4rt,
-                     const uint4 *__restrict__ M4, uint64_t *scratch, uint64_t *count_out) {
+                     const uint4 *__restrict__ M4, const __grid_constant__ ParamMask pmask,
+                     uint64_t *scratch, uint64_t *count_out) {
     extern __shared__ uint4 smem[];
     const uint32_t L4 = L4C ? (uint32_t)L4C : L4rt;
     uint4 *sM2 = smem;                                               // mask, twice over
     uint32_t *sF = reinterpret_cast<uint32_t *>(smem + 2 * L4);      // fail strings
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    for (uint32_t i = threadIdx.x; i < 2 * L4; i += blockDim.x) sM2[i] = M4[i < L4 ? i : i - L4];
+    if (M4 == nullptr) {   // mask in the parameters
+        for (uint32_t i = threadIdx.x; i < 2 * L4; i += blockDim.x) sM2[i] = pmask.u[i < L4 ? i : i - L4];
+    } else {
+        for (uint32_t i = threadIdx.x; i < 2 * L4; i += blockDim.x) sM2[i] = M4[i < L4 ? i : i - L4];
+    }
     __syncthreads();
 
     uint32_t *sFw = sF + warp * L4;
@@ -199,13 +213,18 @@ uint32_t resident_grid(Kernel kernel, size_t smem, uint64_t work_ctas) {
 }
 
 template <int L4C, int UNROLL, int MINB>
-cudaError_t launch_fast(const uint64_t *v, uint64_t T, uint32_t L4, const uint64_t *mask, uint64_t *scratch,
-                        uint64_t *count_out, cudaStream_t stream) {
+cudaError_t launch_fast(const uint64_t *v, uint64_t T, uint32_t L4, const uint64_t *mask, const uint64_t *host_mask,
+                        uint64_t *scratch, uint64_t *count_out, cudaStream_t stream) {
+    ParamMask pm;
+    memset(&pm, 0, sizeof pm);
+    const bool by_param = host_mask && L4 <= (uint32_t)kParamMaskUnits && !env_long("CSGN_DEC_GLOBAL_MASK", 0);
+    if (by_param) memcpy(&pm, host_mask, (size_t)L4 * sizeof(uint4));
     const uint64_t n_chunks = (T + 31) / 32;
     const size_t smem = (size_t)2 * L4 * sizeof(uint4) + (size_t)kDecWarps * L4 * sizeof(uint32_t);
     const uint32_t grid = resident_grid(decrypt_count_kernel<L4C, UNROLL, MINB>, smem, (n_chunks + kDecWarps - 1) / kDecWarps);
     decrypt_count_kernel<L4C, UNROLL, MINB><<<grid, kDecThreads, smem, stream>>>(
-        reinterpret_cast<const uint4 *>(v), T, L4, reinterpret_cast<const uint4 *>(mask), scratch, count_out);
+        reinterpret_cast<const uint4 *>(v), T, L4, by_param ? nullptr : reinterpret_cast<const uint4 *>(mask), pm,
+        scratch, count_out);
     return cudaGetLastError();
 }
 
@@ -222,7 +241,8 @@ cudaError_t launch_wide(const uint64_t *v, uint64_t T, const uint64_t *mask, uin
 }  // namespace
 
 cudaError_t launch_decrypt_count(const uint64_t *v, uint64_t T, uint32_t L, const uint64_t *mask,
-                                 uint64_t *scratch, uint64_t *count_out, cudaStream_t stream) {
+                                 const uint64_t *host_mask, uint64_t *scratch, uint64_t *count_out,
+                                 cudaStream_t stream) {
     if (T == 0 || L == 0) return cudaMemsetAsync(count_out, 0, sizeof(uint64_t), stream);
     const DeviceProps &dp = device_props();
     const uint64_t ctas_per_sm = (uint64_t)env_long("CSGN_DEC_CTAS_PER_SM", 8);
@@ -237,16 +257,16 @@ cudaError_t launch_decrypt_count(const uint64_t *v, uint64_t T, uint32_t L, cons
         err = cudaGetLastError();
     } else {
         const long variant = env_long("CSGN_DEC_VARIANT", 0);
-        if (L4 == 10 && variant == 1) err = launch_fast<10, 10, 4>(v, T, L4, mask, scratch, count_out, stream);
-        else if (L4 == 10 && variant == 2) err = launch_fast<10, 5, 5>(v, T, L4, mask, scratch, count_out, stream);
-        else if (L4 == 10 && variant == 3) err = launch_fast<10, 5, 6>(v, T, L4, mask, scratch, count_out, stream);
-        else if (L4 == 10 && variant == 4) err = launch_fast<10, 2, 8>(v, T, L4, mask, scratch, count_out, stream);
-        else if (L4 == 10) err = launch_fast<10, 10, 3>(v, T, L4, mask, scratch, count_out, stream);     // N=1247
+        if (L4 == 10 && variant == 1) err = launch_fast<10, 10, 4>(v, T, L4, mask, host_mask, scratch, count_out, stream);
+        else if (L4 == 10 && variant == 2) err = launch_fast<10, 5, 5>(v, T, L4, mask, host_mask, scratch, count_out, stream);
+        else if (L4 == 10 && variant == 3) err = launch_fast<10, 5, 6>(v, T, L4, mask, host_mask, scratch, count_out, stream);
+        else if (L4 == 10 && variant == 4) err = launch_fast<10, 2, 8>(v, T, L4, mask, host_mask, scratch, count_out, stream);
+        else if (L4 == 10) err = launch_fast<10, 10, 3>(v, T, L4, mask, host_mask, scratch, count_out, stream);     // N=1247
         else if (L4 == 128 && wide) err = launch_wide<4, 2>(v, T, mask, scratch, count_out, stream);  // N=16383
         else if (L4 == 64 && wide) err = launch_wide<2, 4>(v, T, mask, scratch, count_out, stream);
         else if (L4 == 32 && wide) err = launch_wide<1, 8>(v, T, mask, scratch, count_out, stream);
-        else if (L4 == 128) err = launch_fast<128, 8, 3>(v, T, L4, mask, scratch, count_out, stream);
-        else err = launch_fast<0, 4, 4>(v, T, L4, mask, scratch, count_out, stream);
+        else if (L4 == 128) err = launch_fast<128, 8, 3>(v, T, L4, mask, host_mask, scratch, count_out, stream);
+        else err = launch_fast<0, 4, 4>(v, T, L4, mask, host_mask, scratch, count_out, stream);
     }
     count_launch();
     return err;

@@ -34,8 +34,11 @@ cudaError_t launch_concat(const uint64_t *a, uint64_t n_words_a, const uint64_t 
 // K3  count of blocks with all_w((v[w] & M[w]) == M[w]) (reference src/SecretKey.cpp:126-140)
 // `scratch` is two zero-initialised uint64 (running count, CTA ticket) that the kernel
 // leaves zeroed again; the total is written to *count_out (device memory).
+// `host_mask` (optional) is a host copy of the same L words: small masks ride in the
+// kernel parameters instead of being fetched from global memory.
 cudaError_t launch_decrypt_count(const uint64_t *v, uint64_t T, uint32_t L, const uint64_t *mask,
-                                 uint64_t *scratch, uint64_t *count_out, cudaStream_t stream);
+                                 const uint64_t *host_mask, uint64_t *scratch, uint64_t *count_out,
+                                 cudaStream_t stream);
 
 // K4  out_bit[i] = in_bit[perm[i]] for every block     (reference src/Ciphertext.cpp:24-69)
 // src_map[i] = (perm[i]>>6)<<6 | (63 - (perm[i]&63)): source word and right-shift.
