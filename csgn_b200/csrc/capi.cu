@@ -38,6 +38,7 @@ struct csgn_key {
 
 struct csgn_perm {
     uint32_t *d_map = nullptr;   // N entries: (src_word << 6) | right_shift
+    uint32_t *d_slice_map = nullptr;  // 64*L entries for the bit-sliced kernel (permute.cu), or null
     uint64_t N = 0;
     uint32_t L = 0;
 };
@@ -522,12 +523,35 @@ int csgn_perm_create(uint64_t N, const uint64_t *perm, csgn_perm **out) {
     csgn_perm *h = new csgn_perm;
     h->N = N;
     h->L = csgn_words_per_block(N);
+    // Bit-sliced form: a block is W = 2L 32-bit words; bit j of word c holds position
+    // 64*(c>>1) + (c odd ? 31-j : 63-j).  Entry j*W + c' names the source slice of output
+    // (c', j) as a shared-memory index 33*c + j_src, or the zero slot 33*W for pad bits.
+    std::vector<uint32_t> slices;
+    if (permute_sliced_supported(h->L)) {
+        const uint32_t W = 2 * h->L;
+        slices.assign((size_t)32 * W, 33u * W);
+        for (uint32_t c = 0; c < W; ++c)
+            for (uint32_t j = 0; j < 32; ++j) {
+                const uint64_t i = 64ull * (c >> 1) + ((c & 1u) ? 31u - j : 63u - j);
+                if (i >= N) continue;
+                const uint64_t p = perm[i];
+                const uint32_t sc = 2u * (uint32_t)(p >> 6) + (((p & 63u) < 32u) ? 1u : 0u);
+                slices[(size_t)j * W + c] = 33u * sc + (31u - (uint32_t)(p & 31u));
+            }
+    }
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&h->d_map), (size_t)N * sizeof(uint32_t));
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(h->d_map, map.data(), (size_t)N * sizeof(uint32_t), cudaMemcpyHostToDevice, g.stream);
+    if (e == cudaSuccess && !slices.empty()) {
+        e = cudaMalloc(reinterpret_cast<void **>(&h->d_slice_map), slices.size() * sizeof(uint32_t));
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(h->d_slice_map, slices.data(), slices.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                g.stream);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
     if (e != cudaSuccess) {
         if (h->d_map) cudaFree(h->d_map);
+        if (h->d_slice_map) cudaFree(h->d_slice_map);
         delete h;
         return cuda_fail(e, "permutation upload");
     }
@@ -540,6 +564,7 @@ int csgn_perm_free(csgn_perm *perm) {
     if (g.inited && perm->d_map) {
         cudaStreamSynchronize(g.stream);
         cudaFree(perm->d_map);
+        if (perm->d_slice_map) cudaFree(perm->d_slice_map);
     }
     delete perm;
     return CSGN_OK;
@@ -554,7 +579,8 @@ int csgn_permute_into(const csgn_buf *c, const csgn_perm *perm, csgn_buf *out) {
     if (out->n_blocks > c->n_blocks)
         return fail(CSGN_ERR_SHAPE_MISMATCH, "output holds more blocks than the input");
     if (out->d == c->d) return fail(CSGN_ERR_INVALID_ARGUMENT, "permute cannot run in place");
-    cudaError_t e = launch_permute(c->d, out->n_blocks, c->L, (uint32_t)perm->N, perm->d_map, out->d, g.stream);
+    cudaError_t e = launch_permute(c->d, out->n_blocks, c->L, (uint32_t)perm->N, perm->d_map, perm->d_slice_map, out->d,
+                                   g.stream);
     if (e != cudaSuccess) return cuda_fail(e, "permute kernel");
     return CSGN_OK;
 }

@@ -42,8 +42,10 @@ cudaError_t launch_decrypt_count(const uint64_t *v, uint64_t T, uint32_t L, cons
 
 // K4  out_bit[i] = in_bit[perm[i]] for every block     (reference src/Ciphertext.cpp:24-69)
 // src_map[i] = (perm[i]>>6)<<6 | (63 - (perm[i]&63)): source word and right-shift.
+// slice_map (optional, 64*L entries; see permute.cu) enables the bit-sliced tile kernel.
 cudaError_t launch_permute(const uint64_t *in, uint64_t T, uint32_t L, uint32_t N, const uint32_t *src_map,
-                           uint64_t *out, cudaStream_t stream);
+                           const uint32_t *slice_map, uint64_t *out, cudaStream_t stream);
+bool permute_sliced_supported(uint32_t L);
 
 // xor / wrapping sum / sum(w[i]*(2i+1)) of n_words words, accumulated into acc[0..2]
 // (device, must be zeroed by the caller).

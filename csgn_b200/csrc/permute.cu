@@ -4,16 +4,115 @@
 //
 // Roofline: HBM, 16*L bytes per block (read + write), with the integer pipe as the
 // co-limiter: this is the one kernel of the path whose ALU work per byte matters.
+// A per-bit gather costs ~3 integer ops per bit; the SAME permutation is applied to
+// every block, so the fast kernel works bit-sliced instead (~0.6 op per bit):
 //
-// The permutation is the same for every block, so it is precomputed once per
-// csgn_perm as a source map: src_map[i] = (perm[i]>>6)<<6 | (63-(perm[i]&63)), i.e.
-// the source word of output bit i and the right-shift that brings that bit to bit 0.
+//   1. a tile of 32 blocks is read as 32-bit word columns; thread (tile, column c) holds
+//      the 32x32 bit matrix "block x bit" of that column in registers and transposes it
+//      (PRMT for the 16- and 8-bit stages, SHF+LOP3 for 4/2/1): word j of the result
+//      carries bit j of column c for all 32 blocks -- one *slice* per bit position;
+//   2. slices go to shared memory (rows padded to 33 words: conflict-free);
+//   3. the permutation is now a WORD gather: output slice (c', j) = input slice
+//      slice_map[c', j] (precomputed per csgn_perm; pad positions point at a zero slot);
+//   4. thread (tile, column c') gathers its 32 slices, transposes back and stores the
+//      32-bit word c' of the 32 output blocks (128-byte coalesced per block row).
+//
+// The word-gather kernel below it (one thread builds one 64-bit output word from its 64
+// source bits) covers what the tile kernel cannot hold in shared memory (N > ~54,000).
 #include "kernels.cuh"
 
 #include <algorithm>
 
 namespace csgn {
 namespace {
+
+// ---------------------------------------------------------------------------------------
+// 32x32 bit-matrix transpose in registers: after the call x[j] bit b == (old x[b]) bit j.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void transpose32(uint32_t (&x)[32]) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {   // swap the off-diagonal 16x16 blocks: two byte permutes
+        const uint32_t a = x[k], b = x[k + 16];
+        x[k] = __byte_perm(a, b, 0x5410);
+        x[k + 16] = __byte_perm(a, b, 0x7632);
+    }
+#pragma unroll
+    for (int g = 0; g < 32; g += 16)
+#pragma unroll
+        for (int k = g; k < g + 8; ++k) {   // 8x8 blocks
+            const uint32_t a = x[k], b = x[k + 8];
+            x[k] = __byte_perm(a, b, 0x6240);
+            x[k + 8] = __byte_perm(a, b, 0x7351);
+        }
+#pragma unroll
+    for (int g = 0; g < 32; g += 8)
+#pragma unroll
+        for (int k = g; k < g + 4; ++k) {   // 4x4 blocks
+            const uint32_t a = x[k], b = x[k + 4], m = 0x0f0f0f0fu;
+            x[k] = (a & m) | ((b << 4) & ~m);
+            x[k + 4] = ((a >> 4) & m) | (b & ~m);
+        }
+#pragma unroll
+    for (int g = 0; g < 32; g += 4)
+#pragma unroll
+        for (int k = g; k < g + 2; ++k) {   // 2x2 blocks
+            const uint32_t a = x[k], b = x[k + 2], m = 0x33333333u;
+            x[k] = (a & m) | ((b << 2) & ~m);
+            x[k + 2] = ((a >> 2) & m) | (b & ~m);
+        }
+#pragma unroll
+    for (int k = 0; k < 32; k += 2) {       // single bits
+        const uint32_t a = x[k], b = x[k + 1], m = 0x55555555u;
+        x[k] = (a & m) | ((b << 1) & ~m);
+        x[k + 1] = ((a >> 1) & m) | (b & ~m);
+    }
+}
+
+// slice_map layout: entry j*W + c = padded shared-memory index of the source slice of
+// output (column c, bit j), or the index of the zero slot.
+__global__ void __launch_bounds__(512)
+permute_sliced_kernel(const uint32_t *__restrict__ in, const uint64_t T, const uint32_t W,
+                      const uint32_t *__restrict__ slice_map, uint32_t *__restrict__ out,
+                      const uint32_t tiles_per_cta, const uint64_t n_groups) {
+    extern __shared__ uint32_t S[];                  // tiles_per_cta * (33*W + 1) words
+    const uint32_t tile_words = 33u * W + 1u;        // last word = the zero slot
+    const uint32_t items = tiles_per_cta * W;
+
+    for (uint32_t t = threadIdx.x; t < tiles_per_cta; t += blockDim.x) S[t * tile_words + 33u * W] = 0u;
+
+    for (uint64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const uint64_t tile0 = grp * tiles_per_cta;
+        // ---- 1+2: columns in, transposed, slices to shared memory -----------------------
+        for (uint32_t it = threadIdx.x; it < items; it += blockDim.x) {
+            const uint32_t tl = it / W, c = it - tl * W;
+            const uint64_t blk0 = (tile0 + tl) * 32u;
+            uint32_t x[32];
+            const uint32_t *src = in + blk0 * W + c;
+#pragma unroll
+            for (int b = 0; b < 32; ++b) x[b] = (blk0 + b < T) ? __ldcs(src + (uint64_t)b * W) : 0u;
+            transpose32(x);
+            uint32_t *dst = S + tl * tile_words + 33u * c;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dst[j] = x[j];
+        }
+        __syncthreads();
+        // ---- 3+4: gather slices, transpose back, columns out ----------------------------
+        for (uint32_t it = threadIdx.x; it < items; it += blockDim.x) {
+            const uint32_t tl = it / W, c = it - tl * W;
+            const uint64_t blk0 = (tile0 + tl) * 32u;
+            const uint32_t *Sl = S + tl * tile_words;
+            uint32_t y[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) y[j] = Sl[__ldg(slice_map + (uint32_t)j * W + c)];
+            transpose32(y);
+            uint32_t *dst = out + blk0 * W + c;
+#pragma unroll
+            for (int b = 0; b < 32; ++b)
+                if (blk0 + b < T) __stcs(dst + (uint64_t)b * W, y[b]);
+        }
+        __syncthreads();   // before the next group overwrites the slices
+    }
+}
 
 // Word-gather kernel: one thread builds one 64-bit output word from its 64 source
 // bits.  Works for any N and L; the input block and the map are read through L1.
@@ -39,10 +138,46 @@ permute_gather_kernel(const uint64_t *__restrict__ in, const uint64_t total_word
 
 }  // namespace
 
+bool permute_sliced_supported(uint32_t L) {
+    const size_t need = ((size_t)33 * 2 * L + 1) * sizeof(uint32_t);
+    return need <= device_props().smem_optin && 2 * L >= 1;
+}
+
 cudaError_t launch_permute(const uint64_t *in, uint64_t T, uint32_t L, uint32_t N, const uint32_t *src_map,
-                           uint64_t *out, cudaStream_t stream) {
+                           const uint32_t *slice_map, uint64_t *out, cudaStream_t stream) {
     if (T == 0 || L == 0) return cudaSuccess;
     const DeviceProps &dp = device_props();
+    const bool aligned4 = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 3u) == 0;
+    if (slice_map && aligned4 && permute_sliced_supported(L) && !env_long("CSGN_PERM_GATHER", 0)) {
+        const uint32_t W = 2 * L;
+        const uint32_t tile_words = 33u * W + 1u;
+        // several tiles per CTA when a block is short (N=1247: W=40 -> 4 tiles, 160 work items)
+        uint32_t tiles_per_cta = std::max<uint32_t>(1, (uint32_t)env_long("CSGN_PERM_ITEMS", 160) / W);
+        const uint64_t n_tiles = (T + 31) / 32;
+        tiles_per_cta = (uint32_t)std::min<uint64_t>(tiles_per_cta, n_tiles);
+        while (tiles_per_cta > 1 && (size_t)tiles_per_cta * tile_words * 4 > 48 * 1024) --tiles_per_cta;
+        const size_t smem = (size_t)tiles_per_cta * tile_words * sizeof(uint32_t);
+        const uint32_t items = tiles_per_cta * W;
+        const uint32_t tpb = std::min<uint32_t>(512, (items + 31) / 32 * 32);
+        static size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured) {
+            cudaError_t e = cudaFuncSetAttribute(permute_sliced_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)dp.smem_optin);
+            if (e != cudaSuccess) return e;
+            configured = dp.smem_optin;
+        }
+        int per_sm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, permute_sliced_kernel, (int)tpb, smem) != cudaSuccess ||
+            per_sm < 1)
+            per_sm = 1;
+        const uint64_t n_groups = (n_tiles + tiles_per_cta - 1) / tiles_per_cta;
+        const uint32_t grid = (uint32_t)std::max<uint64_t>(
+            1, std::min<uint64_t>(n_groups, (uint64_t)dp.sm_count * per_sm * (uint64_t)env_long("CSGN_PERM_WAVES", 16)));
+        permute_sliced_kernel<<<grid, tpb, smem, stream>>>(reinterpret_cast<const uint32_t *>(in), T, W, slice_map,
+                                                           reinterpret_cast<uint32_t *>(out), tiles_per_cta, n_groups);
+        count_launch();
+        return cudaGetLastError();
+    }
     const uint64_t total = T * L;
     const uint32_t grid = (uint32_t)std::max<uint64_t>(
         1, std::min<uint64_t>((total + 255) / 256, (uint64_t)dp.sm_count * 8));

@@ -232,7 +232,7 @@ def test_add_and_append(engine, oracle, N):
 # ---------------------------------------------------------------------------
 # K4 permute
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize("N", [1247, 16383, 65, 191, 63, 2048, 4097])
+@pytest.mark.parametrize("N", [1247, 16383, 65, 191, 63, 2048, 4097, 70000])
 def test_permute_matches_oracle(engine, oracle, N):
     rng = np.random.default_rng(N + 2)
     L = words_per_block(N)
@@ -247,6 +247,10 @@ def test_permute_matches_oracle(engine, oracle, N):
         assert not np.any(allb.reshape(T, L)[:, -1] & ~pad_mask(N))      # pad bits stay zero
         strict = ct.applyPermutation(p, strict_ref_truncate=True).getValues()
         assert np.array_equal(strict, oracle.permute_block(v[:L], N, perm))
+        with _Env(CSGN_PERM_GATHER=1):      # the word-gather kernel (what very large N falls back to)
+            assert np.array_equal(ct.applyPermutation(p).getValues(), allb)
+        with _Env(CSGN_PERM_ITEMS=64, CSGN_PERM_WAVES=1):
+            assert np.array_equal(ct.applyPermutation(p).getValues(), allb)
     # Dec_{pi(k)}(pi(c)) = Dec_k(c)
     s = random_key(rng, N, 2)
     v = random_blocks(rng, 500 if L <= 64 else 40, N)
