@@ -143,6 +143,160 @@ decrypt_count_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint3
     fold_and_publish(my_count, scratch, count_out);
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Bulk-ring variant of the same fold (small blocks, L4 <= 16, e.g. N=1247).
+//
+// One persistent CTA per SM.  A producer warp streams the ciphertext into a ring of
+// shared-memory stages with 1-D bulk async copies (cp.async.bulk -> the TMA engine,
+// completion counted in bytes on an mbarrier); a stage is kRingWarps chunks of 32 blocks.
+// Consumer warp w folds chunk w of each stage out of shared memory exactly as above
+// (ballot -> fail string -> one lane per block) and releases the stage through a second
+// mbarrier.  The amount of data in flight is the ring (here ~160 KB per SM), not what the
+// register file can hold, and HBM sees long sequential bursts.
+// ---------------------------------------------------------------------------------------
+constexpr int kRingWarps = 8;     // consumer warps = chunks per stage
+constexpr int kRingThreads = (kRingWarps + 1) * 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int L4C, int STAGES>
+__global__ void __launch_bounds__(kRingThreads, 1)
+decrypt_count_ring_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint32_t L4rt,
+                          const uint4 *__restrict__ M4, const __grid_constant__ ParamMask pmask,
+                          uint64_t *scratch, uint64_t *count_out) {
+    extern __shared__ __align__(128) unsigned char ring_raw[];
+    const uint32_t L4 = L4C ? (uint32_t)L4C : L4rt;
+    const uint32_t chunk_units = 32u * L4;                       // uint4 per 32-block chunk
+    const uint32_t stage_units = chunk_units * kRingWarps;
+    uint4 *ring = reinterpret_cast<uint4 *>(ring_raw);           // STAGES * stage_units
+    uint4 *sM2 = ring + (size_t)STAGES * stage_units;            // mask twice over
+    uint32_t *sF = reinterpret_cast<uint32_t *>(sM2 + 2 * L4);   // fail strings, L4 words per warp
+    uint64_t *full = reinterpret_cast<uint64_t *>(sF + kRingWarps * L4 + (((kRingWarps * L4) & 1u) ? 1u : 0u));
+    uint64_t *empty = full + STAGES;
+
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (M4 == nullptr) {
+        for (uint32_t i = threadIdx.x; i < 2 * L4; i += blockDim.x) sM2[i] = pmask.u[i < L4 ? i : i - L4];
+    } else {
+        for (uint32_t i = threadIdx.x; i < 2 * L4; i += blockDim.x) sM2[i] = M4[i < L4 ? i : i - L4];
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, kRingWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint64_t n_units = T * L4;
+    const uint64_t n_stage_units = (n_units + stage_units - 1) / stage_units;   // stage-sized pieces of the stream
+    uint64_t my_count = 0;
+
+    if (warp == kRingWarps) {
+        // ---- producer: one lane keeps the ring full ------------------------------------
+        if (lane == 0) {
+            uint32_t slot = 0, phase = 0;
+            for (uint64_t u = blockIdx.x; u < n_stage_units; u += gridDim.x) {
+                mbar_wait(empty + slot, phase ^ 1u);             // consumers are done with this slot
+                const uint64_t first = u * stage_units;
+                const uint32_t units = (uint32_t)min((uint64_t)stage_units, n_units - first);
+                mbar_expect_tx(full + slot, units * 16u);
+                bulk_g2s(ring + (size_t)slot * stage_units, V4 + first, units * 16u, full + slot);
+                if (++slot == STAGES) { slot = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        // ---- consumers: warp w folds chunk w of every stage ---------------------------
+        uint32_t *sFw = sF + warp * L4;
+        const uint4 *mk = sM2 + (lane % L4);
+        const uint32_t step = 32u % L4;
+        uint32_t slot = 0, phase = 0;
+        for (uint64_t u = blockIdx.x; u < n_stage_units; u += gridDim.x) {
+            mbar_wait(full + slot, phase);
+            const uint4 *src = ring + (size_t)slot * stage_units + warp * chunk_units + lane;
+            uint32_t koff = 0;
+#pragma unroll
+            for (uint32_t r = 0; r < (L4C ? (uint32_t)L4C : 16u); ++r) {
+                if (L4C || r < L4) {
+                    const uint4 v = src[32u * r];
+                    const uint32_t bal = __ballot_sync(0xffffffffu, unit_fails(v, mk[koff]));
+                    if (lane == 0) sFw[r] = bal;
+                    koff += step;
+                    if (koff >= L4) koff -= L4;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + slot);            // this warp's reads of the slot are done
+            const uint64_t blk = (u * kRingWarps + warp) * 32u + lane;
+            const uint32_t lo = lane * L4, hi = lo + L4;
+            uint32_t any = 0;
+            for (uint32_t w = lo >> 5; w <= (hi - 1) >> 5; ++w) {
+                const uint32_t first = max(lo, w << 5) - (w << 5);
+                const uint32_t last = min(hi, (w + 1) << 5) - (w << 5);
+                const uint32_t m = (last - first == 32u) ? 0xffffffffu : (((1u << (last - first)) - 1u) << first);
+                any |= sFw[w] & m;
+            }
+            my_count += (blk < T && any == 0u) ? 1u : 0u;
+            __syncwarp();
+            if (++slot == STAGES) { slot = 0; phase ^= 1u; }
+        }
+    }
+    fold_and_publish(my_count, scratch, count_out);
+}
+
+template <int L4C, int STAGES>
+cudaError_t launch_ring(const uint64_t *v, uint64_t T, uint32_t L4, const uint64_t *mask, const uint64_t *host_mask,
+                        uint64_t *scratch, uint64_t *count_out, cudaStream_t stream) {
+    ParamMask pm;
+    memset(&pm, 0, sizeof pm);
+    const bool by_param = host_mask && L4 <= (uint32_t)kParamMaskUnits;
+    if (by_param) memcpy(&pm, host_mask, (size_t)L4 * sizeof(uint4));
+    const size_t stage_bytes = (size_t)32 * L4 * kRingWarps * sizeof(uint4);
+    const size_t smem = STAGES * stage_bytes + 2 * L4 * sizeof(uint4) + ((size_t)kRingWarps * L4 + 1) * sizeof(uint32_t) +
+                        2 * STAGES * sizeof(uint64_t) + 16;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(decrypt_count_ring_kernel<L4C, STAGES>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    const uint64_t n_stage_units = (T * L4 + (uint64_t)32 * L4 * kRingWarps - 1) / ((uint64_t)32 * L4 * kRingWarps);
+    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_stage_units, device_props().sm_count));
+    decrypt_count_ring_kernel<L4C, STAGES><<<grid, kRingThreads, smem, stream>>>(
+        reinterpret_cast<const uint4 *>(v), T, L4, by_param ? nullptr : reinterpret_cast<const uint4 *>(mask), pm,
+        scratch, count_out);
+    return cudaGetLastError();
+}
+
 // L4 a multiple of 32 (e.g. N=16383: L4=128): a block is UPL = L4/32 coalesced warp
 // loads; one warp folds BPI blocks per iteration (BPI*UPL independent 16-byte loads in
 // flight per lane) and votes once per block.
@@ -257,7 +411,10 @@ cudaError_t launch_decrypt_count(const uint64_t *v, uint64_t T, uint32_t L, cons
         err = cudaGetLastError();
     } else {
         const long variant = env_long("CSGN_DEC_VARIANT", 0);
-        if (L4 == 10 && variant == 1) err = launch_fast<10, 10, 4>(v, T, L4, mask, host_mask, scratch, count_out, stream);
+        if (L4 == 10 && variant == 5) err = launch_ring<10, 4>(v, T, L4, mask, host_mask, scratch, count_out, stream);
+        else if (L4 == 10 && variant == 6) err = launch_ring<10, 3>(v, T, L4, mask, host_mask, scratch, count_out, stream);
+        else if (L4 == 10 && variant == 7) err = launch_ring<10, 5>(v, T, L4, mask, host_mask, scratch, count_out, stream);
+        else if (L4 == 10 && variant == 1) err = launch_fast<10, 10, 4>(v, T, L4, mask, host_mask, scratch, count_out, stream);
         else if (L4 == 10 && variant == 2) err = launch_fast<10, 5, 5>(v, T, L4, mask, host_mask, scratch, count_out, stream);
         else if (L4 == 10 && variant == 3) err = launch_fast<10, 5, 6>(v, T, L4, mask, host_mask, scratch, count_out, stream);
         else if (L4 == 10 && variant == 4) err = launch_fast<10, 2, 8>(v, T, L4, mask, host_mask, scratch, count_out, stream);

@@ -175,6 +175,19 @@ def test_decrypt_count_matches_oracle(engine, oracle, N, D):
         assert engine.SecretKey(ctx, s).count_satisfied(engine.Ciphertext.from_host(v, ctx)) == oracle.count_satisfied(v, N, s)
 
 
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
+def test_decrypt_every_kernel_variant(engine, oracle, variant):
+    """N=1247 has several tuned forms of the fold (register-streamed and the bulk-copy ring)."""
+    N, D = 1247, 2
+    rng = np.random.default_rng(variant)
+    ctx = engine.Context(N, D)
+    for T in (1, 31, 32, 33, 255, 256, 257, 300, 5000, 70001):
+        v, s = random_blocks(rng, T, N), random_key(rng, N, D)
+        ct, key = engine.Ciphertext.from_host(v, ctx), engine.SecretKey(ctx, s)
+        with _Env(CSGN_DEC_VARIANT=variant):
+            assert key.count_satisfied(ct) == oracle.count_satisfied(v, N, s), (variant, T)
+
+
 def test_decrypt_real_ciphertexts(engine, oracle):
     # fresh encryptions by the oracle's reference-order encrypt; D = 16 and 64
     for N, D, n in ((1247, 16, 200), (16383, 64, 12)):

@@ -52,13 +52,6 @@ def run(label, outs, distinct_ops, sampler=False, interleave=False, K=30):
     print("%-46s mul %6.2f us  dec %6.2f us  pair %6.2f us  (cpu enqueue %5.1f us/launch)" % (label, mul, dec, tot, t_enq * 1e6 / (K * P * 2)), flush=True)
 
 sep = [torch.empty(T1 * T2 * L, dtype=torch.int64, device=dev) for _ in range(P)]
-import itertools, random
-cfgs = [(1, 0), (2, 1), (2, 2), (2, 4)]
-for rep in range(3):
-    order = list(itertools.product(cfgs, (True, False)))
-    random.Random(rep).shuffle(order)
-    for (kern, u), distinct in order:
-        os.environ["CSGN_MUL_KERNEL"] = str(kern)
-        if u: os.environ["CSGN_MUL_U"] = str(u)
-        else: os.environ.pop("CSGN_MUL_U", None)
-        run("rep%d kernel v%d U=%d %s" % (rep, kern, u, "distinct" if distinct else "same-ops"), sep, distinct)
+for var in (0, 1, 2, 5, 6, 7):
+    os.environ["CSGN_DEC_VARIANT"] = str(var)
+    run("decrypt variant %d" % var, sep, True)
