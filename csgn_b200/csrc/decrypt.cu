@@ -21,6 +21,7 @@
 // lane).  Counts fold lane -> warp -> CTA -> one atomicAdd per CTA; the last CTA to
 // finish publishes the total and re-arms the scratch words, so a decrypt is ONE launch.
 #include "kernels.cuh"
+#include "launch.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -78,6 +79,7 @@ decrypt_count_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint3
                      uint64_t *scratch, uint64_t *count_out) {
     extern __shared__ uint4 smem[];
     const uint32_t L4 = L4C ? (uint32_t)L4C : L4rt;
+    pdl_enter();
     uint4 *sM2 = smem;                                               // mask, twice over
     uint32_t *sF = reinterpret_cast<uint32_t *>(smem + 2 * L4);      // fail strings
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -201,6 +203,7 @@ decrypt_count_ring_kernel(const uint4 *__restrict__ V4, const uint64_t T, const 
     uint64_t *empty = full + STAGES;
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    pdl_enter();
     if (M4 == nullptr) {
         for (uint32_t i = threadIdx.x; i < 2 * L4; i += blockDim.x) sM2[i] = pmask.u[i < L4 ? i : i - L4];
     } else {
@@ -291,10 +294,9 @@ cudaError_t launch_ring(const uint64_t *v, uint64_t T, uint32_t L4, const uint64
     }
     const uint64_t n_stage_units = (T * L4 + (uint64_t)32 * L4 * kRingWarps - 1) / ((uint64_t)32 * L4 * kRingWarps);
     const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_stage_units, device_props().sm_count));
-    decrypt_count_ring_kernel<L4C, STAGES><<<grid, kRingThreads, smem, stream>>>(
-        reinterpret_cast<const uint4 *>(v), T, L4, by_param ? nullptr : reinterpret_cast<const uint4 *>(mask), pm,
-        scratch, count_out);
-    return cudaGetLastError();
+    return launch_kernel(decrypt_count_ring_kernel<L4C, STAGES>, grid, kRingThreads, smem, stream,
+                         reinterpret_cast<const uint4 *>(v), T, L4,
+                         by_param ? nullptr : reinterpret_cast<const uint4 *>(mask), pm, scratch, count_out);
 }
 
 // L4 a multiple of 32 (e.g. N=16383: L4=128): a block is UPL = L4/32 coalesced warp
@@ -305,6 +307,7 @@ __global__ void __launch_bounds__(kDecThreads, 4)
 decrypt_count_wide_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint4 *__restrict__ M4,
                           uint64_t *scratch, uint64_t *count_out) {
     const uint32_t lane = threadIdx.x & 31u;
+    pdl_enter();
     uint4 m[UPL];
 #pragma unroll
     for (int u = 0; u < UPL; ++u) m[u] = __ldg(M4 + 32 * u + lane);
@@ -341,6 +344,7 @@ decrypt_count_generic_kernel(const uint64_t *__restrict__ V, const uint64_t T, c
     const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     uint64_t my_count = 0;
+    pdl_enter();
     for (uint64_t blk = warp_global; blk < T; blk += n_warps) {
         const uint64_t *row = V + blk * L;
         bool f = false;
@@ -376,10 +380,9 @@ cudaError_t launch_fast(const uint64_t *v, uint64_t T, uint32_t L4, const uint64
     const uint64_t n_chunks = (T + 31) / 32;
     const size_t smem = (size_t)2 * L4 * sizeof(uint4) + (size_t)kDecWarps * L4 * sizeof(uint32_t);
     const uint32_t grid = resident_grid(decrypt_count_kernel<L4C, UNROLL, MINB>, smem, (n_chunks + kDecWarps - 1) / kDecWarps);
-    decrypt_count_kernel<L4C, UNROLL, MINB><<<grid, kDecThreads, smem, stream>>>(
-        reinterpret_cast<const uint4 *>(v), T, L4, by_param ? nullptr : reinterpret_cast<const uint4 *>(mask), pm,
-        scratch, count_out);
-    return cudaGetLastError();
+    return launch_kernel(decrypt_count_kernel<L4C, UNROLL, MINB>, grid, kDecThreads, smem, stream,
+                         reinterpret_cast<const uint4 *>(v), T, L4,
+                         by_param ? nullptr : reinterpret_cast<const uint4 *>(mask), pm, scratch, count_out);
 }
 
 template <int UPL, int BPI>
@@ -387,9 +390,8 @@ cudaError_t launch_wide(const uint64_t *v, uint64_t T, const uint64_t *mask, uin
                         uint64_t *count_out, cudaStream_t stream) {
     const uint64_t n_groups = (T + BPI - 1) / BPI;
     const uint32_t grid = resident_grid(decrypt_count_wide_kernel<UPL, BPI>, 0, (n_groups + kDecWarps - 1) / kDecWarps);
-    decrypt_count_wide_kernel<UPL, BPI><<<grid, kDecThreads, 0, stream>>>(
-        reinterpret_cast<const uint4 *>(v), T, reinterpret_cast<const uint4 *>(mask), scratch, count_out);
-    return cudaGetLastError();
+    return launch_kernel(decrypt_count_wide_kernel<UPL, BPI>, grid, kDecThreads, 0, stream,
+                         reinterpret_cast<const uint4 *>(v), T, reinterpret_cast<const uint4 *>(mask), scratch, count_out);
 }
 
 }  // namespace
@@ -407,8 +409,7 @@ cudaError_t launch_decrypt_count(const uint64_t *v, uint64_t T, uint32_t L, cons
     if ((L & 1u) || !aligned || L4 > kDecMaxL4 || env_long("CSGN_DEC_GENERIC", 0)) {
         const uint64_t want = (T + kDecWarps - 1) / kDecWarps;
         const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, dp.sm_count * ctas_per_sm));
-        decrypt_count_generic_kernel<<<grid, kDecThreads, 0, stream>>>(v, T, L, mask, scratch, count_out);
-        err = cudaGetLastError();
+        err = launch_kernel(decrypt_count_generic_kernel, grid, kDecThreads, 0, stream, v, T, L, mask, scratch, count_out);
     } else {
         const long variant = env_long("CSGN_DEC_VARIANT", 0);
         if (L4 == 10 && variant == 5) err = launch_ring<10, 4>(v, T, L4, mask, host_mask, scratch, count_out, stream);

@@ -4,6 +4,7 @@
 // Roofline: HBM copy bandwidth, 16*L bytes per block moved (8*L read + 8*L written).
 // operator+= appends in place (out == a): only b moves.
 #include "kernels.cuh"
+#include "launch.cuh"
 
 #include <algorithm>
 
@@ -21,6 +22,7 @@ concat_kernel(const VecT *__restrict__ a, const uint64_t na, const VecT *__restr
               VecT *__restrict__ out) {
     const uint64_t total = na + nb;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * kCopyUnroll;
+    pdl_enter();
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x * kCopyUnroll + threadIdx.x; base < total; base += stride) {
         VecT v[kCopyUnroll];
         bool live[kCopyUnroll];
@@ -42,6 +44,7 @@ __global__ void __launch_bounds__(256)
 checksum_kernel(const uint64_t *__restrict__ v, const uint64_t n_words, uint64_t *acc) {
     uint64_t x = 0, s = 0, h = 0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    pdl_enter();
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) {
         const uint64_t w = __ldcs(v + i);
         x ^= w;
@@ -79,14 +82,12 @@ cudaError_t launch_concat(const uint64_t *a, uint64_t n_words_a, const uint64_t 
     const uint64_t per_cta = (uint64_t)kCopyThreads * kCopyUnroll;
     const uint32_t grid = (uint32_t)std::max<uint64_t>(
         1, std::min<uint64_t>((units + per_cta - 1) / per_cta, (uint64_t)dp.sm_count * 16));
-    if (vec)
-        concat_kernel<uint4><<<grid, kCopyThreads, 0, stream>>>(
-            reinterpret_cast<const uint4 *>(a), n_words_a / 2, reinterpret_cast<const uint4 *>(b), n_words_b / 2,
-            reinterpret_cast<uint4 *>(out));
-    else
-        concat_kernel<uint64_t><<<grid, kCopyThreads, 0, stream>>>(a, n_words_a, b, n_words_b, out);
     count_launch();
-    return cudaGetLastError();
+    if (vec)
+        return launch_kernel(concat_kernel<uint4>, grid, kCopyThreads, 0, stream, reinterpret_cast<const uint4 *>(a),
+                             n_words_a / 2, reinterpret_cast<const uint4 *>(b), n_words_b / 2,
+                             reinterpret_cast<uint4 *>(out));
+    return launch_kernel(concat_kernel<uint64_t>, grid, kCopyThreads, 0, stream, a, n_words_a, b, n_words_b, out);
 }
 
 cudaError_t launch_checksum(const uint64_t *v, uint64_t n_words, uint64_t *acc, cudaStream_t stream) {
@@ -94,9 +95,8 @@ cudaError_t launch_checksum(const uint64_t *v, uint64_t n_words, uint64_t *acc, 
     const DeviceProps &dp = device_props();
     const uint32_t grid = (uint32_t)std::max<uint64_t>(
         1, std::min<uint64_t>((n_words + 255) / 256, (uint64_t)dp.sm_count * 8));
-    checksum_kernel<<<grid, 256, 0, stream>>>(v, n_words, acc);
     count_launch();
-    return cudaGetLastError();
+    return launch_kernel(checksum_kernel, grid, 256, 0, stream, v, n_words, acc);
 }
 
 }  // namespace csgn

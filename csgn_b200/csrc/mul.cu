@@ -18,6 +18,7 @@
 // b is re-read from L2 once per R rows, so L2 read traffic is 1/R of the write
 // stream; no integer division happens inside the row loop.
 #include "kernels.cuh"
+#include "launch.cuh"
 
 #include <algorithm>
 
@@ -49,6 +50,7 @@ mul_outer_kernel(const uint4 *__restrict__ A4, const uint4 *__restrict__ B4, uin
     const uint32_t tpb = blockDim.x;
     const uint32_t k4 = threadIdx.x % L4;
     const uint64_t tile_q = (uint64_t)tpb * U;
+    pdl_enter();
 
     // In real use the left operand is DRAM-cold (the previous product flushed L2) and an
     // item is short, so a cold a-chunk is a full DRAM latency in front of every item.
@@ -129,6 +131,7 @@ mul_strip_kernel(const uint4 *__restrict__ A4, const uint4 *__restrict__ B4, uin
     const uint32_t row_step = G * m;
     const uint64_t a_step = (uint64_t)row_step * L4;
     const uint64_t o_step = (uint64_t)row_step * Q;
+    pdl_enter();
 
     for (uint32_t s = blockIdx.x; s < n_strips; s += gridDim.x) {
         const uint32_t ct = s % n_tiles;
@@ -199,10 +202,9 @@ template <int U, bool RAGGED>
 cudaError_t launch_strip(const uint64_t *a, uint64_t T1, const uint64_t *b, uint64_t Q, uint32_t L4, uint64_t *out,
                          const StripPlan &pl, cudaStream_t stream) {
     constexpr int MINB = U >= 4 ? 2 : 3;
-    mul_strip_kernel<U, 2, RAGGED, MINB><<<pl.grid, pl.tpb, 0, stream>>>(
-        reinterpret_cast<const uint4 *>(a), reinterpret_cast<const uint4 *>(b), reinterpret_cast<uint4 *>(out), L4,
-        (uint32_t)T1, Q, pl.n_tiles, pl.G, pl.m, pl.n_strips);
-    return cudaGetLastError();
+    return launch_kernel(mul_strip_kernel<U, 2, RAGGED, MINB>, pl.grid, pl.tpb, 0, stream,
+                         reinterpret_cast<const uint4 *>(a), reinterpret_cast<const uint4 *>(b),
+                         reinterpret_cast<uint4 *>(out), L4, (uint32_t)T1, Q, pl.n_tiles, pl.G, pl.m, pl.n_strips);
 }
 
 int strip_occupancy(int U, bool ragged, uint32_t tpb) {
@@ -280,6 +282,7 @@ mul_outer_generic_kernel(const uint64_t *__restrict__ A, const uint64_t *__restr
                          uint64_t *__restrict__ out, const uint32_t L, const uint64_t row_words,
                          const uint64_t total_words) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    pdl_enter();
     for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total_words; idx += stride) {
         const uint64_t i = idx / row_words;
         const uint64_t in_row = idx - i * row_words;
@@ -302,10 +305,9 @@ cudaError_t launch_v4m(const uint64_t *a, uint64_t T1, const uint64_t *b, uint64
     const uint64_t ahead_items = (uint64_t)device_props().sm_count * (uint64_t)env_long("CSGN_MUL_PF_CTAS_PER_SM", 8);
     const uint32_t pf_chunks =
         env_long("CSGN_MUL_PF_CTAS_PER_SM", 8) > 0 ? (uint32_t)((ahead_items + n_col_tiles - 1) / n_col_tiles) : 0u;
-    mul_outer_kernel<U, MODE><<<grid, tpb, smem, stream>>>(
-        reinterpret_cast<const uint4 *>(a), reinterpret_cast<const uint4 *>(b),
-        reinterpret_cast<uint4 *>(out), L4, T1, Q, R, (uint32_t)n_col_tiles, n_items, pf_chunks);
-    return cudaGetLastError();
+    return launch_kernel(mul_outer_kernel<U, MODE>, grid, tpb, smem, stream, reinterpret_cast<const uint4 *>(a),
+                         reinterpret_cast<const uint4 *>(b), reinterpret_cast<uint4 *>(out), L4, T1, Q, R,
+                         (uint32_t)n_col_tiles, n_items, pf_chunks);
 }
 
 template <int U>
@@ -342,9 +344,8 @@ cudaError_t launch_mul(const uint64_t *a, uint64_t T1, const uint64_t *b, uint64
         const uint64_t row_words = T2 * L, total = T1 * row_words;
         const uint64_t want = (total + 255) / 256;
         const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)dp.sm_count * 16);
-        mul_outer_generic_kernel<<<grid, 256, 0, stream>>>(a, b, out, L, row_words, total);
         count_launch();
-        return cudaGetLastError();
+        return launch_kernel(mul_outer_generic_kernel, grid, 256, 0, stream, a, b, out, L, row_words, total);
     }
 
     const uint64_t Q = T2 * L4;

@@ -20,6 +20,7 @@
 // The word-gather kernel below it (one thread builds one 64-bit output word from its 64
 // source bits) covers what the tile kernel cannot hold in shared memory (N > ~54,000).
 #include "kernels.cuh"
+#include "launch.cuh"
 
 #include <algorithm>
 
@@ -77,6 +78,7 @@ permute_sliced_kernel(const uint32_t *__restrict__ in, const uint64_t T, const u
     extern __shared__ uint32_t S[];                  // tiles_per_cta * (33*W + 1) words
     const uint32_t tile_words = 33u * W + 1u;        // last word = the zero slot
     const uint32_t items = tiles_per_cta * W;
+    pdl_enter();
 
     for (uint32_t t = threadIdx.x; t < tiles_per_cta; t += blockDim.x) S[t * tile_words + 33u * W] = 0u;
 
@@ -120,6 +122,7 @@ __global__ void __launch_bounds__(256)
 permute_gather_kernel(const uint64_t *__restrict__ in, const uint64_t total_words, const uint32_t L,
                       const uint32_t N, const uint32_t *__restrict__ src_map, uint64_t *__restrict__ out) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    pdl_enter();
     for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total_words; idx += stride) {
         const uint64_t blk = idx / L;
         const uint32_t w = (uint32_t)(idx - blk * L);
@@ -173,17 +176,15 @@ cudaError_t launch_permute(const uint64_t *in, uint64_t T, uint32_t L, uint32_t 
         const uint64_t n_groups = (n_tiles + tiles_per_cta - 1) / tiles_per_cta;
         const uint32_t grid = (uint32_t)std::max<uint64_t>(
             1, std::min<uint64_t>(n_groups, (uint64_t)dp.sm_count * per_sm * (uint64_t)env_long("CSGN_PERM_WAVES", 16)));
-        permute_sliced_kernel<<<grid, tpb, smem, stream>>>(reinterpret_cast<const uint32_t *>(in), T, W, slice_map,
-                                                           reinterpret_cast<uint32_t *>(out), tiles_per_cta, n_groups);
         count_launch();
-        return cudaGetLastError();
+        return launch_kernel(permute_sliced_kernel, grid, tpb, smem, stream, reinterpret_cast<const uint32_t *>(in), T, W,
+                             slice_map, reinterpret_cast<uint32_t *>(out), tiles_per_cta, n_groups);
     }
     const uint64_t total = T * L;
     const uint32_t grid = (uint32_t)std::max<uint64_t>(
         1, std::min<uint64_t>((total + 255) / 256, (uint64_t)dp.sm_count * 8));
-    permute_gather_kernel<<<grid, 256, 0, stream>>>(in, total, L, N, src_map, out);
     count_launch();
-    return cudaGetLastError();
+    return launch_kernel(permute_gather_kernel, grid, 256, 0, stream, in, total, L, N, src_map, out);
 }
 
 }  // namespace csgn
