@@ -44,6 +44,10 @@ WORKLOADS = {
     # name: (N, D, T1, T2, description)
     "cfg2": (1247, 16, 1000, 1000, "Context(1247,16): 1000x1000 -> 1M output blocks, multiply then decrypt"),
     "cfg5": (16383, 64, 300, 300, "Context(16383,64): 300x300 -> 90k output blocks, multiply then decrypt"),
+    # BASELINE.json configs[3]: deep product chain (a*b)*d; per GPU 1000 x 1000 x chain_d blocks, the left
+    # operand sharded by block range, b and d replicated, decrypt finished by a one-word all-reduce.
+    # chain_d = 125 gives 1.25e8 blocks = 20 GB per GPU, 1e9 blocks at 8 GPUs.
+    "cfg4": (1247, 16, 1000, 1000, "Context(1247,16): chain (a*b)*d, 1000 x 1000 x chain_d blocks per GPU, decrypt + all-reduce"),
 }
 METRIC = "ctxt-mul+decrypt output blocks/s"
 UNIT = "blocks/s"
@@ -57,6 +61,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--pairs", type=int, default=16, help="independent ciphertext pairs per step")
+    ap.add_argument("--chain-d", type=int, default=125, help="cfg4: blocks of the third operand (125 -> 20 GB/GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -406,10 +411,173 @@ def run_ours(args):
     return 0
 
 
+def run_chain(args):
+    """cfg4: x = a_shard * b (1M blocks), y = x * d (1e6*chain_d blocks), decrypt(y), all-reduce."""
+    import torch
+    import torch.distributed as dist
+    from csgn_b200 import engine as eng
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    N, D, T1, T2, desc = WORKLOADS["cfg4"]
+    Td, L = args.chain_d, words_per_block(N)
+    eng.init(local)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
+    ctx = eng.Context(N, D)
+    key_pos = np.random.default_rng(7).permutation(N)[:D].astype(np.uint64)
+    key = eng.SecretKey(ctx, key_pos)
+    key_mask = np.zeros(L, dtype=np.uint64)
+    for s_ in key_pos:
+        key_mask[int(s_) >> 6] |= np.uint64(1 << (63 - (int(s_) & 63)))
+
+    def planted(rng, T, k):
+        w = seeded_blocks(rng, T, N).reshape(T, L)
+        w[rng.choice(T, size=min(T, k), replace=False)] |= key_mask
+        return w.reshape(-1)
+
+    first, count = eng.shard_range(T1 * world, rank, world)
+    host = {"a": planted(np.random.default_rng([1, rank]), T1, 31), "b": planted(np.random.default_rng([2]), T2, 17),
+            "d": planted(np.random.default_rng([3]), Td, 5)}
+    pinned = {k: torch.from_numpy(v.view(np.int64)).pin_memory() for k, v in host.items()}
+    devt = {k: v.to(dev) for k, v in pinned.items()}
+    va, vb, vd = (eng.Ciphertext.from_tensor(devt[k], ctx) for k in ("a", "b", "d"))
+    x = torch.empty(T1 * T2 * L, dtype=torch.int64, device=dev)
+    y = torch.empty(T1 * T2 * Td * L, dtype=torch.int64, device=dev)
+    vx, vy = eng.Ciphertext.from_tensor(x, ctx), eng.Ciphertext.from_tensor(y, ctx)
+    counts = torch.zeros(1, dtype=torch.int64, device=dev)
+    host_counts = torch.zeros(1, dtype=torch.int64).pin_memory()
+
+    def step(evs=None):
+        if evs:
+            evs[0].record()
+        va.mul_into(vb, vx)
+        if evs:
+            evs[1].record()
+        vx.mul_into(vd, vy)
+        if evs:
+            evs[2].record()
+        key.count_satisfied_async(vy, counts.data_ptr())
+        if evs:
+            evs[3].record()
+        if world > 1:
+            dist.all_reduce(counts)
+        if evs:
+            evs[4].record()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    W = max(3, args.warmup)
+    for _ in range(W):
+        step()
+    barrier()
+    want = torch.tensor([key.count_satisfied(va) * key.count_satisfied(vb) * key.count_satisfied(vd)],
+                        dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(want)
+    if not torch.equal(want, counts):
+        raise SystemExit("cfg4 sanity failed: count((a*b)*d) %s != count(a)count(b)count(d) %s" % (counts, want))
+
+    K = args.steps
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
+    sampler = ClockSampler(local)
+    barrier()
+    launches0 = eng.launch_count()
+    sampler.start()
+    for k in range(K):
+        step(evs[k])
+    barrier()
+    clocks = sampler.stop()
+    launches = eng.launch_count() - launches0
+    phases = [sum(e[i].elapsed_time(e[i + 1]) for e in evs) for i in range(4)]
+    t = torch.tensor([evs[0][0].elapsed_time(evs[K - 1][4])] + phases, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, mul1_ms, mul2_ms, dec_ms, ar_ms = (float(v) for v in t.tolist())
+    out_blocks = T1 * T2 * Td                      # per GPU
+    value = out_blocks * world * K / (total_ms * 1e-3)
+    peak, peak_src = measured_peak_gbs()
+    mul2_gbs = out_blocks * 8 * L * K / (mul2_ms * 1e-3) / 1e9
+    dec_gbs = out_blocks * 8 * L * K / (dec_ms * 1e-3) / 1e9
+
+    # e2e: the three operands come from pinned host memory every step; the bit goes back
+    def step_e2e():
+        ha = eng.Ciphertext.from_host_ptr(pinned["a"].data_ptr(), T1, ctx)
+        hb = eng.Ciphertext.from_host_ptr(pinned["b"].data_ptr(), T2, ctx)
+        hd = eng.Ciphertext.from_host_ptr(pinned["d"].data_ptr(), Td, ctx)
+        ha.mul_into(hb, vx)
+        vx.mul_into(hd, vy)          # the 20 GB product is written in place: no room for two of them
+        key.count_satisfied_async(vy, counts.data_ptr())
+        if world > 1:
+            dist.all_reduce(counts)
+        host_counts.copy_(counts, non_blocking=True)
+        stream.synchronize()
+
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(W):
+            step_e2e()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            step_e2e()
+        e1.record()
+        barrier()
+        ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        if int(host_counts.item()) != int(want.item()):
+            raise SystemExit("cfg4 e2e result differs")
+        e2e = {"value": out_blocks * world * K / (float(ems.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int((T1 + T2 + Td) * L * 8), "d2h_bytes_per_step": 8,
+               "ms_per_step": float(ems.item()) / K,
+               "path": "csgn_buf_upload x3 (pinned host) -> csgn_mul_into x2 -> csgn_decrypt_count_async -> D2H count"}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u64", "data": "synthetic",
+                "config": {"workload": "cfg4: " + desc, "chain_d": Td, "blocks_per_gpu": out_blocks,
+                           "blocks_total": out_blocks * world, "product_bytes_per_gpu": out_blocks * 8 * L,
+                           "l2": "no flush needed: the product (%.1f GB per GPU) is far larger than L2" % (out_blocks * 8 * L / 1e9),
+                           "sharding": "left operand by block range, b and d replicated, one-word NCCL all-reduce per decrypt"},
+                "roofline": {"bound": "hbm", "kernel": "mul_outer_kernel", "achieved": mul2_gbs, "peak": peak, "unit": "GB/s",
+                             "frac": mul2_gbs / peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": out_blocks * 8 * L, "avg_launch_us": mul2_ms * 1e3 / K},
+                "kernels": {"multiply_1M": {"avg_launch_us": mul1_ms * 1e3 / K},
+                            "multiply_chain": {"gbs": mul2_gbs, "frac_of_peak": mul2_gbs / peak, "avg_launch_us": mul2_ms * 1e3 / K},
+                            "decrypt": {"gbs": dec_gbs, "frac_of_peak": dec_gbs / peak, "avg_launch_us": dec_ms * 1e3 / K},
+                            "allreduce_ms_per_step": ar_ms / K},
+                "clocks": clocks, "gpu_launches": int(launches)}
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_baseline(N, D, T1, T2)
+            cb["sample"] += "; per-block cost of the chain is the same multiply+decrypt work"
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.workload == "cfg4":
+        return run_chain(args)
     return run_ours(args)
 
 

@@ -53,12 +53,26 @@ mul_outer_kernel(const uint4 *__restrict__ A4, const uint4 *__restrict__ B4, uin
     pdl_enter();
 
     // In real use the left operand is DRAM-cold (the previous product flushed L2) and an
-    // item is short, so a cold a-chunk is a full DRAM latency in front of every item.
-    // CTA i warms L2 with the i-th 128-byte line of a; a is consumed far more slowly than
-    // CTAs are launched, so every line is resident long before its rows come up.
-    if (pf_chunks && threadIdx.x == 0) {
-        const uint64_t line = blockIdx.x;
-        if (line * 8u < T1 * L4) asm volatile("prefetch.global.L2 [%0];" ::"l"(A4 + line * 8u));
+    // item is short, so a cold a-chunk is a full DRAM latency in front of every item.  CTAs
+    // start in blockIdx order, so CTA j warms L2 for the items that start ~two waves later:
+    // the chunk of item j + pf_chunks*n_col_tiles (done by the column-0 CTA of each chunk);
+    // the first pf_chunks chunks, which nobody is ahead of, are requested line by line by
+    // the first CTAs.
+    if (pf_chunks) {
+        const uint64_t a_bytes = T1 * L4 * 16u;
+        const uint64_t head_bytes = min(a_bytes, (uint64_t)pf_chunks * R * L4 * 16u);
+        if (threadIdx.x == 0 && (uint64_t)blockIdx.x * 128u < head_bytes)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(A4) + (uint64_t)blockIdx.x * 128u));
+        if (blockIdx.x % n_col_tiles == 0) {
+            const uint64_t row0 = ((uint64_t)blockIdx.x / n_col_tiles + pf_chunks) * R;
+            if (row0 < T1) {
+                const uint32_t bytes = (uint32_t)min((uint64_t)R, T1 - row0) * L4 * 16u;
+                const uint32_t off = threadIdx.x * 128u;
+                if (off < bytes + 128u)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(A4 + row0 * L4) +
+                                                                   min(off, bytes - 1u)));
+            }
+        }
     }
 
     for (uint64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -320,13 +334,23 @@ cudaError_t launch_v4(const uint64_t *a, uint64_t T1, const uint64_t *b, uint64_
     }
 }
 
-// Largest CTA size <= cap that is a multiple of L4, preferring whole warps.
-uint32_t pick_tpb(uint32_t L4, uint32_t cap) {
+// CTA size for the tiled kernel: a multiple of L4 in [192, cap].  A partial last warp costs
+// issue slots in every item; a ragged last column tile only makes that tile's items shorter
+// (items are scheduled dynamically), so it weighs a quarter.
+uint32_t pick_tpb(uint32_t L4, uint64_t Q, int U, uint32_t cap) {
     uint32_t best = 0;
+    double best_cost = 1e30;
     for (uint32_t t = (cap / L4) * L4; t >= L4 && t > 0; t -= L4) {
-        if (t % 32 == 0) return t;
-        if (!best) best = t;
-        if (t < cap / 2) break;
+        const uint64_t tile = (uint64_t)t * U;
+        const uint64_t n_tiles = (Q + tile - 1) / tile;
+        const double pad = (double)(n_tiles * tile) / (double)Q;
+        const double warp = (double)((t + 31) / 32 * 32) / (double)t;
+        const double cost = warp * (1.0 + 0.25 * (pad - 1.0)) * (t < 256 ? 1.03 : 1.0);
+        if (cost < best_cost - 1e-9) {
+            best_cost = cost;
+            best = t;
+        }
+        if (t < 192 + L4) break;
     }
     return best;
 }
@@ -356,12 +380,13 @@ cudaError_t launch_mul(const uint64_t *a, uint64_t T1, const uint64_t *b, uint64
     }
     const long kernel_choice = env_long("CSGN_MUL_KERNEL", 0);
     const bool strip_ok = T1 < (1ull << 31) && Q * T1 < (1ull << 62);
-    // Measured on B200 (tools/mul_ab.py): rows of 64 KB and more run fastest on the tiled
-    // kernel below (memset speed); shorter rows on the strip kernel, which covers several
-    // rows per CTA step.  With very few rows there is nothing to amortise a strip over.
-    if (strip_ok && (kernel_choice == 2 || (kernel_choice == 0 && T1 >= 4 && Q < 4096))) {
-        const StripPlan pl = plan_strips(L4, T1, Q, (uint32_t)env_long("CSGN_MUL_TPB", 512),
-                                         (int)env_long("CSGN_MUL_U", 0), (uint64_t)env_long("CSGN_MUL_GRID", 1 << 30));
+    // Measured on B200 (tools/mul_ab.py, profiles/): the tiled kernel below runs at memset speed
+    // for rows of a few KB and more; rows shorter than one CTA go to the strip kernel, which
+    // covers several rows per CTA step.  With very few rows there is nothing to amortise a strip over.
+    const uint32_t tpb_cap = (uint32_t)env_long("CSGN_MUL_TPB", 512);
+    if (strip_ok && (kernel_choice == 2 || (kernel_choice == 0 && T1 >= 4 && Q < tpb_cap))) {
+        const StripPlan pl = plan_strips(L4, T1, Q, tpb_cap, (int)env_long("CSGN_MUL_U", 0),
+                                         (uint64_t)env_long("CSGN_MUL_GRID", 1 << 30));
         if (pl.tpb) {
             cudaError_t err;
             if (pl.U >= 4) err = pl.ragged ? launch_strip<4, true>(a, T1, b, Q, L4, out, pl, stream)
@@ -374,21 +399,22 @@ cudaError_t launch_mul(const uint64_t *a, uint64_t T1, const uint64_t *b, uint64
             return err;
         }
     }
-    // Tuned on B200 (tools/sweep.py, profiles/): many small work items balance best, but
-    // an item must keep R >= 3 rows per load of its b tile or the L2 re-reads show;
-    // products of a GiB and more prefer wider tiles and even more items.
+    // Tiled kernel.  Many small work items balance best, but an item must keep R >= 3 rows per
+    // load of its b tile or the L2 re-reads show.  Units per thread: 1 for rows up to 128 KB
+    // (chains: many rows of a few hundred blocks), 2 beyond, 4 for products of a GiB and more
+    // with long rows.
     const bool huge = T1 * Q >= (1ull << 26);     // >= 1 GiB of output
-    uint32_t tpb = pick_tpb(L4, (uint32_t)env_long("CSGN_MUL_TPB", 512));
-    if (tpb == 0) tpb = L4;
+    int U = (int)env_long("CSGN_MUL_U", Q < 8192 ? 1 : (huge && Q >= 32768) ? 4 : 2);
+    U = U >= 8 ? 8 : U >= 4 ? 4 : U >= 2 ? 2 : 1;
+    while (U > 1 && (uint64_t)L4 * U > Q) U >>= 1;
     const uint32_t r_max = std::max<uint32_t>(1, std::min<uint32_t>(64, kMulMaxSmem / (L4 * 16)));
     const uint64_t target_items =
         (uint64_t)dp.sm_count * (uint64_t)env_long("CSGN_MUL_ITEMS_PER_SM", huge ? 128 : 32);
-    int U = (int)env_long("CSGN_MUL_U", huge ? 4 : 2);
-    U = U >= 8 ? 8 : U >= 4 ? 4 : U >= 2 ? 2 : 1;
+    uint32_t tpb = 0;
     uint64_t R = 1;
     for (;; U >>= 1) {
-        // units of b per thread: no wider than the row can feed
-        while (U > 1 && (uint64_t)tpb * U > std::max<uint64_t>(Q, tpb)) U >>= 1;
+        tpb = pick_tpb(L4, Q, U, tpb_cap);
+        if (tpb == 0) tpb = L4;
         const uint64_t n_col_tiles = (Q + (uint64_t)tpb * U - 1) / ((uint64_t)tpb * U);
         R = (T1 * n_col_tiles + target_items - 1) / target_items;
         if (R >= 3 || U == 1 || env_long("CSGN_MUL_U", 0) > 0) break;

@@ -365,6 +365,31 @@ def test_chain_to_1e7_blocks(engine, oracle):
     assert key.count_satisfied(x) == want and key.decrypt(x) == want & 1
 
 
+def test_chain_to_1e8_blocks_16GB(engine, oracle):
+    """1000 x 1000 x 100 blocks = 10^8 blocks = 16 GB: the single-GPU point of config 4's scaling curve."""
+    N, L = 1247, 20
+    rng = np.random.default_rng(40)
+    a, b, d = random_blocks(rng, 1000, N), random_blocks(rng, 1000, N), random_blocks(rng, 100, N)
+    ctx = engine.Context(N, 1)
+    s = random_key(rng, N, 1)
+    key = engine.SecretKey(ctx, s)
+    x = engine.Ciphertext.from_host(a, ctx) * engine.Ciphertext.from_host(b, ctx)
+    y = x * engine.Ciphertext.from_host(d, ctx)
+    assert y.n_blocks == 10**8
+    want = oracle.count_satisfied(a, N, s) * oracle.count_satisfied(b, N, s) * oracle.count_satisfied(d, N, s)
+    assert key.count_satisfied(y) == want and key.decrypt(y) == want & 1
+    # rows of the 10^8-block product, bit-exact: block (i*1000+j)*100+k = a_i & b_j & d_k
+    for i, j in ((0, 0), (999, 999), (123, 456)):
+        ab = oracle.mul(a[i * L:(i + 1) * L], b[j * L:(j + 1) * L], L)
+        assert np.array_equal(y.download_range((i * 1000 + j) * 100, 100), oracle.mul(ab, d, L))
+    # chunk identity against an independent, smaller product: rows 500..509 of a
+    part = (engine.Ciphertext.from_host(a[500 * L:510 * L], ctx) * engine.Ciphertext.from_host(b, ctx)) \
+        * engine.Ciphertext.from_host(d, ctx)
+    assert part.checksum() == oracle.mul_checksum(oracle.mul(a[500 * L:510 * L], b, L), d, L)
+    assert np.array_equal(part.download_range(999999, 1), y.download_range(500 * 100000 + 999999, 1))
+    del y, x, part
+
+
 # ---------------------------------------------------------------------------
 # interop: caller-owned device memory and an external stream
 # ---------------------------------------------------------------------------

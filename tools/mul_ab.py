@@ -10,7 +10,8 @@ stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); eng.set_stream(stre
 g = torch.Generator(device=dev); g.manual_seed(1)
 SHAPES = {"cfg2": (1247, 1000, 1000, 16), "cfg5": (16383, 300, 300, 14), "big": (1247, 5000, 5000, 2),
           "cfg5big": (16383, 1000, 1000, 3), "tallx1": (1247, 1000000, 1, 12), "1xwide": (1247, 1, 1000000, 12),
-          "tallx7": (1247, 150000, 7, 12), "100x10k": (1247, 100, 10000, 12), "10kx100": (1247, 10000, 100, 12)}
+          "tallx7": (1247, 150000, 7, 12), "100x10k": (1247, 100, 10000, 12), "10kx100": (1247, 10000, 100, 12), "chain125": (1247, 1000000, 125, 1), "chain25": (1247, 1000000, 25, 2),
+          "1Mx400": (1247, 1000000, 400, 1), "100kx1000": (1247, 100000, 1000, 1)}
 which = sys.argv[1:] or list(SHAPES)
 for name in which:
     N, T1, T2, P = SHAPES[name]
@@ -33,7 +34,7 @@ for name in which:
         torch.cuda.synchronize()
         return float(np.median([a.elapsed_time(b) for a, b in evs])) / P
     res = []
-    for kern, u in ((1, 0), (2, 0), (2, 1), (2, 2), (2, 4)):
+    for kern, u in ((0, 0), (1, 0), (1, 1), (1, 4), (2, 0), (2, 1), (2, 2), (2, 4)):
         os.environ["CSGN_MUL_KERNEL"] = str(kern)
         if u: os.environ["CSGN_MUL_U"] = str(u)
         else: os.environ.pop("CSGN_MUL_U", None)
