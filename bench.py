@@ -88,6 +88,19 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel_prefix, workload):
+    """dram bytes (read + write) per launch of the dominant kernel, from the committed ncu --set full
+    capture of this workload (profiles/r1_<workload>_ncu_summary.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_%s_ncu_summary.json" % workload)) as f:
+            for name, k in json.load(f)["kernels"].items():
+                if name.startswith(kernel_prefix):
+                    return k["dram_traffic_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler(threading.Thread):
     """SM clock + throttle reasons during the timed region (NVML, ~2 ms period)."""
 
@@ -387,7 +400,11 @@ def run_ours(args):
                        "inputs": "numpy default_rng raw blocks, pad bits zero, key bits set in 20-60 blocks per operand; "
                                  "key = default_rng(7).permutation(N)[:D]"},
             "roofline": {"bound": "hbm", "kernel": "mul_outer_kernel", "achieved": mul_gbs, "peak": peak,
-                         "unit": "GB/s", "frac": mul_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": mul_gbs / peak, "traffic": ncu_traffic("mul_outer", args.workload),
+                         "traffic_note": "ncu --set full, one isolated cold-cache launch: dram read+write bytes; the rest "
+                                         "of the 160 MB product is still dirty in the 126 MB L2 when the launch ends and "
+                                         "is written back under the next kernel (profiles/README.md)",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": T1 * T2 * bytes_per_block,
                          "avg_launch_us": mul_ms * 1e3 / (K * P)},
             "kernels": {"multiply": {"blocks_per_s_per_gpu": P * T1 * T2 * K / (mul_ms * 1e-3), "gbs": mul_gbs,
