@@ -27,6 +27,7 @@ struct csgn_buf {
     uint32_t L = 0;
     uint64_t cap_words = 0;    // allocated words (>= n_blocks*L); 0 for views
     bool owns = true;
+    mutable cudaEvent_t ready = nullptr;  // an upload on the copy stream still in flight
 };
 
 struct csgn_key {
@@ -51,6 +52,8 @@ struct State {
     int device = -1;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // H2D uploads run here, overlapping kernels of the work stream
+    std::vector<cudaEvent_t> event_pool;
     uint64_t *d_scratch = nullptr;   // [0..1] decrypt fold scratch, [2] result, [4..6] checksum
     uint64_t *h_result = nullptr;    // pinned, 8 words
 };
@@ -89,11 +92,11 @@ int cuda_fail(cudaError_t e, const char *what) {
         if (cudaGetDevice(&cur_) != cudaSuccess || cur_ != g.device) CU(cudaSetDevice(g.device)); \
     } while (0)
 
-int dev_alloc(uint64_t words, uint64_t **out) {
+int dev_alloc(uint64_t words, uint64_t **out, cudaStream_t stream = nullptr) {
     *out = nullptr;
     if (words == 0) return CSGN_OK;
     void *p = nullptr;
-    cudaError_t e = cudaMallocAsync(&p, words * sizeof(uint64_t), g.stream);
+    cudaError_t e = cudaMallocAsync(&p, words * sizeof(uint64_t), stream ? stream : g.stream);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync");
     *out = static_cast<uint64_t *>(p);
     return CSGN_OK;
@@ -103,14 +106,34 @@ void dev_free(void *p) {
     if (p) cudaFreeAsync(p, g.stream);
 }
 
-int new_buf(uint64_t n_blocks, uint32_t L, uint64_t cap_words, csgn_buf **out) {
+cudaEvent_t take_event() {
+    if (!g.event_pool.empty()) {
+        cudaEvent_t e = g.event_pool.back();
+        g.event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    return e;
+}
+
+// Order the work stream after a pending upload of `b` (first consumer only).
+void await_upload(const csgn_buf *b) {
+    if (b && b->ready) {
+        cudaStreamWaitEvent(g.stream, b->ready, 0);
+        g.event_pool.push_back(b->ready);
+        b->ready = nullptr;
+    }
+}
+
+int new_buf(uint64_t n_blocks, uint32_t L, uint64_t cap_words, csgn_buf **out, cudaStream_t stream = nullptr) {
     if (L == 0) return fail(CSGN_ERR_INVALID_ARGUMENT, "words per block must be > 0");
     if (n_blocks > (UINT64_MAX / 8) / L) return fail(CSGN_ERR_INVALID_ARGUMENT, "block count overflows");
     csgn_buf *b = new csgn_buf;
     b->n_blocks = n_blocks;
     b->L = L;
     b->cap_words = std::max<uint64_t>(cap_words, n_blocks * L);
-    int rc = dev_alloc(b->cap_words, &b->d);
+    int rc = dev_alloc(b->cap_words, &b->d, stream);
     if (rc != CSGN_OK) {
         delete b;
         return rc;
@@ -172,6 +195,7 @@ int csgn_init(int device) {
 
     CU(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
     g.stream = g.own_stream;
+    CU(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
     // keep freed blocks in the pool: a*b chains reuse them without going to the driver
     cudaMemPool_t pool;
     CU(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -188,9 +212,12 @@ int csgn_init(int device) {
 int csgn_shutdown(void) {
     if (!g.inited) return CSGN_OK;
     cudaSetDevice(g.device);
+    cudaStreamSynchronize(g.copy_stream);
     cudaStreamSynchronize(g.stream);
     cudaFree(g.d_scratch);
     cudaFreeHost(g.h_result);
+    for (cudaEvent_t e : g.event_pool) cudaEventDestroy(e);
+    cudaStreamDestroy(g.copy_stream);
     cudaStreamDestroy(g.own_stream);
     g = State();
     return CSGN_OK;
@@ -221,6 +248,7 @@ void *csgn_get_stream(void) { return g.inited ? static_cast<void *>(g.stream) : 
 
 int csgn_sync(void) {
     NEED_INIT();
+    CU(cudaStreamSynchronize(g.copy_stream));   // uploads whose buffers nobody has consumed yet
     CU(cudaStreamSynchronize(g.stream));
     return CSGN_OK;
 }
@@ -255,12 +283,18 @@ int csgn_buf_upload(const uint64_t *host_words, uint64_t n_blocks, uint32_t L, c
     NEED_INIT();
     if (!out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null output handle");
     if (n_blocks && !host_words) return fail(CSGN_ERR_INVALID_ARGUMENT, "null host words");
+    // Allocation and copy are ordered on the copy stream, so an upload overlaps whatever the work
+    // stream is running; the first consumer on the work stream waits for the `ready` event.
     csgn_buf *b = nullptr;
-    int rc = new_buf(n_blocks, L, 0, &b);
+    int rc = new_buf(n_blocks, L, 0, &b, g.copy_stream);
     if (rc != CSGN_OK) return rc;
     if (n_blocks) {
         cudaError_t e = cudaMemcpyAsync(b->d, host_words, n_blocks * L * sizeof(uint64_t), cudaMemcpyHostToDevice,
-                                        g.stream);
+                                        g.copy_stream);
+        if (e == cudaSuccess) {
+            b->ready = take_event();
+            e = b->ready ? cudaEventRecord(b->ready, g.copy_stream) : cudaStreamSynchronize(g.copy_stream);
+        }
         if (e != cudaSuccess) {
             csgn_buf_free(b);
             return cuda_fail(e, "cudaMemcpyAsync(H2D)");
@@ -292,6 +326,7 @@ int csgn_buf_clone(const csgn_buf *src, csgn_buf **out) {
     csgn_buf *b = nullptr;
     int rc = new_buf(src->n_blocks, src->L, 0, &b);
     if (rc != CSGN_OK) return rc;
+    await_upload(src);
     cudaError_t e = launch_concat(src->d, src->n_blocks * src->L, nullptr, 0, b->d, g.stream);
     if (e != cudaSuccess) {
         csgn_buf_free(b);
@@ -309,6 +344,7 @@ int csgn_buf_download_range(const csgn_buf *buf, uint64_t first_block, uint64_t 
                     (unsigned long long)first_block, (unsigned long long)n_blocks, (unsigned long long)buf->n_blocks);
     if (n_blocks == 0) return CSGN_OK;
     if (!host_words) return fail(CSGN_ERR_INVALID_ARGUMENT, "null host destination");
+    await_upload(buf);
     CU(cudaMemcpyAsync(host_words, buf->d + first_block * buf->L, n_blocks * buf->L * sizeof(uint64_t),
                        cudaMemcpyDeviceToHost, g.stream));
     CU(cudaStreamSynchronize(g.stream));
@@ -322,6 +358,7 @@ int csgn_buf_download(const csgn_buf *buf, uint64_t *host_words) {
 
 int csgn_buf_free(csgn_buf *buf) {
     if (!buf) return CSGN_OK;
+    if (g.inited) await_upload(buf);     // a never-consumed upload must land before its memory is recycled
     if (g.inited && buf->owns) dev_free(buf->d);
     delete buf;
     return CSGN_OK;
@@ -329,7 +366,10 @@ int csgn_buf_free(csgn_buf *buf) {
 
 uint64_t csgn_buf_blocks(const csgn_buf *buf) { return buf ? buf->n_blocks : 0; }
 uint32_t csgn_buf_words_per_block(const csgn_buf *buf) { return buf ? buf->L : 0; }
-void *csgn_buf_device_ptr(const csgn_buf *buf) { return buf ? buf->d : nullptr; }
+void *csgn_buf_device_ptr(const csgn_buf *buf) {
+    if (buf && g.inited) await_upload(buf);   // whoever reads the pointer is ordered after the work stream
+    return buf ? buf->d : nullptr;
+}
 
 // ---------------------------------------------------------------------------
 // K1 multiply
@@ -345,6 +385,9 @@ int csgn_mul_into(const csgn_buf *a, const csgn_buf *b, csgn_buf *out) {
         return fail(CSGN_ERR_SHAPE_MISMATCH, "output holds %llu blocks, product has %llu",
                     (unsigned long long)out->n_blocks, (unsigned long long)(a->n_blocks * b->n_blocks));
     if (out->d == a->d || out->d == b->d) return fail(CSGN_ERR_INVALID_ARGUMENT, "output aliases an operand");
+    await_upload(a);
+    await_upload(b);
+    await_upload(out);
     cudaError_t e = launch_mul(a->d, a->n_blocks, b->d, b->n_blocks, a->L, out->d, g.stream);
     if (e != cudaSuccess) return cuda_fail(e, "multiply kernel");
     return CSGN_OK;
@@ -378,6 +421,8 @@ int csgn_concat(const csgn_buf *a, const csgn_buf *b, csgn_buf **out) {
     csgn_buf *c = nullptr;
     int rc = new_buf(a->n_blocks + b->n_blocks, a->L, 0, &c);
     if (rc != CSGN_OK) return rc;
+    await_upload(a);
+    await_upload(b);
     cudaError_t e = launch_concat(a->d, a->n_blocks * a->L, b->d, b->n_blocks * b->L, c->d, g.stream);
     if (e != cudaSuccess) {
         csgn_buf_free(c);
@@ -394,6 +439,8 @@ int csgn_append(csgn_buf *a, const csgn_buf *b) {
     if (a->L != b->L) return fail(CSGN_ERR_SHAPE_MISMATCH, "words per block differ (%u vs %u)", a->L, b->L);
     const uint64_t na = a->n_blocks * a->L, nb = b->n_blocks * b->L;
     if (nb == 0) return CSGN_OK;
+    await_upload(a);
+    await_upload(b);
     if (na + nb <= a->cap_words) {
         // b == a is fine: source [0,na) and destination [na,2na) do not overlap
         cudaError_t e = launch_concat(a->d, na, b->d, nb, a->d, g.stream);
@@ -468,6 +515,7 @@ int csgn_decrypt_count_async(const csgn_buf *c, const csgn_key *key, uint64_t *d
     if (!c || !key || !device_count) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
     if (c->L != key->L)
         return fail(CSGN_ERR_SHAPE_MISMATCH, "ciphertext has %u words per block, key expects %u", c->L, key->L);
+    await_upload(c);
     cudaError_t e = launch_decrypt_count(c->d, c->n_blocks, c->L, key->d_mask,
                                          key->h_mask.empty() ? nullptr : key->h_mask.data(), g.d_scratch, device_count,
                                          g.stream);
@@ -579,6 +627,8 @@ int csgn_permute_into(const csgn_buf *c, const csgn_perm *perm, csgn_buf *out) {
     if (out->n_blocks > c->n_blocks)
         return fail(CSGN_ERR_SHAPE_MISMATCH, "output holds more blocks than the input");
     if (out->d == c->d) return fail(CSGN_ERR_INVALID_ARGUMENT, "permute cannot run in place");
+    await_upload(c);
+    await_upload(out);
     cudaError_t e = launch_permute(c->d, out->n_blocks, c->L, (uint32_t)perm->N, perm->d_map, perm->d_slice_map, out->d,
                                    g.stream);
     if (e != cudaSuccess) return cuda_fail(e, "permute kernel");
@@ -608,6 +658,7 @@ int csgn_buf_checksum(const csgn_buf *buf, uint64_t *xor_out, uint64_t *sum_out,
     NEED_INIT();
     if (!buf) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
     uint64_t *acc = g.d_scratch + 4;
+    await_upload(buf);
     CU(cudaMemsetAsync(acc, 0, 3 * sizeof(uint64_t), g.stream));
     cudaError_t e = launch_checksum(buf->d, buf->n_blocks * buf->L, acc, g.stream);
     if (e != cudaSuccess) return cuda_fail(e, "checksum kernel");
