@@ -148,11 +148,11 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------
 # CPU arms (the only place bench.py touches oracle/)
 # ---------------------------------------------------------------------------
-def cpu_reference_once(N, D, T1, T2, threads, reps):
+def cpu_reference_once(N, D, T1, T2, threads, reps, opt="O3"):
     """(kind, mul_s, dec_s) for `threads` replicas of a T1 x T2 multiply + decrypt."""
     from oracle import pyoracle
-    if pyoracle.ref_available():
-        ref = pyoracle.Ref()
+    if pyoracle.ref_available(opt):
+        ref = pyoracle.Ref(opt)
         m, d, _ = ref.bench_mul_decrypt(N, D, T1, T2, threads=threads, reps=reps, seed=1)
         return "reference", m, d
     # the reference build did not travel: time the C restatement (one thread)
@@ -174,11 +174,18 @@ def cpu_reference_once(N, D, T1, T2, threads, reps):
 def cpu_baseline(N, D, T1, T2):
     kind, m, d = cpu_reference_once(N, D, T1, T2, threads=1, reps=2)
     blocks = T1 * T2
-    return {"value": blocks / (m + d), "unit": UNIT, "cores": 1, "kind": kind,
-            "sample": "one %dx%d pair (%d output blocks): public operator* %.3f s + SecretKey::decrypt %.3f s, "
-                      "best of 2, single thread (the reference has no threading)" % (T1, T2, blocks, m, d),
-            "mul_blocks_per_s": blocks / m, "decrypt_blocks_per_s": blocks / d,
-            "host_cores_available": os.cpu_count()}
+    out = {"value": blocks / (m + d), "unit": UNIT, "cores": 1, "kind": kind,
+           "sample": "one %dx%d pair (%d output blocks): public operator* %.3f s + SecretKey::decrypt %.3f s, "
+                     "best of 2, single thread (the reference has no threading), built -O3 -DNDEBUG"
+                     % (T1, T2, blocks, m, d),
+           "mul_blocks_per_s": blocks / m, "decrypt_blocks_per_s": blocks / d,
+           "host_cores_available": os.cpu_count()}
+    from oracle import pyoracle
+    if kind == "reference" and pyoracle.ref_available("O0"):
+        # what the shipped CMakeLists (no build type, hence no -O flag) really produces; a quarter-size sample
+        _, m0, d0 = cpu_reference_once(N, D, max(1, T1 // 4), T2, threads=1, reps=1, opt="O0")
+        out["as_shipped_no_opt_flag_blocks_per_s"] = max(1, T1 // 4) * T2 / (m0 + d0)
+    return out
 
 
 def run_reference_arm(args):
@@ -274,14 +281,30 @@ def run_ours(args):
         host_b[p].numpy().view(np.uint64)[:] = planted(rng_b, T2)
     dev_a, dev_b = host_a.to(dev), host_b.to(dev)
     out = torch.empty((P, T1 * T2 * L), dtype=torch.int64, device=dev)
-    counts = torch.zeros(P, dtype=torch.int64, device=dev)
+    # two result buffers: the all-reduce of step k runs on NCCL's stream while step k+1 computes
+    counts2 = [torch.zeros(P, dtype=torch.int64, device=dev) for _ in range(2)]
+    counts = counts2[0]
+    pending = [None, None]
     host_counts = torch.zeros(P, dtype=torch.int64).pin_memory()
     va = [eng.Ciphertext.from_tensor(dev_a[p], ctx) for p in range(P)]
     vb = [eng.Ciphertext.from_tensor(dev_b[p], ctx) for p in range(P)]
     vo = [eng.Ciphertext.from_tensor(out[p], ctx) for p in range(P)]
-    count_ptrs = [counts.data_ptr() + 8 * p for p in range(P)]
+    count_ptrs2 = [[c.data_ptr() + 8 * p for p in range(P)] for c in counts2]
+    count_ptrs = count_ptrs2[0]
+    step_no = [0]
+
+    def drain():
+        for i in (0, 1):
+            if pending[i] is not None:
+                pending[i].wait()
+                pending[i] = None
 
     def step_device(evs=None):
+        slot = step_no[0] & 1
+        step_no[0] += 1
+        if pending[slot] is not None:        # the all-reduce issued two steps ago: long finished
+            pending[slot].wait()
+            pending[slot] = None
         if evs:
             evs[0].record()
         for p in range(P):
@@ -289,15 +312,16 @@ def run_ours(args):
         if evs:
             evs[1].record()
         for p in range(P):
-            key.count_satisfied_async(vo[p], count_ptrs[p])
+            key.count_satisfied_async(vo[p], count_ptrs2[slot][p])
         if evs:
             evs[2].record()
         if world > 1:
-            dist.all_reduce(counts)
+            pending[slot] = dist.all_reduce(counts2[slot], async_op=True)
         if evs:
             evs[3].record()
 
     def barrier():
+        drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -313,8 +337,9 @@ def run_ours(args):
     local_counts = torch.tensor([a * b for a, b in zip(ca, cb)], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(local_counts)
-    if not torch.equal(local_counts, counts):
-        raise SystemExit("bench sanity failed: count(a*b) != count(a)*count(b): %s vs %s" % (counts, local_counts))
+    for c in counts2:
+        if not torch.equal(local_counts, c):
+            raise SystemExit("bench sanity failed: count(a*b) != count(a)*count(b): %s vs %s" % (c, local_counts))
 
     K = args.steps
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
@@ -396,7 +421,8 @@ def run_ours(args):
                        "l2": "no flush needed: a step writes then reads %d x %.0f MB of products (>> 126 MB L2), "
                              "each product is read %d kernels after it was written" % (P, T1 * T2 * L * 8 / 1e6, P),
                        "sharding": "left operand by block range, right operand replicated, one %d-word NCCL "
-                                   "all-reduce per step" % P if world > 1 else "single GPU",
+                                   "all-reduce per step, overlapped with the next step's kernels" % P
+                                   if world > 1 else "single GPU",
                        "inputs": "numpy default_rng raw blocks, pad bits zero, key bits set in 20-60 blocks per operand; "
                                  "key = default_rng(7).permutation(N)[:D]"},
             "roofline": {"bound": "hbm", "kernel": "mul_outer_kernel", "achieved": mul_gbs, "peak": peak,

@@ -69,13 +69,21 @@ __device__ __forceinline__ void transpose32(uint32_t (&x)[32]) {
     }
 }
 
-// slice_map layout: entry j*W + c = padded shared-memory index of the source slice of
-// output (column c, bit j), or the index of the zero slot.
+// slice_map layout: entry j*W + c = BYTE offset, inside a tile's slice area, of the source
+// slice of output (column c, bit j), or the byte offset of the zero slot.
+//
+// WC > 0 fixes the words per block at compile time (40 for N=1247, 512 for N=16383): every
+// one of the 32+32+32 global accesses and 32+32 shared accesses of a column then uses an
+// immediate offset from one base register, and a tile that lies fully inside the ciphertext
+// takes a path without per-access bounds.  That is a third of the instructions of the
+// runtime-W form -- this kernel is bound by the integer/issue pipes, not by HBM.
+template <int WC>
 __global__ void __launch_bounds__(512)
-permute_sliced_kernel(const uint32_t *__restrict__ in, const uint64_t T, const uint32_t W,
+permute_sliced_kernel(const uint32_t *__restrict__ in, const uint64_t T, const uint32_t Wrt,
                       const uint32_t *__restrict__ slice_map, uint32_t *__restrict__ out,
                       const uint32_t tiles_per_cta, const uint64_t n_groups) {
     extern __shared__ uint32_t S[];                  // tiles_per_cta * (33*W + 1) words
+    const uint32_t W = WC ? (uint32_t)WC : Wrt;
     const uint32_t tile_words = 33u * W + 1u;        // last word = the zero slot
     const uint32_t items = tiles_per_cta * W;
     pdl_enter();
@@ -90,8 +98,13 @@ permute_sliced_kernel(const uint32_t *__restrict__ in, const uint64_t T, const u
             const uint64_t blk0 = (tile0 + tl) * 32u;
             uint32_t x[32];
             const uint32_t *src = in + blk0 * W + c;
+            if (blk0 + 32u <= T) {
 #pragma unroll
-            for (int b = 0; b < 32; ++b) x[b] = (blk0 + b < T) ? __ldcs(src + (uint64_t)b * W) : 0u;
+                for (int b = 0; b < 32; ++b) x[b] = __ldcs(src + (uint32_t)b * W);
+            } else {
+#pragma unroll
+                for (int b = 0; b < 32; ++b) x[b] = (blk0 + b < T) ? __ldcs(src + (uint64_t)b * W) : 0u;
+            }
             transpose32(x);
             uint32_t *dst = S + tl * tile_words + 33u * c;
 #pragma unroll
@@ -102,15 +115,22 @@ permute_sliced_kernel(const uint32_t *__restrict__ in, const uint64_t T, const u
         for (uint32_t it = threadIdx.x; it < items; it += blockDim.x) {
             const uint32_t tl = it / W, c = it - tl * W;
             const uint64_t blk0 = (tile0 + tl) * 32u;
-            const uint32_t *Sl = S + tl * tile_words;
+            const unsigned char *Sl = reinterpret_cast<const unsigned char *>(S + tl * tile_words);
+            const uint32_t *map = slice_map + c;
             uint32_t y[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) y[j] = Sl[__ldg(slice_map + (uint32_t)j * W + c)];
+            for (int j = 0; j < 32; ++j)
+                y[j] = *reinterpret_cast<const uint32_t *>(Sl + __ldg(map + (uint32_t)j * W));
             transpose32(y);
             uint32_t *dst = out + blk0 * W + c;
+            if (blk0 + 32u <= T) {
 #pragma unroll
-            for (int b = 0; b < 32; ++b)
-                if (blk0 + b < T) __stcs(dst + (uint64_t)b * W, y[b]);
+                for (int b = 0; b < 32; ++b) __stcs(dst + (uint32_t)b * W, y[b]);
+            } else {
+#pragma unroll
+                for (int b = 0; b < 32; ++b)
+                    if (blk0 + b < T) __stcs(dst + (uint64_t)b * W, y[b]);
+            }
         }
         __syncthreads();   // before the next group overwrites the slices
     }
@@ -141,6 +161,41 @@ permute_gather_kernel(const uint64_t *__restrict__ in, const uint64_t total_word
 
 }  // namespace
 
+namespace {
+
+template <int WC>
+cudaError_t launch_sliced(const uint64_t *in, uint64_t T, uint32_t W, const uint32_t *slice_map, uint64_t *out,
+                          uint32_t tiles_per_cta, uint32_t tpb, size_t smem, cudaStream_t stream) {
+    const DeviceProps &dp = device_props();
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(permute_sliced_kernel<WC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)dp.smem_optin);
+        if (e != cudaSuccess) return e;
+        configured = dp.smem_optin;
+    }
+    static int per_sm_cache = 0;
+    static uint32_t cache_tpb = 0;
+    static size_t cache_smem = 0;
+    if (per_sm_cache == 0 || cache_tpb != tpb || cache_smem != smem) {
+        int per_sm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, permute_sliced_kernel<WC>, (int)tpb, smem) !=
+                cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        per_sm_cache = per_sm;
+        cache_tpb = tpb;
+        cache_smem = smem;
+    }
+    const uint64_t n_tiles = (T + 31) / 32;
+    const uint64_t n_groups = (n_tiles + tiles_per_cta - 1) / tiles_per_cta;
+    const uint32_t grid = (uint32_t)std::max<uint64_t>(
+        1, std::min<uint64_t>(n_groups, (uint64_t)dp.sm_count * per_sm_cache * (uint64_t)env_long("CSGN_PERM_WAVES", 16)));
+    return launch_kernel(permute_sliced_kernel<WC>, grid, tpb, smem, stream, reinterpret_cast<const uint32_t *>(in), T, W,
+                         slice_map, reinterpret_cast<uint32_t *>(out), tiles_per_cta, n_groups);
+}
+
+}  // namespace
+
 bool permute_sliced_supported(uint32_t L) {
     const size_t need = ((size_t)33 * 2 * L + 1) * sizeof(uint32_t);
     return need <= device_props().smem_optin && 2 * L >= 1;
@@ -162,23 +217,10 @@ cudaError_t launch_permute(const uint64_t *in, uint64_t T, uint32_t L, uint32_t 
         const size_t smem = (size_t)tiles_per_cta * tile_words * sizeof(uint32_t);
         const uint32_t items = tiles_per_cta * W;
         const uint32_t tpb = std::min<uint32_t>(512, (items + 31) / 32 * 32);
-        static size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
-            cudaError_t e = cudaFuncSetAttribute(permute_sliced_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)dp.smem_optin);
-            if (e != cudaSuccess) return e;
-            configured = dp.smem_optin;
-        }
-        int per_sm = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, permute_sliced_kernel, (int)tpb, smem) != cudaSuccess ||
-            per_sm < 1)
-            per_sm = 1;
-        const uint64_t n_groups = (n_tiles + tiles_per_cta - 1) / tiles_per_cta;
-        const uint32_t grid = (uint32_t)std::max<uint64_t>(
-            1, std::min<uint64_t>(n_groups, (uint64_t)dp.sm_count * per_sm * (uint64_t)env_long("CSGN_PERM_WAVES", 16)));
         count_launch();
-        return launch_kernel(permute_sliced_kernel, grid, tpb, smem, stream, reinterpret_cast<const uint32_t *>(in), T, W,
-                             slice_map, reinterpret_cast<uint32_t *>(out), tiles_per_cta, n_groups);
+        if (W == 40) return launch_sliced<40>(in, T, W, slice_map, out, tiles_per_cta, tpb, smem, stream);
+        if (W == 512) return launch_sliced<512>(in, T, W, slice_map, out, tiles_per_cta, tpb, smem, stream);
+        return launch_sliced<0>(in, T, W, slice_map, out, tiles_per_cta, tpb, smem, stream);
     }
     const uint64_t total = T * L;
     const uint32_t grid = (uint32_t)std::max<uint64_t>(
