@@ -23,6 +23,7 @@
 
 #include "utils.h"
 
+#include <memory>
 #include <stdexcept>
 
 struct csgn_buf;
@@ -56,6 +57,14 @@ public:
     static bool getStrictReferencePermutation();
     // Block until every enqueued GPU operation has finished (for timing).
     static void synchronize();
+    // Lazy products (off by default; also CSGN_LAZY_PRODUCTS=1).  When on, operator* / *= do
+    // not materialise the T1*T2 product: the result remembers its factors.  decrypt of such a
+    // ciphertext folds the factors only (Dec(a*b) = Dec(a) & Dec(b), exact for this scheme),
+    // applyPermutation permutes the factors, and anything that needs the words (getValues,
+    // operator<<, +, +=) multiplies them out first.  Results are identical either way; a
+    // 10^9-block chain that is only ever decrypted never touches 160 GB of HBM.
+    static void setLazyProducts(bool lazy);
+    static bool getLazyProducts();
 };
 
 class Helper {
@@ -132,7 +141,11 @@ public:
 
 // ---- Ciphertext (reference src/Ciphertext.h:15-144) -----------------------------------
 class Ciphertext {
-    csgn_buf *dev;             // device-resident blocks (null while empty or staged)
+    // Device-resident blocks.  Buffers are immutable once shared, so copies share them
+    // (the reference deep-copies on every by-value return); += clones first if shared.
+    mutable std::shared_ptr<csgn_buf> dev;
+    // Non-empty: the value is the product of these buffers, not multiplied out (lazy mode).
+    mutable std::vector<std::shared_ptr<csgn_buf> > factors;
     Context *certFHEcontext;   // context of encryption (null for a default-constructed object)
     mutable uint64_t *host_v;  // host mirror of the words / host staging before upload
     mutable uint64_t *host_bitlen;
@@ -143,6 +156,8 @@ class Ciphertext {
     void invalidate_mirror() const;
     void release();
     void upload_staged();
+    void materialize() const;  // multiply pending factors out into `dev`
+    void collect_factors(std::vector<std::shared_ptr<csgn_buf> > &into) const;
     friend class SecretKey;
 
 public:

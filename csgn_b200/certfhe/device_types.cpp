@@ -54,9 +54,17 @@ uint64_t *copy_words(const uint64_t *src, uint64_t n) {
 // =========================================================================================
 // Ciphertext
 // =========================================================================================
+namespace {
+
+std::shared_ptr<csgn_buf> adopt(csgn_buf *b) {
+    return std::shared_ptr<csgn_buf>(b, [](csgn_buf *p) { csgn_buf_free(p); });
+}
+
+}  // namespace
+
 Ciphertext::Ciphertext()
-    : dev(nullptr), certFHEcontext(nullptr), host_v(nullptr), host_bitlen(nullptr), host_len(0),
-      host_v_valid(false), staged(false) {}
+    : certFHEcontext(nullptr), host_v(nullptr), host_bitlen(nullptr), host_len(0), host_v_valid(false),
+      staged(false) {}
 
 Ciphertext::Ciphertext(const uint64_t *V, const uint64_t *Bitlen, const uint64_t len, const Context &context)
     : Ciphertext() {
@@ -68,11 +76,15 @@ Ciphertext::Ciphertext(const uint64_t *V, const uint64_t *Bitlen, const uint64_t
                     " words per block");
     if (Bitlen) require_canonical_bitlen(Bitlen, len, context);
     glue::ensure_engine();
-    glue::check(csgn_buf_upload(V, len / L, (uint32_t)L, &dev), "csgn_buf_upload");
+    csgn_buf *b = nullptr;
+    glue::check(csgn_buf_upload(V, len / L, (uint32_t)L, &b), "csgn_buf_upload");
+    dev = adopt(b);
     glue::check(csgn_sync(), "csgn_sync");  // the caller may free V right after the constructor
 }
 
 Ciphertext::Ciphertext(const Ciphertext &o) : Ciphertext() {
+    // The reference deep-copies (src/Ciphertext.cpp:360-363).  Device buffers are never
+    // modified in place once shared, so a copy shares them; += clones first when needed.
     if (o.certFHEcontext) certFHEcontext = new Context(*o.certFHEcontext);
     if (o.staged) {
         host_v = copy_words(o.host_v, o.host_len);
@@ -80,15 +92,16 @@ Ciphertext::Ciphertext(const Ciphertext &o) : Ciphertext() {
         host_len = o.host_len;
         host_v_valid = true;
         staged = true;
-    } else if (o.dev) {
-        glue::check(csgn_buf_clone(o.dev, &dev), "csgn_buf_clone");
+    } else {
+        dev = o.dev;
+        factors = o.factors;
     }
 }
 
 Ciphertext::Ciphertext(Ciphertext &&o) noexcept
-    : dev(o.dev), certFHEcontext(o.certFHEcontext), host_v(o.host_v), host_bitlen(o.host_bitlen),
-      host_len(o.host_len), host_v_valid(o.host_v_valid), staged(o.staged) {
-    o.dev = nullptr;
+    : dev(std::move(o.dev)), factors(std::move(o.factors)), certFHEcontext(o.certFHEcontext), host_v(o.host_v),
+      host_bitlen(o.host_bitlen), host_len(o.host_len), host_v_valid(o.host_v_valid), staged(o.staged) {
+    o.factors.clear();
     o.certFHEcontext = nullptr;
     o.host_v = o.host_bitlen = nullptr;
     o.host_len = 0;
@@ -110,8 +123,8 @@ void Ciphertext::invalidate_mirror() const {
 }
 
 void Ciphertext::release() {
-    if (dev) csgn_buf_free(dev);
-    dev = nullptr;
+    dev.reset();
+    factors.clear();
     invalidate_mirror();
     staged = false;
 }
@@ -125,10 +138,32 @@ void Ciphertext::upload_staged() {
                     " words per block");
     if (host_bitlen) require_canonical_bitlen(host_bitlen, host_len, *certFHEcontext);
     glue::ensure_engine();
-    glue::check(csgn_buf_upload(host_v, host_len / L, (uint32_t)L, &dev), "csgn_buf_upload");
+    csgn_buf *b = nullptr;
+    glue::check(csgn_buf_upload(host_v, host_len / L, (uint32_t)L, &b), "csgn_buf_upload");
+    dev = adopt(b);
     glue::check(csgn_sync(), "csgn_sync");
     staged = false;  // host_v stays behind as a valid mirror
     host_v_valid = true;
+}
+
+void Ciphertext::materialize() const {
+    // multiply the pending factors out, left to right: ((f0*f1)*f2)... -- the reference's own
+    // i-major block order, whatever the grouping (block order of a product is associative)
+    if (factors.empty()) return;
+    std::shared_ptr<csgn_buf> acc = factors[0];
+    for (size_t i = 1; i < factors.size(); ++i) {
+        csgn_buf *prod = nullptr;
+        glue::check(csgn_mul(acc.get(), factors[i].get(), &prod), "csgn_mul");
+        acc = adopt(prod);
+    }
+    dev = acc;
+    factors.clear();
+}
+
+void Ciphertext::collect_factors(std::vector<std::shared_ptr<csgn_buf> > &into) const {
+    const_cast<Ciphertext *>(this)->upload_staged();
+    if (!factors.empty()) into.insert(into.end(), factors.begin(), factors.end());
+    else if (dev) into.push_back(dev);
 }
 
 void Ciphertext::setValues(const uint64_t *V, const uint64_t length) {
@@ -179,12 +214,23 @@ uint64_t Ciphertext::getBlocks() const {
         const uint64_t L = certFHEcontext ? certFHEcontext->getDefaultN() : 0;
         return L ? host_len / L : 0;
     }
-    return dev ? csgn_buf_blocks(dev) : 0;
+    if (!factors.empty()) {   // lazy product: the block counts multiply (saturating)
+        uint64_t n = 1;
+        for (size_t i = 0; i < factors.size(); ++i) {
+            const uint64_t t = csgn_buf_blocks(factors[i].get());
+            n = (t != 0 && n > UINT64_MAX / t) ? UINT64_MAX : n * t;
+        }
+        return n;
+    }
+    return dev ? csgn_buf_blocks(dev.get()) : 0;
 }
 
 uint64_t Ciphertext::getLen() const {
     if (staged) return host_len;
-    return dev ? csgn_buf_blocks(dev) * csgn_buf_words_per_block(dev) : 0;
+    const csgn_buf *any = !factors.empty() ? factors[0].get() : dev.get();
+    if (!any) return 0;
+    const uint64_t n = getBlocks(), L = csgn_buf_words_per_block(any);
+    return (n > UINT64_MAX / L) ? UINT64_MAX : n * L;
 }
 
 Context Ciphertext::getContext() const {
@@ -194,12 +240,14 @@ Context Ciphertext::getContext() const {
 
 const csgn_buf *Ciphertext::deviceBuffer() const {
     const_cast<Ciphertext *>(this)->upload_staged();
-    return dev;
+    materialize();
+    return dev.get();
 }
 
 uint64_t *Ciphertext::getValues() const {
     if (staged) return host_v;
-    if (!dev) return nullptr;
+    const csgn_buf *buf = deviceBuffer();
+    if (!buf) return nullptr;
     const uint64_t len = getLen();
     if (!host_v_valid || host_len != len) {
         delete[] host_v;
@@ -209,7 +257,7 @@ uint64_t *Ciphertext::getValues() const {
             host_bitlen = nullptr;
         }
         host_len = len;
-        glue::check(csgn_buf_download(dev, host_v), "csgn_buf_download");
+        glue::check(csgn_buf_download(buf, host_v), "csgn_buf_download");
         host_v_valid = true;
     }
     return host_v;
@@ -217,6 +265,7 @@ uint64_t *Ciphertext::getValues() const {
 
 uint64_t *Ciphertext::getBitlen() const {
     if (staged && !certFHEcontext) return host_bitlen;
+    if (!factors.empty()) materialize();   // the caller is about to index len words
     const uint64_t len = getLen();
     if (!len || !certFHEcontext) return nullptr;
     if (!host_bitlen || host_len != len) {
@@ -252,7 +301,7 @@ long Ciphertext::size() {
 
 Ciphertext &Ciphertext::operator=(const Ciphertext &c) {
     // the reference frees the context here and never restores it (src/Ciphertext.cpp:306-329);
-    // this is a complete deep copy
+    // this is a complete copy
     if (this == &c) return *this;
     Ciphertext tmp(c);
     *this = std::move(tmp);
@@ -263,14 +312,15 @@ Ciphertext &Ciphertext::operator=(Ciphertext &&o) noexcept {
     if (this == &o) return *this;
     release();
     delete certFHEcontext;
-    dev = o.dev;
+    dev = std::move(o.dev);
+    factors = std::move(o.factors);
+    o.factors.clear();
     certFHEcontext = o.certFHEcontext;
     host_v = o.host_v;
     host_bitlen = o.host_bitlen;
     host_len = o.host_len;
     host_v_valid = o.host_v_valid;
     staged = o.staged;
-    o.dev = nullptr;
     o.certFHEcontext = nullptr;
     o.host_v = o.host_bitlen = nullptr;
     o.host_len = 0;
@@ -283,63 +333,107 @@ Ciphertext Ciphertext::operator+(const Ciphertext &c) const {
     Ciphertext out;
     const Context *ctx = certFHEcontext ? certFHEcontext : c.certFHEcontext;
     if (ctx) out.certFHEcontext = new Context(*ctx);
-    if (a && b) glue::check(csgn_concat(a, b, &out.dev), "csgn_concat");
-    else if (a || b) glue::check(csgn_buf_clone(a ? a : b, &out.dev), "csgn_buf_clone");
+    if (a && b) {
+        csgn_buf *sum = nullptr;
+        glue::check(csgn_concat(a, b, &sum), "csgn_concat");
+        out.dev = adopt(sum);
+    } else if (a || b) {
+        out.dev = a ? dev : c.dev;   // x + (empty) is x: share it
+    }
     return out;
 }
 
 Ciphertext &Ciphertext::operator+=(const Ciphertext &c) {
-    const csgn_buf *b = c.deviceBuffer();
-    upload_staged();
-    if (!b) return *this;
+    std::shared_ptr<csgn_buf> rhs;   // keep the operand alive (and unchanged) when &c == this
+    {
+        c.deviceBuffer();
+        rhs = c.dev;
+    }
+    deviceBuffer();
+    if (!rhs) return *this;
     if (!certFHEcontext && c.certFHEcontext) certFHEcontext = new Context(*c.certFHEcontext);
-    if (!dev) glue::check(csgn_buf_clone(b, &dev), "csgn_buf_clone");
-    else glue::check(csgn_append(dev, b), "csgn_append");
+    if (!dev) {
+        dev = rhs;
+    } else {
+        if (dev.use_count() > 1 + (dev == rhs ? 1 : 0)) {   // shared with a copy: do not grow it under the other owner
+            csgn_buf *mine = nullptr;
+            glue::check(csgn_buf_clone(dev.get(), &mine), "csgn_buf_clone");
+            dev = adopt(mine);
+        }
+        glue::check(csgn_append(dev.get(), rhs.get()), "csgn_append");
+    }
     invalidate_mirror();
     return *this;
 }
 
 Ciphertext Ciphertext::operator*(const Ciphertext &c) const {
-    const csgn_buf *a = deviceBuffer(), *b = c.deviceBuffer();
-    if (!a || !b) throw Error("Ciphertext::operator*: empty operand");
     Ciphertext out;
     // the reference multiplies in the LEFT operand's context (src/Ciphertext.cpp:239)
     if (certFHEcontext) out.certFHEcontext = new Context(*certFHEcontext);
-    glue::check(csgn_mul(a, b, &out.dev), "csgn_mul");
+    if (Library::getLazyProducts()) {
+        collect_factors(out.factors);
+        const size_t mine = out.factors.size();
+        c.collect_factors(out.factors);
+        if (mine == 0 || out.factors.size() == mine) throw Error("Ciphertext::operator*: empty operand");
+        return out;
+    }
+    const csgn_buf *a = deviceBuffer(), *b = c.deviceBuffer();
+    if (!a || !b) throw Error("Ciphertext::operator*: empty operand");
+    csgn_buf *prod = nullptr;
+    glue::check(csgn_mul(a, b, &prod), "csgn_mul");
+    out.dev = adopt(prod);
     return out;
 }
 
 Ciphertext &Ciphertext::operator*=(const Ciphertext &c) {
+    if (Library::getLazyProducts()) {
+        std::vector<std::shared_ptr<csgn_buf> > f;
+        collect_factors(f);
+        const size_t mine = f.size();
+        c.collect_factors(f);
+        if (mine == 0 || f.size() == mine) throw Error("Ciphertext::operator*=: empty operand");
+        dev.reset();
+        factors.swap(f);
+        invalidate_mirror();
+        return *this;
+    }
     const csgn_buf *a = deviceBuffer(), *b = c.deviceBuffer();
     if (!a || !b) throw Error("Ciphertext::operator*=: empty operand");
     csgn_buf *prod = nullptr;
     glue::check(csgn_mul(a, b, &prod), "csgn_mul");
-    csgn_buf_free(dev);  // stream-ordered: the multiply still reads it safely (also when &c == this)
-    dev = prod;
+    dev = adopt(prod);   // the old buffer is released in stream order, after the multiply that reads it
     invalidate_mirror();
     return *this;
 }
 
 void Ciphertext::applyPermutation_inplace(const Permutation &permutation) {
-    const csgn_buf *a = deviceBuffer();
-    if (!a || !certFHEcontext) throw Error("Ciphertext::applyPermutation: empty ciphertext or no Context");
-    csgn_buf *out = nullptr;
-    glue::check(csgn_permute(a, permutation.deviceMap(certFHEcontext->getN()),
-                             Library::getStrictReferencePermutation() ? 1 : 0, &out),
-                "csgn_permute");
-    csgn_buf_free(dev);
-    dev = out;
+    Ciphertext permuted = applyPermutation(permutation);
+    dev = std::move(permuted.dev);
+    factors.swap(permuted.factors);
     invalidate_mirror();
 }
 
 Ciphertext Ciphertext::applyPermutation(const Permutation &permutation) {
-    const csgn_buf *a = deviceBuffer();
-    if (!a || !certFHEcontext) throw Error("Ciphertext::applyPermutation: empty ciphertext or no Context");
+    upload_staged();
+    if (!certFHEcontext || (!dev && factors.empty()))
+        throw Error("Ciphertext::applyPermutation: empty ciphertext or no Context");
+    const csgn_perm *map = permutation.deviceMap(certFHEcontext->getN());
+    const bool strict = Library::getStrictReferencePermutation();
     Ciphertext out;
     out.certFHEcontext = new Context(*certFHEcontext);
-    glue::check(csgn_permute(a, permutation.deviceMap(certFHEcontext->getN()),
-                             Library::getStrictReferencePermutation() ? 1 : 0, &out.dev),
-                "csgn_permute");
+    if (!factors.empty() && !strict) {
+        // a permutation acts on each block, and a product block is an AND of factor blocks:
+        // pi(a_i & b_j) = pi(a_i) & pi(b_j) -- permute the factors, stay lazy
+        for (size_t i = 0; i < factors.size(); ++i) {
+            csgn_buf *pf = nullptr;
+            glue::check(csgn_permute(factors[i].get(), map, 0, &pf), "csgn_permute");
+            out.factors.push_back(adopt(pf));
+        }
+        return out;
+    }
+    csgn_buf *res = nullptr;
+    glue::check(csgn_permute(deviceBuffer(), map, strict ? 1 : 0, &res), "csgn_permute");
+    out.dev = adopt(res);
     return out;
 }
 
@@ -464,14 +558,21 @@ Ciphertext SecretKey::encrypt(Plaintext &plaintext) {
 }
 
 Plaintext SecretKey::decrypt(Ciphertext &ciphertext) {
-    const csgn_buf *buf = ciphertext.deviceBuffer();
-    if (!buf) return Plaintext(0);
+    ciphertext.upload_staged();
+    if (!ciphertext.dev && ciphertext.factors.empty()) return Plaintext(0);
     if (!device_key) {
         glue::ensure_engine();
         glue::check(csgn_key_create(certFHEContext->getN(), s, (uint32_t)length, &device_key), "csgn_key_create");
     }
     uint8_t bit = 0;
-    glue::check(csgn_decrypt(buf, device_key, &bit), "csgn_decrypt");
+    if (!ciphertext.factors.empty()) {
+        // a product that was never multiplied out: Dec(f0*f1*...) = Dec(f0) & Dec(f1) & ...
+        std::vector<const csgn_buf *> fs;
+        for (size_t i = 0; i < ciphertext.factors.size(); ++i) fs.push_back(ciphertext.factors[i].get());
+        glue::check(csgn_decrypt_product(fs.data(), (uint32_t)fs.size(), device_key, &bit, nullptr), "csgn_decrypt_product");
+    } else {
+        glue::check(csgn_decrypt(ciphertext.dev.get(), device_key, &bit), "csgn_decrypt");
+    }
     return Plaintext(bit);
 }
 

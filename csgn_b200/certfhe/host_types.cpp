@@ -13,6 +13,8 @@ namespace certFHE {
 namespace {
 bool g_strict_permute = false;
 bool g_strict_permute_set = false;
+bool g_lazy_products = false;
+bool g_lazy_products_set = false;
 }  // namespace
 
 void Library::initializeLibrary() {
@@ -33,6 +35,20 @@ bool Library::getStrictReferencePermutation() {
         g_strict_permute_set = true;
     }
     return g_strict_permute;
+}
+
+void Library::setLazyProducts(bool lazy) {
+    g_lazy_products = lazy;
+    g_lazy_products_set = true;
+}
+
+bool Library::getLazyProducts() {
+    if (!g_lazy_products_set) {
+        const char *e = getenv("CSGN_LAZY_PRODUCTS");
+        g_lazy_products = e && *e && strcmp(e, "0") != 0;
+        g_lazy_products_set = true;
+    }
+    return g_lazy_products;
 }
 
 void Library::synchronize() {

@@ -542,6 +542,42 @@ int csgn_decrypt(const csgn_buf *c, const csgn_key *key, uint8_t *bit) {
     return CSGN_OK;
 }
 
+int csgn_decrypt_product(const csgn_buf *const *factors, uint32_t n_factors, const csgn_key *key, uint8_t *bit,
+                         uint64_t *count) {
+    NEED_INIT();
+    if (!factors || !key || !bit || n_factors == 0) return fail(CSGN_ERR_INVALID_ARGUMENT, "bad product arguments");
+    for (uint32_t i = 0; i < n_factors; ++i) {
+        if (!factors[i]) return fail(CSGN_ERR_INVALID_ARGUMENT, "null factor %u", i);
+        if (factors[i]->L != key->L)
+            return fail(CSGN_ERR_SHAPE_MISMATCH, "factor %u has %u words per block, key expects %u", i, factors[i]->L,
+                        key->L);
+    }
+    uint64_t *d_counts = nullptr;
+    int rc = dev_alloc(n_factors, &d_counts);
+    if (rc != CSGN_OK) return rc;
+    for (uint32_t i = 0; i < n_factors; ++i) {
+        rc = csgn_decrypt_count_async(factors[i], key, d_counts + i);
+        if (rc != CSGN_OK) {
+            dev_free(d_counts);
+            return rc;
+        }
+    }
+    std::vector<uint64_t> h(n_factors);
+    cudaError_t e = cudaMemcpyAsync(h.data(), d_counts, n_factors * sizeof(uint64_t), cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    dev_free(d_counts);
+    if (e != cudaSuccess) return cuda_fail(e, "product decrypt readback");
+    uint64_t prod = 1;
+    uint8_t parity = 1;
+    for (uint32_t i = 0; i < n_factors; ++i) {
+        parity &= (uint8_t)(h[i] & 1u);
+        prod = (h[i] != 0 && prod > UINT64_MAX / h[i]) ? UINT64_MAX : prod * h[i];
+    }
+    *bit = parity;
+    if (count) *count = prod;
+    return CSGN_OK;
+}
+
 int csgn_decrypt_positions(const csgn_buf *c, uint64_t N, const uint64_t *positions, uint32_t D, uint8_t *bit) {
     csgn_key *k = nullptr;
     int rc = csgn_key_create(N, positions, D, &k);

@@ -249,6 +249,14 @@ class SecretKey:
         check(_lib().csgn_decrypt_count(ct._h, self._h, ctypes.byref(c)))
         return int(c.value)
 
+    def decrypt_product(self, factors):
+        """Dec(f1*f2*...*fn) without materialising the product (csgn_decrypt_product).
+        Returns (bit, count) with count saturated at 2**64-1."""
+        arr = (_vp * len(factors))(*[f._h for f in factors])
+        bit, cnt = ctypes.c_uint8(), ctypes.c_uint64()
+        check(_lib().csgn_decrypt_product(arr, len(factors), self._h, ctypes.byref(bit), ctypes.byref(cnt)))
+        return int(bit.value), int(cnt.value)
+
     def count_satisfied_async(self, ct, device_count_ptr):
         check(_lib().csgn_decrypt_count_async(ct._h, self._h, _vp(device_count_ptr)))
 

@@ -122,6 +122,14 @@ int csgn_decrypt_count(const csgn_buf *c, const csgn_key *key, uint64_t *count);
 /* Same, asynchronous: the count is written to a device uint64 (caller-owned, e.g.
  * the tensor handed to the NCCL all-reduce); no host synchronisation. */
 int csgn_decrypt_count_async(const csgn_buf *c, const csgn_key *key, uint64_t *device_count);
+/* Decrypt of a product that is never materialised (the caller side of the path:
+ * operator* followed by decrypt).  For raw blocks the satisfied-block count is multiplicative,
+ * count(f1*f2*...*fn) = count(f1)*...*count(fn), because block (i,j) of a product is a_i & b_j and
+ * (a_i & b_j) & M == M  <=>  a_i & M == M and b_j & M == M; so Dec(f1*...*fn) is the AND of the factors'
+ * decryptions.  Folds the n factors (n launches, one synchronisation); *bit receives the plaintext bit,
+ * *count (optional) the product of the counts, saturated at UINT64_MAX. */
+int csgn_decrypt_product(const csgn_buf *const *factors, uint32_t n_factors, const csgn_key *key, uint8_t *bit,
+                         uint64_t *count);
 /* One-shot convenience without a key handle. */
 int csgn_decrypt_positions(const csgn_buf *c, uint64_t N, const uint64_t *positions, uint32_t D,
                            uint8_t *bit);

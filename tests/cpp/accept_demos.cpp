@@ -135,6 +135,61 @@ static void random_circuits(uint64_t N, uint64_t D, unsigned seed, int rounds) {
     }
 }
 
+// Lazy products: operator* keeps the factors; decrypt, permutation and copies never multiply out.
+static void lazy_products() {
+    Context context(1247, 16);
+    SecretKey seckey(context);
+    srand(77);
+    auto sum_of = [&](int n, int &parity) {
+        Ciphertext acc;
+        parity = 0;
+        for (int i = 0; i < n; ++i) {
+            Plaintext p(rand() % 2);
+            parity ^= p.getValue();
+            Ciphertext e = seckey.encrypt(p);
+            if (i == 0) acc = e; else acc += e;
+        }
+        return acc;
+    };
+    int pa, pb, pd;
+    Ciphertext A = sum_of(40, pa), B = sum_of(30, pb), Dd = sum_of(20, pd);
+    Ciphertext eager = (A * B) * Dd;                         // 24,000 blocks, multiplied out
+    Library::setLazyProducts(true);
+    Ciphertext lazy = (A * B) * Dd;                          // three factors, nothing multiplied
+    EXPECT(lazy.getLen() == eager.getLen() && lazy.getBlocks() == 24000);
+    EXPECT(seckey.decrypt(lazy).getValue() == (pa & pb & pd));
+    EXPECT(seckey.decrypt(eager).getValue() == (pa & pb & pd));
+    Permutation pi(context);
+    SecretKey pk = seckey.applyPermutation(pi);
+    Ciphertext lazy_p = lazy.applyPermutation(pi);           // permutes 90 blocks, not 24,000
+    EXPECT(pk.decrypt(lazy_p).getValue() == (pa & pb & pd));
+    // a chain far beyond any memory: 10^3 * 10^3 * 10^3 * 10^3 = 10^12 blocks, decrypted from its factors
+    int p1, p2, p3, p4;
+    Ciphertext c1 = sum_of(1000, p1), c2 = sum_of(1000, p2), c3 = sum_of(1000, p3), c4 = sum_of(1000, p4);
+    Ciphertext huge = c1 * c2;
+    huge *= c3;
+    huge = huge * c4;
+    EXPECT(huge.getBlocks() == 1000000000000ull);
+    EXPECT(seckey.decrypt(huge).getValue() == (p1 & p2 & p3 & p4));
+    // words on demand: multiplying out gives exactly the eager product; copies are independent
+    Ciphertext copy = lazy;
+    EXPECT(memcmp(lazy.getValues(), eager.getValues(), eager.getLen() * 8) == 0);
+    EXPECT(memcmp(lazy_p.getValues(), eager.applyPermutation(pi).getValues(), eager.getLen() * 8) == 0);
+    copy += A;
+    EXPECT(copy.getLen() == eager.getLen() + A.getLen() && lazy.getLen() == eager.getLen());
+    EXPECT(seckey.decrypt(copy).getValue() == ((pa & pb & pd) ^ pa));
+    Ciphertext mixed = lazy + (A * B);                       // sums multiply their operands out
+    EXPECT(seckey.decrypt(mixed).getValue() == ((pa & pb & pd) ^ (pa & pb)));
+    Library::setLazyProducts(false);
+    // copy-on-write: a copy shares the buffer until one side grows
+    Ciphertext x = A, y = x;
+    y += B;
+    EXPECT(x.getLen() == A.getLen() && y.getLen() == A.getLen() + B.getLen());
+    EXPECT(memcmp(x.getValues(), A.getValues(), A.getLen() * 8) == 0);
+    x += x;
+    EXPECT(x.getLen() == 2 * A.getLen() && seckey.decrypt(x).getValue() == 0);
+}
+
 static void misuse_is_loud() {
     Context context(1247, 16);
     uint64_t words[20] = {0}, bitlen[20];
@@ -167,6 +222,10 @@ int main() {
     random_circuits(16383, 64, 2, 2);
     random_circuits(191, 5, 3, 4);   // odd number of words per block
     random_circuits(128, 4, 4, 4);   // N % 64 == 0 (the reference overflows its arrays here)
+    lazy_products();
+    Library::setLazyProducts(true);
+    random_circuits(1247, 16, 5, 4);  // the same circuits with products kept lazy
+    Library::setLazyProducts(false);
     misuse_is_loud();
     if (failures) {
         std::cerr << failures << " expectation(s) failed" << endl;

@@ -236,6 +236,10 @@ int main() {
     encrypted_circuits(65, 2, 104, 6, 5);
     encrypted_circuits(191, 5, 105, 4, 3);  // odd words per block
     encrypted_circuits(63, 4, 106, 3, 3);   // one word per block
+    ours::Library::setLazyProducts(true);    // lazy products must be observationally identical
+    encrypted_circuits(1247, 16, 107, 4, 3);
+    encrypted_circuits(191, 5, 108, 3, 2);
+    ours::Library::setLazyProducts(false);
     config2_full_size(1247, 16, 1000, 1000);
     config2_full_size(16383, 64, 300, 300);
     if (failures) {

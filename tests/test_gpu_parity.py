@@ -209,6 +209,31 @@ def test_decrypt_real_ciphertexts(engine, oracle):
         assert engine.SecretKey(ctx, s2).count_satisfied(ct) == oracle.count_satisfied(enc, N, s2)
 
 
+def test_decrypt_product_without_materialising(engine, oracle):
+    """csgn_decrypt_product: Dec(f1*...*fn) from the factors alone equals the fold of the real product."""
+    N, D = 1247, 1
+    rng = np.random.default_rng(21)
+    ctx = engine.Context(N, D)
+    s = random_key(rng, N, D)
+    key = engine.SecretKey(ctx, s)
+    hosts = [random_blocks(rng, t, N) for t in (40, 33, 17)]
+    fs = [engine.Ciphertext.from_host(h, ctx) for h in hosts]
+    counts = [oracle.count_satisfied(h, N, s) for h in hosts]
+    bit, count = key.decrypt_product(fs)
+    assert count == counts[0] * counts[1] * counts[2] and bit == (counts[0] & counts[1] & counts[2] & 1)
+    prod = (fs[0] * fs[1]) * fs[2]                       # the real 22,440-block product
+    assert key.count_satisfied(prod) == count and key.decrypt(prod) == bit
+    assert oracle.count_satisfied(prod.getValues(), N, s) == count
+    # a product nobody could store: 10 factors of 1000 blocks = 10^30 blocks; the count saturates, the bit is exact
+    big = [engine.Ciphertext.from_host(random_blocks(rng, 1000, N), ctx) for _ in range(10)]
+    bit, count = key.decrypt_product(big)
+    cs = [key.count_satisfied(f) for f in big]
+    want = 1
+    for c in cs:
+        want = min(want * c, 2**64 - 1)
+    assert count == want and bit == int(all(c & 1 for c in cs))
+
+
 def test_key_rejects_out_of_range_position(engine):
     with pytest.raises(engine.CsgnError):
         engine.SecretKey(engine.Context(1247, 2), [5, 1247])
