@@ -52,6 +52,8 @@ SIGNATURES = {
     "csgn_permute": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vpp]),
     "csgn_permute_into": (ctypes.c_int, [_vp, _vp, _vp]),
     "csgn_buf_checksum": (ctypes.c_int, [_vp, _u64p, _u64p, _u64p]),
+    "csgn_buf_save": (ctypes.c_int, [_vp, _u64, _u64, ctypes.c_char_p]),
+    "csgn_buf_load": (ctypes.c_int, [ctypes.c_char_p, _u64p, _u64p, _vpp]),
     "csgn_shard_range": (ctypes.c_int, [_u64, ctypes.c_int, ctypes.c_int, _u64p, _u64p]),
 }
 

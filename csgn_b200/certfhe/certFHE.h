@@ -189,6 +189,10 @@ public:
     long size();
 
     // engine side (extensions)
+    // Binary file: 64-byte header (N, D, L, blocks, checksum) + raw words, streamed GPU <-> file
+    // through pinned staging (csgn_buf_save / csgn_buf_load).  The reference has no serialisation.
+    void save(const std::string &path) const;
+    static Ciphertext load(const std::string &path);
     uint64_t getBlocks() const;            // number of N-bit blocks
     const csgn_buf *deviceBuffer() const;  // uploads staged words first
 };

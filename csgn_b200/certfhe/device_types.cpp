@@ -406,6 +406,23 @@ Ciphertext &Ciphertext::operator*=(const Ciphertext &c) {
     return *this;
 }
 
+void Ciphertext::save(const std::string &path) const {
+    const csgn_buf *buf = deviceBuffer();
+    if (!buf || !certFHEcontext) throw Error("Ciphertext::save: empty ciphertext or no Context");
+    glue::check(csgn_buf_save(buf, certFHEcontext->getN(), certFHEcontext->getD(), path.c_str()), "csgn_buf_save");
+}
+
+Ciphertext Ciphertext::load(const std::string &path) {
+    glue::ensure_engine();
+    uint64_t n = 0, d = 0;
+    csgn_buf *buf = nullptr;
+    glue::check(csgn_buf_load(path.c_str(), &n, &d, &buf), "csgn_buf_load");
+    Ciphertext out;
+    out.dev = adopt(buf);
+    out.certFHEcontext = new Context(n, d);
+    return out;
+}
+
 void Ciphertext::applyPermutation_inplace(const Permutation &permutation) {
     Ciphertext permuted = applyPermutation(permutation);
     dev = std::move(permuted.dev);

@@ -181,6 +181,16 @@ class Ciphertext:
         check(_lib().csgn_buf_checksum(self._h, ctypes.byref(x), ctypes.byref(s), ctypes.byref(h)))
         return x.value, s.value, h.value
 
+    def save(self, path):
+        """csgn_buf_save: header + raw words, streamed through pinned staging."""
+        check(_lib().csgn_buf_save(self._h, self.ctx.N, self.ctx.D, str(path).encode()))
+
+    @classmethod
+    def load(cls, path):
+        h, n, d = _vp(), ctypes.c_uint64(), ctypes.c_uint64()
+        check(_lib().csgn_buf_load(str(path).encode(), ctypes.byref(n), ctypes.byref(d), ctypes.byref(h)))
+        return cls(h, Context(n.value, d.value))
+
     def clone(self):
         h = _vp()
         check(_lib().csgn_buf_clone(self._h, ctypes.byref(h)))

@@ -151,6 +151,14 @@ int csgn_permute_into(const csgn_buf *c, const csgn_perm *perm, csgn_buf *out);
  * compare products that are too large to download. */
 int csgn_buf_checksum(const csgn_buf *buf, uint64_t *xor_out, uint64_t *sum_out, uint64_t *wsum_out);
 
+/* ---- serialisation (absent upstream, which only reports size()) -------------
+ * File = 64-byte little-endian header {magic "CSGNCT01", N, D, L, n_blocks, xor-of-words,
+ * reserved} followed by n_blocks*L raw uint64 words.  Blocks stream between the device and
+ * the file through two pinned staging buffers, so a ciphertext far larger than host memory
+ * can be written or read; the checksum is verified on load. */
+int csgn_buf_save(const csgn_buf *buf, uint64_t N, uint64_t D, const char *path);
+int csgn_buf_load(const char *path, uint64_t *N, uint64_t *D, csgn_buf **out);
+
 /* ---- sharding helpers (one process per GPU) ------------------------------- */
 
 /* Contiguous range of the LEFT operand's blocks owned by `rank` of `world`:

@@ -181,6 +181,14 @@ static void lazy_products() {
     Ciphertext mixed = lazy + (A * B);                       // sums multiply their operands out
     EXPECT(seckey.decrypt(mixed).getValue() == ((pa & pb & pd) ^ (pa & pb)));
     Library::setLazyProducts(false);
+    // save / load: the words, the context and the decrypted bit survive the file
+    const std::string path = "/tmp/csgn_accept_demo.ct";
+    eager.save(path);
+    Ciphertext loaded = Ciphertext::load(path);
+    EXPECT(loaded.getLen() == eager.getLen() && loaded.getContext().getN() == 1247 && loaded.getContext().getD() == 16);
+    EXPECT(memcmp(loaded.getValues(), eager.getValues(), eager.getLen() * 8) == 0);
+    EXPECT(seckey.decrypt(loaded).getValue() == (pa & pb & pd));
+    remove(path.c_str());
     // copy-on-write: a copy shares the buffer until one side grows
     Ciphertext x = A, y = x;
     y += B;

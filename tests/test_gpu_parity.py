@@ -415,6 +415,35 @@ def test_chain_to_1e8_blocks_16GB(engine, oracle):
     del y, x, part
 
 
+def test_save_load_round_trip(engine, oracle, tmp_path):
+    """csgn_buf_save / csgn_buf_load: header + raw words through pinned staging; corruption is detected."""
+    rng = np.random.default_rng(77)
+    for N, D, T in ((1247, 16, 1), (1247, 16, 500000), (16383, 64, 3000), (191, 5, 77)):
+        ctx = engine.Context(N, D)
+        v = random_blocks(rng, T, N)
+        path = tmp_path / ("ct_%d_%d.csgn" % (N, T))
+        engine.Ciphertext.from_host(v, ctx).save(path)
+        raw = np.fromfile(path, dtype=np.uint64)
+        assert raw.size == 8 + v.size and bytes(raw[:1].tobytes()) == b"CSGNCT01"
+        assert [int(x) for x in raw[1:5]] == [N, D, ctx.L, T] and int(raw[5]) == oracle.checksum(v)[0]
+        assert np.array_equal(raw[8:], v)                      # the file holds the reference's words verbatim
+        back = engine.Ciphertext.load(path)
+        assert (back.ctx.N, back.ctx.D, back.n_blocks) == (N, D, T)
+        assert np.array_equal(back.getValues(), v)
+    # a flipped bit, a truncated file and a foreign file are refused
+    raw = np.fromfile(path, dtype=np.uint64)
+    raw[20] ^= np.uint64(1)
+    raw.tofile(tmp_path / "bad.csgn")
+    with pytest.raises(engine.CsgnError, match="checksum"):
+        engine.Ciphertext.load(tmp_path / "bad.csgn")
+    np.fromfile(path, dtype=np.uint64)[:-5].tofile(tmp_path / "short.csgn")
+    with pytest.raises(engine.CsgnError, match="truncated"):
+        engine.Ciphertext.load(tmp_path / "short.csgn")
+    (tmp_path / "other.bin").write_bytes(b"x" * 200)
+    with pytest.raises(engine.CsgnError, match="not a CSGN"):
+        engine.Ciphertext.load(tmp_path / "other.bin")
+
+
 # ---------------------------------------------------------------------------
 # interop: caller-owned device memory and an external stream
 # ---------------------------------------------------------------------------
