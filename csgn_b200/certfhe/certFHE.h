@@ -215,6 +215,10 @@ public:
 
     Ciphertext encrypt(Plaintext &plaintext);
     Plaintext decrypt(Ciphertext &ciphertext);
+    // Extension: n fresh encryptions built on the GPU in one call (csgn_encrypt_batch) -- the
+    // ciphertext Enc(bits[0]) + ... + Enc(bits[n-1]), n blocks, decrypting to the XOR of the bits.
+    // Same construction as encrypt(); randomness is Philox keyed by `seed` instead of rand().
+    Ciphertext encryptBatch(const unsigned char *bits, uint64_t n, uint64_t seed);
     void applyPermutation_inplace(const Permutation &permutation);
     SecretKey applyPermutation(const Permutation &permutation);
 

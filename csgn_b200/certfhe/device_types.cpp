@@ -574,6 +574,19 @@ Ciphertext SecretKey::encrypt(Plaintext &plaintext) {
     return c;
 }
 
+Ciphertext SecretKey::encryptBatch(const unsigned char *bits, uint64_t n, uint64_t seed) {
+    if (!device_key) {
+        glue::ensure_engine();
+        glue::check(csgn_key_create(certFHEContext->getN(), s, (uint32_t)length, &device_key), "csgn_key_create");
+    }
+    csgn_buf *buf = nullptr;
+    glue::check(csgn_encrypt_batch(device_key, bits, n, 0, seed, &buf), "csgn_encrypt_batch");
+    Ciphertext out;
+    out.dev = adopt(buf);
+    out.certFHEcontext = new Context(*certFHEContext);
+    return out;
+}
+
 Plaintext SecretKey::decrypt(Ciphertext &ciphertext) {
     ciphertext.upload_staged();
     if (!ciphertext.dev && ciphertext.factors.empty()) return Plaintext(0);

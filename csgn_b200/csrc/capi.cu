@@ -31,6 +31,7 @@ struct csgn_buf {
 };
 
 struct csgn_key {
+    uint64_t *d_positions = nullptr;  // D secret positions (for batched encryption)
     uint64_t *d_mask = nullptr;  // L words
     std::vector<uint64_t> h_mask;  // the same, host side (small masks ride in kernel parameters)
     uint64_t N = 0;
@@ -486,11 +487,15 @@ int csgn_key_create(uint64_t N, const uint64_t *positions, uint32_t D, csgn_key 
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&k->d_mask), (size_t)L * sizeof(uint64_t));
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(k->d_mask, mask.data(), (size_t)L * sizeof(uint64_t), cudaMemcpyHostToDevice, g.stream);
+    if (e == cudaSuccess && D) e = cudaMalloc(reinterpret_cast<void **>(&k->d_positions), (size_t)D * sizeof(uint64_t));
+    if (e == cudaSuccess && D)
+        e = cudaMemcpyAsync(k->d_positions, positions, (size_t)D * sizeof(uint64_t), cudaMemcpyHostToDevice, g.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);  // `mask` dies with this frame
     if (e == cudaSuccess) k->h_mask = mask;
     std::fill(mask.begin(), mask.end(), 0);
     if (e != cudaSuccess) {
         if (k->d_mask) cudaFree(k->d_mask);
+        if (k->d_positions) cudaFree(k->d_positions);
         delete k;
         return cuda_fail(e, "key upload");
     }
@@ -502,8 +507,10 @@ int csgn_key_free(csgn_key *key) {
     if (!key) return CSGN_OK;
     if (g.inited && key->d_mask) {
         cudaMemsetAsync(key->d_mask, 0, (size_t)key->L * sizeof(uint64_t), g.stream);  // zeroise, as the reference's dtor does
+        if (key->d_positions) cudaMemsetAsync(key->d_positions, 0, (size_t)key->D * sizeof(uint64_t), g.stream);
         cudaStreamSynchronize(g.stream);
         cudaFree(key->d_mask);
+        if (key->d_positions) cudaFree(key->d_positions);
     }
     std::fill(key->h_mask.begin(), key->h_mask.end(), 0);
     delete key;
@@ -585,6 +592,37 @@ int csgn_decrypt_positions(const csgn_buf *c, uint64_t N, const uint64_t *positi
     rc = csgn_decrypt(c, k, bit);
     csgn_key_free(k);
     return rc;
+}
+
+// ---------------------------------------------------------------------------
+// batched encryption
+// ---------------------------------------------------------------------------
+int csgn_encrypt_batch(const csgn_key *key, const uint8_t *bits, uint64_t n, uint64_t first_block, uint64_t seed,
+                       csgn_buf **out) {
+    NEED_INIT();
+    if (!key || !out || (n && !bits)) return fail(CSGN_ERR_INVALID_ARGUMENT, "null argument");
+    if (key->D == 0) return fail(CSGN_ERR_INVALID_ARGUMENT, "the key has no secret positions");
+    csgn_buf *b = nullptr;
+    int rc = new_buf(n, key->L, 0, &b);
+    if (rc != CSGN_OK) return rc;
+    if (n) {
+        uint8_t *d_bits = nullptr;
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&d_bits), n, g.stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_bits, bits, n, cudaMemcpyHostToDevice, g.stream);
+        const uint64_t rem = key->N % 64;
+        const uint64_t pad = rem ? ~0ull << (64 - rem) : ~0ull;
+        if (e == cudaSuccess)
+            e = launch_encrypt_batch(d_bits, n, first_block, key->L, pad, key->d_mask, key->d_positions, key->D, seed,
+                                     b->d, g.stream);
+        if (d_bits) cudaFreeAsync(d_bits, g.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);   // `bits` may be a temporary of the caller
+        if (e != cudaSuccess) {
+            csgn_buf_free(b);
+            return cuda_fail(e, "batched encryption");
+        }
+    }
+    *out = b;
+    return CSGN_OK;
 }
 
 // ---------------------------------------------------------------------------

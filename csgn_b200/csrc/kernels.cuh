@@ -47,6 +47,11 @@ cudaError_t launch_permute(const uint64_t *in, uint64_t T, uint32_t L, uint32_t 
                            const uint32_t *slice_map, uint64_t *out, cudaStream_t stream);
 bool permute_sliced_supported(uint32_t L);
 
+// n fresh encryptions (one block per plaintext bit) with Philox-4x32-10 keyed by `seed`; see encrypt.cu.
+cudaError_t launch_encrypt_batch(const uint8_t *bits, uint64_t n, uint64_t first_block, uint32_t L, uint64_t pad_mask,
+                                 const uint64_t *mask, const uint64_t *positions, uint32_t D, uint64_t seed,
+                                 uint64_t *out, cudaStream_t stream);
+
 // xor / wrapping sum / sum(w[i]*(2i+1)) of n_words words, accumulated into acc[0..2]
 // (device, must be zeroed by the caller).
 cudaError_t launch_checksum(const uint64_t *v, uint64_t n_words, uint64_t *acc, cudaStream_t stream);

@@ -259,6 +259,13 @@ class SecretKey:
         check(_lib().csgn_decrypt_count(ct._h, self._h, ctypes.byref(c)))
         return int(c.value)
 
+    def encrypt_batch(self, bits, seed, first_block=0):
+        """n fresh blocks on the GPU, block i encrypting bits[i] (csgn_encrypt_batch, Philox keyed by seed)."""
+        b = np.ascontiguousarray(np.asarray(bits, dtype=np.uint8))
+        h = _vp()
+        check(_lib().csgn_encrypt_batch(self._h, b.ctypes.data_as(_vp), b.size, int(first_block), int(seed), ctypes.byref(h)))
+        return Ciphertext(h, self.ctx)
+
     def decrypt_product(self, factors):
         """Dec(f1*f2*...*fn) without materialising the product (csgn_decrypt_product).
         Returns (bit, count) with count saturated at 2**64-1."""

@@ -134,6 +134,15 @@ int csgn_decrypt_product(const csgn_buf *const *factors, uint32_t n_factors, con
 int csgn_decrypt_positions(const csgn_buf *c, uint64_t N, const uint64_t *positions, uint32_t D,
                            uint8_t *bit);
 
+/* Batched fresh encryptions on the GPU (the reference encrypts one bit per call on the
+ * host from glibc rand(), src/SecretKey.cpp:35-80 -- that path, rand() order included, stays in
+ * csgn_b200/certfhe for seeded parity).  Block i of *out encrypts bits[i] (host array, 0/1) under
+ * `key`, with the reference's construction and Philox-4x32-10 keyed by `seed`, counter
+ * (first_block + i, unit): the result does not depend on how a batch is split.  The n-block buffer
+ * is the ciphertext Enc(bits[0]) + ... + Enc(bits[n-1]) and decrypts to the XOR of the bits. */
+int csgn_encrypt_batch(const csgn_key *key, const uint8_t *bits, uint64_t n, uint64_t first_block, uint64_t seed,
+                       csgn_buf **out);
+
 /* Permutation as a device source map: out_bit[i] = in_bit[perm[i]], i < N
  * (src/Ciphertext.cpp:33-34).  Fails unless perm is a bijection of [0,N). */
 int csgn_perm_create(uint64_t N, const uint64_t *perm, csgn_perm **out);

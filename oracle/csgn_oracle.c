@@ -241,3 +241,53 @@ void csgn_oracle_bits_text(const uint64_t *v, uint64_t T, uint64_t N, char *out)
         for (uint64_t p = 0; p < N; p++) out[o++] = (char)('0' + bit_at(v + b * L, p));
     out[o] = 0;
 }
+
+/* ---- counter-based batched encryption (restated for the GPU kernel csrc/encrypt.cu) ---------- */
+void csgn_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+void csgn_oracle_encrypt_batch(const uint8_t *bits, uint64_t n, uint64_t first_block, uint64_t N,
+                               const uint64_t *s, uint64_t D, uint64_t seed, uint64_t *out) {
+    const uint64_t L = csgn_oracle_words_per_block(N), rem = N % 64;
+    const uint64_t pad = rem ? ~0ull << (64 - rem) : ~0ull;
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint64_t *mask = (uint64_t *)calloc(L ? L : 1, sizeof(uint64_t));
+    csgn_oracle_key_mask(N, s, D, mask);
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t b = first_block + i;
+        uint64_t *blk = out + i * L;
+        for (uint64_t u = 0; 2 * u < L; u++) {
+            const uint32_t ctr[4] = {(uint32_t)b, (uint32_t)(b >> 32), (uint32_t)u, 0x43534731u};
+            uint32_t r[4];
+            csgn_oracle_philox4x32_10(ctr, key, r);
+            blk[2 * u] = (uint64_t)r[0] | ((uint64_t)r[1] << 32);
+            if (2 * u + 1 < L) blk[2 * u + 1] = (uint64_t)r[2] | ((uint64_t)r[3] << 32);
+        }
+        blk[L - 1] &= pad;
+        if (bits[i] & 1) {
+            for (uint64_t w = 0; w < L; w++) blk[w] |= mask[w];
+        } else {
+            const uint32_t ctr[4] = {(uint32_t)b, (uint32_t)(b >> 32), 0xffffffffu, 0x43534731u};
+            uint32_t r[4];
+            csgn_oracle_philox4x32_10(ctr, key, r);
+            const uint64_t hole = s[r[0] % D];
+            const uint64_t hbit = 1ull << (63u - (hole & 63u));
+            int others = 1;   /* AND over the other secret positions (vacuously 1 when D == 1) */
+            for (uint64_t w = 0; w < L; w++) {
+                const uint64_t m = (w == (hole >> 6)) ? (mask[w] & ~hbit) : mask[w];
+                if ((blk[w] & m) != m) others = 0;
+            }
+            if (others) blk[hole >> 6] &= ~hbit;
+        }
+    }
+    free(mask);
+}

@@ -81,6 +81,18 @@ void csgn_oracle_perm_generate(uint64_t n, uint64_t *out);
  * scans uninitialised memory, so upstream keys are not reproducible). */
 void csgn_oracle_keygen(uint64_t N, uint64_t D, uint64_t *s);
 
+/* Batched encryption with a counter-based generator (not in the reference,
+ * which draws from glibc rand()).  Same construction as src/SecretKey.cpp:35-80 per block:
+ *   Enc(1): ones at the secret positions, random bits elsewhere;
+ *   Enc(0): a random secret position h ("hole"); random bits everywhere else; the bit at h is
+ *           forced to 0 if every other secret position came out 1, otherwise it is random.
+ * Randomness: Philox-4x32-10 keyed by `seed`; block b (global index first_block + i), 16-byte
+ * unit u of the block uses counter (b_lo, b_hi, u, 0x43534731); the hole index is
+ * philox(b_lo, b_hi, 0xffffffff, 0x43534731).x % D into `s` as given.  out holds n*L words. */
+void csgn_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void csgn_oracle_encrypt_batch(const uint8_t *bits, uint64_t n, uint64_t first_block, uint64_t N,
+                               const uint64_t *s, uint64_t D, uint64_t seed, uint64_t *out);
+
 /* src/Ciphertext.cpp:185-202 -- '0'/'1' text of the valid bits; out holds T*N+1 chars. */
 void csgn_oracle_bits_text(const uint64_t *v, uint64_t T, uint64_t N, char *out);
 

@@ -94,6 +94,7 @@ class Oracle:
         lib.csgn_oracle_perm_generate.argtypes = [_u64, _u64p]
         lib.csgn_oracle_keygen.argtypes = [_u64, _u64, _u64p]
         lib.csgn_oracle_bits_text.argtypes = [_u64p, _u64, _u64, ctypes.c_char_p]
+        lib.csgn_oracle_encrypt_batch.argtypes = [ctypes.POINTER(ctypes.c_uint8), _u64, _u64, _u64, _u64p, _u64, _u64, _u64p]
 
     def canonical_bitlen(self, N, T):
         out = np.empty(T * words_per_block(N), dtype=np.uint64)
@@ -186,6 +187,14 @@ class Oracle:
     def keygen(self, N, D):
         out = np.empty(D, dtype=np.uint64)
         self.lib.csgn_oracle_keygen(N, D, _p(out))
+        return out
+
+    def encrypt_batch(self, bits, N, s, seed, first_block=0):
+        bits = np.ascontiguousarray(np.asarray(bits, dtype=np.uint8))
+        s = _arr(s)
+        out = np.empty(bits.size * words_per_block(N), dtype=np.uint64)
+        self.lib.csgn_oracle_encrypt_batch(bits.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), bits.size, first_block,
+                                           N, _p(s), s.size, seed, _p(out))
         return out
 
     def bits_text(self, v, N):

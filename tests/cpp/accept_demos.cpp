@@ -189,6 +189,14 @@ static void lazy_products() {
     EXPECT(memcmp(loaded.getValues(), eager.getValues(), eager.getLen() * 8) == 0);
     EXPECT(seckey.decrypt(loaded).getValue() == (pa & pb & pd));
     remove(path.c_str());
+    // batched GPU encryption: 100,000 fresh blocks in one call, decrypting to the XOR of the bits
+    std::vector<unsigned char> many(100000);
+    int xorbits = 0;
+    for (size_t i = 0; i < many.size(); ++i) { many[i] = rand() & 1; xorbits ^= many[i]; }
+    Ciphertext batch = seckey.encryptBatch(many.data(), many.size(), 2024);
+    EXPECT(batch.getBlocks() == many.size() && seckey.decrypt(batch).getValue() == xorbits);
+    Ciphertext batch_sq = batch * A;
+    EXPECT(seckey.decrypt(batch_sq).getValue() == (xorbits & pa));
     // copy-on-write: a copy shares the buffer until one side grows
     Ciphertext x = A, y = x;
     y += B;

@@ -415,6 +415,50 @@ def test_chain_to_1e8_blocks_16GB(engine, oracle):
     del y, x, part
 
 
+@pytest.mark.parametrize("N,D", [(1247, 16), (16383, 64), (191, 5), (63, 4), (65, 1), (2048, 8)])
+def test_encrypt_batch_matches_oracle(engine, oracle, N, D):
+    """csgn_encrypt_batch vs the C restatement (same Philox counters), and vs the scheme itself."""
+    rng = np.random.default_rng(N + D)
+    L = words_per_block(N)
+    ctx = engine.Context(N, D)
+    s = rng.permutation(N)[:D].astype(np.uint64)
+    key = engine.SecretKey(ctx, s)
+    n = 5000 if L <= 64 else 300
+    bits = rng.integers(0, 2, size=n).astype(np.uint8)
+    ct = key.encrypt_batch(bits, seed=0xC0FFEE)
+    got = ct.getValues()
+    assert np.array_equal(got, oracle.encrypt_batch(bits, N, s, 0xC0FFEE))
+    # a batch may be split anywhere (sharding): block i depends on (seed, first_block + i) only
+    tail = key.encrypt_batch(bits[n // 3:], seed=0xC0FFEE, first_block=n // 3)
+    assert np.array_equal(tail.getValues(), got[(n // 3) * L:])
+    assert not np.array_equal(key.encrypt_batch(bits, seed=0xC0FFEF).getValues(), got)
+    # it is an encryption: the sum decrypts to the XOR, every block to its own bit, pad bits are zero
+    assert key.count_satisfied(ct) == int(bits.sum()) and key.decrypt(ct) == int(bits.sum() & 1)
+    blocks = got.reshape(n, L)
+    for i in range(0, n, max(1, n // 40)):
+        assert oracle.decrypt(blocks[i], N, s) == int(bits[i])
+    assert not np.any(blocks[:, -1] & ~pad_mask(N))
+    # products of GPU-made ciphertexts obey the homomorphism
+    other = key.encrypt_batch(bits[:37][::-1].copy(), seed=5)
+    assert key.decrypt(ct * other) == (int(bits.sum() & 1) & int(bits[:37].sum() & 1))
+    # non-secret positions look uniform
+    m = oracle.key_mask(N, s)
+    free_bits = np.unpackbits((blocks & ~m).view(np.uint8)).sum() / (n * (N - D))
+    assert 0.47 < free_bits < 0.53
+
+
+def test_encrypt_batch_decrypts_under_the_reference(engine, ref):
+    N, D = 1247, 16
+    rng = np.random.default_rng(9)
+    s = rng.permutation(N)[:D].astype(np.uint64)
+    bits = rng.integers(0, 2, size=64).astype(np.uint8)
+    got = engine.SecretKey(engine.Context(N, D), s).encrypt_batch(bits, seed=1).getValues()
+    L = words_per_block(N)
+    for i in range(64):
+        assert ref.decrypt(got[i * L:(i + 1) * L], N, D, s) == int(bits[i])
+    assert ref.decrypt(got, N, D, s) == int(bits.sum() & 1)
+
+
 def test_save_load_round_trip(engine, oracle, tmp_path):
     """csgn_buf_save / csgn_buf_load: header + raw words through pinned staging; corruption is detected."""
     rng = np.random.default_rng(77)

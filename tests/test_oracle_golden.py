@@ -98,6 +98,30 @@ def test_raw_block_cases_against_golden(oracle, golden):
         assert oracle.mul_checksum(a, b, L) == oracle.checksum(prod)
 
 
+def test_philox_known_answers_and_batch_encrypt(oracle):
+    """The counter-based generator behind csgn_encrypt_batch: Random123's published philox4x32-10 vectors,
+    and the construction itself (every block decrypts to its bit; splitting a batch changes nothing)."""
+    import ctypes
+    u32x4, u32x2 = ctypes.c_uint32 * 4, ctypes.c_uint32 * 2
+    for ctr, key, want in (((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+                           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+                           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+                            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))):
+        out = u32x4()
+        oracle.lib.csgn_oracle_philox4x32_10(u32x4(*ctr), u32x2(*key), out)
+        assert tuple(out) == want
+    rng = np.random.default_rng(4)
+    for N, D in ((1247, 16), (191, 5), (63, 4), (65, 1)):
+        L = words_per_block(N)
+        s = rng.permutation(N)[:D].astype(np.uint64)
+        bits = rng.integers(0, 2, size=200).astype(np.uint8)
+        enc = oracle.encrypt_batch(bits, N, s, seed=77)
+        assert [oracle.decrypt(enc[i * L:(i + 1) * L], N, s) for i in range(200)] == [int(b) for b in bits]
+        assert oracle.decrypt(enc, N, s) == int(bits.sum() & 1)
+        assert np.array_equal(oracle.encrypt_batch(bits[50:], N, s, seed=77, first_block=50), enc[50 * L:])
+        assert not np.any(enc.reshape(200, L)[:, -1] & ~pad_mask(N))
+
+
 def test_chunk_identities(oracle):
     # SURVEY 8c: (A1||A2)*B = (A1*B)||(A2*B);  Dec(C1||C2) = Dec(C1)^Dec(C2)
     rng = np.random.default_rng(5)
