@@ -118,178 +118,6 @@ mul_outer_kernel(const uint4 *__restrict__ A4, const uint4 *__restrict__ B4, uin
 }
 
 
-// ---------------------------------------------------------------------------------------
-// Strip kernel.  Persistent CTAs, no shared memory, no barrier.
-//
-//   wide rows  (Q >= CTA size): a strip is one column tile (U*blockDim units of b, held in
-//       registers for the strip's whole life) times every G-th row; per row a thread loads
-//       ONE 16-byte fragment of a_i and issues U coalesced streaming stores.
-//   narrow rows (Q < CTA size, e.g. a big ciphertext times a few fresh blocks): the CTA
-//       size is m*Q, a CTA covers m whole rows at a time (thread t sits in row t/Q at unit
-//       t%Q); the m rows are one contiguous run of the output.
-// Both are the same loop: fixed b registers, a ring of PF prefetched a-fragments (in real
-// use the operands are DRAM-cold -- the previous product flushed L2 -- so a fragment is
-// requested PF rows before its turn), streaming stores.  A short work item pays its
-// operand latency in front of every item; here it is paid once per strip.  b is read
-// exactly once per strip; rows are dealt round-robin, so every strip has T1/G rows (+-1)
-// and all CTAs sweep the output together, front to back.
-template <int U, int PF, bool RAGGED, int MINB>
-__global__ void __launch_bounds__(kMulMaxThreads, MINB)
-mul_strip_kernel(const uint4 *__restrict__ A4, const uint4 *__restrict__ B4, uint4 *__restrict__ out4,
-                 const uint32_t L4, const uint32_t T1, const uint64_t Q, const uint32_t n_tiles,
-                 const uint32_t G, const uint32_t m, const uint32_t n_strips) {
-    const uint32_t tpb = blockDim.x;
-    const uint32_t k4 = threadIdx.x % L4;
-    const uint32_t roff = m > 1 ? threadIdx.x / (uint32_t)Q : 0u;   // row within the m-row group
-    const uint32_t qin = m > 1 ? threadIdx.x - roff * (uint32_t)Q : threadIdx.x;
-    const uint32_t row_step = G * m;
-    const uint64_t a_step = (uint64_t)row_step * L4;
-    const uint64_t o_step = (uint64_t)row_step * Q;
-    pdl_enter();
-
-    for (uint32_t s = blockIdx.x; s < n_strips; s += gridDim.x) {
-        const uint32_t ct = s % n_tiles;
-        const uint32_t g = s / n_tiles;
-        const uint64_t q0 = (uint64_t)ct * tpb * U + qin;
-        uint4 b[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint64_t q = q0 + (uint64_t)u * tpb;
-            b[u] = (!RAGGED || q < Q) ? __ldg(B4 + q) : make_uint4(0u, 0u, 0u, 0u);
-        }
-        const uint32_t row = g * m + roff;
-        const uint32_t n = row < T1 ? (T1 - 1u - row) / row_step + 1u : 0u;   // rows of this thread
-        const uint4 *ap = A4 + (uint64_t)row * L4 + k4;
-        uint4 *op = out4 + (uint64_t)row * Q + q0;
-        uint4 ring[PF];
-#pragma unroll
-        for (int j = 0; j < PF; ++j) {
-            ring[j] = (uint32_t)j < n ? __ldg(ap) : make_uint4(0u, 0u, 0u, 0u);
-            ap += a_step;
-        }
-        uint32_t left = n;
-#pragma unroll 1
-        while (left >= (uint32_t)PF) {
-#pragma unroll
-            for (int j = 0; j < PF; ++j) {
-                const uint4 a = ring[j];
-                if (left > (uint32_t)PF) ring[j] = __ldg(ap);   // PF rows ahead
-                ap += a_step;
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (!RAGGED || q0 + (uint64_t)u * tpb < Q) __stcs(op + (uint32_t)u * tpb, and4(a, b[u]));
-                op += o_step;
-                --left;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < PF - 1; ++j) {
-            if ((uint32_t)j < left) {
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (!RAGGED || q0 + (uint64_t)u * tpb < Q) __stcs(op + (uint32_t)u * tpb, and4(ring[j], b[u]));
-                op += o_step;
-            }
-        }
-    }
-}
-
-int strip_occupancy_query(int U, bool ragged, uint32_t tpb);
-
-struct StripPlan {
-    uint32_t tpb = 0, m = 1, n_tiles = 0, G = 0, n_strips = 0, grid = 0;
-    int U = 1;
-    bool ragged = false;
-};
-
-template <int U, bool RAGGED>
-int strip_ctas_per_sm(uint32_t tpb) {
-    int per_sm = 0;
-    constexpr int MINB = U >= 4 ? 2 : 3;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mul_strip_kernel<U, 2, RAGGED, MINB>, (int)tpb, 0) !=
-            cudaSuccess || per_sm < 1)
-        per_sm = 1;
-    return per_sm;
-}
-
-template <int U, bool RAGGED>
-cudaError_t launch_strip(const uint64_t *a, uint64_t T1, const uint64_t *b, uint64_t Q, uint32_t L4, uint64_t *out,
-                         const StripPlan &pl, cudaStream_t stream) {
-    constexpr int MINB = U >= 4 ? 2 : 3;
-    return launch_kernel(mul_strip_kernel<U, 2, RAGGED, MINB>, pl.grid, pl.tpb, 0, stream,
-                         reinterpret_cast<const uint4 *>(a), reinterpret_cast<const uint4 *>(b),
-                         reinterpret_cast<uint4 *>(out), L4, (uint32_t)T1, Q, pl.n_tiles, pl.G, pl.m, pl.n_strips);
-}
-
-int strip_occupancy(int U, bool ragged, uint32_t tpb) {
-    // the occupancy query costs microseconds; remember the answers (single-threaded library)
-    static int cache[3][2][kMulMaxThreads + 1];
-    const int ui = U >= 4 ? 2 : U >= 2 ? 1 : 0;
-    int &slot = cache[ui][ragged ? 1 : 0][tpb <= (uint32_t)kMulMaxThreads ? tpb : 0];
-    if (slot == 0) slot = strip_occupancy_query(U, ragged, tpb);
-    return slot;
-}
-
-int strip_occupancy_query(int U, bool ragged, uint32_t tpb) {
-    if (U >= 4) return ragged ? strip_ctas_per_sm<4, true>(tpb) : strip_ctas_per_sm<4, false>(tpb);
-    if (U >= 2) return ragged ? strip_ctas_per_sm<2, true>(tpb) : strip_ctas_per_sm<2, false>(tpb);
-    return ragged ? strip_ctas_per_sm<1, true>(tpb) : strip_ctas_per_sm<1, false>(tpb);
-}
-
-// Shape of the strips for a T1 x (Q units) product: CTA size, units per thread, row
-// classes.  Wide rows: pick the tile that wastes the fewest lanes (ragged last column
-// tile, partial last warp) and the fewest resident-CTA slots.
-StripPlan plan_strips(uint32_t L4, uint64_t T1, uint64_t Q, uint32_t tpb_cap, int force_u, uint64_t ctas_cap) {
-    const int sms = device_props().sm_count;
-    StripPlan best;
-    if (Q < tpb_cap && Q <= (uint64_t)kMulMaxThreads) {   // narrow rows: m whole rows per CTA step
-        best.m = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(tpb_cap / Q, T1));
-        best.tpb = (uint32_t)(best.m * Q);
-        best.U = 1;
-        best.n_tiles = 1;
-        const uint64_t resident = std::min<uint64_t>((uint64_t)sms * strip_occupancy(1, false, best.tpb), ctas_cap);
-        const uint64_t row_groups = (T1 + best.m - 1) / best.m;
-        best.G = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(row_groups, resident));
-        best.n_strips = best.G;
-        best.grid = best.G;
-        return best;
-    }
-    double best_cost = 1e30;
-    for (int U = 4; U >= 1; U >>= 1) {
-        if (force_u > 0 && U != force_u) continue;
-        for (uint32_t tpb = (tpb_cap / L4) * L4; tpb >= L4 && tpb >= 192; tpb -= L4) {
-            const uint64_t tile = (uint64_t)tpb * U;
-            if (tile > Q && !(U == 1 && tpb <= Q + L4)) continue;
-            const uint64_t n_tiles = (Q + tile - 1) / tile;
-            if (n_tiles >= (1ull << 31)) continue;
-            const bool ragged = n_tiles * tile != Q;
-            const uint64_t resident = std::min<uint64_t>((uint64_t)sms * strip_occupancy(U, ragged, tpb), ctas_cap);
-            uint64_t G = std::max<uint64_t>(1, std::min<uint64_t>(T1, resident / n_tiles));
-            const uint64_t n_strips = n_tiles * G;
-            // rounds of strips over the resident CTAs, and how full the last round is
-            const uint64_t rounds = (n_strips + resident - 1) / resident;
-            const double slot_use = (double)n_strips / (double)(rounds * resident);
-            const double pad = (double)(n_tiles * tile) / (double)Q;
-            const double warp = (double)((tpb + 31) / 32 * 32) / (double)tpb;
-            const double rows = (double)((T1 + G - 1) / G) / ((double)T1 / (double)G);   // row imbalance
-            const double cost = pad * warp * rows / slot_use * (U == 4 ? 1.02 : 1.0);
-            if (cost < best_cost - 1e-9) {
-                best_cost = cost;
-                best.tpb = tpb;
-                best.U = U;
-                best.m = 1;
-                best.n_tiles = (uint32_t)n_tiles;
-                best.G = (uint32_t)G;
-                best.n_strips = (uint32_t)std::min<uint64_t>(n_strips, 0xffffffffull);
-                best.grid = (uint32_t)std::min<uint64_t>(n_strips, resident);
-                best.ragged = ragged;
-            }
-            if (tpb < L4 + 192) break;
-        }
-    }
-    return best;
-}
-
 // Any L (odd included), any alignment: one 64-bit word per thread-iteration.
 __global__ void __launch_bounds__(256)
 mul_outer_generic_kernel(const uint64_t *__restrict__ A, const uint64_t *__restrict__ B,
@@ -378,27 +206,7 @@ cudaError_t launch_mul(const uint64_t *a, uint64_t T1, const uint64_t *b, uint64
         // either way) -- and the swapped form is one long row instead of T1 tiny ones
         return launch_mul(b, 1, a, T1, L, out, stream);
     }
-    const long kernel_choice = env_long("CSGN_MUL_KERNEL", 0);
-    const bool strip_ok = T1 < (1ull << 31) && Q * T1 < (1ull << 62);
-    // Measured on B200 (tools/mul_ab.py, profiles/): the tiled kernel below runs at memset speed
-    // for rows of a few KB and more; rows shorter than one CTA go to the strip kernel, which
-    // covers several rows per CTA step.  With very few rows there is nothing to amortise a strip over.
     const uint32_t tpb_cap = (uint32_t)env_long("CSGN_MUL_TPB", 512);
-    if (strip_ok && (kernel_choice == 2 || (kernel_choice == 0 && T1 >= 4 && Q < tpb_cap))) {
-        const StripPlan pl = plan_strips(L4, T1, Q, tpb_cap, (int)env_long("CSGN_MUL_U", 0),
-                                         (uint64_t)env_long("CSGN_MUL_GRID", 1 << 30));
-        if (pl.tpb) {
-            cudaError_t err;
-            if (pl.U >= 4) err = pl.ragged ? launch_strip<4, true>(a, T1, b, Q, L4, out, pl, stream)
-                                           : launch_strip<4, false>(a, T1, b, Q, L4, out, pl, stream);
-            else if (pl.U >= 2) err = pl.ragged ? launch_strip<2, true>(a, T1, b, Q, L4, out, pl, stream)
-                                                : launch_strip<2, false>(a, T1, b, Q, L4, out, pl, stream);
-            else err = pl.ragged ? launch_strip<1, true>(a, T1, b, Q, L4, out, pl, stream)
-                                 : launch_strip<1, false>(a, T1, b, Q, L4, out, pl, stream);
-            count_launch();
-            return err;
-        }
-    }
     // Tiled kernel.  Many small work items balance best, but an item must keep R >= 3 rows per
     // load of its b tile or the L2 re-reads show.  Units per thread: 1 for rows up to 128 KB
     // (chains: many rows of a few hundred blocks), 2 beyond, 4 for products of a GiB and more

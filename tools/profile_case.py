@@ -4,7 +4,7 @@
 
 Launches, per iteration: multiply (rotating output buffers), decrypt of an older
 product, then one permute and one concat at the end.  No timing is reported here:
-numbers taken under a profiler are never bench values.
+numbers taken under a profiler are never bench values.  Also one batched encryption of T1*T2 bits.
 """
 import os
 import sys
@@ -43,6 +43,7 @@ def main():
         va.mul_into(vb, vo[i % nbuf])
         key.count_satisfied_async(vo[(i + 1) % nbuf], cnt.data_ptr())
     vo[0].permute_into(perm, vo[1])
+    fresh = key.encrypt_batch(np.random.default_rng(9).integers(0, 2, size=T1 * T2).astype(np.uint8), seed=1)
     s = va + vb
     torch.cuda.synchronize()
     print("profile_case", which, "done; launches:", eng.launch_count(), "sum blocks", s.n_blocks)

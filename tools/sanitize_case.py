@@ -2,7 +2,7 @@
 
     compute-sanitizer --tool memcheck python tools/sanitize_case.py
 
-Touches every kernel (tiled, strip and generic multiply; all decrypt forms incl. the bulk-copy ring;
+Touches every kernel (tiled and generic multiply; all decrypt forms incl. the bulk-copy ring;
 concat/append; sliced and gather permute; checksum) at sizes with ragged tails, and checks results
 against the oracle so that a silent corruption cannot pass."""
 import os, sys
@@ -22,7 +22,7 @@ for N in (1247, 16383, 191, 2048):
     for T1, T2 in shapes:
         a, b = random_blocks(rng, T1, N), random_blocks(rng, T2, N)
         ca, cb = eng.Ciphertext.from_host(a, ctx), eng.Ciphertext.from_host(b, ctx)
-        for env in ({}, {"CSGN_MUL_KERNEL": "2"}, {"CSGN_MUL_KERNEL": "1"}, {"CSGN_MUL_GENERIC": "1"}):
+        for env in ({}, {"CSGN_MUL_U": "1"}, {"CSGN_MUL_U": "4", "CSGN_MUL_R": "2"}, {"CSGN_MUL_GENERIC": "1"}):
             os.environ.update(env)
             assert np.array_equal((ca * cb).getValues(), o.mul(a, b, L)); n_checks += 1
             for k in env: del os.environ[k]
