@@ -428,6 +428,8 @@ def test_encrypt_batch_matches_oracle(engine, oracle, N, D):
     ct = key.encrypt_batch(bits, seed=0xC0FFEE)
     got = ct.getValues()
     assert np.array_equal(got, oracle.encrypt_batch(bits, N, s, 0xC0FFEE))
+    with _Env(CSGN_ENC_LANE=1):      # the lane-per-block form (what odd L uses)
+        assert np.array_equal(key.encrypt_batch(bits, seed=0xC0FFEE).getValues(), got)
     # a batch may be split anywhere (sharding): block i depends on (seed, first_block + i) only
     tail = key.encrypt_batch(bits[n // 3:], seed=0xC0FFEE, first_block=n // 3)
     assert np.array_equal(tail.getValues(), got[(n // 3) * L:])
