@@ -103,7 +103,7 @@ def build_cpp_tests(force=False, verbose=False):
         cmd = ["g++", "-O2", "-std=c++11", "-Wall", "-I" + CERTFHE, "-I" + INCLUDE, "-o", out, src,
                "-L" + LIBDIR, "-lcertFHE", "-lcsgn", rpath]
         deps = [src, libcertfhe_path()] + hdrs
-        if name == "diff_vs_reference":
+        if name in ("diff_vs_reference", "host_vs_reference"):
             ref_hdr = os.path.join(REFERENCE, "src", "certFHE.h")
             ref_lib = os.path.join(ROOT, "oracle", "_ref", "libcertfhe_ref.so")
             if not (os.path.exists(ref_hdr) and os.path.exists(ref_lib)):

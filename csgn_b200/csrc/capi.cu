@@ -531,6 +531,7 @@ int csgn_decrypt_count_async(const csgn_buf *c, const csgn_key *key, uint64_t *d
 }
 
 int csgn_decrypt_count(const csgn_buf *c, const csgn_key *key, uint64_t *count) {
+    NEED_INIT();
     if (!count) return fail(CSGN_ERR_INVALID_ARGUMENT, "null output");
     int rc = csgn_decrypt_count_async(c, key, g.d_scratch + 2);
     if (rc != CSGN_OK) return rc;

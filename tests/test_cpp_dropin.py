@@ -67,6 +67,16 @@ def test_cpp_test_programs_are_built():
     assert os.path.exists(os.path.join(BIN, "accept_demos"))
 
 
+def test_host_side_classes_match_the_reference_without_a_gpu():
+    """Context / Plaintext / Permutation / SecretKey host logic, one process with the unmodified reference."""
+    exe = os.path.join(BIN, "host_vs_reference")
+    if not os.path.exists(exe) or not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libcertfhe_ref.so")):
+        pytest.skip("host_vs_reference is built only where /root/reference was present")
+    r = _run(exe)
+    assert r.returncode == 0, r.stdout[-4000:]
+    assert "host-side classes identical to the reference" in r.stdout
+
+
 @pytest.mark.gpu
 def test_acceptance_program():
     r = _run(os.path.join(BIN, "accept_demos"))

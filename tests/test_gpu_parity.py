@@ -86,6 +86,18 @@ def test_mul_inplace_and_chain(engine, oracle):
     assert x.size() == 32 + 16 * 120 * L
 
 
+def test_out_of_memory_is_an_error_not_a_crash(engine, oracle):
+    """A product that cannot fit (2e5 x 2e5 blocks = 6.4 TB) is refused with a status; the engine stays usable."""
+    N, L = 1247, 20
+    ctx = engine.Context(N, 16)
+    big = engine.Ciphertext.empty(200000, ctx)
+    with pytest.raises(engine.CsgnError) as e:
+        big * big
+    assert e.value.code == -6
+    a, b = random_blocks(np.random.default_rng(1), 5, N), random_blocks(np.random.default_rng(2), 4, N)
+    assert np.array_equal((_ct(engine, a, N) * _ct(engine, b, N)).getValues(), oracle.mul(a, b, L))
+
+
 def test_mul_error_behaviour(engine):
     a = _ct(engine, np.zeros(20, dtype=np.uint64), 1247)
     b = _ct(engine, np.zeros(256, dtype=np.uint64), 16383, 64)
