@@ -79,16 +79,20 @@ decrypt_count_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint3
                      uint64_t *scratch, uint64_t *count_out) {
     extern __shared__ uint4 smem[];
     const uint32_t L4 = L4C ? (uint32_t)L4C : L4rt;
-    pdl_enter();
     uint4 *sM2 = smem;                                               // mask, twice over
     uint32_t *sF = reinterpret_cast<uint32_t *>(smem + 2 * L4);      // fail strings
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    if (M4 == nullptr) {   // mask in the parameters
+    if (M4 == nullptr) {
+        // mask in the parameters: staged BEFORE waiting for the previous kernel (parameters are not
+        // produced by it), so that under PDL this prologue overlaps the predecessor's tail
         for (uint32_t i = threadIdx.x; i < 2 * L4; i += blockDim.x) sM2[i] = pmask.u[i < L4 ? i : i - L4];
+        __syncthreads();
+        pdl_enter();
     } else {
+        pdl_enter();
         for (uint32_t i = threadIdx.x; i < 2 * L4; i += blockDim.x) sM2[i] = M4[i < L4 ? i : i - L4];
+        __syncthreads();
     }
-    __syncthreads();
 
     uint32_t *sFw = sF + warp * L4;
     const uint4 *mk = sM2 + (lane % L4);

@@ -33,10 +33,11 @@ def run(label, K=30):
     print("%-40s mul %6.2f us  dec %6.2f us" % (label, mul, dec), flush=True)
 def setenv(**kv):
     for k in list(os.environ):
-        if k.startswith("CSGN_MUL_") or k.startswith("CSGN_DEC_"): del os.environ[k]
+        if k.startswith("CSGN_MUL_") or k.startswith("CSGN_DEC_") or k == "CSGN_PDL": del os.environ[k]
     for k, v in kv.items(): os.environ[k] = str(v)
 setenv(); run("default")
+setenv(CSGN_PDL=0); run("no PDL")
+for var in (1, 2, 6): setenv(CSGN_DEC_VARIANT=var); run("decrypt variant %d" % var)
+for c in (2, 3): setenv(CSGN_DEC_CTAS_PER_SM=c); run("decrypt <= %d CTAs/SM" % c)
 setenv(CSGN_MUL_PF_CTAS_PER_SM=0); run("no L2 warm-up")
-for pf in (2, 4, 16): setenv(CSGN_MUL_PF_CTAS_PER_SM=pf); run("warm-up distance %d CTAs/SM" % pf)
-for u, tpb in ((1, 512), (2, 512), (2, 480), (1, 400)): setenv(CSGN_MUL_U=u, CSGN_MUL_TPB=tpb); run("U=%d tpb<=%d" % (u, tpb))
 for ips in (16, 64): setenv(CSGN_MUL_ITEMS_PER_SM=ips); run("items/SM=%d" % ips)
