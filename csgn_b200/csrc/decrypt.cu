@@ -75,7 +75,7 @@ struct ParamMask {
 template <int L4C, int UNROLL, int MINB>
 __global__ void __launch_bounds__(kDecThreads, MINB)
 decrypt_count_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint32_t L4rt,
-                     const uint4 *__restrict__ M4, const __grid_constant__ ParamMask pmask,
+                     const uint4 *__restrict__ M4, const __grid_constant__ ParamMask pmask, const uint32_t cpw,
                      uint64_t *scratch, uint64_t *count_out) {
     extern __shared__ uint4 smem[];
     const uint32_t L4 = L4C ? (uint32_t)L4C : L4rt;
@@ -101,9 +101,13 @@ decrypt_count_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint3
     const uint64_t n_chunks = (T + 31) >> 5;
     uint64_t my_count = 0;
 
-    // persistent warps sweep the stream together: round k covers chunks [k*W, (k+1)*W)
-    for (uint64_t chunk = (uint64_t)blockIdx.x * kDecWarps + warp; chunk < n_chunks;
-         chunk += (uint64_t)gridDim.x * kDecWarps) {
+    // cpw == 0: persistent warps sweep the stream together, round k covers chunks [k*W, (k+1)*W).
+    // cpw  > 0: many short CTAs, each owning cpw*8 consecutive chunks, placed by the hardware
+    //           scheduler as SMs free up (SMs do not all stream at the same speed).
+    const uint64_t first = cpw ? (uint64_t)blockIdx.x * kDecWarps * cpw + warp : (uint64_t)blockIdx.x * kDecWarps + warp;
+    const uint64_t stride = cpw ? (uint64_t)kDecWarps : (uint64_t)gridDim.x * kDecWarps;
+    const uint64_t last = cpw ? min(n_chunks, ((uint64_t)blockIdx.x + 1) * kDecWarps * cpw) : n_chunks;
+    for (uint64_t chunk = first; chunk < last; chunk += stride) {
         const uint4 *src = V4 + (chunk * 32u * L4 + lane);
         const bool full = (chunk + 1) * 32u <= T;    // warp-uniform: no per-load bounds in the common case
         uint32_t koff = 0;                           // (32*r) % L4
@@ -383,10 +387,15 @@ cudaError_t launch_fast(const uint64_t *v, uint64_t T, uint32_t L4, const uint64
     if (by_param) memcpy(&pm, host_mask, (size_t)L4 * sizeof(uint4));
     const uint64_t n_chunks = (T + 31) / 32;
     const size_t smem = (size_t)2 * L4 * sizeof(uint4) + (size_t)kDecWarps * L4 * sizeof(uint32_t);
-    const uint32_t grid = resident_grid(decrypt_count_kernel<L4C, UNROLL, MINB>, smem, (n_chunks + kDecWarps - 1) / kDecWarps);
+    const uint32_t cpw = (uint32_t)env_long("CSGN_DEC_CPW", 0);
+    uint32_t grid;
+    if (cpw)
+        grid = (uint32_t)std::max<uint64_t>(1, (n_chunks + (uint64_t)kDecWarps * cpw - 1) / ((uint64_t)kDecWarps * cpw));
+    else
+        grid = resident_grid(decrypt_count_kernel<L4C, UNROLL, MINB>, smem, (n_chunks + kDecWarps - 1) / kDecWarps);
     return launch_kernel(decrypt_count_kernel<L4C, UNROLL, MINB>, grid, kDecThreads, smem, stream,
                          reinterpret_cast<const uint4 *>(v), T, L4,
-                         by_param ? nullptr : reinterpret_cast<const uint4 *>(mask), pm, scratch, count_out);
+                         by_param ? nullptr : reinterpret_cast<const uint4 *>(mask), pm, cpw, scratch, count_out);
 }
 
 template <int UPL, int BPI>

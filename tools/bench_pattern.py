@@ -37,7 +37,10 @@ def setenv(**kv):
     for k, v in kv.items(): os.environ[k] = str(v)
 setenv(); run("default")
 setenv(CSGN_PDL=0); run("no PDL")
-for var in (1, 2, 6): setenv(CSGN_DEC_VARIANT=var); run("decrypt variant %d" % var)
+for cpw in (1, 2, 3, 4, 6, 8):
+    setenv(CSGN_DEC_CPW=cpw); run("decrypt short CTAs, %d chunks/warp" % cpw)
+    setenv(CSGN_DEC_CPW=cpw, CSGN_DEC_VARIANT=1); run("  same, 64 regs (4 CTAs/SM)")
+    setenv(CSGN_DEC_CPW=cpw, CSGN_DEC_VARIANT=2); run("  same, half-chunk unroll (5 CTAs/SM)")
 for c in (2, 3): setenv(CSGN_DEC_CTAS_PER_SM=c); run("decrypt <= %d CTAs/SM" % c)
 setenv(CSGN_MUL_PF_CTAS_PER_SM=0); run("no L2 warm-up")
 for ips in (16, 64): setenv(CSGN_MUL_ITEMS_PER_SM=ips); run("items/SM=%d" % ips)
