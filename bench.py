@@ -172,11 +172,11 @@ def cpu_reference_once(N, D, T1, T2, threads, reps, opt="O3"):
 
 
 def cpu_baseline(N, D, T1, T2):
-    kind, m, d = cpu_reference_once(N, D, T1, T2, threads=1, reps=2)
+    kind, m, d = cpu_reference_once(N, D, T1, T2, threads=1, reps=3)
     blocks = T1 * T2
     out = {"value": blocks / (m + d), "unit": UNIT, "cores": 1, "kind": kind,
            "sample": "one %dx%d pair (%d output blocks): public operator* %.3f s + SecretKey::decrypt %.3f s, "
-                     "best of 2, single thread (the reference has no threading), built -O3 -DNDEBUG"
+                     "best of 3, single thread (the reference has no threading), built -O3 -DNDEBUG"
                      % (T1, T2, blocks, m, d),
            "mul_blocks_per_s": blocks / m, "decrypt_blocks_per_s": blocks / d,
            "host_cores_available": os.cpu_count()}

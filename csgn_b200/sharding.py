@@ -83,7 +83,10 @@ class ShardedCiphertext:
     def decrypt(self, key, counts_out=None, device=None):
         """Local fold, then the one-word all-reduce.  Returns the plaintext bit (int)."""
         if counts_out is None:
-            c = torch.tensor([key.count_satisfied(self.local)], dtype=torch.int64, device=device or "cpu")
+            if device is None:
+                nccl = dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl"
+                device = "cuda" if nccl else "cpu"
+            c = torch.tensor([key.count_satisfied(self.local)], dtype=torch.int64, device=device)
         else:
             c = counts_out
         allreduce_counts(c)

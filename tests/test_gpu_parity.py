@@ -502,6 +502,41 @@ def test_save_load_round_trip(engine, oracle, tmp_path):
         engine.Ciphertext.load(tmp_path / "other.bin")
 
 
+def test_sharded_path_world_size_1_nccl(engine, oracle):
+    """The N>1 code path (block-range shard, shard-local multiply chain, NCCL all-reduce of the count)
+    at world size 1 on the one GPU this box has -- same calls bench.py makes under torchrun."""
+    import socket
+    import torch
+    import torch.distributed as dist
+    from csgn_b200 import sharding
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", torch.cuda.current_device()))
+    try:
+        N, L = 1247, 20
+        rng = np.random.default_rng(31)
+        a, b, d = random_blocks(rng, 64, N), random_blocks(rng, 50, N), random_blocks(rng, 9, N)
+        ctx = engine.Context(N, 1)
+        s = random_key(rng, N, 1)
+        key = engine.SecretKey(ctx, s)
+        A = sharding.ShardedCiphertext.scatter_from_host(a, ctx, engine.Ciphertext.from_host)
+        assert (A.first, A.count, A.global_blocks) == (0, 64, 64)
+        P = A.mul_replicated(engine.Ciphertext.from_host(b, ctx)).mul_replicated(engine.Ciphertext.from_host(d, ctx))
+        full = oracle.mul(oracle.mul(a, b, L), d, L)
+        assert np.array_equal(P.local.getValues(), full)
+        assert P.decrypt(key) == oracle.decrypt(full, N, s)
+        counts = torch.zeros(2, dtype=torch.int64, device="cuda")
+        key.count_satisfied_async(P.local, counts.data_ptr())
+        key.count_satisfied_async(A.local, counts.data_ptr() + 8)
+        engine.sync()
+        sharding.allreduce_counts(counts)
+        assert counts.tolist() == [oracle.count_satisfied(full, N, s), oracle.count_satisfied(a, N, s)]
+    finally:
+        dist.destroy_process_group()
+
+
 # ---------------------------------------------------------------------------
 # interop: caller-owned device memory and an external stream
 # ---------------------------------------------------------------------------
