@@ -150,7 +150,13 @@ void set_device_props(const DeviceProps &p) { g_props = p; }
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 uint64_t launches() { return g_launches.load(std::memory_order_relaxed); }
 
+// Tuning knobs (CSGN_MUL_*, CSGN_DEC_*, CSGN_PERM_*, CSGN_PDL ...) are looked up only when
+// CSGN_TUNING is set in the environment at csgn_init: a production launch does not pay a
+// dozen getenv() scans (~4 us per launch), tests and tools/ opt in.
+static bool g_tuning = true;   // until csgn_init has looked
+
 long env_long(const char *name, long dflt) {
+    if (!g_tuning) return dflt;
     const char *s = std::getenv(name);
     if (!s || !*s) return dflt;
     char *end = nullptr;
@@ -168,7 +174,9 @@ using namespace csgn;
 extern "C" {
 
 int csgn_init(int device) {
+    csgn::g_tuning = true;
     if (device < 0) device = (int)env_long("CSGN_DEVICE", env_long("LOCAL_RANK", 0));
+    csgn::g_tuning = std::getenv("CSGN_TUNING") != nullptr;
     if (g.inited) {
         if (g.device == device) return CSGN_OK;
         return fail(CSGN_ERR_INVALID_ARGUMENT, "already bound to device %d (one process per GPU)", g.device);

@@ -16,8 +16,14 @@ from ._native import CsgnError, check  # noqa: F401
 _vp = ctypes.c_void_p
 
 
+_LIB = None
+
+
 def _lib():
-    return _native.load()
+    global _LIB
+    if _LIB is None:
+        _LIB = _native.load()
+    return _LIB
 
 
 def init(device=-1):
@@ -113,7 +119,9 @@ class Ciphertext:
     def from_host_ptr(cls, host_ptr, n_blocks, ctx):
         """Asynchronous upload from caller-managed (ideally pinned) host memory."""
         h = _vp()
-        check(_lib().csgn_buf_upload(_vp(host_ptr), int(n_blocks), ctx.L, ctypes.byref(h)))
+        rc = _LIB.csgn_buf_upload(host_ptr, n_blocks, ctx.L, ctypes.byref(h))
+        if rc:
+            check(rc)
         return cls(h, ctx)
 
     @classmethod
@@ -136,9 +144,9 @@ class Ciphertext:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and _LIB is not None:
             try:
-                _lib().csgn_buf_free(h)
+                _LIB.csgn_buf_free(h)
             except Exception:
                 pass
 
@@ -199,11 +207,15 @@ class Ciphertext:
     # -- the hot path ---------------------------------------------------------
     def __mul__(self, other):
         h = _vp()
-        check(_lib().csgn_mul(self._h, other._h, ctypes.byref(h)))
+        rc = _LIB.csgn_mul(self._h, other._h, ctypes.byref(h))
+        if rc:
+            check(rc)
         return Ciphertext(h, self.ctx)
 
     def mul_into(self, other, out):
-        check(_lib().csgn_mul_into(self._h, other._h, out._h))
+        rc = _LIB.csgn_mul_into(self._h, other._h, out._h)
+        if rc:
+            check(rc)
         return out
 
     def __imul__(self, other):
@@ -275,7 +287,9 @@ class SecretKey:
         return int(bit.value), int(cnt.value)
 
     def count_satisfied_async(self, ct, device_count_ptr):
-        check(_lib().csgn_decrypt_count_async(ct._h, self._h, _vp(device_count_ptr)))
+        rc = _LIB.csgn_decrypt_count_async(ct._h, self._h, device_count_ptr)
+        if rc:
+            check(rc)
 
     def size(self):
         return 16 + 8 * int(self.s.size)

@@ -5,6 +5,8 @@ import sys
 import numpy as np
 import pytest
 
+os.environ.setdefault("CSGN_TUNING", "1")   # the launchers honour CSGN_* knobs only when this is set at csgn_init
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

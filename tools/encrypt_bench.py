@@ -1,6 +1,7 @@
 import os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("CSGN_TUNING", "1")
 from csgn_b200 import engine as eng
 torch.cuda.set_device(0); eng.init(0)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); eng.set_stream(stream.cuda_stream)

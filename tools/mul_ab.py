@@ -2,6 +2,7 @@
 import os, sys, itertools
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("CSGN_TUNING", "1")
 from csgn_b200 import engine as eng
 
 torch.cuda.set_device(0); dev = torch.device("cuda", 0)

@@ -8,6 +8,7 @@ against the oracle so that a silent corruption cannot pass."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("CSGN_TUNING", "1")
 from csgn_b200 import engine as eng
 from oracle.pyoracle import Oracle, random_blocks, random_key, words_per_block
 

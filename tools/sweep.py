@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("CSGN_TUNING", "1")
 from csgn_b200 import engine as eng  # noqa: E402
 
 
