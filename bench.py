@@ -62,6 +62,12 @@ def parse_args():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--pairs", type=int, default=16, help="independent ciphertext pairs per step")
     ap.add_argument("--chain-d", type=int, default=125, help="cfg4: blocks of the third operand (125 -> 20 GB/GPU)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: decrypt's cross-GPU sum inside the fold kernel over NVLink mailboxes (peer) "
+                         "or as a separate NCCL all-reduce (nccl, the baseline it replaces)")
+    ap.add_argument("--collect", default="lagged", choices=["lagged", "same-step"],
+                    help="peer exchange: the launch closing step k collects step k-1's sums (never waits for a slower "
+                         "rank; the last step's sums are collected before the timed region ends) or its own step's")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -228,6 +234,30 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
+
+def connect_exchange(args, world, dev):
+    """(comm, description).  comm is None at N=1 and for --exchange nccl.  Every rank must take the same
+    path, so a rank that cannot map its peers' mailboxes makes all of them fall back to NCCL -- loudly."""
+    if world == 1:
+        return None, "single GPU: no exchange"
+    if args.exchange == "nccl":
+        return None, "separate NCCL all-reduce of the counts"
+    import torch
+    import torch.distributed as dist
+    from csgn_b200 import sharding
+    comm, err = None, ""
+    try:
+        comm = sharding.connect_peers()
+    except Exception as e:  # noqa: BLE001
+        err = str(e)
+    ok = torch.tensor([1 if comm is not None else 0], dtype=torch.int64, device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) == 1:
+        return comm, ("fused into the decrypt kernel: its last CTA stores the count into every rank's mailbox over "
+                      "NVLink and the launch closing the batch collects the sums (csrc/peer.cuh); no NCCL call in the step")
+    sys.stderr.write("bench: peer mailboxes unavailable (%s); using the NCCL all-reduce\n" % err)
+    return None, "separate NCCL all-reduce (peer mailboxes unavailable: %s)" % (err or "on another rank")
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -253,6 +283,7 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     ctx = eng.Context(N, D)
+    comm, exchange = connect_exchange(args, world, dev)
 
     # --- synthetic inputs: pinned host copies (e2e) and device copies (value) ---------
     # Global left operand of pair p has T1*world blocks; this rank owns csgn_shard_range.
@@ -299,7 +330,9 @@ def run_ours(args):
                 pending[i].wait()
                 pending[i] = None
 
-    def step_device(evs=None):
+    lagged = comm is not None and args.collect == "lagged"
+
+    def step_device(evs=None, final=True):
         slot = step_no[0] & 1
         step_no[0] += 1
         if pending[slot] is not None:        # the all-reduce issued two steps ago: long finished
@@ -311,11 +344,23 @@ def run_ours(args):
             va[p].mul_into(vb[p], vo[p])
         if evs:
             evs[1].record()
-        for p in range(P):
-            key.count_satisfied_async(vo[p], count_ptrs2[slot][p])
+        if comm is not None:
+            for p in range(P - 1):
+                comm.push(key, vo[p])                # fold; the count stays in the rank's local ring
+            # the launch that closes the batch publishes the P counts to every rank and collects P sums:
+            # this step's, or (lagged) the previous step's, which have long arrived
+            if lagged and step_no[0] > 1:
+                comm.push(key, vo[P - 1], P, count_ptrs2[slot ^ 1][0], lag=P)
+                if final:                            # nothing follows: fetch this step's sums too
+                    comm.collect(P, count_ptrs2[slot][0])
+            else:
+                comm.push(key, vo[P - 1], P, count_ptrs2[slot][0])
+        else:
+            for p in range(P):
+                key.count_satisfied_async(vo[p], count_ptrs2[slot][p])
         if evs:
             evs[2].record()
-        if world > 1:
+        if world > 1 and comm is None:
             pending[slot] = dist.all_reduce(counts2[slot], async_op=True)
         if evs:
             evs[3].record()
@@ -327,8 +372,9 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
-        step_device()
+    W_ = max(3, args.warmup)
+    for i in range(W_):
+        step_device(final=(i == W_ - 1))
     barrier()
 
     # sanity (outside the timed region, no oracle): satisfied-block counts are multiplicative
@@ -349,7 +395,7 @@ def run_ours(args):
     sampler.start()
     t_wall = time.perf_counter()
     for k in range(K):
-        step_device(evs[k])
+        step_device(evs[k], final=(k == K - 1))
     barrier()
     t_wall = time.perf_counter() - t_wall
     clocks = sampler.stop()
@@ -385,9 +431,12 @@ def run_ours(args):
                 ha = eng.Ciphertext.from_host_ptr(a_ptrs[p], T1, ctx)      # H2D, async (pinned), on the copy stream
                 hb = eng.Ciphertext.from_host_ptr(b_ptrs[p], T2, ctx)
                 prod = ha * hb                                             # csgn_mul (allocates)
-                key.count_satisfied_async(prod, count_ptrs[p])
+                if comm is not None:
+                    comm.push(key, prod, P if p == P - 1 else 0, count_ptrs[0])
+                else:
+                    key.count_satisfied_async(prod, count_ptrs[p])
                 del ha, hb, prod                                           # stream-ordered frees
-            if world > 1:
+            if world > 1 and comm is None:
                 dist.all_reduce(counts)
             host_counts.copy_(counts, non_blocking=True)                   # D2H of this step's result
             stream.synchronize()                                           # ... which the host now holds
@@ -411,8 +460,9 @@ def run_ours(args):
         e2e = {"value": blocks_per_step * K / (float(e2e_ms.item()) * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(P * (T1 + T2) * L * 8), "d2h_bytes_per_step": int(P * 8),
                "ms_per_step": float(e2e_ms.item()) / K,
-               "path": "csgn_buf_upload x2 (pinned host) -> csgn_mul -> csgn_decrypt_count_async; one D2H of the "
-                       "P counts per step, checked on the host every step; per GPU"}
+               "path": "csgn_buf_upload x2 (pinned host) -> csgn_mul -> %s; one D2H of the "
+                       "P counts per step, checked on the host every step; per GPU"
+                       % ("csgn_decrypt_sharded_async" if comm is not None else "csgn_decrypt_count_async")}
 
     if rank == 0:
         line = {
@@ -423,9 +473,9 @@ def run_ours(args):
                        "blocks_per_step": blocks_per_step, "bytes_per_block": bytes_per_block,
                        "l2": "no flush needed: a step writes then reads %d x %.0f MB of products (>> 126 MB L2), "
                              "each product is read %d kernels after it was written" % (P, T1 * T2 * L * 8 / 1e6, P),
-                       "sharding": "left operand by block range, right operand replicated, one %d-word NCCL "
-                                   "all-reduce per step, overlapped with the next step's kernels" % P
-                                   if world > 1 else "single GPU",
+                       "sharding": "left operand by block range, right operand replicated; per step one %d-word "
+                                   "exchange of the counts" % P if world > 1 else "single GPU",
+                       "exchange": exchange + ((" [collect: %s]" % args.collect) if comm is not None else ""),
                        "inputs": "numpy default_rng raw blocks, pad bits zero, key bits set in 20-60 blocks per operand; "
                                  "key = default_rng(7).permutation(N)[:D]"},
             "roofline": {"bound": "hbm", "kernel": "mul_outer_kernel", "achieved": mul_gbs, "peak": peak,
@@ -479,6 +529,7 @@ def run_chain(args):
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     ctx = eng.Context(N, D)
+    comm, exchange = connect_exchange(args, world, dev)
     key_pos = np.random.default_rng(7).permutation(N)[:D].astype(np.uint64)
     key = eng.SecretKey(ctx, key_pos)
     key_mask = np.zeros(L, dtype=np.uint64)
@@ -511,10 +562,13 @@ def run_chain(args):
         vx.mul_into(vd, vy)
         if evs:
             evs[2].record()
-        key.count_satisfied_async(vy, counts.data_ptr())
+        if comm is not None:
+            comm.push(key, vy, 1, counts.data_ptr())     # fold, push and collect in the one kernel
+        else:
+            key.count_satisfied_async(vy, counts.data_ptr())
         if evs:
             evs[3].record()
-        if world > 1:
+        if world > 1 and comm is None:
             dist.all_reduce(counts)
         if evs:
             evs[4].record()
@@ -565,8 +619,11 @@ def run_chain(args):
         hd = eng.Ciphertext.from_host_ptr(pinned["d"].data_ptr(), Td, ctx)
         ha.mul_into(hb, vx)
         vx.mul_into(hd, vy)          # the 20 GB product is written in place: no room for two of them
-        key.count_satisfied_async(vy, counts.data_ptr())
-        if world > 1:
+        if comm is not None:
+            comm.push(key, vy, 1, counts.data_ptr())
+        else:
+            key.count_satisfied_async(vy, counts.data_ptr())
+        if world > 1 and comm is None:
             dist.all_reduce(counts)
         host_counts.copy_(counts, non_blocking=True)
         stream.synchronize()
@@ -598,7 +655,8 @@ def run_chain(args):
                 "config": {"workload": "cfg4: " + desc, "chain_d": Td, "blocks_per_gpu": out_blocks,
                            "blocks_total": out_blocks * world, "product_bytes_per_gpu": out_blocks * 8 * L,
                            "l2": "no flush needed: the product (%.1f GB per GPU) is far larger than L2" % (out_blocks * 8 * L / 1e9),
-                           "sharding": "left operand by block range, b and d replicated, one-word NCCL all-reduce per decrypt"},
+                           "sharding": "left operand by block range, b and d replicated, one-word exchange per decrypt",
+                           "exchange": exchange},
                 "roofline": {"bound": "hbm", "kernel": "mul_outer_kernel", "achieved": mul2_gbs, "peak": peak, "unit": "GB/s",
                              "frac": mul2_gbs / peak, "traffic": None, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": out_blocks * 8 * L, "avg_launch_us": mul2_ms * 1e3 / K},

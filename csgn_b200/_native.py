@@ -56,6 +56,16 @@ SIGNATURES = {
     "csgn_buf_save": (ctypes.c_int, [_vp, _u64, _u64, ctypes.c_char_p]),
     "csgn_buf_load": (ctypes.c_int, [ctypes.c_char_p, _u64p, _u64p, _vpp]),
     "csgn_shard_range": (ctypes.c_int, [_u64, ctypes.c_int, ctypes.c_int, _u64p, _u64p]),
+    "csgn_comm_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vpp, _vp]),
+    "csgn_comm_connect": (ctypes.c_int, [_vp, _vp]),
+    "csgn_comm_connect_ptrs": (ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
+    "csgn_comm_mailbox": (_vp, [_vp, ctypes.POINTER(ctypes.c_size_t)]),
+    "csgn_comm_free": (ctypes.c_int, [_vp]),
+    "csgn_comm_pending": (ctypes.c_uint32, [_vp]),
+    "csgn_decrypt_sharded_async": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp]),
+    "csgn_comm_collect_async": (ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, _vp]),
+    "csgn_decrypt_sharded": (ctypes.c_int, [_vp, _vp, _vp, ctypes.POINTER(ctypes.c_uint8), _u64p]),
+    "csgn_comm_slot_tag": (None, [_u64, ctypes.POINTER(ctypes.c_uint32), _u64p]),
 }
 
 _lib = None

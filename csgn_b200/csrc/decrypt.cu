@@ -22,6 +22,7 @@
 // finish publishes the total and re-arms the scratch words, so a decrypt is ONE launch.
 #include "kernels.cuh"
 #include "launch.cuh"
+#include "peer.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -40,9 +41,14 @@ __device__ __forceinline__ bool unit_fails(const uint4 v, const uint4 m) {
     return (((~v.x) & m.x) | ((~v.y) & m.y) | ((~v.z) & m.z) | ((~v.w) & m.w)) != 0u;
 }
 
-// Publish the CTA's count; the last CTA writes the grand total and resets scratch.
-__device__ __forceinline__ void fold_and_publish(uint64_t lane_count, uint64_t *scratch, uint64_t *count_out) {
+// Publish the CTA's count; the last CTA writes the grand total and resets scratch.  With a
+// PeerPush (sharded decrypt) the total also goes into the rank's local ring, and if this launch
+// closes a batch its last CTA publishes the batch to every rank's mailbox over NVLink and
+// collects the requested totals (peer.cuh).
+__device__ __forceinline__ void fold_and_publish(uint64_t lane_count, uint64_t *scratch, uint64_t *count_out,
+                                                 const PeerPush &pp) {
     __shared__ uint64_t s_warp[32];
+    __shared__ int s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) lane_count += __shfl_xor_sync(0xffffffffu, lane_count, off);
@@ -55,11 +61,19 @@ __device__ __forceinline__ void fold_and_publish(uint64_t lane_count, uint64_t *
         if (cta) atomicAdd(reinterpret_cast<unsigned long long *>(scratch), (unsigned long long)cta);
         __threadfence();
         const unsigned long long ticket = atomicAdd(reinterpret_cast<unsigned long long *>(scratch + 1), 1ull);
-        if (ticket == (unsigned long long)gridDim.x - 1) {
+        const bool last = ticket == (unsigned long long)gridDim.x - 1;
+        if (last) {
             __threadfence();
-            *count_out = atomicExch(reinterpret_cast<unsigned long long *>(scratch), 0ull);
+            const uint64_t total = atomicExch(reinterpret_cast<unsigned long long *>(scratch), 0ull);
             scratch[1] = 0;
+            if (count_out) *count_out = total;
+            if (pp.world) pp.local_ring[peer_slot(pp.seq)] = total;
         }
+        s_last = last ? 1 : 0;
+    }
+    if (pp.world && (pp.publish_n | pp.collect_n)) {      // grid-uniform: the barrier is not divergent
+        __syncthreads();
+        if (s_last) peer_publish_collect(pp);
     }
 }
 
@@ -76,7 +90,7 @@ template <int L4C, int UNROLL, int MINB>
 __global__ void __launch_bounds__(kDecThreads, MINB)
 decrypt_count_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint32_t L4rt,
                      const uint4 *__restrict__ M4, const __grid_constant__ ParamMask pmask, const uint32_t cpw,
-                     uint64_t *scratch, uint64_t *count_out) {
+                     uint64_t *scratch, uint64_t *count_out, const __grid_constant__ PeerPush pp) {
     extern __shared__ uint4 smem[];
     const uint32_t L4 = L4C ? (uint32_t)L4C : L4rt;
     uint4 *sM2 = smem;                                               // mask, twice over
@@ -150,7 +164,7 @@ decrypt_count_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint3
         my_count += (blk < T && any == 0u) ? 1u : 0u;
         __syncwarp();                        // before the next chunk overwrites sFw
     }
-    fold_and_publish(my_count, scratch, count_out);
+    fold_and_publish(my_count, scratch, count_out, pp);
 }
 
 
@@ -199,7 +213,7 @@ template <int L4C, int STAGES>
 __global__ void __launch_bounds__(kRingThreads, 1)
 decrypt_count_ring_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint32_t L4rt,
                           const uint4 *__restrict__ M4, const __grid_constant__ ParamMask pmask,
-                          uint64_t *scratch, uint64_t *count_out) {
+                          uint64_t *scratch, uint64_t *count_out, const __grid_constant__ PeerPush pp) {
     extern __shared__ __align__(128) unsigned char ring_raw[];
     const uint32_t L4 = L4C ? (uint32_t)L4C : L4rt;
     const uint32_t chunk_units = 32u * L4;                       // uint4 per 32-block chunk
@@ -280,12 +294,12 @@ decrypt_count_ring_kernel(const uint4 *__restrict__ V4, const uint64_t T, const 
             if (++slot == STAGES) { slot = 0; phase ^= 1u; }
         }
     }
-    fold_and_publish(my_count, scratch, count_out);
+    fold_and_publish(my_count, scratch, count_out, pp);
 }
 
 template <int L4C, int STAGES>
 cudaError_t launch_ring(const uint64_t *v, uint64_t T, uint32_t L4, const uint64_t *mask, const uint64_t *host_mask,
-                        uint64_t *scratch, uint64_t *count_out, cudaStream_t stream) {
+                        uint64_t *scratch, uint64_t *count_out, const PeerPush &pp, cudaStream_t stream) {
     ParamMask pm;
     memset(&pm, 0, sizeof pm);
     const bool by_param = host_mask && L4 <= (uint32_t)kParamMaskUnits;
@@ -304,7 +318,7 @@ cudaError_t launch_ring(const uint64_t *v, uint64_t T, uint32_t L4, const uint64
     const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_stage_units, device_props().sm_count));
     return launch_kernel(decrypt_count_ring_kernel<L4C, STAGES>, grid, kRingThreads, smem, stream,
                          reinterpret_cast<const uint4 *>(v), T, L4,
-                         by_param ? nullptr : reinterpret_cast<const uint4 *>(mask), pm, scratch, count_out);
+                         by_param ? nullptr : reinterpret_cast<const uint4 *>(mask), pm, scratch, count_out, pp);
 }
 
 // L4 a multiple of 32 (e.g. N=16383: L4=128): a block is UPL = L4/32 coalesced warp
@@ -313,7 +327,7 @@ cudaError_t launch_ring(const uint64_t *v, uint64_t T, uint32_t L4, const uint64
 template <int UPL, int BPI>
 __global__ void __launch_bounds__(kDecThreads, 4)
 decrypt_count_wide_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint4 *__restrict__ M4,
-                          uint64_t *scratch, uint64_t *count_out) {
+                          uint64_t *scratch, uint64_t *count_out, const __grid_constant__ PeerPush pp) {
     const uint32_t lane = threadIdx.x & 31u;
     pdl_enter();
     uint4 m[UPL];
@@ -341,13 +355,14 @@ decrypt_count_wide_kernel(const uint4 *__restrict__ V4, const uint64_t T, const 
             if (lane == 0 && !bad && grp * BPI + b < T) ++my_count;
         }
     }
-    fold_and_publish(my_count, scratch, count_out);
+    fold_and_publish(my_count, scratch, count_out, pp);
 }
 
 // Any L (odd, or too long for the fail string), any alignment: one warp per block.
 __global__ void __launch_bounds__(kDecThreads)
 decrypt_count_generic_kernel(const uint64_t *__restrict__ V, const uint64_t T, const uint32_t L,
-                             const uint64_t *__restrict__ M, uint64_t *scratch, uint64_t *count_out) {
+                             const uint64_t *__restrict__ M, uint64_t *scratch, uint64_t *count_out,
+                             const __grid_constant__ PeerPush pp) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -363,7 +378,7 @@ decrypt_count_generic_kernel(const uint64_t *__restrict__ V, const uint64_t T, c
         const bool bad = __any_sync(0xffffffffu, f);
         if (lane == 0 && !bad) ++my_count;
     }
-    fold_and_publish(my_count, scratch, count_out);
+    fold_and_publish(my_count, scratch, count_out, pp);
 }
 
 // Persistent grid: exactly the CTAs that are resident at once (a partial second wave
@@ -380,7 +395,7 @@ uint32_t resident_grid(Kernel kernel, size_t smem, uint64_t work_ctas) {
 
 template <int L4C, int UNROLL, int MINB>
 cudaError_t launch_fast(const uint64_t *v, uint64_t T, uint32_t L4, const uint64_t *mask, const uint64_t *host_mask,
-                        uint64_t *scratch, uint64_t *count_out, cudaStream_t stream) {
+                        uint64_t *scratch, uint64_t *count_out, const PeerPush &pp, cudaStream_t stream) {
     ParamMask pm;
     memset(&pm, 0, sizeof pm);
     const bool by_param = host_mask && L4 <= (uint32_t)kParamMaskUnits && !env_long("CSGN_DEC_GLOBAL_MASK", 0);
@@ -395,24 +410,52 @@ cudaError_t launch_fast(const uint64_t *v, uint64_t T, uint32_t L4, const uint64
         grid = resident_grid(decrypt_count_kernel<L4C, UNROLL, MINB>, smem, (n_chunks + kDecWarps - 1) / kDecWarps);
     return launch_kernel(decrypt_count_kernel<L4C, UNROLL, MINB>, grid, kDecThreads, smem, stream,
                          reinterpret_cast<const uint4 *>(v), T, L4,
-                         by_param ? nullptr : reinterpret_cast<const uint4 *>(mask), pm, cpw, scratch, count_out);
+                         by_param ? nullptr : reinterpret_cast<const uint4 *>(mask), pm, cpw, scratch, count_out, pp);
 }
 
 template <int UPL, int BPI>
 cudaError_t launch_wide(const uint64_t *v, uint64_t T, const uint64_t *mask, uint64_t *scratch,
-                        uint64_t *count_out, cudaStream_t stream) {
+                        uint64_t *count_out, const PeerPush &pp, cudaStream_t stream) {
     const uint64_t n_groups = (T + BPI - 1) / BPI;
     const uint32_t grid = resident_grid(decrypt_count_wide_kernel<UPL, BPI>, 0, (n_groups + kDecWarps - 1) / kDecWarps);
     return launch_kernel(decrypt_count_wide_kernel<UPL, BPI>, grid, kDecThreads, 0, stream,
-                         reinterpret_cast<const uint4 *>(v), T, reinterpret_cast<const uint4 *>(mask), scratch, count_out);
+                         reinterpret_cast<const uint4 *>(v), T, reinterpret_cast<const uint4 *>(mask), scratch, count_out, pp);
+}
+
+
+// Push and/or publish + collect without a fold (an empty local shard still owes its peers a
+// word; a collect may also be issued on its own).  One CTA.
+__global__ void __launch_bounds__(kDecThreads)
+peer_exchange_kernel(const __grid_constant__ PeerPush pp, const int do_push, const uint64_t value, uint64_t *count_out) {
+    pdl_enter();
+    if (do_push && threadIdx.x == 0) {
+        if (count_out) *count_out = value;
+        pp.local_ring[peer_slot(pp.seq)] = value;
+    }
+    if (pp.publish_n | pp.collect_n) {
+        __syncthreads();
+        peer_publish_collect(pp);
+    }
 }
 
 }  // namespace
 
+cudaError_t launch_peer_exchange(const PeerPush &pp, bool do_push, uint64_t value, uint64_t *count_out,
+                                 cudaStream_t stream) {
+    count_launch();
+    return launch_kernel(peer_exchange_kernel, 1, kDecThreads, 0, stream, pp, do_push ? 1 : 0, value, count_out);
+}
+
 cudaError_t launch_decrypt_count(const uint64_t *v, uint64_t T, uint32_t L, const uint64_t *mask,
                                  const uint64_t *host_mask, uint64_t *scratch, uint64_t *count_out,
-                                 cudaStream_t stream) {
-    if (T == 0 || L == 0) return cudaMemsetAsync(count_out, 0, sizeof(uint64_t), stream);
+                                 cudaStream_t stream, const PeerPush *peer) {
+    PeerPush pp;
+    if (peer) pp = *peer;
+    else memset(&pp, 0, sizeof pp);
+    if (T == 0 || L == 0) {
+        if (pp.world) return launch_peer_exchange(pp, true, 0, count_out, stream);
+        return count_out ? cudaMemsetAsync(count_out, 0, sizeof(uint64_t), stream) : cudaSuccess;
+    }
     const DeviceProps &dp = device_props();
     const uint64_t ctas_per_sm = (uint64_t)env_long("CSGN_DEC_CTAS_PER_SM", 8);
     const long wide = env_long("CSGN_DEC_WIDE", 1);
@@ -422,22 +465,22 @@ cudaError_t launch_decrypt_count(const uint64_t *v, uint64_t T, uint32_t L, cons
     if ((L & 1u) || !aligned || L4 > kDecMaxL4 || env_long("CSGN_DEC_GENERIC", 0)) {
         const uint64_t want = (T + kDecWarps - 1) / kDecWarps;
         const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, dp.sm_count * ctas_per_sm));
-        err = launch_kernel(decrypt_count_generic_kernel, grid, kDecThreads, 0, stream, v, T, L, mask, scratch, count_out);
+        err = launch_kernel(decrypt_count_generic_kernel, grid, kDecThreads, 0, stream, v, T, L, mask, scratch, count_out, pp);
     } else {
         const long variant = env_long("CSGN_DEC_VARIANT", 0);
-        if (L4 == 10 && variant == 5) err = launch_ring<10, 4>(v, T, L4, mask, host_mask, scratch, count_out, stream);
-        else if (L4 == 10 && variant == 6) err = launch_ring<10, 3>(v, T, L4, mask, host_mask, scratch, count_out, stream);
-        else if (L4 == 10 && variant == 7) err = launch_ring<10, 5>(v, T, L4, mask, host_mask, scratch, count_out, stream);
-        else if (L4 == 10 && variant == 1) err = launch_fast<10, 10, 4>(v, T, L4, mask, host_mask, scratch, count_out, stream);
-        else if (L4 == 10 && variant == 2) err = launch_fast<10, 5, 5>(v, T, L4, mask, host_mask, scratch, count_out, stream);
-        else if (L4 == 10 && variant == 3) err = launch_fast<10, 5, 6>(v, T, L4, mask, host_mask, scratch, count_out, stream);
-        else if (L4 == 10 && variant == 4) err = launch_fast<10, 2, 8>(v, T, L4, mask, host_mask, scratch, count_out, stream);
-        else if (L4 == 10) err = launch_fast<10, 10, 3>(v, T, L4, mask, host_mask, scratch, count_out, stream);     // N=1247
-        else if (L4 == 128 && wide) err = launch_wide<4, 2>(v, T, mask, scratch, count_out, stream);  // N=16383
-        else if (L4 == 64 && wide) err = launch_wide<2, 4>(v, T, mask, scratch, count_out, stream);
-        else if (L4 == 32 && wide) err = launch_wide<1, 8>(v, T, mask, scratch, count_out, stream);
-        else if (L4 == 128) err = launch_fast<128, 8, 3>(v, T, L4, mask, host_mask, scratch, count_out, stream);
-        else err = launch_fast<0, 4, 4>(v, T, L4, mask, host_mask, scratch, count_out, stream);
+        if (L4 == 10 && variant == 5) err = launch_ring<10, 4>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
+        else if (L4 == 10 && variant == 6) err = launch_ring<10, 3>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
+        else if (L4 == 10 && variant == 7) err = launch_ring<10, 5>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
+        else if (L4 == 10 && variant == 1) err = launch_fast<10, 10, 4>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
+        else if (L4 == 10 && variant == 2) err = launch_fast<10, 5, 5>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
+        else if (L4 == 10 && variant == 3) err = launch_fast<10, 5, 6>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
+        else if (L4 == 10 && variant == 4) err = launch_fast<10, 2, 8>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
+        else if (L4 == 10) err = launch_fast<10, 10, 3>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);     // N=1247
+        else if (L4 == 128 && wide) err = launch_wide<4, 2>(v, T, mask, scratch, count_out, pp, stream);  // N=16383
+        else if (L4 == 64 && wide) err = launch_wide<2, 4>(v, T, mask, scratch, count_out, pp, stream);
+        else if (L4 == 32 && wide) err = launch_wide<1, 8>(v, T, mask, scratch, count_out, pp, stream);
+        else if (L4 == 128) err = launch_fast<128, 8, 3>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
+        else err = launch_fast<0, 4, 4>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
     }
     count_launch();
     return err;

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "peer.cuh"
+
 namespace csgn {
 
 struct DeviceProps {
@@ -38,6 +40,11 @@ cudaError_t launch_concat(const uint64_t *a, uint64_t n_words_a, const uint64_t 
 // kernel parameters instead of being fetched from global memory.
 cudaError_t launch_decrypt_count(const uint64_t *v, uint64_t T, uint32_t L, const uint64_t *mask,
                                  const uint64_t *host_mask, uint64_t *scratch, uint64_t *count_out,
+                                 cudaStream_t stream, const PeerPush *peer = nullptr);
+// `peer` (optional, sharded decrypt): the kernel's last CTA also pushes the count into every
+// rank's mailbox and, when peer->collect_n > 0, collects the batch's totals (peer.cuh);
+// count_out may then be null.  launch_peer_exchange does the push/collect without a fold.
+cudaError_t launch_peer_exchange(const PeerPush &pp, bool do_push, uint64_t value, uint64_t *count_out,
                                  cudaStream_t stream);
 
 // K4  out_bit[i] = in_bit[perm[i]] for every block     (reference src/Ciphertext.cpp:24-69)

@@ -295,6 +295,67 @@ class SecretKey:
         return 16 + 8 * int(self.s.size)
 
 
+IPC_HANDLE_BYTES = 64
+COMM_MAX_PENDING = 64
+
+
+def comm_slot_tag(seq):
+    """(slot, tag) of push number `seq` in a mailbox -- csgn_comm_slot_tag."""
+    slot, tag = ctypes.c_uint32(), ctypes.c_uint64()
+    _lib().csgn_comm_slot_tag(int(seq), ctypes.byref(slot), ctypes.byref(tag))
+    return slot.value, tag.value
+
+
+class PeerComm:
+    """csgn_comm: per-rank mailboxes mapped over NVLink, so that a sharded decrypt's fold
+    kernel also does the cross-GPU exchange (csrc/peer.cuh).  `allgather_bytes(b)` must return
+    the list of every rank's 64-byte handle in rank order (see sharding.connect_peers for the
+    torch.distributed version); it is not needed for world == 1."""
+
+    def __init__(self, rank, world, allgather_bytes=None):
+        self.rank, self.world = int(rank), int(world)
+        self._h = _vp()
+        handle = (ctypes.c_ubyte * IPC_HANDLE_BYTES)()
+        check(_lib().csgn_comm_create(self.rank, self.world, ctypes.byref(self._h), handle))
+        if self.world > 1:
+            if allgather_bytes is None:
+                raise ValueError("world > 1 needs an allgather_bytes callable to exchange the mailbox handles")
+            handles = allgather_bytes(bytes(handle))
+            if len(handles) != self.world or any(len(h) != IPC_HANDLE_BYTES for h in handles):
+                raise ValueError("allgather_bytes must return %d handles of %d bytes" % (self.world, IPC_HANDLE_BYTES))
+            blob = (ctypes.c_ubyte * (IPC_HANDLE_BYTES * self.world)).from_buffer_copy(b"".join(handles))
+            check(_lib().csgn_comm_connect(self._h, blob))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _LIB is not None:
+            try:
+                _LIB.csgn_comm_free(h)
+            except Exception:
+                pass
+
+    @property
+    def pending(self):
+        return int(_lib().csgn_comm_pending(self._h))
+
+    def push(self, key, ct, collect_n=0, device_totals_ptr=0, device_local_ptr=0, lag=0):
+        """Enqueue the fold of this rank's shard (push number seq).  collect_n > 0 closes a batch in the
+        same kernel: publish everything unpublished, collect the collect_n pushes ending `lag` pushes ago."""
+        rc = _LIB.csgn_decrypt_sharded_async(ct._h, key._h, self._h, collect_n, lag, device_totals_ptr or None,
+                                             device_local_ptr or None)
+        if rc:
+            check(rc)
+
+    def collect(self, n, device_totals_ptr, lag=0):
+        check(_lib().csgn_comm_collect_async(self._h, int(n), int(lag), device_totals_ptr))
+
+    def decrypt(self, key, ct):
+        """Blocking sharded SecretKey::decrypt: (bit, global satisfied-block count), the same on every rank."""
+        bit, tot = ctypes.c_uint8(), ctypes.c_uint64()
+        check(_lib().csgn_decrypt_sharded(ct._h, key._h, self._h, ctypes.byref(bit), ctypes.byref(tot)))
+        return int(bit.value), int(tot.value)
+
+
 class Permutation:
     """Permutation of [0,N) held as a device bit-source map (csgn_perm)."""
 

@@ -9,8 +9,13 @@ per block.  So
   * for a*b the LEFT operand is the sharded one and b is replicated: rank g then owns
     output blocks [first*T2, (first+count)*T2) -- contiguous and in the reference's own
     i-major order, so chains (a*b)*d with replicated d stay shard-local;
-  * the only exchange is decrypt's: the per-rank satisfied-block counts are summed by ONE
-    all-reduce (NCCL has no XOR; the parity of the sum is the XOR of the parities).
+  * the only exchange is decrypt's: the per-rank satisfied-block counts are summed (the parity
+    of the sum is the XOR of the parities).  On GPUs the fold kernel does that exchange itself:
+    its last CTA stores the count into every rank's mailbox over NVLink and the launch that
+    closes a batch collects the sums (engine.PeerComm, csrc/peer.cuh) -- no collective library
+    on the data path.  torch.distributed is only the rendezvous that carries the 64-byte
+    mailbox handles (connect_peers).  allreduce_counts (one all-reduce) remains for gloo/CPU
+    test doubles and as the baseline the fused path is measured against.
 
 The compute (engine.Ciphertext) is passed in, so the same logic runs under gloo on CPU
 in tests/ with the oracle standing in for the kernels.
@@ -44,6 +49,22 @@ def allreduce_counts(counts, group=None):
     if world() > 1:
         dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
     return counts
+
+
+def connect_peers(group=None):
+    """engine.PeerComm over the ranks of `group`: exchanges the mailbox handles with one all_gather."""
+    from . import engine
+    w, r = world(), rank()
+
+    def allgather_bytes(b):
+        nccl = dist.get_backend(group) == "nccl"
+        dev = torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu")
+        mine = torch.tensor(list(b), dtype=torch.uint8, device=dev)
+        out = [torch.empty_like(mine) for _ in range(w)]
+        dist.all_gather(out, mine, group=group)
+        return [bytes(t.cpu().tolist()) for t in out]
+
+    return engine.PeerComm(r, w, allgather_bytes if w > 1 else None)
 
 
 def parity(counts):
@@ -80,8 +101,11 @@ class ShardedCiphertext:
         """applyPermutation on every block: shard-local."""
         return ShardedCiphertext(self.local.applyPermutation(perm), self.first, self.global_blocks)
 
-    def decrypt(self, key, counts_out=None, device=None):
-        """Local fold, then the one-word all-reduce.  Returns the plaintext bit (int)."""
+    def decrypt(self, key, counts_out=None, device=None, comm=None):
+        """Local fold and the one-word exchange.  Returns the plaintext bit (int).
+        With a PeerComm the fold kernel does the exchange itself; otherwise one all-reduce follows."""
+        if comm is not None:
+            return comm.decrypt(key, self.local)[0]
         if counts_out is None:
             if device is None:
                 nccl = dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl"

@@ -39,7 +39,8 @@ typedef enum csgn_status {
     CSGN_ERR_CUDA = -3,
     CSGN_ERR_NO_DEVICE = -4,
     CSGN_ERR_SHAPE_MISMATCH = -5,
-    CSGN_ERR_OUT_OF_MEMORY = -6
+    CSGN_ERR_OUT_OF_MEMORY = -6,
+    CSGN_ERR_TIMEOUT = -7
 } csgn_status;
 
 typedef struct csgn_buf csgn_buf;   /* device-resident ciphertext words            */
@@ -168,12 +169,61 @@ int csgn_buf_checksum(const csgn_buf *buf, uint64_t *xor_out, uint64_t *sum_out,
 int csgn_buf_save(const csgn_buf *buf, uint64_t N, uint64_t D, const char *path);
 int csgn_buf_load(const char *path, uint64_t *N, uint64_t *D, csgn_buf **out);
 
-/* ---- sharding helpers (one process per GPU) ------------------------------- */
+/* ---- sharding (one process per GPU) ------------------------------------------ */
 
 /* Contiguous range of the LEFT operand's blocks owned by `rank` of `world`:
  * rank g multiplies a[first..first+count) by the replicated right operand and owns
  * output blocks [first*T2, (first+count)*T2) -- globally i-major like the reference. */
 int csgn_shard_range(uint64_t n_blocks, int rank, int world, uint64_t *first, uint64_t *count);
+
+/* Sharded decrypt: the fold and its cross-GPU exchange in ONE kernel.
+ *
+ * A ciphertext sharded by block range decrypts to the parity of the SUM of the per-shard
+ * satisfied-block counts (src/SecretKey.cpp:139 folds blocks with (dec + _dec) % 2).  That
+ * one word per rank is the only exchange step of the path.  A csgn_comm gives every rank a
+ * small mailbox in device memory that all its peers map over NVLink / NVSwitch; the decrypt
+ * kernel that closes a batch has its last CTA store the batch's counts straight into every
+ * rank's mailbox ("publish": posted 8-byte peer stores) and then poll its own mailbox until
+ * every rank's words have arrived, writing the sums ("collect").  There is no separate
+ * all-reduce launch and no collective library on the data path.
+ *
+ * Set-up:  csgn_comm_create on every rank -> exchange the CSGN_IPC_HANDLE_BYTES handles by
+ * any means (torch.distributed / MPI all-gather, a file) -> csgn_comm_connect with all
+ * `world` handles in rank order.  csgn_comm_connect_ptrs takes mailbox pointers that are
+ * already peer-mapped (symmetric-memory allocators); world == 1 needs neither.
+ * Contract (as for any collective): every rank issues the same sequence of pushes and
+ * collects; at most CSGN_COMM_MAX_PENDING pushes may stay unpublished, and a collect window
+ * (n + lag) spans at most as many.  A rank that never arrives makes the collect time out
+ * (CSGN_PEER_TIMEOUT_MS, default 30000): the totals read UINT64_MAX, blocking calls return
+ * CSGN_ERR_TIMEOUT, the GPU is never left spinning. */
+typedef struct csgn_comm csgn_comm;
+#define CSGN_IPC_HANDLE_BYTES 64
+#define CSGN_COMM_MAX_PENDING 64
+int csgn_comm_create(int rank, int world, csgn_comm **out, unsigned char *handle_out);
+int csgn_comm_connect(csgn_comm *comm, const unsigned char *handles);
+int csgn_comm_connect_ptrs(csgn_comm *comm, void *const *peer_mailboxes);
+/* This rank's mailbox (device pointer) and its size in bytes. */
+void *csgn_comm_mailbox(const csgn_comm *comm, size_t *bytes);
+int csgn_comm_free(csgn_comm *comm);
+/* Pushes issued but not yet published to the peers. */
+uint32_t csgn_comm_pending(const csgn_comm *comm);
+/* Enqueue: fold this rank's shard `c`; its count becomes push number seq (0, 1, 2, ...) of this
+ * communicator and stays in a local ring.  collect_n > 0 makes this launch close the batch: the
+ * same kernel's last CTA publishes every unpublished push to every rank's mailbox and then collects
+ * the collect_n pushes that end collect_lag pushes before this one (lag 0: ending with this one),
+ * writing their sums over all ranks to device_totals[0..collect_n), oldest first.  Collecting the
+ * previous batch (lag = batch size) never waits for a slower rank.  device_local (optional)
+ * receives this rank's own count.  No host synchronisation. */
+int csgn_decrypt_sharded_async(const csgn_buf *c, const csgn_key *key, csgn_comm *comm, uint32_t collect_n,
+                               uint32_t collect_lag, uint64_t *device_totals, uint64_t *device_local);
+/* Enqueue a publish + collect on its own (one small launch): the n pushes ending lag pushes before
+ * the most recent one. */
+int csgn_comm_collect_async(csgn_comm *comm, uint32_t n, uint32_t lag, uint64_t *device_totals);
+/* Blocking convenience = SecretKey::decrypt of a sharded ciphertext: push + collect of one
+ * decrypt; *bit = total & 1 on every rank; *total (optional) the global count. */
+int csgn_decrypt_sharded(const csgn_buf *c, const csgn_key *key, csgn_comm *comm, uint8_t *bit, uint64_t *total);
+/* Mailbox addressing of push number `seq` (host-side mirror of the kernel's arithmetic). */
+void csgn_comm_slot_tag(uint64_t seq, uint32_t *slot, uint64_t *tag);
 
 #ifdef __cplusplus
 }
