@@ -12,6 +12,7 @@
 
 #include <ctime>
 #include <utility>
+#include <vector>
 
 namespace certFHE {
 
@@ -537,10 +538,15 @@ long SecretKey::size() {
 
 uint64_t *SecretKey::encrypt(unsigned char bit, uint64_t n, uint64_t d, uint64_t *key) {
     // One value (0/1) per position, drawn in the reference's order (src/SecretKey.cpp:35-80).
+    // The reference asks Helper::exists(key, d, i) for every position (O(N*D)); an indicator
+    // vector answers the same question, with the same rand() calls in the same order.
     uint64_t *res = new uint64_t[n ? n : 1];
+    std::vector<unsigned char> secret(n ? n : 1, 0);
+    for (uint64_t k = 0; k < d; ++k)
+        if (key[k] < n) secret[key[k]] = 1;
     if (bit & 0x01) {
         // Enc(1): secret positions are 1, one rand() for every other position, in index order
-        for (uint64_t i = 0; i < n; ++i) res[i] = Helper::exists(key, d, i) ? 1 : (uint64_t)(rand() % 2);
+        for (uint64_t i = 0; i < n; ++i) res[i] = secret[i] ? 1 : (uint64_t)(rand() % 2);
         return res;
     }
     // Enc(0): pick the secret position that may break the all-ones pattern, randomise the
@@ -551,7 +557,7 @@ uint64_t *SecretKey::encrypt(unsigned char bit, uint64_t n, uint64_t d, uint64_t
     for (uint64_t i = 0; i < n; ++i) {
         if (i == hole) continue;
         res[i] = (uint64_t)(rand() % 2);
-        if (Helper::exists(key, d, i)) {
+        if (secret[i]) {
             others = seen ? (others & res[i]) : res[i];
             seen = true;
         }

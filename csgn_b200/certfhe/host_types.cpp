@@ -3,6 +3,8 @@
 // file (citations inline); where the reference's random generation defines results
 // (Permutation(size)), glibc rand() is consumed in exactly its order.
 #include "certFHE.h"
+
+#include <vector>
 #include "engine_glue.h"
 
 #include <ctime>
@@ -141,12 +143,17 @@ Permutation::Permutation(const uint64_t *perm, const uint64_t len) : Permutation
 Permutation::Permutation(const uint64_t size) : Permutation() {
     // reference src/Permutation.cpp:139-157: every slot starts at (uint64_t)-1; slot i
     // draws rand()%size until the value is not yet present anywhere in the array.
+    // The reference's membership test is a linear scan (Helper::exists), O(n^2 log n) in all --
+    // seconds at N=16383.  A taken-map answers the same question in O(1); the rand() draws, their
+    // order and therefore the permutation are unchanged.
     length = size;
     permutation = new uint64_t[size ? size : 1];
     for (uint64_t i = 0; i < size; ++i) permutation[i] = (uint64_t)-1;
+    std::vector<unsigned char> taken(size ? size : 1, 0);
     for (uint64_t i = 0; i < size; ++i) {
         uint64_t r = (uint64_t)rand() % size;
-        while (Helper::exists(permutation, size, r)) r = (uint64_t)rand() % size;
+        while (taken[r]) r = (uint64_t)rand() % size;
+        taken[r] = 1;
         permutation[i] = r;
     }
 }

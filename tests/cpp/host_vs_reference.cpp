@@ -52,8 +52,8 @@ int main() {
             EXPECT(op.getValue() == rp.getValue() && text(op) == text(rp));
         }
 
-        if (N <= 2000) {   // the reference's generation is O(n^2 log n)
-            for (unsigned seed = 1; seed <= 3; ++seed) {
+        {   // the reference's generation is O(n^2 log n): one seed only at N=16383 (seconds)
+            for (unsigned seed = 1; seed <= (N <= 2000 ? 3u : 1u); ++seed) {
                 srand(seed);
                 ref::Permutation rp(rc);
                 srand(seed);
