@@ -669,18 +669,18 @@ int csgn_perm_create(uint64_t N, const uint64_t *perm, csgn_perm **out) {
     h->L = csgn_words_per_block(N);
     // Bit-sliced form: a block is W = 2L 32-bit words; bit j of word c holds position
     // 64*(c>>1) + (c odd ? 31-j : 63-j).  Entry j*W + c' names the source slice of output
-    // (c', j) as a shared-memory BYTE offset 4*(33*c + j_src), or the zero slot 4*33*W for pad bits.
+    // (c', j) as a shared-memory BYTE offset 4*(stride*c + j_src), or the zero slot 4*stride*W for pad bits.
     std::vector<uint32_t> slices;
     if (permute_sliced_supported(h->L)) {
-        const uint32_t W = 2 * h->L;
-        slices.assign((size_t)32 * W, 4u * 33u * W);   // byte offsets; default = the zero slot
+        const uint32_t W = 2 * h->L, stride = kPermSliceStride;
+        slices.assign((size_t)32 * W, 4u * stride * W);   // byte offsets; default = the zero slot
         for (uint32_t c = 0; c < W; ++c)
             for (uint32_t j = 0; j < 32; ++j) {
                 const uint64_t i = 64ull * (c >> 1) + ((c & 1u) ? 31u - j : 63u - j);
                 if (i >= N) continue;
                 const uint64_t p = perm[i];
                 const uint32_t sc = 2u * (uint32_t)(p >> 6) + (((p & 63u) < 32u) ? 1u : 0u);
-                slices[(size_t)j * W + c] = 4u * (33u * sc + (31u - (uint32_t)(p & 31u)));
+                slices[(size_t)j * W + c] = 4u * (stride * sc + (31u - (uint32_t)(p & 31u)));
             }
     }
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&h->d_map), (size_t)N * sizeof(uint32_t));

@@ -53,6 +53,9 @@ cudaError_t launch_peer_exchange(const PeerPush &pp, bool do_push, uint64_t valu
 cudaError_t launch_permute(const uint64_t *in, uint64_t T, uint32_t L, uint32_t N, const uint32_t *src_map,
                            const uint32_t *slice_map, uint64_t *out, cudaStream_t stream);
 bool permute_sliced_supported(uint32_t L);
+// Words between consecutive slice rows of a tile in shared memory (32 slices + padding; 16-byte
+// aligned rows, conflict-free 128-bit stores).  The slice map's byte offsets are built with it.
+constexpr uint32_t kPermSliceStride = 36;
 
 // n fresh encryptions (one block per plaintext bit) with Philox-4x32-10 keyed by `seed`; see encrypt.cu.
 cudaError_t launch_encrypt_batch(const uint8_t *bits, uint64_t n, uint64_t first_block, uint32_t L, uint64_t pad_mask,

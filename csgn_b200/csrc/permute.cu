@@ -11,7 +11,8 @@
 //      the 32x32 bit matrix "block x bit" of that column in registers and transposes it
 //      (PRMT for the 16- and 8-bit stages, SHF+LOP3 for 4/2/1): word j of the result
 //      carries bit j of column c for all 32 blocks -- one *slice* per bit position;
-//   2. slices go to shared memory (rows padded to 33 words: conflict-free);
+//   2. slices go to shared memory with 128-bit stores (rows padded to kPermSliceStride = 36
+//      words: 16-byte aligned and conflict-free per quarter-warp);
 //   3. the permutation is now a WORD gather: output slice (c', j) = input slice
 //      slice_map[c', j] (precomputed per csgn_perm; pad positions point at a zero slot);
 //   4. thread (tile, column c') gathers its 32 slices, transposes back and stores the
@@ -29,7 +30,18 @@ namespace {
 
 // ---------------------------------------------------------------------------------------
 // 32x32 bit-matrix transpose in registers: after the call x[j] bit b == (old x[b]) bit j.
+//
+// bitsel<M>(a, b) = (a & M) | (b & ~M) as ONE LOP3: written as `(a & m) | (b & ~m)` in C++ the
+// two masks reach ptxas as two unrelated immediates (four inputs) and every output costs two
+// LOP3 -- 192 of the ~620 integer-pipe instructions of a column, in a kernel bound by that pipe.
 // ---------------------------------------------------------------------------------------
+template <uint32_t M>
+__device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "n"(M));   // (a & c) | (b & ~c)
+    return d;
+}
+
 __device__ __forceinline__ void transpose32(uint32_t (&x)[32]) {
 #pragma unroll
     for (int k = 0; k < 16; ++k) {   // swap the off-diagonal 16x16 blocks: two byte permutes
@@ -49,87 +61,177 @@ __device__ __forceinline__ void transpose32(uint32_t (&x)[32]) {
     for (int g = 0; g < 32; g += 8)
 #pragma unroll
         for (int k = g; k < g + 4; ++k) {   // 4x4 blocks
-            const uint32_t a = x[k], b = x[k + 4], m = 0x0f0f0f0fu;
-            x[k] = (a & m) | ((b << 4) & ~m);
-            x[k + 4] = ((a >> 4) & m) | (b & ~m);
+            const uint32_t a = x[k], b = x[k + 4];
+            x[k] = bitsel<0x0f0f0f0fu>(a, b << 4);
+            x[k + 4] = bitsel<0x0f0f0f0fu>(a >> 4, b);
         }
 #pragma unroll
     for (int g = 0; g < 32; g += 4)
 #pragma unroll
         for (int k = g; k < g + 2; ++k) {   // 2x2 blocks
-            const uint32_t a = x[k], b = x[k + 2], m = 0x33333333u;
-            x[k] = (a & m) | ((b << 2) & ~m);
-            x[k + 2] = ((a >> 2) & m) | (b & ~m);
+            const uint32_t a = x[k], b = x[k + 2];
+            x[k] = bitsel<0x33333333u>(a, b << 2);
+            x[k + 2] = bitsel<0x33333333u>(a >> 2, b);
         }
 #pragma unroll
     for (int k = 0; k < 32; k += 2) {       // single bits
-        const uint32_t a = x[k], b = x[k + 1], m = 0x55555555u;
-        x[k] = (a & m) | ((b << 1) & ~m);
-        x[k + 1] = ((a >> 1) & m) | (b & ~m);
+        const uint32_t a = x[k], b = x[k + 1];
+        x[k] = bitsel<0x55555555u>(a, b << 1);
+        x[k + 1] = bitsel<0x55555555u>(a >> 1, b);
     }
 }
 
 // slice_map layout: entry j*W + c = BYTE offset, inside a tile's slice area, of the source
-// slice of output (column c, bit j), or the byte offset of the zero slot.
-//
-// WC > 0 fixes the words per block at compile time (40 for N=1247, 512 for N=16383): every
-// one of the 32+32+32 global accesses and 32+32 shared accesses of a column then uses an
-// immediate offset from one base register, and a tile that lies fully inside the ciphertext
-// takes a path without per-access bounds.  That is a third of the instructions of the
-// runtime-W form -- this kernel is bound by the integer/issue pipes, not by HBM.
+// slice of output (column c, bit j), or the byte offset of the zero slot (4*kPermSliceStride*W).
+constexpr uint32_t kStride = kPermSliceStride;
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ void store_slices(uint32_t *dst, const uint32_t (&x)[32]) {
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);      // rows are 16-byte aligned (stride 36 words)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) d4[q] = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+}
+
+// ---- phase A: one 32-bit column of 32 blocks in, transposed, 32 slices to shared memory ----
+// FULL = the tile lies inside the ciphertext: 32 loads at immediate offsets from one base, no
+// bounds.  The ragged form is a separate, never-inlined function so that its 64-bit compares do
+// not leak predicates into the common path (they did: 140 ISETP per column, a fifth of the
+// integer work of a kernel that is bound by the integer pipe).
+template <int WC, bool FULL>
+__device__ __forceinline__ void column_in(const uint32_t *__restrict__ src, uint64_t blk0, uint64_t T, uint32_t W,
+                                          uint32_t *dst) {
+    uint32_t x[32];
+    if (FULL) {
+#pragma unroll
+        for (int b = 0; b < 32; ++b) x[b] = __ldcs(src + (uint32_t)b * (WC ? (uint32_t)WC : W));
+    } else {
+#pragma unroll
+        for (int b = 0; b < 32; ++b) x[b] = (blk0 + b < T) ? __ldcs(src + (uint64_t)b * W) : 0u;
+    }
+    transpose32(x);
+    store_slices(dst, x);
+}
 template <int WC>
-__global__ void __launch_bounds__(512)
-permute_sliced_kernel(const uint32_t *__restrict__ in, const uint64_t T, const uint32_t Wrt,
+__device__ __noinline__ void column_in_ragged(const uint32_t *__restrict__ src, uint64_t blk0, uint64_t T, uint32_t W,
+                                              uint32_t *dst) {
+    column_in<WC, false>(src, blk0, T, W, dst);
+}
+
+// ---- phase B: transpose the 32 gathered slices back, one column of 32 blocks out -------------
+template <int WC, bool FULL>
+__device__ __forceinline__ void column_out(uint32_t (&y)[32], uint32_t *__restrict__ dst, uint64_t blk0, uint64_t T,
+                                           uint32_t W) {
+    transpose32(y);
+    if (FULL) {
+#pragma unroll
+        for (int b = 0; b < 32; ++b) __stcs(dst + (uint32_t)b * (WC ? (uint32_t)WC : W), y[b]);
+    } else {
+#pragma unroll
+        for (int b = 0; b < 32; ++b)
+            if (blk0 + b < T) __stcs(dst + (uint64_t)b * W, y[b]);
+    }
+}
+// The ragged form gathers for itself (through the map in global memory): handing it the caller's
+// register array by reference would force that array into local memory on the common path too.
+template <int WC>
+__device__ __noinline__ void column_out_ragged(uint32_t tile_addr, const uint32_t *__restrict__ map, uint32_t *__restrict__ dst,
+                                               uint64_t blk0, uint64_t T, uint32_t W) {
+    uint32_t y[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) y[j] = lds_u32(tile_addr + __ldg(map + (uint32_t)j * W));
+    column_out<WC, false>(y, dst, blk0, T, W);
+}
+
+// Fixed-shape kernel: WC words per block and TILES tiles per CTA at compile time, WC*TILES
+// threads; thread (g, c) owns column c of the CTA's tile slot g for the whole launch.  The
+// CTA is persistent over groups of TILES tiles.  HOIST keeps the thread's 32 gather addresses
+// (shared-window byte addresses, tile slot included) in registers for the whole launch: the
+// gather is then 32 LDS and nothing else.
+template <int WC, int TILES, bool HOIST, int MINB>
+__global__ void __launch_bounds__(WC *TILES, MINB)
+permute_fixed_kernel(const uint32_t *__restrict__ in, const uint64_t T, const uint32_t *__restrict__ slice_map,
+                     uint32_t *__restrict__ out, const uint64_t n_groups) {
+    extern __shared__ __align__(16) uint32_t S[];
+    constexpr uint32_t tile_words = kStride * WC + 4u;     // last 4 words = the zero slot (keeps tiles 16-byte aligned)
+    const uint32_t g = threadIdx.x / WC, c = threadIdx.x - g * WC;
+    uint32_t *tile = S + g * tile_words;
+    const uint32_t tile_addr = (uint32_t)__cvta_generic_to_shared(tile);
+    // the slice map was uploaded and synchronised when the csgn_perm was created: reading it does
+    // not depend on the previous kernel, so it is staged before the PDL wait
+    uint32_t addr[HOIST ? 32 : 1];
+    if (HOIST) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) addr[j] = tile_addr + __ldg(slice_map + (uint32_t)j * WC + c);
+    }
+    if (c == 0) tile[kStride * WC] = 0u;
+    pdl_enter();
+
+    for (uint64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const uint64_t blk0 = (grp * TILES + g) * 32u;
+        const bool full = blk0 + 32u <= T;
+        const uint32_t *src = in + blk0 * WC + c;
+        if (full) column_in<WC, true>(src, blk0, T, WC, tile + kStride * c);
+        else column_in_ragged<WC>(src, blk0, T, WC, tile + kStride * c);
+        __syncthreads();
+        uint32_t *dst = out + blk0 * WC + c;
+        if (full) {
+            uint32_t y[32];
+            if (HOIST) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) y[j] = lds_u32(addr[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) y[j] = lds_u32(tile_addr + __ldg(slice_map + (uint32_t)j * WC + c));
+            }
+            column_out<WC, true>(y, dst, blk0, T, WC);
+        } else {
+            column_out_ragged<WC>(tile_addr, slice_map + c, dst, blk0, T, WC);
+        }
+        __syncthreads();   // before the next group overwrites the slices
+    }
+}
+
+// Any W (runtime): work items (tile, column) strided over the CTA's threads.
+__global__ void __launch_bounds__(512, 2)
+permute_sliced_kernel(const uint32_t *__restrict__ in, const uint64_t T, const uint32_t W,
                       const uint32_t *__restrict__ slice_map, uint32_t *__restrict__ out,
                       const uint32_t tiles_per_cta, const uint64_t n_groups) {
-    extern __shared__ uint32_t S[];                  // tiles_per_cta * (33*W + 1) words
-    const uint32_t W = WC ? (uint32_t)WC : Wrt;
-    const uint32_t tile_words = 33u * W + 1u;        // last word = the zero slot
+    extern __shared__ __align__(16) uint32_t S[];    // tiles_per_cta * (36*W + 4) words
+    const uint32_t tile_words = kStride * W + 4u;
     const uint32_t items = tiles_per_cta * W;
     pdl_enter();
 
-    for (uint32_t t = threadIdx.x; t < tiles_per_cta; t += blockDim.x) S[t * tile_words + 33u * W] = 0u;
+    for (uint32_t t = threadIdx.x; t < tiles_per_cta; t += blockDim.x) S[t * tile_words + kStride * W] = 0u;
 
     for (uint64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         const uint64_t tile0 = grp * tiles_per_cta;
-        // ---- 1+2: columns in, transposed, slices to shared memory -----------------------
         for (uint32_t it = threadIdx.x; it < items; it += blockDim.x) {
             const uint32_t tl = it / W, c = it - tl * W;
             const uint64_t blk0 = (tile0 + tl) * 32u;
-            uint32_t x[32];
             const uint32_t *src = in + blk0 * W + c;
-            if (blk0 + 32u <= T) {
-#pragma unroll
-                for (int b = 0; b < 32; ++b) x[b] = __ldcs(src + (uint32_t)b * W);
-            } else {
-#pragma unroll
-                for (int b = 0; b < 32; ++b) x[b] = (blk0 + b < T) ? __ldcs(src + (uint64_t)b * W) : 0u;
-            }
-            transpose32(x);
-            uint32_t *dst = S + tl * tile_words + 33u * c;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) dst[j] = x[j];
+            uint32_t *dst = S + tl * tile_words + kStride * c;
+            if (blk0 + 32u <= T) column_in<0, true>(src, blk0, T, W, dst);
+            else column_in_ragged<0>(src, blk0, T, W, dst);
         }
         __syncthreads();
-        // ---- 3+4: gather slices, transpose back, columns out ----------------------------
         for (uint32_t it = threadIdx.x; it < items; it += blockDim.x) {
             const uint32_t tl = it / W, c = it - tl * W;
             const uint64_t blk0 = (tile0 + tl) * 32u;
-            const unsigned char *Sl = reinterpret_cast<const unsigned char *>(S + tl * tile_words);
+            const uint32_t tile_addr = (uint32_t)__cvta_generic_to_shared(S + tl * tile_words);
             const uint32_t *map = slice_map + c;
-            uint32_t y[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                y[j] = *reinterpret_cast<const uint32_t *>(Sl + __ldg(map + (uint32_t)j * W));
-            transpose32(y);
             uint32_t *dst = out + blk0 * W + c;
             if (blk0 + 32u <= T) {
+                uint32_t y[32];
 #pragma unroll
-                for (int b = 0; b < 32; ++b) __stcs(dst + (uint32_t)b * W, y[b]);
+                for (int j = 0; j < 32; ++j) y[j] = lds_u32(tile_addr + __ldg(map + (uint32_t)j * W));
+                column_out<0, true>(y, dst, blk0, T, W);
             } else {
-#pragma unroll
-                for (int b = 0; b < 32; ++b)
-                    if (blk0 + b < T) __stcs(dst + (uint64_t)b * W, y[b]);
+                column_out_ragged<0>(tile_addr, map, dst, blk0, T, W);
             }
         }
         __syncthreads();   // before the next group overwrites the slices
@@ -163,26 +265,47 @@ permute_gather_kernel(const uint64_t *__restrict__ in, const uint64_t total_word
 
 namespace {
 
-template <int WC>
+template <typename Kernel>
+cudaError_t resident_ctas(Kernel kernel, int tpb, size_t smem, int *per_sm) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)device_props().smem_optin);
+        if (e != cudaSuccess) return e;
+    }
+    int n = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, tpb, smem) != cudaSuccess || n < 1) n = 1;
+    *per_sm = n;
+    return cudaSuccess;
+}
+
+template <int WC, int TILES, bool HOIST, int MINB, int WAVES>
+cudaError_t launch_fixed(const uint64_t *in, uint64_t T, const uint32_t *slice_map, uint64_t *out, cudaStream_t stream) {
+    constexpr size_t smem = (size_t)TILES * (kStride * WC + 4u) * sizeof(uint32_t);
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        cudaError_t e = resident_ctas(permute_fixed_kernel<WC, TILES, HOIST, MINB>, WC * TILES, smem, &per_sm);
+        if (e != cudaSuccess) return e;
+    }
+    const uint64_t n_tiles = (T + 31) / 32;
+    const uint64_t n_groups = (n_tiles + TILES - 1) / TILES;
+    // WAVES x the resident CTAs loop over the groups: a few waves balance the tail better than a strictly
+    // persistent grid (B200 sweeps in profiles/), while the per-CTA set-up stays amortised
+    const uint64_t cap =
+        (uint64_t)device_props().sm_count * per_sm * (uint64_t)std::max<long>(1, env_long("CSGN_PERM_WAVES", WAVES));
+    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_groups, cap));
+    return launch_kernel(permute_fixed_kernel<WC, TILES, HOIST, MINB>, grid, WC * TILES, smem, stream,
+                         reinterpret_cast<const uint32_t *>(in), T, slice_map, reinterpret_cast<uint32_t *>(out), n_groups);
+}
+
 cudaError_t launch_sliced(const uint64_t *in, uint64_t T, uint32_t W, const uint32_t *slice_map, uint64_t *out,
                           uint32_t tiles_per_cta, uint32_t tpb, size_t smem, cudaStream_t stream) {
     const DeviceProps &dp = device_props();
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(permute_sliced_kernel<WC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)dp.smem_optin);
-        if (e != cudaSuccess) return e;
-        configured = dp.smem_optin;
-    }
     static int per_sm_cache = 0;
     static uint32_t cache_tpb = 0;
     static size_t cache_smem = 0;
     if (per_sm_cache == 0 || cache_tpb != tpb || cache_smem != smem) {
-        int per_sm = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, permute_sliced_kernel<WC>, (int)tpb, smem) !=
-                cudaSuccess || per_sm < 1)
-            per_sm = 1;
-        per_sm_cache = per_sm;
+        cudaError_t e = resident_ctas(permute_sliced_kernel, (int)tpb, smem, &per_sm_cache);
+        if (e != cudaSuccess) return e;
         cache_tpb = tpb;
         cache_smem = smem;
     }
@@ -190,14 +313,14 @@ cudaError_t launch_sliced(const uint64_t *in, uint64_t T, uint32_t W, const uint
     const uint64_t n_groups = (n_tiles + tiles_per_cta - 1) / tiles_per_cta;
     const uint32_t grid = (uint32_t)std::max<uint64_t>(
         1, std::min<uint64_t>(n_groups, (uint64_t)dp.sm_count * per_sm_cache * (uint64_t)env_long("CSGN_PERM_WAVES", 16)));
-    return launch_kernel(permute_sliced_kernel<WC>, grid, tpb, smem, stream, reinterpret_cast<const uint32_t *>(in), T, W,
+    return launch_kernel(permute_sliced_kernel, grid, tpb, smem, stream, reinterpret_cast<const uint32_t *>(in), T, W,
                          slice_map, reinterpret_cast<uint32_t *>(out), tiles_per_cta, n_groups);
 }
 
 }  // namespace
 
 bool permute_sliced_supported(uint32_t L) {
-    const size_t need = ((size_t)33 * 2 * L + 1) * sizeof(uint32_t);
+    const size_t need = ((size_t)kStride * 2 * L + 4) * sizeof(uint32_t);
     return need <= device_props().smem_optin && 2 * L >= 1;
 }
 
@@ -208,8 +331,15 @@ cudaError_t launch_permute(const uint64_t *in, uint64_t T, uint32_t L, uint32_t 
     const bool aligned4 = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 3u) == 0;
     if (slice_map && aligned4 && permute_sliced_supported(L) && !env_long("CSGN_PERM_GATHER", 0)) {
         const uint32_t W = 2 * L;
-        const uint32_t tile_words = 33u * W + 1u;
-        // several tiles per CTA when a block is short (N=1247: W=40 -> 4 tiles, 160 work items)
+        const long variant = env_long("CSGN_PERM_VARIANT", 0);   // 1: the runtime-W kernel even for known shapes
+        count_launch();
+        if (W == 40 && variant == 0) return launch_fixed<40, 4, true, 4, 4>(in, T, slice_map, out, stream);     // N=1247
+        if (W == 40 && variant == 2) return launch_fixed<40, 4, false, 6, 4>(in, T, slice_map, out, stream);
+        if (W == 40 && variant == 3) return launch_fixed<40, 8, true, 2, 4>(in, T, slice_map, out, stream);
+        if (W == 512 && variant == 0) return launch_fixed<512, 1, false, 2, 16>(in, T, slice_map, out, stream);  // N=16383
+        if (W == 512 && variant == 2) return launch_fixed<512, 1, true, 1, 16>(in, T, slice_map, out, stream);
+        const uint32_t tile_words = kStride * W + 4u;
+        // several tiles per CTA when a block is short
         uint32_t tiles_per_cta = std::max<uint32_t>(1, (uint32_t)env_long("CSGN_PERM_ITEMS", 160) / W);
         const uint64_t n_tiles = (T + 31) / 32;
         tiles_per_cta = (uint32_t)std::min<uint64_t>(tiles_per_cta, n_tiles);
@@ -217,10 +347,7 @@ cudaError_t launch_permute(const uint64_t *in, uint64_t T, uint32_t L, uint32_t 
         const size_t smem = (size_t)tiles_per_cta * tile_words * sizeof(uint32_t);
         const uint32_t items = tiles_per_cta * W;
         const uint32_t tpb = std::min<uint32_t>(512, (items + 31) / 32 * 32);
-        count_launch();
-        if (W == 40) return launch_sliced<40>(in, T, W, slice_map, out, tiles_per_cta, tpb, smem, stream);
-        if (W == 512) return launch_sliced<512>(in, T, W, slice_map, out, tiles_per_cta, tpb, smem, stream);
-        return launch_sliced<0>(in, T, W, slice_map, out, tiles_per_cta, tpb, smem, stream);
+        return launch_sliced(in, T, W, slice_map, out, tiles_per_cta, tpb, smem, stream);
     }
     const uint64_t total = T * L;
     const uint32_t grid = (uint32_t)std::max<uint64_t>(
