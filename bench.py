@@ -68,6 +68,9 @@ def parse_args():
     ap.add_argument("--collect", default="lagged", choices=["lagged", "same-step"],
                     help="peer exchange: the launch closing step k collects step k-1's sums (never waits for a slower "
                          "rank; the last step's sums are collected before the timed region ends) or its own step's")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="enqueue the independent pairs of a step round-robin on this many CUDA streams (csgn_set_stream "
+                         "between calls): the tail of one kernel overlaps the ramp of the next pair's")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -331,6 +334,26 @@ def run_ours(args):
                 pending[i] = None
 
     lagged = comm is not None and args.collect == "lagged"
+    S = max(1, min(args.streams, P))
+    streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(S - 1)]
+    sptr = [s_.cuda_stream for s_ in streams]
+    fork_ev = [torch.cuda.Event() for _ in range(4)]
+    join_ev = [[torch.cuda.Event() for _ in range(S)] for _ in range(4)]
+
+    def fork(i):
+        """side streams wait for what the main stream holds so far"""
+        if S > 1:
+            fork_ev[i].record(stream)
+            for s_ in streams[1:]:
+                s_.wait_event(fork_ev[i])
+
+    def join(i):
+        """the main stream waits for the side streams"""
+        for k in range(1, S):
+            join_ev[i][k].record(streams[k])
+            stream.wait_event(join_ev[i][k])
+        if S > 1:
+            eng.set_stream(sptr[0])
 
     def step_device(evs=None, final=True):
         slot = step_no[0] & 1
@@ -340,13 +363,21 @@ def run_ours(args):
             pending[slot] = None
         if evs:
             evs[0].record()
+        fork(0)
         for p in range(P):
+            if S > 1:
+                eng.set_stream(sptr[p % S])
             va[p].mul_into(vb[p], vo[p])
+        join(0)
         if evs:
             evs[1].record()
+        fork(1)
         if comm is not None:
             for p in range(P - 1):
+                if S > 1:
+                    eng.set_stream(sptr[p % S])
                 comm.push(key, vo[p])                # fold; the count stays in the rank's local ring
+            join(1)
             # the launch that closes the batch publishes the P counts to every rank and collects P sums:
             # this step's, or (lagged) the previous step's, which have long arrived
             if lagged and step_no[0] > 1:
@@ -357,7 +388,10 @@ def run_ours(args):
                 comm.push(key, vo[P - 1], P, count_ptrs2[slot][0])
         else:
             for p in range(P):
+                if S > 1:
+                    eng.set_stream(sptr[p % S])
                 key.count_satisfied_async(vo[p], count_ptrs2[slot][p])
+            join(1)
         if evs:
             evs[2].record()
         if world > 1 and comm is None:
@@ -427,7 +461,13 @@ def run_ours(args):
         want_host = local_counts.cpu()
 
         def step_e2e():
+            fork(2)
             for p in range(P):
+                if S > 1:
+                    if comm is not None and p == P - 1:
+                        join(2)                                            # the closing launch follows every push
+                    else:
+                        eng.set_stream(sptr[p % S])
                 ha = eng.Ciphertext.from_host_ptr(a_ptrs[p], T1, ctx)      # H2D, async (pinned), on the copy stream
                 hb = eng.Ciphertext.from_host_ptr(b_ptrs[p], T2, ctx)
                 prod = ha * hb                                             # csgn_mul (allocates)
@@ -435,7 +475,9 @@ def run_ours(args):
                     comm.push(key, prod, P if p == P - 1 else 0, count_ptrs[0])
                 else:
                     key.count_satisfied_async(prod, count_ptrs[p])
-                del ha, hb, prod                                           # stream-ordered frees
+                del ha, hb, prod                                           # stream-ordered frees (on the pair's stream)
+            if comm is None:
+                join(2)
             if world > 1 and comm is None:
                 dist.all_reduce(counts)
             host_counts.copy_(counts, non_blocking=True)                   # D2H of this step's result
@@ -469,7 +511,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": args.workload + ": " + desc, "pairs_per_step": P,
+            "config": {"workload": args.workload + ": " + desc, "pairs_per_step": P, "streams": S,
                        "blocks_per_step": blocks_per_step, "bytes_per_block": bytes_per_block,
                        "l2": "no flush needed: a step writes then reads %d x %.0f MB of products (>> 126 MB L2), "
                              "each product is read %d kernels after it was written" % (P, T1 * T2 * L * 8 / 1e6, P),

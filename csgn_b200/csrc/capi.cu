@@ -68,7 +68,8 @@ struct State {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // H2D uploads run here, overlapping kernels of the work stream
     std::vector<cudaEvent_t> event_pool;
-    uint64_t *d_scratch = nullptr;   // [0..1] decrypt fold scratch, [2] result, [4..6] checksum
+    uint64_t *d_scratch = nullptr;   // [2] blocking-call result, [4..6] checksum, [8 + 2k, 9 + 2k] fold scratch of launch k mod 64
+    uint32_t fold_slot = 0;
     uint64_t *h_result = nullptr;    // pinned, 8 words
 };
 State g;
@@ -105,6 +106,15 @@ int cuda_fail(cudaError_t e, const char *what) {
         int cur_ = -1;                                                                           \
         if (cudaGetDevice(&cur_) != cudaSuccess || cur_ != g.device) CU(cudaSetDevice(g.device)); \
     } while (0)
+
+// Every fold launch takes the next pair of scratch words (running count, CTA ticket) and leaves them
+// zeroed, so decrypts enqueued on different streams (csgn_set_stream between calls) may run concurrently.
+constexpr uint32_t kFoldSlots = 64;
+uint64_t *next_fold_scratch() {
+    uint64_t *p = g.d_scratch + 8 + 2 * (g.fold_slot % kFoldSlots);
+    g.fold_slot += 1;
+    return p;
+}
 
 int dev_alloc(uint64_t words, uint64_t **out, cudaStream_t stream = nullptr) {
     *out = nullptr;
@@ -223,8 +233,8 @@ int csgn_init(int device) {
     CU(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t keep = UINT64_MAX;
     CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    CU(cudaMalloc(reinterpret_cast<void **>(&g.d_scratch), 8 * sizeof(uint64_t)));
-    CU(cudaMemset(g.d_scratch, 0, 8 * sizeof(uint64_t)));
+    CU(cudaMalloc(reinterpret_cast<void **>(&g.d_scratch), (8 + 2 * kFoldSlots) * sizeof(uint64_t)));
+    CU(cudaMemset(g.d_scratch, 0, (8 + 2 * kFoldSlots) * sizeof(uint64_t)));
     CU(cudaHostAlloc(reinterpret_cast<void **>(&g.h_result), 8 * sizeof(uint64_t), cudaHostAllocDefault));
     g.device = device;
     g.inited = true;
@@ -545,7 +555,7 @@ int csgn_decrypt_count_async(const csgn_buf *c, const csgn_key *key, uint64_t *d
         return fail(CSGN_ERR_SHAPE_MISMATCH, "ciphertext has %u words per block, key expects %u", c->L, key->L);
     await_upload(c);
     cudaError_t e = launch_decrypt_count(c->d, c->n_blocks, c->L, key->d_mask,
-                                         key->h_mask.empty() ? nullptr : key->h_mask.data(), g.d_scratch, device_count,
+                                         key->h_mask.empty() ? nullptr : key->h_mask.data(), next_fold_scratch(), device_count,
                                          g.stream);
     if (e != cudaSuccess) return cuda_fail(e, "decrypt kernel");
     return CSGN_OK;
@@ -1077,7 +1087,7 @@ int csgn_decrypt_sharded_async(const csgn_buf *c, const csgn_key *key, csgn_comm
     if (rc != CSGN_OK) return rc;
     await_upload(c);
     cudaError_t e = launch_decrypt_count(c->d, c->n_blocks, c->L, key->d_mask,
-                                         key->h_mask.empty() ? nullptr : key->h_mask.data(), g.d_scratch, device_local,
+                                         key->h_mask.empty() ? nullptr : key->h_mask.data(), next_fold_scratch(), device_local,
                                          g.stream, &pp);
     if (e != cudaSuccess) return cuda_fail(e, "sharded decrypt kernel");
     comm->seq += 1;
