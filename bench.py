@@ -99,14 +99,15 @@ def measured_peak_gbs():
 
 def ncu_traffic(kernel_prefix, workload):
     """dram bytes (read + write) per launch of the dominant kernel, from the committed ncu --set full
-    capture of this workload (profiles/r1_<workload>_ncu_summary.json), or None."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_%s_ncu_summary.json" % workload)) as f:
-            for name, k in json.load(f)["kernels"].items():
-                if name.startswith(kernel_prefix):
-                    return k["dram_traffic_bytes_per_launch"]
-    except Exception:
-        pass
+    capture of this workload (profiles/r1b_<workload>_ncu_summary.json), or None."""
+    for tag in ("r1b", "r1"):                      # the latest capture first
+        try:
+            with open(os.path.join(ROOT, "profiles", "%s_%s_ncu_summary.json" % (tag, workload))) as f:
+                for name, k in json.load(f)["kernels"].items():
+                    if name.startswith(kernel_prefix):
+                        return k["dram_traffic_bytes_per_launch"]
+        except Exception:
+            pass
     return None
 
 

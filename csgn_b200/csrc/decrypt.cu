@@ -169,6 +169,61 @@ decrypt_count_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint3
 
 
 // ---------------------------------------------------------------------------------------
+// Lane-aligned fold for short blocks (L4 <= 16, e.g. N=1247: L4 = 10).
+//
+// A warp step covers BPS = 32 / L4 whole blocks with the first BPS*L4 lanes (30 of 32 at L4 = 10;
+// the step is still one contiguous, sector-aligned run of 480 bytes).  A lane therefore always
+// sits on the SAME 16-byte unit of a block: its key-mask unit lives in four registers for the
+// whole launch, a block's verdict is L4 adjacent bits of one ballot, and every lane computes the
+// same count from it -- no fail string in shared memory, no __syncwarp, no per-unit mask lookup.
+// What is left per 480 bytes is one load, four logic ops, a vote and a handful of uniform
+// integer ops, so U independent loads per lane stay in flight with registers to spare.
+// ---------------------------------------------------------------------------------------
+template <int L4, int U, int MINB>
+__global__ void __launch_bounds__(kDecThreads, MINB)
+decrypt_count_lanes_kernel(const uint4 *__restrict__ V4, const uint64_t T, const __grid_constant__ ParamMask pmask,
+                           uint64_t *scratch, uint64_t *count_out, const __grid_constant__ PeerPush pp) {
+    constexpr uint32_t BPS = 32u / L4, ACTIVE = BPS * L4, BLKMASK = (1u << L4) - 1u;
+    const uint32_t lane = threadIdx.x & 31u;
+    const bool active = lane < ACTIVE;
+    const uint4 m = active ? pmask.u[lane % L4] : make_uint4(0u, 0u, 0u, 0u);   // parameters: nothing to wait for
+    pdl_enter();
+
+    const uint64_t n_steps = (T + BPS - 1) / BPS;
+    const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    uint32_t cnt = 0;                         // warp-uniform: satisfied blocks seen by this warp
+    for (uint64_t base = warp_global * U; base < n_steps; base += n_warps * U) {
+        const uint4 *src = V4 + (base * ACTIVE + lane);
+        uint4 v[U];
+        if ((base + U) * BPS <= T) {          // warp-uniform: all U steps lie inside the ciphertext
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = active ? ld_stream(src + (uint32_t)u * ACTIVE) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t bal = __ballot_sync(0xffffffffu, unit_fails(v[u], m));
+#pragma unroll
+                for (uint32_t b = 0; b < BPS; ++b) cnt += ((bal >> (b * L4)) & BLKMASK) == 0u ? 1u : 0u;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint64_t blk = (base + u) * BPS + lane / L4;        // this lane's block
+                v[u] = (active && blk < T) ? ld_stream(src + (uint32_t)u * ACTIVE) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t bal = __ballot_sync(0xffffffffu, unit_fails(v[u], m));
+#pragma unroll
+                for (uint32_t b = 0; b < BPS; ++b)
+                    cnt += ((base + u) * BPS + b < T && ((bal >> (b * L4)) & BLKMASK) == 0u) ? 1u : 0u;
+            }
+        }
+    }
+    fold_and_publish(lane == 0 ? (uint64_t)cnt : 0ull, scratch, count_out, pp);
+}
+
+// ---------------------------------------------------------------------------------------
 // Bulk-ring variant of the same fold (small blocks, L4 <= 16, e.g. N=1247).
 //
 // One persistent CTA per SM.  A producer warp streams the ciphertext into a ring of
@@ -413,6 +468,20 @@ cudaError_t launch_fast(const uint64_t *v, uint64_t T, uint32_t L4, const uint64
                          by_param ? nullptr : reinterpret_cast<const uint4 *>(mask), pm, cpw, scratch, count_out, pp);
 }
 
+template <int L4, int U, int MINB>
+cudaError_t launch_lanes(const uint64_t *v, uint64_t T, const uint64_t *host_mask, uint64_t *scratch, uint64_t *count_out,
+                         const PeerPush &pp, cudaStream_t stream) {
+    ParamMask pm;
+    memset(&pm, 0, sizeof pm);
+    memcpy(&pm, host_mask, (size_t)L4 * sizeof(uint4));
+    constexpr uint32_t BPS = 32u / L4;
+    const uint64_t n_steps = (T + BPS - 1) / BPS;
+    const uint64_t work_ctas = (n_steps + (uint64_t)kDecWarps * U - 1) / ((uint64_t)kDecWarps * U);
+    const uint32_t grid = resident_grid(decrypt_count_lanes_kernel<L4, U, MINB>, 0, work_ctas);
+    return launch_kernel(decrypt_count_lanes_kernel<L4, U, MINB>, grid, kDecThreads, 0, stream,
+                         reinterpret_cast<const uint4 *>(v), T, pm, scratch, count_out, pp);
+}
+
 template <int UPL, int BPI>
 cudaError_t launch_wide(const uint64_t *v, uint64_t T, const uint64_t *mask, uint64_t *scratch,
                         uint64_t *count_out, const PeerPush &pp, cudaStream_t stream) {
@@ -471,11 +540,18 @@ cudaError_t launch_decrypt_count(const uint64_t *v, uint64_t T, uint32_t L, cons
         if (L4 == 10 && variant == 5) err = launch_ring<10, 4>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
         else if (L4 == 10 && variant == 6) err = launch_ring<10, 3>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
         else if (L4 == 10 && variant == 7) err = launch_ring<10, 5>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
+        else if (L4 == 10 && host_mask && variant == 8) err = launch_lanes<10, 10, 4>(v, T, host_mask, scratch, count_out, pp, stream);
+        else if (L4 == 10 && host_mask && variant == 9) err = launch_lanes<10, 8, 4>(v, T, host_mask, scratch, count_out, pp, stream);
+        else if (L4 == 10 && host_mask && variant == 10) err = launch_lanes<10, 12, 3>(v, T, host_mask, scratch, count_out, pp, stream);
+        else if (L4 == 10 && host_mask && variant == 11) err = launch_lanes<10, 6, 6>(v, T, host_mask, scratch, count_out, pp, stream);
+        else if (L4 == 10 && host_mask && variant == 12) err = launch_lanes<10, 16, 3>(v, T, host_mask, scratch, count_out, pp, stream);
         else if (L4 == 10 && variant == 1) err = launch_fast<10, 10, 4>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
         else if (L4 == 10 && variant == 2) err = launch_fast<10, 5, 5>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
         else if (L4 == 10 && variant == 3) err = launch_fast<10, 5, 6>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
         else if (L4 == 10 && variant == 4) err = launch_fast<10, 2, 8>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
-        else if (L4 == 10) err = launch_fast<10, 10, 3>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);     // N=1247
+        else if (L4 == 10 && host_mask && variant != 13)                                                               // N=1247
+            err = launch_lanes<10, 12, 3>(v, T, host_mask, scratch, count_out, pp, stream);
+        else if (L4 == 10) err = launch_fast<10, 10, 3>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
         else if (L4 == 128 && wide) err = launch_wide<4, 2>(v, T, mask, scratch, count_out, pp, stream);  // N=16383
         else if (L4 == 64 && wide) err = launch_wide<2, 4>(v, T, mask, scratch, count_out, pp, stream);
         else if (L4 == 32 && wide) err = launch_wide<1, 8>(v, T, mask, scratch, count_out, pp, stream);

@@ -187,7 +187,7 @@ def test_decrypt_count_matches_oracle(engine, oracle, N, D):
         assert engine.SecretKey(ctx, s).count_satisfied(engine.Ciphertext.from_host(v, ctx)) == oracle.count_satisfied(v, N, s)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13])
 def test_decrypt_every_kernel_variant(engine, oracle, variant):
     """N=1247 has several tuned forms of the fold (register-streamed and the bulk-copy ring)."""
     N, D = 1247, 2

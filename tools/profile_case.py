@@ -42,6 +42,11 @@ def main():
     for i in range(iters):
         va.mul_into(vb, vo[i % nbuf])
         key.count_satisfied_async(vo[(i + 1) % nbuf], cnt.data_ptr())
+    # the sharded-decrypt path at world size 1: fold + publish + collect in the one kernel (csrc/peer.cuh)
+    comm = eng.PeerComm(0, 1)
+    tot = torch.zeros(2, dtype=torch.int64, device=dev)
+    comm.push(key, vo[0])
+    comm.push(key, vo[1 % nbuf], 2, tot.data_ptr())
     vo[0].permute_into(perm, vo[1])
     fresh = key.encrypt_batch(np.random.default_rng(9).integers(0, 2, size=T1 * T2).astype(np.uint8), seed=1)
     s = va + vb
