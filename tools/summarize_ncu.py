@@ -21,7 +21,9 @@ per = collections.defaultdict(list)
 for d in data:
     name = d[idx["Kernel Name"]]
     short = name.split("::")[-1].split("(")[0]
-    if "ParamMask" in short or short.strip() == "": short = [p for p in name.split("::") if "kernel" in p][-1].split("(")[0]
+    if "kernel" not in short:
+        cand = [p for p in name.split("::") if "kernel" in p]
+        if cand: short = cand[0].split("(")[0]
     per[short].append({w: num(d[idx[w]]) for w in WANT if w in idx})
 out = {"report": rep, "units": {w: units[idx[w]] for w in WANT if w in idx}, "kernels": {}}
 for k, lst in per.items():
