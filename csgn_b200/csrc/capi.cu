@@ -27,6 +27,7 @@ struct csgn_buf {
     uint32_t L = 0;
     uint64_t cap_words = 0;    // allocated words (>= n_blocks*L); 0 for views
     bool owns = true;
+    bool recycle = false;      // storage of an upload: goes back to the upload cache, not to the pool
     mutable cudaEvent_t ready = nullptr;  // an upload on the copy stream still in flight
 };
 
@@ -68,6 +69,16 @@ struct State {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // H2D uploads run here, overlapping kernels of the work stream
     std::vector<cudaEvent_t> event_pool;
+    // Storage of freed uploads, each with the event that marks its last use: an upload takes a slot whose event has
+    // COMPLETED, so its copy can start at once on the copy stream and no allocation (which across streams may go to the
+    // driver, milliseconds) sits on the steady-state path of "upload operands, multiply, decrypt, free".
+    struct UploadSlot {
+        uint64_t *d;
+        uint64_t cap_words;
+        cudaEvent_t freed;
+    };
+    std::vector<UploadSlot> upload_cache;
+    uint64_t upload_cache_words = 0;
     uint64_t *d_scratch = nullptr;   // [2] blocking-call result, [4..6] checksum, [8 + 2k, 9 + 2k] fold scratch of launch k mod 64
     uint32_t fold_slot = 0;
     uint64_t *h_result = nullptr;    // pinned, 8 words
@@ -139,6 +150,56 @@ cudaEvent_t take_event() {
     cudaEvent_t e = nullptr;
     if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     return e;
+}
+
+constexpr uint64_t kUploadCacheMaxWords = (64ull << 20) / 8;      // per buffer: larger uploads are not latency-bound
+constexpr uint64_t kUploadCacheTotalWords = (1ull << 30) / 8;     // all slots together
+constexpr size_t kUploadCacheSlots = 512;
+
+// Storage for an upload of `words` words: a cached slot whose last use has completed, or null.
+uint64_t *take_upload_slot(uint64_t words, uint64_t *cap_words) {
+    size_t best = SIZE_MAX;
+    for (size_t i = 0; i < g.upload_cache.size(); ++i) {
+        const State::UploadSlot &sl = g.upload_cache[i];
+        if (sl.cap_words < words || sl.cap_words > 2 * words + 64) continue;
+        if (best != SIZE_MAX && g.upload_cache[best].cap_words <= sl.cap_words) continue;
+        if (cudaEventQuery(sl.freed) != cudaSuccess) {
+            cudaGetLastError();      // cudaErrorNotReady is not an error
+            continue;
+        }
+        best = i;
+    }
+    if (best == SIZE_MAX) return nullptr;
+    State::UploadSlot sl = g.upload_cache[best];
+    g.upload_cache[best] = g.upload_cache.back();
+    g.upload_cache.pop_back();
+    g.upload_cache_words -= sl.cap_words;
+    g.event_pool.push_back(sl.freed);
+    *cap_words = sl.cap_words;
+    return sl.d;
+}
+
+// Hand the storage of a freed upload to the cache (true), or decline (the caller frees it).
+bool give_upload_slot(uint64_t *d, uint64_t cap_words) {
+    if (!d || cap_words == 0 || cap_words > kUploadCacheMaxWords || g.upload_cache.size() >= kUploadCacheSlots ||
+        g.upload_cache_words + cap_words > kUploadCacheTotalWords)
+        return false;
+    cudaEvent_t e = nullptr;
+    if (!g.event_pool.empty()) {
+        e = g.event_pool.back();
+        g.event_pool.pop_back();
+    } else if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    if (cudaEventRecord(e, g.stream) != cudaSuccess) {      // everything enqueued so far may still read the buffer
+        cudaGetLastError();
+        g.event_pool.push_back(e);
+        return false;
+    }
+    g.upload_cache.push_back({d, cap_words, e});
+    g.upload_cache_words += cap_words;
+    return true;
 }
 
 // Order the work stream after a pending upload of `b` (first consumer only).
@@ -233,6 +294,11 @@ int csgn_init(int device) {
     CU(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t keep = UINT64_MAX;
     CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    // Callers may enqueue independent ciphertexts on several streams (csgn_set_stream) so that kernels overlap.  An
+    // allocation must then never make its stream wait for another stream's pending frees -- that would serialise the
+    // streams again -- so the pool only reuses memory whose free has completed or is ordered by the caller's own events.
+    int off = 0;
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off));
     CU(cudaMalloc(reinterpret_cast<void **>(&g.d_scratch), (8 + 2 * kFoldSlots) * sizeof(uint64_t)));
     CU(cudaMemset(g.d_scratch, 0, (8 + 2 * kFoldSlots) * sizeof(uint64_t)));
     CU(cudaHostAlloc(reinterpret_cast<void **>(&g.h_result), 8 * sizeof(uint64_t), cudaHostAllocDefault));
@@ -245,6 +311,11 @@ int csgn_shutdown(void) {
     if (!g.inited) return CSGN_OK;
     cudaSetDevice(g.device);
     cudaStreamSynchronize(g.copy_stream);
+    cudaStreamSynchronize(g.stream);
+    for (const State::UploadSlot &sl : g.upload_cache) {
+        cudaFreeAsync(sl.d, g.stream);
+        cudaEventDestroy(sl.freed);
+    }
     cudaStreamSynchronize(g.stream);
     cudaFree(g.d_scratch);
     cudaFreeHost(g.h_result);
@@ -318,8 +389,19 @@ int csgn_buf_upload(const uint64_t *host_words, uint64_t n_blocks, uint32_t L, c
     // Allocation and copy are ordered on the copy stream, so an upload overlaps whatever the work
     // stream is running; the first consumer on the work stream waits for the `ready` event.
     csgn_buf *b = nullptr;
-    int rc = new_buf(n_blocks, L, 0, &b, g.copy_stream);
-    if (rc != CSGN_OK) return rc;
+    uint64_t cap = 0;
+    uint64_t *cached = (n_blocks && n_blocks <= kUploadCacheMaxWords / L) ? take_upload_slot(n_blocks * L, &cap) : nullptr;
+    if (cached) {
+        b = new csgn_buf;
+        b->d = cached;
+        b->n_blocks = n_blocks;
+        b->L = L;
+        b->cap_words = cap;
+    } else {
+        int rc = new_buf(n_blocks, L, 0, &b, g.copy_stream);
+        if (rc != CSGN_OK) return rc;
+    }
+    b->recycle = true;
     if (n_blocks) {
         cudaError_t e = cudaMemcpyAsync(b->d, host_words, n_blocks * L * sizeof(uint64_t), cudaMemcpyHostToDevice,
                                         g.copy_stream);
@@ -391,7 +473,7 @@ int csgn_buf_download(const csgn_buf *buf, uint64_t *host_words) {
 int csgn_buf_free(csgn_buf *buf) {
     if (!buf) return CSGN_OK;
     if (g.inited) await_upload(buf);     // a never-consumed upload must land before its memory is recycled
-    if (g.inited && buf->owns) dev_free(buf->d);
+    if (g.inited && buf->owns && !(buf->recycle && give_upload_slot(buf->d, buf->cap_words))) dev_free(buf->d);
     delete buf;
     return CSGN_OK;
 }
@@ -491,6 +573,7 @@ int csgn_append(csgn_buf *a, const csgn_buf *b) {
         dev_free(a->d);  // stream-ordered: the copy above still reads it safely
         a->d = nd;
         a->cap_words = cap;
+        a->recycle = false;
     }
     a->n_blocks += b->n_blocks;
     return CSGN_OK;
