@@ -71,6 +71,12 @@ def parse_args():
     ap.add_argument("--streams", type=int, default=2,
                     help="enqueue the independent pairs of a step round-robin on this many CUDA streams (csgn_set_stream "
                          "between calls): the tail of one kernel overlaps the ramp of the next pair's")
+    ap.add_argument("--t1", type=int, default=0, help="blocks of the left operand (overrides the workload's; with --scaling "
+                                                      "strong: of the WHOLE left operand, sharded over the ranks)")
+    ap.add_argument("--t2", type=int, default=0, help="blocks of the right operand (overrides the workload's)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = every rank multiplies t1 x t2 (default, the headline); strong = the t1 blocks of the "
+                         "left operand are split over the ranks (SURVEY 8d, the cfg5 sweep)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -279,6 +285,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     N, D, T1, T2, desc = WORKLOADS[args.workload]
+    T1g, T2 = args.t1 or T1, args.t2 or T2          # T1g: the left operand as given on the command line
+    if args.t1 or args.t2:
+        desc = "Context(%d,%d): %dx%d -> %d output blocks, multiply then decrypt" % (N, D, T1g, T2, T1g * T2)
     L, P = words_per_block(N), args.pairs
     eng.init(local)
     # a real (non-default) stream: handle 0 would mean "the library's own stream" to csgn_set_stream,
@@ -291,8 +300,11 @@ def run_ours(args):
 
     # --- synthetic inputs: pinned host copies (e2e) and device copies (value) ---------
     # Global left operand of pair p has T1*world blocks; this rank owns csgn_shard_range.
-    first, count = eng.shard_range(T1 * world, rank, world)
-    assert count == T1
+    strong = args.scaling == "strong" and world > 1
+    first, count = eng.shard_range(T1g if strong else T1g * world, rank, world)
+    T1 = count                                        # this rank's blocks of the left operand
+    if strong and T1g % world:
+        raise SystemExit("--scaling strong needs --t1 divisible by the number of GPUs")
     host_a = torch.empty((P, T1 * L), dtype=torch.int64).pin_memory()
     host_b = torch.empty((P, T2 * L), dtype=torch.int64).pin_memory()
     key_pos = np.random.default_rng(7).permutation(N)[:D].astype(np.uint64)
@@ -305,7 +317,7 @@ def run_ours(args):
         # raw random blocks almost never satisfy a D=16 key; set the key bits in a few
         # of them so that the decrypt fold has something to count
         w = seeded_blocks(rng, T, N).reshape(T, L)
-        rows = rng.choice(T, size=int(rng.integers(20, 60)), replace=False)
+        rows = rng.choice(T, size=min(T, int(rng.integers(20, 60))), replace=False)
         w[rows] |= key_mask
         return w.reshape(-1)
 
@@ -446,7 +458,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, mul_ms, dec_ms, ar_ms = (float(x) for x in t.tolist())
 
-    blocks_per_step = P * T1 * T2 * world            # whole job
+    blocks_per_step = P * T1 * T2 * world            # whole job (T1 = per-rank share)
     value = blocks_per_step * K / (total_ms * 1e-3)
     bytes_per_block = 8 * L
     peak, peak_src = measured_peak_gbs()
@@ -532,9 +544,10 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
-            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u64", "data": "synthetic",
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": args.workload + ": " + desc, "pairs_per_step": P, "streams": S,
+                       "left_blocks_per_rank": T1, "right_blocks": T2,
                        "blocks_per_step": blocks_per_step, "bytes_per_block": bytes_per_block,
                        "l2": "no flush needed: a step writes then reads %d x %.0f MB of products (>> 126 MB L2), "
                              "each product is read %d kernels after it was written" % (P, T1 * T2 * L * 8 / 1e6, P),
@@ -566,7 +579,9 @@ def run_ours(args):
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(N, D, T1, T2)
+            # the reference overflows its int counters above 131,080 blocks at N=16383 (SURVEY hazard 4): the CPU
+            # sample always uses the workload's own sizes, whatever --t1/--t2 say
+            line["cpu_baseline"] = cpu_baseline(N, D, *WORKLOADS[args.workload][2:4])
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
