@@ -22,6 +22,7 @@
 // finish publishes the total and re-arms the scratch words, so a decrypt is ONE launch.
 #include "kernels.cuh"
 #include "launch.cuh"
+#include "bulk.cuh"
 #include "peer.cuh"
 
 #include <algorithm>
@@ -237,33 +238,6 @@ decrypt_count_lanes_kernel(const uint4 *__restrict__ V4, const uint64_t T, const
 constexpr int kRingWarps = 8;     // consumer warps = chunks per stage
 constexpr int kRingThreads = (kRingWarps + 1) * 32;
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 template <int L4C, int STAGES>
 __global__ void __launch_bounds__(kRingThreads, 1)
 decrypt_count_ring_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint32_t L4rt,
@@ -291,8 +265,7 @@ decrypt_count_ring_kernel(const uint4 *__restrict__ V4, const uint64_t T, const 
             mbar_init(full + s, 1);
             mbar_init(empty + s, kRingWarps);
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_init_fence();
     }
     __syncthreads();
 

@@ -20,6 +20,7 @@
 //
 // The word-gather kernel below it (one thread builds one 64-bit output word from its 64
 // source bits) covers what the tile kernel cannot hold in shared memory (N > ~54,000).
+#include "bulk.cuh"
 #include "kernels.cuh"
 #include "launch.cuh"
 
@@ -196,6 +197,91 @@ permute_fixed_kernel(const uint32_t *__restrict__ in, const uint64_t T, const ui
     }
 }
 
+// The same kernel with phase A fed from shared memory: one thread keeps a bulk asynchronous copy
+// (cp.async.bulk -> the TMA engine, completion counted on an mbarrier) of the NEXT group's tiles in
+// flight -- a group's TILES tiles are one contiguous run of TILES*32*W words -- while the CTA works
+// on the current group.  The input of a group is then in flight across the two block-wide barriers
+// and costs no registers; phase A reads its column from the raw tile (conflict-free: lanes are
+// consecutive words of a row).  NBUF = 2: the copy is issued a whole iteration ahead; NBUF = 1: after
+// phase A has consumed the buffer, i.e. half an iteration ahead, for less shared memory per CTA.
+template <int WC, int TILES, int NBUF, int MINB>
+__global__ void __launch_bounds__(WC *TILES, MINB)
+permute_prefetch_kernel(const uint32_t *__restrict__ in, const uint64_t T, const uint32_t *__restrict__ slice_map,
+                        uint32_t *__restrict__ out, const uint64_t n_groups) {
+    extern __shared__ __align__(128) uint32_t S[];
+    constexpr uint32_t tile_words = kStride * WC + 4u;
+    constexpr uint32_t group_words = TILES * 32u * WC;            // raw input of one group
+    uint32_t *raw = S;                                            // NBUF * group_words
+    uint32_t *slices = S + NBUF * group_words;                    // TILES * tile_words
+    uint64_t *bar = reinterpret_cast<uint64_t *>(slices + TILES * tile_words);   // NBUF mbarriers (8-byte aligned)
+    const uint32_t g = threadIdx.x / WC, c = threadIdx.x - g * WC;
+    uint32_t *tile = slices + g * tile_words;
+    const uint32_t tile_addr = smem_u32(tile);
+    uint32_t addr[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) addr[j] = tile_addr + __ldg(slice_map + (uint32_t)j * WC + c);
+    if (c == 0) tile[kStride * WC] = 0u;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NBUF; ++i) mbar_init(bar + i, 1);
+        mbar_init_fence();
+    }
+    __syncthreads();
+    pdl_enter();
+
+    // bytes of group `grp` that lie inside the ciphertext (the last group may be ragged)
+    auto issue = [&](uint64_t grp, uint32_t buf) {
+        const uint64_t first_blk = grp * TILES * 32u;
+        const uint64_t blocks = min((uint64_t)TILES * 32u, T - first_blk);
+        const uint32_t bytes = (uint32_t)blocks * WC * 4u;
+        mbar_expect_tx(bar + buf, bytes);
+        bulk_g2s(raw + buf * group_words, in + first_blk * WC, bytes, bar + buf);
+    };
+    if (threadIdx.x == 0 && blockIdx.x < n_groups) issue(blockIdx.x, 0);
+
+    uint32_t it = 0;
+    for (uint64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++it) {
+        const uint32_t buf = NBUF == 2 ? (it & 1u) : 0u;
+        const uint32_t parity = NBUF == 2 ? ((it >> 1) & 1u) : (it & 1u);
+        const uint64_t nxt = grp + gridDim.x;
+        if (NBUF == 2 && threadIdx.x == 0 && nxt < n_groups) {
+            proxy_fence_async();             // the other buffer was read (phase A, previous iteration) before the last barrier
+            issue(nxt, buf ^ 1u);
+        }
+        mbar_wait(bar + buf, parity);
+        const uint64_t blk0 = (grp * TILES + g) * 32u;
+        const bool full = blk0 + 32u <= T;
+        {
+            const uint32_t *col = raw + buf * group_words + g * 32u * WC + c;
+            uint32_t x[32];
+            if (full) {
+#pragma unroll
+                for (int b = 0; b < 32; ++b) x[b] = col[b * WC];
+            } else {
+#pragma unroll
+                for (int b = 0; b < 32; ++b) x[b] = (blk0 + b < T) ? col[b * WC] : 0u;   // rows past the end were not copied
+            }
+            transpose32(x);
+            store_slices(tile + kStride * c, x);
+        }
+        __syncthreads();
+        if (NBUF == 1 && threadIdx.x == 0 && nxt < n_groups) {
+            proxy_fence_async();             // every thread has read its column of the buffer before the barrier
+            issue(nxt, 0);
+        }
+        uint32_t *dst = out + blk0 * WC + c;
+        if (full) {
+            uint32_t y[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) y[j] = lds_u32(addr[j]);
+            column_out<WC, true>(y, dst, blk0, T, WC);
+        } else {
+            column_out_ragged<WC>(tile_addr, slice_map + c, dst, blk0, T, WC);
+        }
+        __syncthreads();   // before the next group overwrites the slices
+    }
+}
+
 // Any W (runtime): work items (tile, column) strided over the CTA's threads.
 __global__ void __launch_bounds__(512, 2)
 permute_sliced_kernel(const uint32_t *__restrict__ in, const uint64_t T, const uint32_t W,
@@ -297,6 +383,24 @@ cudaError_t launch_fixed(const uint64_t *in, uint64_t T, const uint32_t *slice_m
                          reinterpret_cast<const uint32_t *>(in), T, slice_map, reinterpret_cast<uint32_t *>(out), n_groups);
 }
 
+template <int WC, int TILES, int NBUF, int MINB, int WAVES>
+cudaError_t launch_prefetch(const uint64_t *in, uint64_t T, const uint32_t *slice_map, uint64_t *out, cudaStream_t stream) {
+    constexpr size_t smem = ((size_t)NBUF * TILES * 32u * WC + (size_t)TILES * (kStride * WC + 4u)) * sizeof(uint32_t) +
+                            NBUF * sizeof(uint64_t);
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        cudaError_t e = resident_ctas(permute_prefetch_kernel<WC, TILES, NBUF, MINB>, WC * TILES, smem, &per_sm);
+        if (e != cudaSuccess) return e;
+    }
+    const uint64_t n_tiles = (T + 31) / 32;
+    const uint64_t n_groups = (n_tiles + TILES - 1) / TILES;
+    const uint64_t cap =
+        (uint64_t)device_props().sm_count * per_sm * (uint64_t)std::max<long>(1, env_long("CSGN_PERM_WAVES", WAVES));
+    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_groups, cap));
+    return launch_kernel(permute_prefetch_kernel<WC, TILES, NBUF, MINB>, grid, WC * TILES, smem, stream,
+                         reinterpret_cast<const uint32_t *>(in), T, slice_map, reinterpret_cast<uint32_t *>(out), n_groups);
+}
+
 cudaError_t launch_sliced(const uint64_t *in, uint64_t T, uint32_t W, const uint32_t *slice_map, uint64_t *out,
                           uint32_t tiles_per_cta, uint32_t tpb, size_t smem, cudaStream_t stream) {
     const DeviceProps &dp = device_props();
@@ -333,7 +437,17 @@ cudaError_t launch_permute(const uint64_t *in, uint64_t T, uint32_t L, uint32_t 
         const uint32_t W = 2 * L;
         const long variant = env_long("CSGN_PERM_VARIANT", 0);   // 1: the runtime-W kernel even for known shapes
         count_launch();
-        if (W == 40 && variant == 0) return launch_fixed<40, 4, true, 4, 4>(in, T, slice_map, out, stream);     // N=1247
+        const bool aligned16 = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;      // bulk copies need it
+        if (W == 40 && variant == 0 && aligned16) {                                                            // N=1247
+            // B200 sweeps (profiles/): 2 waves of resident CTAs up to a few million blocks, 4 beyond
+            if (T >= 4000000) return launch_prefetch<40, 4, 1, 4, 4>(in, T, slice_map, out, stream);
+            return launch_prefetch<40, 4, 1, 4, 2>(in, T, slice_map, out, stream);
+        }
+        if (W == 40 && (variant == 0 || variant == 8)) return launch_fixed<40, 4, true, 4, 4>(in, T, slice_map, out, stream);
+        if (W == 40 && variant == 4 && aligned16) return launch_prefetch<40, 4, 2, 3, 1>(in, T, slice_map, out, stream);
+        if (W == 40 && variant == 5 && aligned16) return launch_prefetch<40, 4, 1, 4, 1>(in, T, slice_map, out, stream);
+        if (W == 40 && variant == 6 && aligned16) return launch_prefetch<40, 4, 2, 3, 4>(in, T, slice_map, out, stream);
+        if (W == 40 && variant == 7 && aligned16) return launch_prefetch<40, 4, 1, 4, 4>(in, T, slice_map, out, stream);
         if (W == 40 && variant == 2) return launch_fixed<40, 4, false, 6, 4>(in, T, slice_map, out, stream);
         if (W == 40 && variant == 3) return launch_fixed<40, 8, true, 2, 4>(in, T, slice_map, out, stream);
         if (W == 512 && variant == 0) return launch_fixed<512, 1, false, 2, 16>(in, T, slice_map, out, stream);  // N=16383

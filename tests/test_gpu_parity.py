@@ -315,6 +315,24 @@ def test_permute_matches_oracle(engine, oracle, N):
     assert np.array_equal(ct.applyPermutation(p).applyPermutation(inv).getValues(), v)
 
 
+@pytest.mark.parametrize("N", [1247, 16383])
+def test_permute_every_kernel_variant(engine, oracle, N):
+    """The tuned shapes have several forms of the bit-sliced kernel (registers vs global slice map, tiles per CTA,
+    the runtime-W kernel, the bulk-copy prefetch of the next group's tiles); ragged and multi-wave sizes."""
+    rng = np.random.default_rng(N + 5)
+    ctx = engine.Context(N, 4)
+    perm = rng.permutation(N).astype(np.uint64)
+    p = engine.Permutation(ctx, perm)
+    for T in ([1, 31, 32, 127, 128, 129, 255, 300, 4097, 70001] if N == 1247 else [1, 33, 700]):
+        v = random_blocks(rng, T, N)
+        ct = engine.Ciphertext.from_host(v, ctx)
+        want = oracle.permute_all(v, N, perm)
+        for variant in (0, 1, 2, 3, 4, 5, 6, 7, 8):
+            for waves in (1, 3):
+                with _Env(CSGN_PERM_VARIANT=variant, CSGN_PERM_WAVES=waves):
+                    assert np.array_equal(ct.applyPermutation(p).getValues(), want), (N, T, variant, waves)
+
+
 def test_permutation_must_be_a_bijection(engine):
     ctx = engine.Context(65, 2)
     bad = np.arange(65, dtype=np.uint64)
@@ -570,3 +588,53 @@ def test_torch_views_and_stream(engine, oracle):
     va.mul_into(vb, vo)
     engine.sync()
     assert engine.launch_count() == before + 1
+
+
+# ---------------------------------------------------------------------------
+# independent ciphertexts on several streams; upload storage recycling
+# ---------------------------------------------------------------------------
+def test_concurrent_streams_and_upload_recycling(engine, oracle):
+    """Pairs enqueued round-robin on three streams (csgn_set_stream between calls, as bench.py does): folds of
+    different streams run concurrently (per-launch scratch), uploads reuse the storage of freed uploads
+    (completion-event cache) while earlier consumers may still be in flight.  Every count and every product
+    checksum must still match the oracle."""
+    import torch
+    N, D, L = 1247, 2, 20
+    rng = np.random.default_rng(99)
+    ctx = engine.Context(N, D)
+    s = random_key(rng, N, D)
+    key = engine.SecretKey(ctx, s)
+    P, rounds = 12, 6
+    sizes = [(rng.integers(50, 400), rng.integers(50, 400)) for _ in range(P)]
+    host = [[(random_blocks(rng, int(t1), N), random_blocks(rng, int(t2), N)) for (t1, t2) in sizes] for _ in range(rounds)]
+    want = [[oracle.count_satisfied(oracle.mul(a, b, L), N, s) for (a, b) in row] for row in host]
+    pinned = [[(torch.from_numpy(a.view(np.int64)).pin_memory(), torch.from_numpy(b.view(np.int64)).pin_memory())
+               for (a, b) in row] for row in host]
+    main = torch.cuda.Stream()
+    streams = [main, torch.cuda.Stream(), torch.cuda.Stream()]
+    counts = torch.full((rounds, P), -1, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    try:
+        for r in range(rounds):
+            for p in range(P):
+                st = streams[p % 3]
+                engine.set_stream(st.cuda_stream)
+                ta, tb = pinned[r][p]
+                ha = engine.Ciphertext.from_host_ptr(ta.data_ptr(), sizes[p][0], ctx)
+                hb = engine.Ciphertext.from_host_ptr(tb.data_ptr(), sizes[p][1], ctx)
+                prod = ha * hb
+                key.count_satisfied_async(prod, counts[r, p].data_ptr())
+                del ha, hb, prod             # storage goes back while the kernels above may still be running
+        torch.cuda.synchronize()
+    finally:
+        engine.set_stream(None)
+    assert counts.tolist() == want
+    # a recycled upload never shows stale words: upload, free, upload something else of the same size, download
+    a1, a2 = random_blocks(rng, 300, N), random_blocks(rng, 300, N)
+    c1 = engine.Ciphertext.from_host(a1, ctx)
+    del c1
+    engine.sync()
+    c2 = engine.Ciphertext.from_host(a2, ctx)
+    assert np.array_equal(c2.getValues(), a2)
+    c2 += engine.Ciphertext.from_host(a1, ctx)      # growing an upload moves it out of the recycled storage
+    assert np.array_equal(c2.getValues(), np.concatenate([a2, a1]))

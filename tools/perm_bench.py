@@ -28,11 +28,14 @@ for N, T, nbuf in ((1247, 1000000, 6), (16383, 90000, 6), (1247, 10000000, 2)):
                        ("fixed waves=16", {"CSGN_PERM_WAVES": "16"}),
                        ("fixed variant 2", {"CSGN_PERM_VARIANT": "2"}), ("fixed variant 2 waves=4", {"CSGN_PERM_VARIANT": "2", "CSGN_PERM_WAVES": "4"}),
                        ("fixed variant 3", {"CSGN_PERM_VARIANT": "3"}),
+                       ("prefetch 2 buffers", {"CSGN_PERM_VARIANT": "4"}), ("prefetch 1 buffer", {"CSGN_PERM_VARIANT": "5"}),
+                       ("prefetch 2 buffers waves=4", {"CSGN_PERM_VARIANT": "6"}), ("prefetch 1 buffer waves=4", {"CSGN_PERM_VARIANT": "7"}),
+                       ("prefetch 1 buffer waves=2", {"CSGN_PERM_VARIANT": "5", "CSGN_PERM_WAVES": "2"}),
                        ("runtime-W kernel", {"CSGN_PERM_VARIANT": "1"}), ("runtime-W waves=1", {"CSGN_PERM_VARIANT": "1", "CSGN_PERM_WAVES": "1"}),
                        ("gather", {"CSGN_PERM_GATHER": "1"})):
         for k in ("CSGN_PERM_ITEMS", "CSGN_PERM_WAVES", "CSGN_PERM_GATHER", "CSGN_PERM_VARIANT"): os.environ.pop(k, None)
         os.environ.update(env)
         ms = timed()
-        print("N=%d T=%d %-24s %9.2f us  %7.1f GB/s (read+write)  %.3g blocks/s" % (N, T, label, ms * 1e3, nbytes / ms / 1e6, T / ms * 1e3), flush=True)
+        print("N=%d T=%d %-28s %9.2f us  %7.1f GB/s (read+write)  %.3g blocks/s" % (N, T, label, ms * 1e3, nbytes / ms / 1e6, T / ms * 1e3), flush=True)
     del ins, outs, vi, vo
     torch.cuda.empty_cache()
