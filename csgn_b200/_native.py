@@ -32,6 +32,7 @@ SIGNATURES = {
     "csgn_buf_clone": (ctypes.c_int, [_vp, _vpp]),
     "csgn_buf_download": (ctypes.c_int, [_vp, _vp]),
     "csgn_buf_download_range": (ctypes.c_int, [_vp, _u64, _u64, _vp]),
+    "csgn_buf_slice": (ctypes.c_int, [_vp, _u64, _u64, _vpp]),
     "csgn_buf_free": (ctypes.c_int, [_vp]),
     "csgn_buf_blocks": (_u64, [_vp]),
     "csgn_buf_words_per_block": (ctypes.c_uint32, [_vp]),
@@ -59,6 +60,7 @@ SIGNATURES = {
     "csgn_comm_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vpp, _vp]),
     "csgn_comm_connect": (ctypes.c_int, [_vp, _vp]),
     "csgn_comm_connect_ptrs": (ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
+    "csgn_comm_connect_dir": (ctypes.c_int, [_vp, _vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]),
     "csgn_comm_mailbox": (_vp, [_vp, ctypes.POINTER(ctypes.c_size_t)]),
     "csgn_comm_free": (ctypes.c_int, [_vp]),
     "csgn_comm_pending": (ctypes.c_uint32, [_vp]),

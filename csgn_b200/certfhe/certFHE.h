@@ -65,6 +65,17 @@ public:
     // 10^9-block chain that is only ever decrypted never touches 160 GB of HBM.
     static void setLazyProducts(bool lazy);
     static bool getLazyProducts();
+    // Multi-GPU, one process per GPU.  connectPeers joins the `world` processes of a job: every
+    // rank publishes the handle of its mailbox under rendezvous_dir (csgn_comm_connect_dir; `job_tag` unique per
+    // job) and maps the others' over NVLink.  initializeLibrary() does this by itself when the launcher exports
+    // WORLD_SIZE, RANK, LOCAL_RANK and CSGN_RENDEZVOUS_DIR (optionally CSGN_JOB_TAG; default: MASTER_PORT).
+    // Afterwards Ciphertext::shard() keeps this rank's block range of a replicated ciphertext, products with a
+    // replicated right operand stay shard-local, and SecretKey::decrypt of a sharded ciphertext returns the
+    // GLOBAL bit on every rank (the fold kernel exchanges the counts itself).  Every rank must run the same
+    // sequence of sharded decrypts.
+    static void connectPeers(int rank, int world, const std::string &rendezvous_dir, const std::string &job_tag);
+    static int getRank();
+    static int getWorldSize();
 };
 
 class Helper {
@@ -152,6 +163,7 @@ class Ciphertext {
     mutable uint64_t host_len; // length of the mirrors, in words
     mutable bool host_v_valid;
     bool staged;               // words exist only in host_v (no context yet / not uploadable)
+    bool sharded;              // holds only this rank's block range of a ciphertext spread over the job's GPUs
 
     void invalidate_mirror() const;
     void release();
@@ -193,6 +205,11 @@ public:
     // through pinned staging (csgn_buf_save / csgn_buf_load).  The reference has no serialisation.
     void save(const std::string &path) const;
     static Ciphertext load(const std::string &path);
+    // This rank's contiguous block range (csgn_shard_range) of a ciphertext that every rank holds in full.
+    // The result is marked sharded: * with a replicated right operand, applyPermutation and + of two sharded
+    // ciphertexts stay shard-local; getValues()/getLen()/operator<< see the local blocks only.
+    Ciphertext shard() const;
+    bool isSharded() const;
     uint64_t getBlocks() const;            // number of N-bit blocks
     const csgn_buf *deviceBuffer() const;  // uploads staged words first
 };

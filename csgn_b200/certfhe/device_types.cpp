@@ -65,7 +65,7 @@ std::shared_ptr<csgn_buf> adopt(csgn_buf *b) {
 
 Ciphertext::Ciphertext()
     : certFHEcontext(nullptr), host_v(nullptr), host_bitlen(nullptr), host_len(0), host_v_valid(false),
-      staged(false) {}
+      staged(false), sharded(false) {}
 
 Ciphertext::Ciphertext(const uint64_t *V, const uint64_t *Bitlen, const uint64_t len, const Context &context)
     : Ciphertext() {
@@ -87,6 +87,7 @@ Ciphertext::Ciphertext(const Ciphertext &o) : Ciphertext() {
     // The reference deep-copies (src/Ciphertext.cpp:360-363).  Device buffers are never
     // modified in place once shared, so a copy shares them; += clones first when needed.
     if (o.certFHEcontext) certFHEcontext = new Context(*o.certFHEcontext);
+    sharded = o.sharded;
     if (o.staged) {
         host_v = copy_words(o.host_v, o.host_len);
         if (o.host_bitlen) host_bitlen = copy_words(o.host_bitlen, o.host_len);
@@ -101,7 +102,8 @@ Ciphertext::Ciphertext(const Ciphertext &o) : Ciphertext() {
 
 Ciphertext::Ciphertext(Ciphertext &&o) noexcept
     : dev(std::move(o.dev)), factors(std::move(o.factors)), certFHEcontext(o.certFHEcontext), host_v(o.host_v),
-      host_bitlen(o.host_bitlen), host_len(o.host_len), host_v_valid(o.host_v_valid), staged(o.staged) {
+      host_bitlen(o.host_bitlen), host_len(o.host_len), host_v_valid(o.host_v_valid), staged(o.staged),
+      sharded(o.sharded) {
     o.factors.clear();
     o.certFHEcontext = nullptr;
     o.host_v = o.host_bitlen = nullptr;
@@ -209,6 +211,24 @@ void Ciphertext::setContext(const Context &context) {
     certFHEcontext = fresh;
     if (staged && fresh->getDefaultN() && host_len % fresh->getDefaultN() == 0) upload_staged();
 }
+
+Ciphertext Ciphertext::shard() const {
+    if (sharded) return *this;
+    const csgn_buf *whole = deviceBuffer();
+    if (!whole) throw Error("Ciphertext::shard: empty ciphertext");
+    uint64_t first = 0, count = 0;
+    glue::check(csgn_shard_range(csgn_buf_blocks(whole), Library::getRank(), Library::getWorldSize(), &first, &count),
+                "csgn_shard_range");
+    csgn_buf *mine = nullptr;
+    glue::check(csgn_buf_slice(whole, first, count, &mine), "csgn_buf_slice");
+    Ciphertext out;
+    if (certFHEcontext) out.certFHEcontext = new Context(*certFHEcontext);
+    out.dev = adopt(mine);
+    out.sharded = true;
+    return out;
+}
+
+bool Ciphertext::isSharded() const { return sharded; }
 
 uint64_t Ciphertext::getBlocks() const {
     if (staged) {
@@ -322,6 +342,7 @@ Ciphertext &Ciphertext::operator=(Ciphertext &&o) noexcept {
     host_len = o.host_len;
     host_v_valid = o.host_v_valid;
     staged = o.staged;
+    sharded = o.sharded;
     o.certFHEcontext = nullptr;
     o.host_v = o.host_bitlen = nullptr;
     o.host_len = 0;
@@ -329,9 +350,21 @@ Ciphertext &Ciphertext::operator=(Ciphertext &&o) noexcept {
     return *this;
 }
 
+namespace {
+// a + b over several GPUs: both sharded (each rank concatenates its parts; block ORDER across ranks is then no
+// longer the single-process order, which decrypt does not observe) or neither
+void require_same_sharding(bool a, bool b, bool a_empty, bool b_empty, const char *op) {
+    if (a != b && !a_empty && !b_empty)
+        throw Error(string(op) + ": one operand is sharded and the other replicated (the replicated blocks would be "
+                    "counted once per rank); call shard() on it first");
+}
+}  // namespace
+
 Ciphertext Ciphertext::operator+(const Ciphertext &c) const {
     const csgn_buf *a = deviceBuffer(), *b = c.deviceBuffer();
+    require_same_sharding(sharded, c.sharded, !a, !b, "Ciphertext::operator+");
     Ciphertext out;
+    out.sharded = (a && sharded) || (b && c.sharded);
     const Context *ctx = certFHEcontext ? certFHEcontext : c.certFHEcontext;
     if (ctx) out.certFHEcontext = new Context(*ctx);
     if (a && b) {
@@ -352,8 +385,10 @@ Ciphertext &Ciphertext::operator+=(const Ciphertext &c) {
     }
     deviceBuffer();
     if (!rhs) return *this;
+    require_same_sharding(sharded, c.sharded, !dev, false, "Ciphertext::operator+=");
     if (!certFHEcontext && c.certFHEcontext) certFHEcontext = new Context(*c.certFHEcontext);
     if (!dev) {
+        sharded = c.sharded;
         dev = rhs;
     } else {
         if (dev.use_count() > 1 + (dev == rhs ? 1 : 0)) {   // shared with a copy: do not grow it under the other owner
@@ -368,7 +403,11 @@ Ciphertext &Ciphertext::operator+=(const Ciphertext &c) {
 }
 
 Ciphertext Ciphertext::operator*(const Ciphertext &c) const {
+    if (c.sharded)
+        throw Error("Ciphertext::operator*: the right operand of a product must be replicated (the LEFT operand is the "
+                    "sharded one: rank g then owns output blocks [first*T2, (first+count)*T2), SURVEY.md 8e)");
     Ciphertext out;
+    out.sharded = sharded;
     // the reference multiplies in the LEFT operand's context (src/Ciphertext.cpp:239)
     if (certFHEcontext) out.certFHEcontext = new Context(*certFHEcontext);
     if (Library::getLazyProducts()) {
@@ -387,6 +426,7 @@ Ciphertext Ciphertext::operator*(const Ciphertext &c) const {
 }
 
 Ciphertext &Ciphertext::operator*=(const Ciphertext &c) {
+    if (c.sharded) throw Error("Ciphertext::operator*=: the right operand of a product must be replicated");
     if (Library::getLazyProducts()) {
         std::vector<std::shared_ptr<csgn_buf> > f;
         collect_factors(f);
@@ -439,6 +479,7 @@ Ciphertext Ciphertext::applyPermutation(const Permutation &permutation) {
     const bool strict = Library::getStrictReferencePermutation();
     Ciphertext out;
     out.certFHEcontext = new Context(*certFHEcontext);
+    out.sharded = sharded;
     if (!factors.empty() && !strict) {
         // a permutation acts on each block, and a product block is an AND of factor blocks:
         // pi(a_i & b_j) = pi(a_i) & pi(b_j) -- permute the factors, stay lazy
@@ -601,6 +642,14 @@ Plaintext SecretKey::decrypt(Ciphertext &ciphertext) {
         glue::check(csgn_key_create(certFHEContext->getN(), s, (uint32_t)length, &device_key), "csgn_key_create");
     }
     uint8_t bit = 0;
+    if (ciphertext.sharded) {
+        // this rank's blocks only: the fold kernel publishes its count to the peers and collects theirs
+        if (!glue::comm()) throw Error("SecretKey::decrypt: sharded ciphertext but no peers (Library::connectPeers)");
+        const csgn_buf *local = ciphertext.deviceBuffer();   // multiplies pending factors out
+        if (!local) throw Error("SecretKey::decrypt: sharded ciphertext without blocks");
+        glue::check(csgn_decrypt_sharded(local, device_key, glue::comm(), &bit, nullptr), "csgn_decrypt_sharded");
+        return Plaintext(bit);
+    }
     if (!ciphertext.factors.empty()) {
         // a product that was never multiplied out: Dec(f0*f1*...) = Dec(f0) & Dec(f1) & ...
         std::vector<const csgn_buf *> fs;

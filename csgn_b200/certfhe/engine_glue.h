@@ -13,6 +13,9 @@ namespace glue {
 // certFHE::Error when no sm_100 device is usable: there is no CPU path to fall back to.
 void ensure_engine();
 
+// The job's peer communicator (Library::connectPeers), or null in a single-process run.
+csgn_comm *comm();
+
 // Turns a non-zero csgn_status into a certFHE::Error carrying csgn_last_error().
 void check(int status, const char *what);
 

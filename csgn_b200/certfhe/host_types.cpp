@@ -23,7 +23,48 @@ void Library::initializeLibrary() {
     // reference src/Helpers.cpp:8-12: the PRNG is seeded with the local time
     srand(time(NULL));
     glue::ensure_engine();
+    // one process per GPU under a launcher: join the job's peers
+    const char *ws = getenv("WORLD_SIZE"), *rk = getenv("RANK"), *dir = getenv("CSGN_RENDEZVOUS_DIR");
+    if (ws && rk && dir && atoi(ws) >= 1 && !glue::comm()) {
+        const char *tag = getenv("CSGN_JOB_TAG");
+        if (!tag || !*tag) tag = getenv("MASTER_PORT");
+        connectPeers(atoi(rk), atoi(ws), dir, tag && *tag ? tag : "job");
+    }
 }
+
+namespace {
+csgn_comm *g_comm = nullptr;
+int g_rank = 0, g_world = 1;
+}  // namespace
+
+namespace glue {
+csgn_comm *comm() { return g_comm; }
+}  // namespace glue
+
+void Library::connectPeers(int rank, int world, const std::string &rendezvous_dir, const std::string &job_tag) {
+    glue::ensure_engine();
+    if (g_comm) throw Error("Library::connectPeers: already connected");
+    unsigned char handle[CSGN_IPC_HANDLE_BYTES];
+    csgn_comm *c = nullptr;
+    glue::check(csgn_comm_create(rank, world, &c, handle), "csgn_comm_create");
+    const char *t = getenv("CSGN_RENDEZVOUS_TIMEOUT_MS");
+    const int rc = csgn_comm_connect_dir(c, handle, rendezvous_dir.c_str(), job_tag.c_str(), t && *t ? atoi(t) : 60000);
+    if (rc != CSGN_OK) {
+        const std::string why = csgn_last_error();
+        csgn_comm_free(c);
+        throw Error("Library::connectPeers: " + why);
+    }
+    g_comm = c;
+    g_rank = rank;
+    g_world = world;
+    atexit([] {                      // closes the peer mappings and removes this rank's handle file
+        if (g_comm) csgn_comm_free(g_comm);
+        g_comm = nullptr;
+    });
+}
+
+int Library::getRank() { return g_rank; }
+int Library::getWorldSize() { return g_world; }
 
 void Library::setStrictReferencePermutation(bool strict) {
     g_strict_permute = strict;

@@ -4,6 +4,8 @@
 #include "../../include/csgn.h"
 
 #include <cuda_runtime.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -11,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -57,6 +60,7 @@ struct csgn_comm {
     uint64_t *d_local_ring = nullptr;              // kPeerRing words: this rank's counts by slot
     uint64_t *d_status = nullptr;                  // [0] timeout flag, [1] blocking-call total
     uint64_t timeout_ns = 30ull * 1000 * 1000 * 1000;
+    std::string rendezvous_file;                   // written by csgn_comm_connect_dir, removed on free
 };
 
 namespace csgn {
@@ -445,6 +449,25 @@ int csgn_buf_clone(const csgn_buf *src, csgn_buf **out) {
     if (e != cudaSuccess) {
         csgn_buf_free(b);
         return cuda_fail(e, "clone kernel");
+    }
+    *out = b;
+    return CSGN_OK;
+}
+
+int csgn_buf_slice(const csgn_buf *src, uint64_t first_block, uint64_t n_blocks, csgn_buf **out) {
+    NEED_INIT();
+    if (!src || !out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
+    if (first_block > src->n_blocks || n_blocks > src->n_blocks - first_block)
+        return fail(CSGN_ERR_INVALID_ARGUMENT, "block range [%llu,+%llu) outside %llu blocks",
+                    (unsigned long long)first_block, (unsigned long long)n_blocks, (unsigned long long)src->n_blocks);
+    csgn_buf *b = nullptr;
+    int rc = new_buf(n_blocks, src->L, 0, &b);
+    if (rc != CSGN_OK) return rc;
+    await_upload(src);
+    cudaError_t e = launch_concat(src->d + first_block * src->L, n_blocks * src->L, nullptr, 0, b->d, g.stream);
+    if (e != cudaSuccess) {
+        csgn_buf_free(b);
+        return cuda_fail(e, "slice kernel");
     }
     *out = b;
     return CSGN_OK;
@@ -1130,6 +1153,48 @@ int csgn_comm_connect_ptrs(csgn_comm *comm, void *const *peer_mailboxes) {
     return CSGN_OK;
 }
 
+int csgn_comm_connect_dir(csgn_comm *comm, const unsigned char *handle, const char *dir, const char *tag,
+                          int timeout_ms) {
+    NEED_INIT();
+    if (!comm || !handle || !dir || !tag) return fail(CSGN_ERR_INVALID_ARGUMENT, "null argument");
+    if (comm->world == 1) {
+        comm->connected = true;
+        return CSGN_OK;
+    }
+    auto path_of = [&](int r) {
+        return std::string(dir) + "/csgn_" + tag + "_" + std::to_string(comm->world) + "_" + std::to_string(r) + ".handle";
+    };
+    const time_t started = time(nullptr);
+    const std::string mine = path_of(comm->rank), tmp = mine + ".tmp";
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return fail(CSGN_ERR_INVALID_ARGUMENT, "cannot write %s", tmp.c_str());
+    const bool ok = fwrite(handle, 1, CSGN_IPC_HANDLE_BYTES, f) == CSGN_IPC_HANDLE_BYTES;
+    if (fclose(f) != 0 || !ok || rename(tmp.c_str(), mine.c_str()) != 0)
+        return fail(CSGN_ERR_INVALID_ARGUMENT, "cannot publish %s", mine.c_str());
+    comm->rendezvous_file = mine;
+    std::vector<unsigned char> all((size_t)comm->world * CSGN_IPC_HANDLE_BYTES, 0);
+    memcpy(all.data() + (size_t)comm->rank * CSGN_IPC_HANDLE_BYTES, handle, CSGN_IPC_HANDLE_BYTES);
+    for (int q = 0; q < comm->world; ++q) {
+        if (q == comm->rank) continue;
+        const std::string theirs = path_of(q);
+        for (long waited_ms = 0;; waited_ms += 2) {
+            struct stat st;
+            if (stat(theirs.c_str(), &st) == 0 && st.st_size == CSGN_IPC_HANDLE_BYTES && st.st_mtime >= started - 120) {
+                FILE *g2 = fopen(theirs.c_str(), "rb");
+                const bool got = g2 && fread(all.data() + (size_t)q * CSGN_IPC_HANDLE_BYTES, 1, CSGN_IPC_HANDLE_BYTES, g2) ==
+                                           CSGN_IPC_HANDLE_BYTES;
+                if (g2) fclose(g2);
+                if (got) break;
+            }
+            if (waited_ms >= timeout_ms)
+                return fail(CSGN_ERR_TIMEOUT, "rank %d of %d did not publish %s within %d ms", q, comm->world,
+                            theirs.c_str(), timeout_ms);
+            usleep(2000);
+        }
+    }
+    return csgn_comm_connect(comm, all.data());
+}
+
 void *csgn_comm_mailbox(const csgn_comm *comm, size_t *bytes) {
     if (bytes) *bytes = kMailboxBytes;
     return comm ? comm->box_local : nullptr;
@@ -1144,6 +1209,7 @@ void csgn_comm_slot_tag(uint64_t seq, uint32_t *slot, uint64_t *tag) {
 
 int csgn_comm_free(csgn_comm *comm) {
     if (!comm) return CSGN_OK;
+    if (!comm->rendezvous_file.empty()) remove(comm->rendezvous_file.c_str());
     if (g.inited) {
         cudaStreamSynchronize(g.stream);
         for (int q = 0; q < comm->world; ++q)

@@ -89,6 +89,9 @@ int csgn_buf_clone(const csgn_buf *src, csgn_buf **out);
 int csgn_buf_download(const csgn_buf *buf, uint64_t *host_words);
 int csgn_buf_download_range(const csgn_buf *buf, uint64_t first_block, uint64_t n_blocks,
                             uint64_t *host_words);
+/* Device-to-device copy of the block range [first_block, first_block + n_blocks): the shard of a replicated
+ * ciphertext that one rank keeps (with csgn_shard_range). */
+int csgn_buf_slice(const csgn_buf *src, uint64_t first_block, uint64_t n_blocks, csgn_buf **out);
 int csgn_buf_free(csgn_buf *buf);
 uint64_t csgn_buf_blocks(const csgn_buf *buf);
 uint32_t csgn_buf_words_per_block(const csgn_buf *buf);
@@ -202,6 +205,13 @@ typedef struct csgn_comm csgn_comm;
 int csgn_comm_create(int rank, int world, csgn_comm **out, unsigned char *handle_out);
 int csgn_comm_connect(csgn_comm *comm, const unsigned char *handles);
 int csgn_comm_connect_ptrs(csgn_comm *comm, void *const *peer_mailboxes);
+/* Handle exchange through a directory every rank can see (a launcher without a communication library:
+ * N processes started by a shell loop).  Writes `handle` to <dir>/csgn_<tag>_<world>_<rank>.handle, waits up
+ * to timeout_ms for the other ranks' files, connects.  `tag` must be unique per job; files older than two
+ * minutes before this call are taken for leftovers of a dead job and ignored; csgn_comm_free removes
+ * this rank's file. */
+int csgn_comm_connect_dir(csgn_comm *comm, const unsigned char *handle, const char *dir, const char *tag,
+                          int timeout_ms);
 /* This rank's mailbox (device pointer) and its size in bytes. */
 void *csgn_comm_mailbox(const csgn_comm *comm, size_t *bytes);
 int csgn_comm_free(csgn_comm *comm);

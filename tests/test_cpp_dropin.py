@@ -116,3 +116,31 @@ def test_unmodified_reference_demos_run_on_the_dropin(demo, lines):
     assert r.returncode == 0, r.stdout[-4000:]
     for line in lines:
         assert line in r.stdout, (line, r.stdout[-2000:])
+
+
+@pytest.mark.gpu
+def test_cpp_api_sharded_over_the_gpus_of_the_box(tmp_path):
+    """tests/cpp/sharded_demo.cpp: one process per GPU started by a plain loop (no torch, no MPI); the ranks meet through
+    a directory, Ciphertext::shard() + shard-local products + SecretKey::decrypt with the exchange inside the fold
+    kernel.  One process on a one-GPU box (same code path, own mailbox only), min(4, n) processes otherwise."""
+    import torch
+    exe = os.path.join(BIN, "sharded_demo")
+    assert os.path.exists(exe)
+    world = max(1, min(4, torch.cuda.device_count()))
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), CSGN_RENDEZVOUS_DIR=str(tmp_path),
+                   CSGN_JOB_TAG="pytest%d" % os.getpid(), CSGN_PEER_TIMEOUT_MS="20000")
+        procs.append(subprocess.Popen([exe], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=600)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            out, _ = p.communicate()
+        outs.append((p.returncode, out))
+    for r, (rc, out) in enumerate(outs):
+        assert rc == 0, "rank %d:\n%s" % (r, out[-3000:])
+        assert "sharded_demo rank %d/%d: all checks passed" % (r, world) in out
+    assert not [f for f in os.listdir(tmp_path) if f.endswith(".handle")]      # every rank removed its handle file
