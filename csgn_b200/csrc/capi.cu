@@ -235,7 +235,15 @@ int new_buf(uint64_t n_blocks, uint32_t L, uint64_t cap_words, csgn_buf **out, c
 
 const DeviceProps &device_props() { return g_props; }
 void set_device_props(const DeviceProps &p) { g_props = p; }
-void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+// A caller that moves between streams from one call to the next (csgn_set_stream) is enqueueing independent
+// ciphertexts so that their kernels overlap; launchers that care (the decrypt fold) then prefer several shorter waves of
+// CTAs, which back-fill behind another stream's kernel, over one persistent wave, which is best for a kernel running alone.
+static unsigned g_launches_since_switch = 1u << 30;
+void count_launch(unsigned n) {
+    g_launches.fetch_add(n, std::memory_order_relaxed);
+    if (g_launches_since_switch < (1u << 30)) g_launches_since_switch += n;
+}
+bool streams_alternate() { return g_launches_since_switch < 8; }
 uint64_t launches() { return g_launches.load(std::memory_order_relaxed); }
 
 // Tuning knobs (CSGN_MUL_*, CSGN_DEC_*, CSGN_PERM_*, CSGN_PDL ...) are looked up only when
@@ -347,7 +355,9 @@ int csgn_device_info(int *sm_count, uint64_t *hbm_total, uint64_t *hbm_free, int
 
 int csgn_set_stream(void *cuda_stream) {
     NEED_INIT();
-    g.stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : g.own_stream;
+    cudaStream_t next = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : g.own_stream;
+    if (next != g.stream) csgn::g_launches_since_switch = 0;
+    g.stream = next;
     return CSGN_OK;
 }
 

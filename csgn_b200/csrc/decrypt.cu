@@ -450,7 +450,13 @@ cudaError_t launch_lanes(const uint64_t *v, uint64_t T, const uint64_t *host_mas
     constexpr uint32_t BPS = 32u / L4;
     const uint64_t n_steps = (T + BPS - 1) / BPS;
     const uint64_t work_ctas = (n_steps + (uint64_t)kDecWarps * U - 1) / ((uint64_t)kDecWarps * U);
-    const uint32_t grid = resident_grid(decrypt_count_lanes_kernel<L4, U, MINB>, 0, work_ctas);
+    // One persistent wave of resident CTAs is best for a fold running alone at sizes where ramp and tail matter
+    // (160 MB: 26.4 vs 27.4 us); four shorter waves are better beyond a GiB (+3 %) and when the caller overlaps folds
+    // of several streams (back-fill behind the other stream's kernel: 24.5 -> 23.5 us per fold in the bench).
+    const bool many = streams_alternate() || T * (uint64_t)L4 * 16u >= (1ull << 30);
+    const uint64_t waves = (uint64_t)std::max<long>(1, env_long("CSGN_DEC_WAVES", many ? 4 : 1));
+    uint32_t grid = resident_grid(decrypt_count_lanes_kernel<L4, U, MINB>, 0, work_ctas);
+    grid = (uint32_t)std::min<uint64_t>(work_ctas, (uint64_t)grid * waves);
     return launch_kernel(decrypt_count_lanes_kernel<L4, U, MINB>, grid, kDecThreads, 0, stream,
                          reinterpret_cast<const uint4 *>(v), T, pm, scratch, count_out, pp);
 }

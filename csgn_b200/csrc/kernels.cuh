@@ -20,6 +20,8 @@ const DeviceProps &device_props();
 void set_device_props(const DeviceProps &p);
 void count_launch(unsigned n = 1);
 uint64_t launches();
+// true while the caller keeps switching streams between calls (independent work meant to overlap)
+bool streams_alternate();
 
 // Integer environment knob (tuning sweeps only); `dflt` when unset or malformed.
 long env_long(const char *name, long dflt);
