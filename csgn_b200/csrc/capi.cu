@@ -32,6 +32,7 @@ struct csgn_buf {
     bool owns = true;
     bool recycle = false;      // storage of an upload: goes back to the upload cache, not to the pool
     mutable cudaEvent_t ready = nullptr;  // an upload on the copy stream still in flight
+    mutable cudaStream_t last_stream = nullptr;  // the stream of the last operation that touched the words
 };
 
 struct csgn_key {
@@ -206,13 +207,27 @@ bool give_upload_slot(uint64_t *d, uint64_t cap_words) {
     return true;
 }
 
-// Order the work stream after a pending upload of `b` (first consumer only).
+// Called for every operand of every operation: order the work stream after a pending upload of `b`
+// (first consumer only) and remember which stream touched the words last.
 void await_upload(const csgn_buf *b) {
-    if (b && b->ready) {
+    if (!b) return;
+    if (b->ready) {
         cudaStreamWaitEvent(g.stream, b->ready, 0);
         g.event_pool.push_back(b->ready);
         b->ready = nullptr;
     }
+    b->last_stream = g.stream;
+}
+
+// Before storage is handed back (pool or upload cache) on the CURRENT stream: if the last operation on it ran on
+// another stream (the caller multiplexes streams and frees later), the current stream first waits for that one.
+void order_after_last_use(const csgn_buf *b) {
+    if (!b->last_stream || b->last_stream == g.stream) return;
+    cudaEvent_t e = take_event();
+    if (!e) return;
+    if (cudaEventRecord(e, b->last_stream) == cudaSuccess) cudaStreamWaitEvent(g.stream, e, 0);
+    else cudaGetLastError();     // the caller destroyed that stream: its work was enqueued before, nothing to order
+    g.event_pool.push_back(e);
 }
 
 int new_buf(uint64_t n_blocks, uint32_t L, uint64_t cap_words, csgn_buf **out, cudaStream_t stream = nullptr) {
@@ -505,7 +520,10 @@ int csgn_buf_download(const csgn_buf *buf, uint64_t *host_words) {
 
 int csgn_buf_free(csgn_buf *buf) {
     if (!buf) return CSGN_OK;
-    if (g.inited) await_upload(buf);     // a never-consumed upload must land before its memory is recycled
+    if (g.inited) {
+        if (buf->ready) await_upload(buf);     // a never-consumed upload must land before its memory is recycled
+        else order_after_last_use(buf);
+    }
     if (g.inited && buf->owns && !(buf->recycle && give_upload_slot(buf->d, buf->cap_words))) dev_free(buf->d);
     delete buf;
     return CSGN_OK;

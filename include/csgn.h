@@ -19,8 +19,12 @@
  *     fixed pattern [64]*(L-1)+[N%64] and is never materialised on the device;
  *   - `csgn_buf` handles own device memory, are created and freed only here, and
  *     belong to the process' bound device (one process per GPU);
- *   - work is enqueued on one stream (csgn_set_stream); calls that return data to
- *     the host (download, decrypt) synchronise that stream, the others do not.
+ *   - work is enqueued on the current stream (csgn_set_stream); calls that return data to
+ *     the host (download, decrypt) synchronise that stream, the others do not.  A caller may
+ *     move between streams from call to call to overlap independent ciphertexts: operations
+ *     on one buffer must then be ordered by the caller (same stream or events), as with any
+ *     CUDA library; freeing a buffer is always safe -- the library orders the release after
+ *     the stream that used it last.
  */
 #ifndef CSGN_H_
 #define CSGN_H_
@@ -195,7 +199,9 @@ int csgn_shard_range(uint64_t n_blocks, int rank, int world, uint64_t *first, ui
  * `world` handles in rank order.  csgn_comm_connect_ptrs takes mailbox pointers that are
  * already peer-mapped (symmetric-memory allocators); world == 1 needs neither.
  * Contract (as for any collective): every rank issues the same sequence of pushes and
- * collects; at most CSGN_COMM_MAX_PENDING pushes may stay unpublished, and a collect window
+ * collects, and a closing launch is stream-ordered after the pushes it publishes (same stream, or
+ * joined by events when the pushes were spread over several streams);
+ * at most CSGN_COMM_MAX_PENDING pushes may stay unpublished, and a collect window
  * (n + lag) spans at most as many.  A rank that never arrives makes the collect time out
  * (CSGN_PEER_TIMEOUT_MS, default 30000): the totals read UINT64_MAX, blocking calls return
  * CSGN_ERR_TIMEOUT, the GPU is never left spinning. */

@@ -626,6 +626,23 @@ def test_concurrent_streams_and_upload_recycling(engine, oracle):
                 key.count_satisfied_async(prod, counts[r, p].data_ptr())
                 del ha, hb, prod             # storage goes back while the kernels above may still be running
         torch.cuda.synchronize()
+        assert counts.tolist() == want
+        # the same, but every buffer is freed while ANOTHER stream is current: the release (to the pool / the upload
+        # cache, from where the next round takes storage at once) has to wait for the stream that used it last
+        counts.fill_(-1)
+        for r in range(rounds):
+            keep = []
+            for p in range(P):
+                engine.set_stream(streams[p % 3].cuda_stream)
+                ta, tb = pinned[r][p]
+                ha = engine.Ciphertext.from_host_ptr(ta.data_ptr(), sizes[p][0], ctx)
+                hb = engine.Ciphertext.from_host_ptr(tb.data_ptr(), sizes[p][1], ctx)
+                prod = ha * hb
+                key.count_satisfied_async(prod, counts[r, p].data_ptr())
+                keep.append((ha, hb, prod))
+            engine.set_stream(streams[(r + 1) % 3].cuda_stream)
+            del keep, ha, hb, prod
+        torch.cuda.synchronize()
     finally:
         engine.set_stream(None)
     assert counts.tolist() == want
