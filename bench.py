@@ -68,6 +68,14 @@ def parse_args():
     ap.add_argument("--collect", default="lagged", choices=["lagged", "same-step"],
                     help="peer exchange: the launch closing step k collects step k-1's sums (never waits for a slower "
                          "rank; the last step's sums are collected before the timed region ends) or its own step's")
+    ap.add_argument("--enqueue", default="batch", choices=["batch", "streams"],
+                    help="batch: one csgn_mul_into_batch + one csgn_decrypt_count_batch_async per step -- the library "
+                         "spreads the independent pairs over its internal lanes (default); streams: one call per pair, "
+                         "bench.py itself alternates --streams CUDA streams (what the batch calls do inside)")
+    ap.add_argument("--e2e-enqueue", default="batch", choices=["batch", "pairs"],
+                    help="e2e with --enqueue batch: batch = upload all pairs, csgn_mul_batch, one batched fold; pairs = "
+                         "upload/multiply/fold/free pair by pair on alternating streams (each product is folded while "
+                         "part of it is still in L2)")
     ap.add_argument("--streams", type=int, default=2,
                     help="enqueue the independent pairs of a step round-robin on this many CUDA streams (csgn_set_stream "
                          "between calls): the tail of one kernel overlaps the ramp of the next pair's")
@@ -347,6 +355,8 @@ def run_ours(args):
                 pending[i] = None
 
     lagged = comm is not None and args.collect == "lagged"
+    use_batch = args.enqueue == "batch"
+    arr_a, arr_b, arr_o = eng.handle_array(va), eng.handle_array(vb), eng.handle_array(vo)
     S = max(1, min(args.streams, P))
     streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(S - 1)]
     sptr = [s_.cuda_stream for s_ in streams]
@@ -376,6 +386,25 @@ def run_ours(args):
             pending[slot] = None
         if evs:
             evs[0].record()
+        if use_batch:
+            eng.mul_into_batch(None, None, None, arrays=(arr_a, arr_b, arr_o))
+            if evs:
+                evs[1].record()
+            if comm is None:
+                key.count_satisfied_batch_async(None, count_ptrs2[slot][0], array=arr_o)
+            elif lagged and step_no[0] > 1:
+                comm.push_batch(key, None, count_ptrs2[slot ^ 1][0], lag=P, array=arr_o)
+                if final:
+                    comm.collect(P, count_ptrs2[slot][0])
+            else:
+                comm.push_batch(key, None, count_ptrs2[slot][0], array=arr_o)
+            if evs:
+                evs[2].record()
+            if world > 1 and comm is None:
+                pending[slot] = dist.all_reduce(counts2[slot], async_op=True)
+            if evs:
+                evs[3].record()
+            return
         fork(0)
         for p in range(P):
             if S > 1:
@@ -492,6 +521,22 @@ def run_ours(args):
             slot = e2e_no[0] & 1
             e2e_no[0] += 1
             check(slot)                                                    # frees this slot's buffers (step k-2)
+            if use_batch and args.e2e_enqueue == "batch":
+                has = [eng.Ciphertext.from_host_ptr(a_ptrs[p], T1, ctx) for p in range(P)]   # H2D on the copy stream
+                hbs = [eng.Ciphertext.from_host_ptr(b_ptrs[p], T2, ctx) for p in range(P)]
+                prods = eng.mul_batch(has, hbs)                            # csgn_mul_batch (allocates the P products)
+                if comm is not None:
+                    comm.push_batch(key, prods, count_ptrs2[slot][0])
+                else:
+                    key.count_satisfied_batch_async(prods, count_ptrs2[slot][0])
+                del has, hbs, prods
+                if world > 1 and comm is None:
+                    dist.all_reduce(counts2[slot])
+                host_counts2[slot].copy_(counts2[slot], non_blocking=True)
+                done_ev[slot].record(stream)
+                in_flight[slot] = True
+                check(slot ^ 1)
+                return
             fork(2)
             for p in range(P):
                 if S > 1:
@@ -537,16 +582,22 @@ def run_ours(args):
         e2e = {"value": blocks_per_step * K / (float(e2e_ms.item()) * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(P * (T1 + T2) * L * 8), "d2h_bytes_per_step": int(P * 8),
                "ms_per_step": float(e2e_ms.item()) / K,
-               "path": "csgn_buf_upload x2 (pinned host) -> csgn_mul -> %s; one D2H of the "
-                       "P counts per step, read and checked on the host every step (one step behind the enqueue); per GPU"
-                       % ("csgn_decrypt_sharded_async" if comm is not None else "csgn_decrypt_count_async")}
+               "path": (("csgn_buf_upload x2P (pinned host) -> csgn_mul_batch -> %s"
+                         if use_batch and args.e2e_enqueue == "batch" else
+                         "csgn_buf_upload x2 (pinned host) -> csgn_mul -> %s")
+                        % (("csgn_decrypt_sharded" if comm is not None else "csgn_decrypt_count") +
+                           ("_batch_async" if use_batch and args.e2e_enqueue == "batch" else "_async")))
+                       + "; one D2H of the P counts per step, read and checked on the host every step (one step "
+                         "behind the enqueue); per GPU"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": args.workload + ": " + desc, "pairs_per_step": P, "streams": S,
+            "config": {"workload": args.workload + ": " + desc, "pairs_per_step": P, "enqueue": args.enqueue,
+                       "streams": ("library lanes (CSGN_LANES, default 2)" if use_batch else S),
+                       "e2e_enqueue": (args.e2e_enqueue if use_batch else "pairs") + (" on %d streams" % S if not (use_batch and args.e2e_enqueue == "batch") else ""),
                        "left_blocks_per_rank": T1, "right_blocks": T2,
                        "blocks_per_step": blocks_per_step, "bytes_per_block": bytes_per_block,
                        "l2": "no flush needed: a step writes then reads %d x %.0f MB of products (>> 126 MB L2), "

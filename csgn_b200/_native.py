@@ -47,6 +47,11 @@ SIGNATURES = {
     "csgn_decrypt_count": (ctypes.c_int, [_vp, _vp, _u64p]),
     "csgn_decrypt_count_async": (ctypes.c_int, [_vp, _vp, _vp]),
     "csgn_decrypt_product": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_uint32, _vp, ctypes.POINTER(ctypes.c_uint8), _u64p]),
+    "csgn_mul_batch": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.c_uint32, ctypes.POINTER(_vp)]),
+    "csgn_mul_into_batch": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.c_uint32, ctypes.POINTER(_vp)]),
+    "csgn_decrypt_count_batch_async": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_uint32, _vp, _vp]),
+    "csgn_decrypt_batch": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_uint32, _vp, ctypes.POINTER(ctypes.c_uint8), _u64p]),
+    "csgn_decrypt_sharded_batch_async": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_uint32, _vp, _vp, ctypes.c_uint32, _vp]),
     "csgn_decrypt_positions": (ctypes.c_int, [_vp, _u64, _vp, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint8)]),
     "csgn_encrypt_batch": (ctypes.c_int, [_vp, _vp, _u64, _u64, _u64, _vpp]),
     "csgn_perm_create": (ctypes.c_int, [_u64, _vp, _vpp]),

@@ -236,6 +236,9 @@ public:
     // ciphertext Enc(bits[0]) + ... + Enc(bits[n-1]), n blocks, decrypting to the XOR of the bits.
     // Same construction as encrypt(); randomness is Philox keyed by `seed` instead of rand().
     Ciphertext encryptBatch(const unsigned char *bits, uint64_t n, uint64_t seed);
+    // Extension: decrypt n ciphertexts with ONE synchronisation (csgn_decrypt_batch: the folds are spread over
+    // the library's lanes and overlap); bits[i] = decrypt(ciphertexts[i]).getValue().
+    void decryptBatch(Ciphertext *ciphertexts, uint64_t n, unsigned char *bits);
     void applyPermutation_inplace(const Permutation &permutation);
     SecretKey applyPermutation(const Permutation &permutation);
 

@@ -634,6 +634,31 @@ Ciphertext SecretKey::encryptBatch(const unsigned char *bits, uint64_t n, uint64
     return out;
 }
 
+void SecretKey::decryptBatch(Ciphertext *ciphertexts, uint64_t n, unsigned char *bits) {
+    if (n == 0) return;
+    if (!ciphertexts || !bits) throw Error("SecretKey::decryptBatch: null argument");
+    if (!device_key) {
+        glue::ensure_engine();
+        glue::check(csgn_key_create(certFHEContext->getN(), s, (uint32_t)length, &device_key), "csgn_key_create");
+    }
+    std::vector<const csgn_buf *> bufs;
+    std::vector<uint64_t> where;
+    for (uint64_t i = 0; i < n; ++i) {
+        Ciphertext &c = ciphertexts[i];
+        c.upload_staged();
+        if (c.sharded || !c.factors.empty() || (!c.dev && c.factors.empty())) {
+            bits[i] = decrypt(c).getValue();       // sharded, lazy or empty: the single-ciphertext path knows how
+            continue;
+        }
+        bufs.push_back(c.dev.get());
+        where.push_back(i);
+    }
+    if (bufs.empty()) return;
+    std::vector<uint8_t> out(bufs.size());
+    glue::check(csgn_decrypt_batch(bufs.data(), (uint32_t)bufs.size(), device_key, out.data(), nullptr), "csgn_decrypt_batch");
+    for (size_t k = 0; k < bufs.size(); ++k) bits[where[k]] = out[k];
+}
+
 Plaintext SecretKey::decrypt(Ciphertext &ciphertext) {
     ciphertext.upload_staged();
     if (!ciphertext.dev && ciphertext.factors.empty()) return Plaintext(0);

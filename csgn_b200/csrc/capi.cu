@@ -73,6 +73,13 @@ struct State {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // H2D uploads run here, overlapping kernels of the work stream
+    // Batch entry points (csgn_*_batch) spread their independent items over these streams, forked from and joined
+    // back into the current work stream, so that the tail of one kernel overlaps the ramp of the next item's.
+    static constexpr int kMaxLanes = 4;
+    cudaStream_t lane[kMaxLanes] = {};
+    cudaEvent_t lane_done[kMaxLanes] = {};
+    cudaEvent_t fork_point = nullptr;
+    int n_lanes = 2;
     std::vector<cudaEvent_t> event_pool;
     // Storage of freed uploads, each with the event that marks its last use: an upload takes a slot whose event has
     // COMPLETED, so its copy can start at once on the copy stream and no allocation (which across streams may go to the
@@ -89,6 +96,7 @@ struct State {
     uint64_t *h_result = nullptr;    // pinned, 8 words
 };
 State g;
+unsigned g_launches_since_switch = 1u << 30;   // launches since the caller last changed streams (see streams_alternate)
 DeviceProps g_props;
 std::atomic<uint64_t> g_launches{0};
 thread_local std::string t_error;
@@ -230,6 +238,37 @@ void order_after_last_use(const csgn_buf *b) {
     g.event_pool.push_back(e);
 }
 
+// Scope of one batch call: item i runs with the work stream set to way i % n, where way 0 is the caller's own stream
+// and ways 1.. are the library's side lanes, forked from the caller's stream on construction; join() makes the
+// caller's stream wait for every side lane and restores it.
+struct LaneScope {
+    cudaStream_t home;
+    int used = 1;
+    bool active;
+    explicit LaneScope(uint32_t n_items) : home(g.stream), active(g.n_lanes > 1 && n_items > 1) {
+        if (!active) return;
+        used = (int)std::min<uint32_t>(n_items, (uint32_t)g.n_lanes);
+        cudaEventRecord(g.fork_point, home);
+        for (int i = 1; i < used; ++i) cudaStreamWaitEvent(g.lane[i], g.fork_point, 0);
+    }
+    void enter(uint32_t item) {
+        if (!active) return;
+        const uint32_t way = item % (uint32_t)used;
+        g.stream = way == 0 ? home : g.lane[way];
+        g_launches_since_switch = 0;              // the items of a batch overlap: the launchers' multi-wave forms apply
+    }
+    void join() {
+        if (!active) return;
+        g.stream = home;
+        for (int i = 1; i < used; ++i) {
+            cudaEventRecord(g.lane_done[i], g.lane[i]);
+            cudaStreamWaitEvent(home, g.lane_done[i], 0);
+        }
+        active = false;
+    }
+    ~LaneScope() { join(); }
+};
+
 int new_buf(uint64_t n_blocks, uint32_t L, uint64_t cap_words, csgn_buf **out, cudaStream_t stream = nullptr) {
     if (L == 0) return fail(CSGN_ERR_INVALID_ARGUMENT, "words per block must be > 0");
     if (n_blocks > (UINT64_MAX / 8) / L) return fail(CSGN_ERR_INVALID_ARGUMENT, "block count overflows");
@@ -253,7 +292,6 @@ void set_device_props(const DeviceProps &p) { g_props = p; }
 // A caller that moves between streams from one call to the next (csgn_set_stream) is enqueueing independent
 // ciphertexts so that their kernels overlap; launchers that care (the decrypt fold) then prefer several shorter waves of
 // CTAs, which back-fill behind another stream's kernel, over one persistent wave, which is best for a kernel running alone.
-static unsigned g_launches_since_switch = 1u << 30;
 void count_launch(unsigned n) {
     g_launches.fetch_add(n, std::memory_order_relaxed);
     if (g_launches_since_switch < (1u << 30)) g_launches_since_switch += n;
@@ -316,6 +354,15 @@ int csgn_init(int device) {
     CU(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
     g.stream = g.own_stream;
     CU(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+    {
+        const char *e = std::getenv("CSGN_LANES");
+        g.n_lanes = e && *e ? std::max(1, std::min((int)State::kMaxLanes, std::atoi(e))) : 2;
+    }
+    for (int i = 0; i < g.n_lanes; ++i) {
+        CU(cudaStreamCreateWithFlags(&g.lane[i], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&g.lane_done[i], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&g.fork_point, cudaEventDisableTiming));
     // keep freed blocks in the pool: a*b chains reuse them without going to the driver
     cudaMemPool_t pool;
     CU(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -347,6 +394,14 @@ int csgn_shutdown(void) {
     cudaFree(g.d_scratch);
     cudaFreeHost(g.h_result);
     for (cudaEvent_t e : g.event_pool) cudaEventDestroy(e);
+    for (int i = 0; i < State::kMaxLanes; ++i) {
+        if (g.lane[i]) {
+            cudaStreamSynchronize(g.lane[i]);
+            cudaStreamDestroy(g.lane[i]);
+        }
+        if (g.lane_done[i]) cudaEventDestroy(g.lane_done[i]);
+    }
+    if (g.fork_point) cudaEventDestroy(g.fork_point);
     cudaStreamDestroy(g.copy_stream);
     cudaStreamDestroy(g.own_stream);
     g = State();
@@ -371,7 +426,7 @@ int csgn_device_info(int *sm_count, uint64_t *hbm_total, uint64_t *hbm_free, int
 int csgn_set_stream(void *cuda_stream) {
     NEED_INIT();
     cudaStream_t next = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : g.own_stream;
-    if (next != g.stream) csgn::g_launches_since_switch = 0;
+    if (next != g.stream) g_launches_since_switch = 0;
     g.stream = next;
     return CSGN_OK;
 }
@@ -758,6 +813,96 @@ int csgn_decrypt_positions(const csgn_buf *c, uint64_t N, const uint64_t *positi
     rc = csgn_decrypt(c, k, bit);
     csgn_key_free(k);
     return rc;
+}
+
+
+// ---------------------------------------------------------------------------
+// batches of independent items
+// ---------------------------------------------------------------------------
+int csgn_mul_into_batch(const csgn_buf *const *a, const csgn_buf *const *b, uint32_t n, csgn_buf *const *out) {
+    NEED_INIT();
+    if (n && (!a || !b || !out)) return fail(CSGN_ERR_INVALID_ARGUMENT, "null argument");
+    LaneScope lanes(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        lanes.enter(i);
+        int rc = csgn_mul_into(a[i], b[i], out[i]);
+        if (rc != CSGN_OK) return rc;        // ~LaneScope joins what was enqueued
+    }
+    return CSGN_OK;
+}
+
+int csgn_mul_batch(const csgn_buf *const *a, const csgn_buf *const *b, uint32_t n, csgn_buf **out) {
+    NEED_INIT();
+    if (n && (!a || !b || !out)) return fail(CSGN_ERR_INVALID_ARGUMENT, "null argument");
+    for (uint32_t i = 0; i < n; ++i) out[i] = nullptr;
+    LaneScope lanes(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        lanes.enter(i);
+        int rc = csgn_mul(a[i], b[i], &out[i]);
+        if (rc != CSGN_OK) {
+            lanes.join();
+            for (uint32_t k = 0; k < i; ++k) {
+                csgn_buf_free(out[k]);
+                out[k] = nullptr;
+            }
+            return rc;
+        }
+    }
+    return CSGN_OK;
+}
+
+int csgn_decrypt_count_batch_async(const csgn_buf *const *c, uint32_t n, const csgn_key *key, uint64_t *device_counts) {
+    NEED_INIT();
+    if (n && (!c || !device_counts)) return fail(CSGN_ERR_INVALID_ARGUMENT, "null argument");
+    LaneScope lanes(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        lanes.enter(i);
+        int rc = csgn_decrypt_count_async(c[i], key, device_counts + i);
+        if (rc != CSGN_OK) return rc;
+    }
+    return CSGN_OK;
+}
+
+int csgn_decrypt_batch(const csgn_buf *const *c, uint32_t n, const csgn_key *key, uint8_t *bits, uint64_t *counts) {
+    NEED_INIT();
+    if (n == 0) return CSGN_OK;
+    if (!bits && !counts) return fail(CSGN_ERR_INVALID_ARGUMENT, "no output");
+    uint64_t *d = nullptr;
+    int rc = dev_alloc(n, &d);
+    if (rc != CSGN_OK) return rc;
+    rc = csgn_decrypt_count_batch_async(c, n, key, d);
+    std::vector<uint64_t> h(n);
+    cudaError_t e = cudaSuccess;
+    if (rc == CSGN_OK) {
+        e = cudaMemcpyAsync(h.data(), d, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, g.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    }
+    dev_free(d);
+    if (rc != CSGN_OK) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "batch decrypt readback");
+    for (uint32_t i = 0; i < n; ++i) {
+        if (bits) bits[i] = (uint8_t)(h[i] & 1u);
+        if (counts) counts[i] = h[i];
+    }
+    return CSGN_OK;
+}
+
+int csgn_decrypt_sharded_batch_async(const csgn_buf *const *c, uint32_t n, const csgn_key *key, csgn_comm *comm,
+                                     uint32_t collect_lag, uint64_t *device_totals) {
+    NEED_INIT();
+    if (n == 0) return CSGN_OK;
+    if (!c || !device_totals) return fail(CSGN_ERR_INVALID_ARGUMENT, "null argument");
+    if ((uint64_t)n + collect_lag > kPeerMaxPending)
+        return fail(CSGN_ERR_INVALID_ARGUMENT, "batch of %u folds trailing by %u exceeds %u", n, collect_lag, kPeerMaxPending);
+    {
+        LaneScope lanes(n - 1);
+        for (uint32_t i = 0; i + 1 < n; ++i) {
+            lanes.enter(i);
+            int rc = csgn_decrypt_sharded_async(c[i], key, comm, 0, 0, nullptr, nullptr);
+            if (rc != CSGN_OK) return rc;
+        }
+    }   // joined: the closing launch is ordered after every push it publishes
+    return csgn_decrypt_sharded_async(c[n - 1], key, comm, n, collect_lag, device_totals, nullptr);
 }
 
 // ---------------------------------------------------------------------------

@@ -244,6 +244,30 @@ class Ciphertext:
         return out
 
 
+def handle_array(cts):
+    """ctypes array of the csgn_buf handles of `cts` (build once and reuse for a fixed batch)."""
+    return (_vp * len(cts))(*[c._h.value if isinstance(c._h, _vp) else c._h for c in cts])
+
+
+def mul_into_batch(a, b, out, arrays=None):
+    """csgn_mul_into_batch: out[i] = a[i] * b[i]; the library overlaps the independent products on its lanes.
+    `arrays` = (handle_array(a), handle_array(b), handle_array(out)) built beforehand skips the marshalling."""
+    aa, ab, ao = arrays or (handle_array(a), handle_array(b), handle_array(out))
+    rc = _LIB.csgn_mul_into_batch(aa, ab, len(aa), ao)
+    if rc:
+        check(rc)
+
+
+def mul_batch(a, b):
+    """csgn_mul_batch: the list of products a[i] * b[i] (allocated by the library)."""
+    n = len(a)
+    out = (_vp * n)()
+    rc = _LIB.csgn_mul_batch(handle_array(a), handle_array(b), n, out)
+    if rc:
+        check(rc)
+    return [Ciphertext(_vp(out[i]), a[i].ctx) for i in range(n)]
+
+
 class SecretKey:
     """Secret positions held as a device position mask (csgn_key)."""
 
@@ -290,6 +314,20 @@ class SecretKey:
         rc = _LIB.csgn_decrypt_count_async(ct._h, self._h, device_count_ptr)
         if rc:
             check(rc)
+
+    def count_satisfied_batch_async(self, cts, device_counts_ptr, array=None):
+        """csgn_decrypt_count_batch_async: device_counts[i] = satisfied blocks of cts[i], no synchronisation."""
+        arr = array or handle_array(cts)
+        rc = _LIB.csgn_decrypt_count_batch_async(arr, len(arr), self._h, device_counts_ptr)
+        if rc:
+            check(rc)
+
+    def decrypt_batch(self, cts):
+        """csgn_decrypt_batch: (bits, counts) of n ciphertexts with one synchronisation."""
+        n = len(cts)
+        bits, counts = (ctypes.c_uint8 * n)(), (ctypes.c_uint64 * n)()
+        check(_lib().csgn_decrypt_batch(handle_array(cts), n, self._h, bits, counts))
+        return list(bits), list(counts)
 
     def size(self):
         return 16 + 8 * int(self.s.size)
@@ -343,6 +381,14 @@ class PeerComm:
         same kernel: publish everything unpublished, collect the collect_n pushes ending `lag` pushes ago."""
         rc = _LIB.csgn_decrypt_sharded_async(ct._h, key._h, self._h, collect_n, lag, device_totals_ptr or None,
                                              device_local_ptr or None)
+        if rc:
+            check(rc)
+
+    def push_batch(self, key, cts, device_totals_ptr, lag=0, array=None):
+        """csgn_decrypt_sharded_batch_async: fold every shard of `cts` (spread over the library's lanes); the closing
+        launch publishes all of them and collects the len(cts) pushes that end `lag` pushes earlier."""
+        arr = array or handle_array(cts)
+        rc = _LIB.csgn_decrypt_sharded_batch_async(arr, len(arr), key._h, self._h, lag, device_totals_ptr)
         if rc:
             check(rc)
 

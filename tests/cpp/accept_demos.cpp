@@ -197,6 +197,13 @@ static void lazy_products() {
     EXPECT(batch.getBlocks() == many.size() && seckey.decrypt(batch).getValue() == xorbits);
     Ciphertext batch_sq = batch * A;
     EXPECT(seckey.decrypt(batch_sq).getValue() == (xorbits & pa));
+    // n decrypts with one synchronisation (the folds overlap on the library's lanes)
+    {
+        Ciphertext group[5] = {A, B, eager, batch, batch_sq};
+        unsigned char bits[5];
+        seckey.decryptBatch(group, 5, bits);
+        for (int i = 0; i < 5; ++i) EXPECT(bits[i] == seckey.decrypt(group[i]).getValue());
+    }
     // copy-on-write: a copy shares the buffer until one side grows
     Ciphertext x = A, y = x;
     y += B;

@@ -81,6 +81,11 @@ def main():
         eng.sync()
         assert totals.tolist() == want and comm.pending == 0
         checked += 2
+        # the batch call: folds spread over the library's lanes, one closing launch
+        totals.fill_(-1)
+        comm.push_batch(key, shards, totals.data_ptr())
+        eng.sync()
+        assert totals.tolist() == want
         # agrees with the all-reduce it replaces
         ar = locals_.clone()
         dist.all_reduce(ar)

@@ -655,3 +655,44 @@ def test_concurrent_streams_and_upload_recycling(engine, oracle):
     assert np.array_equal(c2.getValues(), a2)
     c2 += engine.Ciphertext.from_host(a1, ctx)      # growing an upload moves it out of the recycled storage
     assert np.array_equal(c2.getValues(), np.concatenate([a2, a1]))
+
+
+def test_batch_entry_points(engine, oracle):
+    """csgn_mul_batch / csgn_mul_into_batch / csgn_decrypt_count_batch_async / csgn_decrypt_batch: n independent items
+    in one call, spread over the library's lanes; results as from n single calls."""
+    import torch
+    N, D, L = 1247, 2, 20
+    rng = np.random.default_rng(4242)
+    ctx = engine.Context(N, D)
+    s = random_key(rng, N, D)
+    key = engine.SecretKey(ctx, s)
+    for n in (1, 2, 5, 16):
+        host = [(random_blocks(rng, int(rng.integers(1, 300)), N), random_blocks(rng, int(rng.integers(1, 300)), N))
+                for _ in range(n)]
+        a = [engine.Ciphertext.from_host(x, ctx) for x, _ in host]
+        b = [engine.Ciphertext.from_host(y, ctx) for _, y in host]
+        want = [oracle.mul(x, y, L) for x, y in host]
+        prods = engine.mul_batch(a, b)
+        for p, w in zip(prods, want):
+            assert np.array_equal(p.getValues(), w)
+        outs = [engine.Ciphertext.empty(p.n_blocks, ctx) for p in prods]
+        engine.mul_into_batch(a, b, outs)
+        for p, w in zip(outs, want):
+            assert np.array_equal(p.getValues(), w)
+        counts = [oracle.count_satisfied(w, N, s) for w in want]
+        dev = torch.full((n,), -1, dtype=torch.int64, device="cuda")
+        key.count_satisfied_batch_async(outs, dev.data_ptr())
+        engine.sync()
+        assert dev.tolist() == counts
+        bits, cnts = key.decrypt_batch(prods)
+        assert cnts == counts and bits == [c & 1 for c in counts]
+        # work enqueued after a batch on the current stream sees its results (the lanes are joined back)
+        again = prods[0] * b[0] if prods[0].n_blocks * b[0].n_blocks < 200000 else None
+        if again is not None:
+            assert np.array_equal(again.getValues(), oracle.mul(want[0], host[0][1], L))
+    # an item that fails stops the batch with an error and leaks nothing
+    bad = engine.Ciphertext.from_host(random_blocks(rng, 3, 191), engine.Context(191, 2))
+    with pytest.raises(engine.CsgnError, match="words per block"):
+        engine.mul_batch([a[0], a[1]], [b[0], bad])
+    with pytest.raises(engine.CsgnError, match="words per block"):
+        key.decrypt_batch([a[0], bad])

@@ -68,6 +68,10 @@ def test_fused_exchange_world_size_1(engine, oracle, N, D):
     engine.sync()
     assert engine.launch_count() == before + n       # fold, push and collect: one launch per ciphertext
     assert totals.tolist() == want and local.tolist() == want
+    totals.fill_(-1)
+    comm.push_batch(key, cts, totals.data_ptr())     # the same through the batch call (folds spread over the lanes)
+    engine.sync()
+    assert totals.tolist() == want and comm.pending == 0
     for ct in cts:
         comm.push(key, ct)
     assert comm.pending == n
