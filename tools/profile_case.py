@@ -42,6 +42,10 @@ def main():
     for i in range(iters):
         va.mul_into(vb, vo[i % nbuf])
         key.count_satisfied_async(vo[(i + 1) % nbuf], cnt.data_ptr())
+    # the batch entry points: two products and two folds spread over the library's lanes
+    eng.mul_into_batch([va, va], [vb, vb], [vo[0], vo[1 % nbuf]])
+    cnt2 = torch.zeros(2, dtype=torch.int64, device=dev)
+    key.count_satisfied_batch_async([vo[0], vo[1 % nbuf]], cnt2.data_ptr())
     # the sharded-decrypt path at world size 1: fold + publish + collect in the one kernel (csrc/peer.cuh)
     comm = eng.PeerComm(0, 1)
     tot = torch.zeros(2, dtype=torch.int64, device=dev)
