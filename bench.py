@@ -114,7 +114,7 @@ def measured_peak_gbs():
 def ncu_traffic(kernel_prefix, workload):
     """dram bytes (read + write) per launch of the dominant kernel, from the committed ncu --set full
     capture of this workload (profiles/r1b_<workload>_ncu_summary.json), or None."""
-    for tag in ("r1b", "r1"):                      # the latest capture first
+    for tag in ("r1c", "r1b", "r1"):                      # the latest capture first
         try:
             with open(os.path.join(ROOT, "profiles", "%s_%s_ncu_summary.json" % (tag, workload))) as f:
                 for name, k in json.load(f)["kernels"].items():
