@@ -465,7 +465,12 @@ template <int UPL, int BPI>
 cudaError_t launch_wide(const uint64_t *v, uint64_t T, const uint64_t *mask, uint64_t *scratch,
                         uint64_t *count_out, const PeerPush &pp, cudaStream_t stream) {
     const uint64_t n_groups = (T + BPI - 1) / BPI;
-    const uint32_t grid = resident_grid(decrypt_count_wide_kernel<UPL, BPI>, 0, (n_groups + kDecWarps - 1) / kDecWarps);
+    const uint64_t work_ctas = (n_groups + kDecWarps - 1) / kDecWarps;
+    // as in launch_lanes: several shorter waves when folds overlap or the fold is a GiB and more
+    const bool many = streams_alternate() || T * (uint64_t)UPL * 512u >= (1ull << 30);
+    const uint64_t waves = (uint64_t)std::max<long>(1, env_long("CSGN_DEC_WAVES", many ? 4 : 1));
+    uint32_t grid = resident_grid(decrypt_count_wide_kernel<UPL, BPI>, 0, work_ctas);
+    grid = (uint32_t)std::min<uint64_t>(work_ctas, (uint64_t)grid * waves);
     return launch_kernel(decrypt_count_wide_kernel<UPL, BPI>, grid, kDecThreads, 0, stream,
                          reinterpret_cast<const uint4 *>(v), T, reinterpret_cast<const uint4 *>(mask), scratch, count_out, pp);
 }
