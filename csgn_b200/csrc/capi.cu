@@ -1,102 +1,18 @@
 // capi.cu -- the C ABI of include/csgn.h: device state, buffer handles, and the
 // thin argument checking in front of the kernel launchers.  No CPU compute path
 // exists here: every operation either launches an sm_100a kernel or fails.
-#include "../../include/csgn.h"
+#include "capi_internal.cuh"
 
-#include <cuda_runtime.h>
-#include <sys/stat.h>
-#include <unistd.h>
-
-#include <algorithm>
 #include <atomic>
 #include <cstdarg>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <ctime>
-#include <string>
-#include <vector>
-
-#include "kernels.cuh"
 
 #define CSGN_VERSION_STRING "csgn-b200 0.1 (sm_100a)"
 
-// ---------------------------------------------------------------------------
-// handles
-// ---------------------------------------------------------------------------
-struct csgn_buf {
-    uint64_t *d = nullptr;     // device words, n_blocks * L valid
-    uint64_t n_blocks = 0;
-    uint32_t L = 0;
-    uint64_t cap_words = 0;    // allocated words (>= n_blocks*L); 0 for views
-    bool owns = true;
-    bool recycle = false;      // storage of an upload: goes back to the upload cache, not to the pool
-    mutable cudaEvent_t ready = nullptr;  // an upload on the copy stream still in flight
-    mutable cudaStream_t last_stream = nullptr;  // the stream of the last operation that touched the words
-};
-
-struct csgn_key {
-    uint64_t *d_positions = nullptr;  // D secret positions (for batched encryption)
-    uint64_t *d_mask = nullptr;  // L words
-    std::vector<uint64_t> h_mask;  // the same, host side (small masks ride in kernel parameters)
-    uint64_t N = 0;
-    uint32_t L = 0, D = 0;
-};
-
-struct csgn_perm {
-    uint32_t *d_map = nullptr;   // N entries: (src_word << 6) | right_shift
-    uint32_t *d_slice_map = nullptr;  // 64*L entries for the bit-sliced kernel (permute.cu), or null
-    uint64_t N = 0;
-    uint32_t L = 0;
-};
-
-struct csgn_comm {
-    int rank = 0, world = 1;
-    uint64_t *box_local = nullptr;                 // this rank's mailbox (cudaMalloc: exportable)
-    uint64_t *box[csgn::kPeerMaxWorld] = {};       // every rank's mailbox as mapped here
-    bool ipc_opened[csgn::kPeerMaxWorld] = {};
-    bool connected = false;
-    uint64_t seq = 0;                              // sequence number of the next push
-    uint64_t published = 0;                        // pushes [0, published) have been stored to the peers
-    uint64_t *d_local_ring = nullptr;              // kPeerRing words: this rank's counts by slot
-    uint64_t *d_status = nullptr;                  // [0] timeout flag, [1] blocking-call total
-    uint64_t timeout_ns = 30ull * 1000 * 1000 * 1000;
-    std::string rendezvous_file;                   // written by csgn_comm_connect_dir, removed on free
-};
-
 namespace csgn {
-namespace {
+namespace detail {
 
-struct State {
-    bool inited = false;
-    int device = -1;
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;   // H2D uploads run here, overlapping kernels of the work stream
-    // Batch entry points (csgn_*_batch) spread their independent items over these streams, forked from and joined
-    // back into the current work stream, so that the tail of one kernel overlaps the ramp of the next item's.
-    static constexpr int kMaxLanes = 4;
-    cudaStream_t lane[kMaxLanes] = {};
-    cudaEvent_t lane_done[kMaxLanes] = {};
-    cudaEvent_t fork_point = nullptr;
-    int n_lanes = 2;
-    std::vector<cudaEvent_t> event_pool;
-    // Storage of freed uploads, each with the event that marks its last use: an upload takes a slot whose event has
-    // COMPLETED, so its copy can start at once on the copy stream and no allocation (which across streams may go to the
-    // driver, milliseconds) sits on the steady-state path of "upload operands, multiply, decrypt, free".
-    struct UploadSlot {
-        uint64_t *d;
-        uint64_t cap_words;
-        cudaEvent_t freed;
-    };
-    std::vector<UploadSlot> upload_cache;
-    uint64_t upload_cache_words = 0;
-    uint64_t *d_scratch = nullptr;   // [2] blocking-call result, [4..6] checksum, [8 + 2k, 9 + 2k] fold scratch of launch k mod 64
-    uint32_t fold_slot = 0;
-    uint64_t *h_result = nullptr;    // pinned, 8 words
-};
 State g;
-unsigned g_launches_since_switch = 1u << 30;   // launches since the caller last changed streams (see streams_alternate)
+unsigned g_launches_since_switch = 1u << 30;
 DeviceProps g_props;
 std::atomic<uint64_t> g_launches{0};
 thread_local std::string t_error;
@@ -118,19 +34,6 @@ int cuda_fail(cudaError_t e, const char *what) {
                 cudaGetErrorString(e), cudaGetErrorName(e));
 }
 
-#define CU(call)                                            \
-    do {                                                    \
-        cudaError_t e_ = (call);                            \
-        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
-    } while (0)
-
-#define NEED_INIT()                                                                              \
-    do {                                                                                         \
-        if (!g.inited) return fail(CSGN_ERR_NOT_INITIALIZED, "csgn_init has not been called");   \
-        int cur_ = -1;                                                                           \
-        if (cudaGetDevice(&cur_) != cudaSuccess || cur_ != g.device) CU(cudaSetDevice(g.device)); \
-    } while (0)
-
 // Every fold launch takes the next pair of scratch words (running count, CTA ticket) and leaves them
 // zeroed, so decrypts enqueued on different streams (csgn_set_stream between calls) may run concurrently.
 constexpr uint32_t kFoldSlots = 64;
@@ -140,7 +43,7 @@ uint64_t *next_fold_scratch() {
     return p;
 }
 
-int dev_alloc(uint64_t words, uint64_t **out, cudaStream_t stream = nullptr) {
+int dev_alloc(uint64_t words, uint64_t **out, cudaStream_t stream) {
     *out = nullptr;
     if (words == 0) return CSGN_OK;
     void *p = nullptr;
@@ -238,38 +141,7 @@ void order_after_last_use(const csgn_buf *b) {
     g.event_pool.push_back(e);
 }
 
-// Scope of one batch call: item i runs with the work stream set to way i % n, where way 0 is the caller's own stream
-// and ways 1.. are the library's side lanes, forked from the caller's stream on construction; join() makes the
-// caller's stream wait for every side lane and restores it.
-struct LaneScope {
-    cudaStream_t home;
-    int used = 1;
-    bool active;
-    explicit LaneScope(uint32_t n_items) : home(g.stream), active(g.n_lanes > 1 && n_items > 1) {
-        if (!active) return;
-        used = (int)std::min<uint32_t>(n_items, (uint32_t)g.n_lanes);
-        cudaEventRecord(g.fork_point, home);
-        for (int i = 1; i < used; ++i) cudaStreamWaitEvent(g.lane[i], g.fork_point, 0);
-    }
-    void enter(uint32_t item) {
-        if (!active) return;
-        const uint32_t way = item % (uint32_t)used;
-        g.stream = way == 0 ? home : g.lane[way];
-        g_launches_since_switch = 0;              // the items of a batch overlap: the launchers' multi-wave forms apply
-    }
-    void join() {
-        if (!active) return;
-        g.stream = home;
-        for (int i = 1; i < used; ++i) {
-            cudaEventRecord(g.lane_done[i], g.lane[i]);
-            cudaStreamWaitEvent(home, g.lane_done[i], 0);
-        }
-        active = false;
-    }
-    ~LaneScope() { join(); }
-};
-
-int new_buf(uint64_t n_blocks, uint32_t L, uint64_t cap_words, csgn_buf **out, cudaStream_t stream = nullptr) {
+int new_buf(uint64_t n_blocks, uint32_t L, uint64_t cap_words, csgn_buf **out, cudaStream_t stream) {
     if (L == 0) return fail(CSGN_ERR_INVALID_ARGUMENT, "words per block must be > 0");
     if (n_blocks > (UINT64_MAX / 8) / L) return fail(CSGN_ERR_INVALID_ARGUMENT, "block count overflows");
     csgn_buf *b = new csgn_buf;
@@ -285,7 +157,9 @@ int new_buf(uint64_t n_blocks, uint32_t L, uint64_t cap_words, csgn_buf **out, c
     return CSGN_OK;
 }
 
-}  // namespace
+}  // namespace detail
+
+using namespace detail;
 
 const DeviceProps &device_props() { return g_props; }
 void set_device_props(const DeviceProps &p) { g_props = p; }
@@ -316,6 +190,7 @@ long env_long(const char *name, long dflt) {
 }  // namespace csgn
 
 using namespace csgn;
+using namespace csgn::detail;
 
 // ---------------------------------------------------------------------------
 // library
@@ -887,23 +762,6 @@ int csgn_decrypt_batch(const csgn_buf *const *c, uint32_t n, const csgn_key *key
     return CSGN_OK;
 }
 
-int csgn_decrypt_sharded_batch_async(const csgn_buf *const *c, uint32_t n, const csgn_key *key, csgn_comm *comm,
-                                     uint32_t collect_lag, uint64_t *device_totals) {
-    NEED_INIT();
-    if (n == 0) return CSGN_OK;
-    if (!c || !device_totals) return fail(CSGN_ERR_INVALID_ARGUMENT, "null argument");
-    if ((uint64_t)n + collect_lag > kPeerMaxPending)
-        return fail(CSGN_ERR_INVALID_ARGUMENT, "batch of %u folds trailing by %u exceeds %u", n, collect_lag, kPeerMaxPending);
-    {
-        LaneScope lanes(n - 1);
-        for (uint32_t i = 0; i + 1 < n; ++i) {
-            lanes.enter(i);
-            int rc = csgn_decrypt_sharded_async(c[i], key, comm, 0, 0, nullptr, nullptr);
-            if (rc != CSGN_OK) return rc;
-        }
-    }   // joined: the closing launch is ordered after every push it publishes
-    return csgn_decrypt_sharded_async(c[n - 1], key, comm, n, collect_lag, device_totals, nullptr);
-}
 
 // ---------------------------------------------------------------------------
 // batched encryption
@@ -1055,149 +913,6 @@ int csgn_buf_checksum(const csgn_buf *buf, uint64_t *xor_out, uint64_t *sum_out,
     return CSGN_OK;
 }
 
-// ---------------------------------------------------------------------------
-// serialisation
-// ---------------------------------------------------------------------------
-namespace {
-
-struct FileHeader {
-    char magic[8];
-    uint64_t N, D, L, n_blocks, xor_words;
-    uint64_t reserved[2];
-};
-static_assert(sizeof(FileHeader) == 64, "header is 64 bytes");
-const char kMagic[8] = {'C', 'S', 'G', 'N', 'C', 'T', '0', '1'};
-constexpr size_t kStageBytes = 32u << 20;   // two pinned staging buffers of 32 MiB
-
-struct Staging {
-    uint64_t *buf[2] = {nullptr, nullptr};
-    cudaEvent_t done[2] = {nullptr, nullptr};
-    ~Staging() {
-        for (int i = 0; i < 2; ++i) {
-            if (buf[i]) cudaFreeHost(buf[i]);
-            if (done[i]) cudaEventDestroy(done[i]);
-        }
-    }
-    cudaError_t init() {
-        for (int i = 0; i < 2; ++i) {
-            cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(&buf[i]), kStageBytes, cudaHostAllocDefault);
-            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
-            if (e != cudaSuccess) return e;
-        }
-        return cudaSuccess;
-    }
-};
-
-uint64_t xor_fold(const uint64_t *w, size_t n) {
-    uint64_t x = 0;
-    for (size_t i = 0; i < n; ++i) x ^= w[i];
-    return x;
-}
-
-}  // namespace
-
-int csgn_buf_save(const csgn_buf *buf, uint64_t N, uint64_t D, const char *path) {
-    NEED_INIT();
-    if (!buf || !path) return fail(CSGN_ERR_INVALID_ARGUMENT, "null argument");
-    if (csgn_words_per_block(N) != buf->L)
-        return fail(CSGN_ERR_SHAPE_MISMATCH, "N = %llu gives %u words per block, buffer has %u", (unsigned long long)N,
-                    csgn_words_per_block(N), buf->L);
-    FILE *f = fopen(path, "wb");
-    if (!f) return fail(CSGN_ERR_INVALID_ARGUMENT, "cannot open %s for writing", path);
-    FileHeader h;
-    memset(&h, 0, sizeof h);
-    memcpy(h.magic, kMagic, 8);
-    h.N = N; h.D = D; h.L = buf->L; h.n_blocks = buf->n_blocks;
-    bool ok = fwrite(&h, sizeof h, 1, f) == 1;
-    Staging st;
-    cudaError_t e = st.init();
-    await_upload(buf);
-    const uint64_t total = buf->n_blocks * buf->L, per = kStageBytes / 8;
-    uint64_t x = 0;
-    // D2H of piece k+1 overlaps the fwrite of piece k
-    uint64_t issued = 0, written = 0;
-    int slot = 0;
-    uint64_t len[2] = {0, 0};
-    while (ok && e == cudaSuccess && written < total) {
-        while (issued < total && issued - written < 2 * per) {
-            const int s = (int)((issued / per) & 1);
-            len[s] = std::min<uint64_t>(per, total - issued);
-            e = cudaMemcpyAsync(st.buf[s], buf->d + issued, len[s] * 8, cudaMemcpyDeviceToHost, g.stream);
-            if (e == cudaSuccess) e = cudaEventRecord(st.done[s], g.stream);
-            if (e != cudaSuccess) break;
-            issued += len[s];
-        }
-        if (e != cudaSuccess) break;
-        e = cudaEventSynchronize(st.done[slot]);
-        if (e != cudaSuccess) break;
-        x ^= xor_fold(st.buf[slot], len[slot]);
-        ok = fwrite(st.buf[slot], 8, len[slot], f) == len[slot];
-        written += len[slot];
-        slot ^= 1;
-    }
-    if (ok && e == cudaSuccess) {
-        h.xor_words = x;
-        ok = fseek(f, 0, SEEK_SET) == 0 && fwrite(&h, sizeof h, 1, f) == 1;
-    }
-    ok = (fclose(f) == 0) && ok;
-    if (e != cudaSuccess) return cuda_fail(e, "save: device to host");
-    if (!ok) return fail(CSGN_ERR_INVALID_ARGUMENT, "short write to %s", path);
-    return CSGN_OK;
-}
-
-int csgn_buf_load(const char *path, uint64_t *N, uint64_t *D, csgn_buf **out) {
-    NEED_INIT();
-    if (!path || !out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null argument");
-    FILE *f = fopen(path, "rb");
-    if (!f) return fail(CSGN_ERR_INVALID_ARGUMENT, "cannot open %s", path);
-    FileHeader h;
-    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, kMagic, 8) != 0) {
-        fclose(f);
-        return fail(CSGN_ERR_INVALID_ARGUMENT, "%s is not a CSGN ciphertext file", path);
-    }
-    if (h.L == 0 || h.L != csgn_words_per_block(h.N) || h.n_blocks > (UINT64_MAX / 8) / h.L) {
-        fclose(f);
-        return fail(CSGN_ERR_INVALID_ARGUMENT, "%s: inconsistent header (N=%llu L=%llu blocks=%llu)", path,
-                    (unsigned long long)h.N, (unsigned long long)h.L, (unsigned long long)h.n_blocks);
-    }
-    csgn_buf *b = nullptr;
-    int rc = new_buf(h.n_blocks, (uint32_t)h.L, 0, &b);
-    if (rc != CSGN_OK) {
-        fclose(f);
-        return rc;
-    }
-    Staging st;
-    cudaError_t e = st.init();
-    const uint64_t total = h.n_blocks * h.L, per = kStageBytes / 8;
-    uint64_t x = 0, done = 0;
-    bool ok = true, used[2] = {false, false};
-    int slot = 0;
-    while (ok && e == cudaSuccess && done < total) {
-        if (used[slot]) e = cudaEventSynchronize(st.done[slot]);   // the H2D that last read this buffer
-        if (e != cudaSuccess) break;
-        const uint64_t n = std::min<uint64_t>(per, total - done);
-        ok = fread(st.buf[slot], 8, n, f) == n;
-        if (!ok) break;
-        x ^= xor_fold(st.buf[slot], n);
-        e = cudaMemcpyAsync(b->d + done, st.buf[slot], n * 8, cudaMemcpyHostToDevice, g.stream);
-        if (e == cudaSuccess) e = cudaEventRecord(st.done[slot], g.stream);
-        used[slot] = true;
-        done += n;
-        slot ^= 1;
-    }
-    fclose(f);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
-    if (e != cudaSuccess || !ok || x != h.xor_words) {
-        csgn_buf_free(b);
-        if (e != cudaSuccess) return cuda_fail(e, "load: host to device");
-        return fail(CSGN_ERR_INVALID_ARGUMENT, ok ? "%s: checksum mismatch (file corrupted)" : "%s: truncated file", path);
-    }
-    if (N) *N = h.N;
-    if (D) *D = h.D;
-    *out = b;
-    return CSGN_OK;
-}
-
 int csgn_shard_range(uint64_t n_blocks, int rank, int world, uint64_t *first, uint64_t *count) {
     if (world < 1 || rank < 0 || rank >= world || !first || !count)
         return fail(CSGN_ERR_INVALID_ARGUMENT, "bad shard arguments (rank %d of %d)", rank, world);
@@ -1205,249 +920,6 @@ int csgn_shard_range(uint64_t n_blocks, int rank, int world, uint64_t *first, ui
     const uint64_t r = (uint64_t)rank;
     *first = r * base + std::min<uint64_t>(r, extra);
     *count = base + (r < extra ? 1 : 0);
-    return CSGN_OK;
-}
-
-// ---------------------------------------------------------------------------
-// sharded decrypt: fold + cross-GPU exchange in one kernel (peer.cuh)
-// ---------------------------------------------------------------------------
-namespace {
-constexpr size_t kMailboxBytes = (size_t)kPeerRing * kPeerMaxWorld * sizeof(uint64_t);
-
-int comm_ready(const csgn_comm *comm) {
-    if (!comm) return fail(CSGN_ERR_INVALID_ARGUMENT, "null communicator");
-    if (!comm->connected)
-        return fail(CSGN_ERR_INVALID_ARGUMENT, "communicator of %d ranks is not connected (csgn_comm_connect)", comm->world);
-    return CSGN_OK;
-}
-
-// Parameters of a launch that pushes (with_push) and, when collect_n > 0, closes the batch:
-// publishes everything unpublished and collects pushes last-lag-collect_n+1 .. last-lag.
-int fill_push(const csgn_comm *comm, bool with_push, uint32_t collect_n, uint32_t lag, uint64_t *totals, PeerPush *pp) {
-    memset(pp, 0, sizeof *pp);
-    const uint64_t last = with_push ? comm->seq : comm->seq - 1;       // most recent push after this launch
-    const uint64_t issued = last + 1;
-    const uint64_t unpublished = issued - comm->published;
-    if (collect_n) {
-        if (!totals) return fail(CSGN_ERR_INVALID_ARGUMENT, "collect without a destination");
-        if ((uint64_t)collect_n + lag > kPeerMaxPending)
-            return fail(CSGN_ERR_INVALID_ARGUMENT, "collect window of %u pushes trailing by %u exceeds %u", collect_n, lag,
-                        kPeerMaxPending);
-        if ((uint64_t)collect_n + lag > issued)
-            return fail(CSGN_ERR_INVALID_ARGUMENT, "collect of %u pushes trailing by %u, only %llu issued so far", collect_n,
-                        lag, (unsigned long long)issued);
-    } else if (unpublished > kPeerMaxPending) {
-        return fail(CSGN_ERR_INVALID_ARGUMENT, "more than %u pushes without a collect", kPeerMaxPending);
-    }
-    for (int q = 0; q < comm->world; ++q) pp->box[q] = comm->box[q];
-    pp->local_ring = comm->d_local_ring;
-    pp->seq = last;
-    pp->totals = totals;
-    pp->status = comm->d_status;
-    pp->timeout_ns = comm->timeout_ns;
-    pp->world = (uint32_t)comm->world;
-    pp->rank = (uint32_t)comm->rank;
-    pp->publish_n = collect_n ? (uint32_t)unpublished : 0u;
-    pp->collect_n = collect_n;
-    pp->collect_lag = lag;
-    return CSGN_OK;
-}
-}  // namespace
-
-int csgn_comm_create(int rank, int world, csgn_comm **out, unsigned char *handle_out) {
-    NEED_INIT();
-    if (!out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null output handle");
-    if (world < 1 || world > kPeerMaxWorld || rank < 0 || rank >= world)
-        return fail(CSGN_ERR_INVALID_ARGUMENT, "bad communicator shape: rank %d of %d (at most %d ranks)", rank, world,
-                    kPeerMaxWorld);
-    csgn_comm *c = new csgn_comm;
-    c->rank = rank;
-    c->world = world;
-    const char *t = std::getenv("CSGN_PEER_TIMEOUT_MS");
-    if (t && *t) c->timeout_ns = (uint64_t)std::max(1L, std::atol(t)) * 1000000ull;
-    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&c->box_local), kMailboxBytes);
-    if (e == cudaSuccess) e = cudaMemset(c->box_local, 0, kMailboxBytes);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&c->d_status), 4 * sizeof(uint64_t));
-    if (e == cudaSuccess) e = cudaMemset(c->d_status, 0, 4 * sizeof(uint64_t));
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&c->d_local_ring), kPeerRing * sizeof(uint64_t));
-    if (e == cudaSuccess) e = cudaMemset(c->d_local_ring, 0, kPeerRing * sizeof(uint64_t));
-    if (e == cudaSuccess) e = cudaDeviceSynchronize();   // the mailbox is zero before any peer can learn of it
-    if (e == cudaSuccess && handle_out) {
-        static_assert(sizeof(cudaIpcMemHandle_t) == CSGN_IPC_HANDLE_BYTES, "IPC handle size");
-        cudaIpcMemHandle_t h;
-        memset(&h, 0, sizeof h);
-        if (world > 1) e = cudaIpcGetMemHandle(&h, c->box_local);
-        if (e == cudaSuccess) memcpy(handle_out, &h, sizeof h);
-    }
-    if (e != cudaSuccess) {
-        if (c->box_local) cudaFree(c->box_local);
-        if (c->d_status) cudaFree(c->d_status);
-        if (c->d_local_ring) cudaFree(c->d_local_ring);
-        delete c;
-        return cuda_fail(e, "communicator mailbox");
-    }
-    c->box[rank] = c->box_local;
-    c->connected = (world == 1);
-    *out = c;
-    return CSGN_OK;
-}
-
-int csgn_comm_connect(csgn_comm *comm, const unsigned char *handles) {
-    NEED_INIT();
-    if (!comm || !handles) return fail(CSGN_ERR_INVALID_ARGUMENT, "null argument");
-    for (int q = 0; q < comm->world; ++q) {
-        if (q == comm->rank || comm->box[q]) continue;
-        cudaIpcMemHandle_t h;
-        memcpy(&h, handles + (size_t)q * CSGN_IPC_HANDLE_BYTES, sizeof h);
-        void *p = nullptr;
-        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            return fail(CSGN_ERR_CUDA, "cannot map the mailbox of rank %d over NVLink (cudaIpcOpenMemHandle: %s)", q,
-                        cudaGetErrorString(e));
-        }
-        comm->box[q] = static_cast<uint64_t *>(p);
-        comm->ipc_opened[q] = true;
-    }
-    comm->connected = true;
-    return CSGN_OK;
-}
-
-int csgn_comm_connect_ptrs(csgn_comm *comm, void *const *peer_mailboxes) {
-    NEED_INIT();
-    if (!comm || !peer_mailboxes) return fail(CSGN_ERR_INVALID_ARGUMENT, "null argument");
-    for (int q = 0; q < comm->world; ++q) {
-        if (q == comm->rank) continue;
-        if (!peer_mailboxes[q] || (reinterpret_cast<uintptr_t>(peer_mailboxes[q]) & 7u))
-            return fail(CSGN_ERR_INVALID_ARGUMENT, "mailbox pointer of rank %d is null or misaligned", q);
-        comm->box[q] = static_cast<uint64_t *>(peer_mailboxes[q]);
-    }
-    comm->connected = true;
-    return CSGN_OK;
-}
-
-int csgn_comm_connect_dir(csgn_comm *comm, const unsigned char *handle, const char *dir, const char *tag,
-                          int timeout_ms) {
-    NEED_INIT();
-    if (!comm || !handle || !dir || !tag) return fail(CSGN_ERR_INVALID_ARGUMENT, "null argument");
-    if (comm->world == 1) {
-        comm->connected = true;
-        return CSGN_OK;
-    }
-    auto path_of = [&](int r) {
-        return std::string(dir) + "/csgn_" + tag + "_" + std::to_string(comm->world) + "_" + std::to_string(r) + ".handle";
-    };
-    const time_t started = time(nullptr);
-    const std::string mine = path_of(comm->rank), tmp = mine + ".tmp";
-    FILE *f = fopen(tmp.c_str(), "wb");
-    if (!f) return fail(CSGN_ERR_INVALID_ARGUMENT, "cannot write %s", tmp.c_str());
-    const bool ok = fwrite(handle, 1, CSGN_IPC_HANDLE_BYTES, f) == CSGN_IPC_HANDLE_BYTES;
-    if (fclose(f) != 0 || !ok || rename(tmp.c_str(), mine.c_str()) != 0)
-        return fail(CSGN_ERR_INVALID_ARGUMENT, "cannot publish %s", mine.c_str());
-    comm->rendezvous_file = mine;
-    std::vector<unsigned char> all((size_t)comm->world * CSGN_IPC_HANDLE_BYTES, 0);
-    memcpy(all.data() + (size_t)comm->rank * CSGN_IPC_HANDLE_BYTES, handle, CSGN_IPC_HANDLE_BYTES);
-    for (int q = 0; q < comm->world; ++q) {
-        if (q == comm->rank) continue;
-        const std::string theirs = path_of(q);
-        for (long waited_ms = 0;; waited_ms += 2) {
-            struct stat st;
-            if (stat(theirs.c_str(), &st) == 0 && st.st_size == CSGN_IPC_HANDLE_BYTES && st.st_mtime >= started - 120) {
-                FILE *g2 = fopen(theirs.c_str(), "rb");
-                const bool got = g2 && fread(all.data() + (size_t)q * CSGN_IPC_HANDLE_BYTES, 1, CSGN_IPC_HANDLE_BYTES, g2) ==
-                                           CSGN_IPC_HANDLE_BYTES;
-                if (g2) fclose(g2);
-                if (got) break;
-            }
-            if (waited_ms >= timeout_ms)
-                return fail(CSGN_ERR_TIMEOUT, "rank %d of %d did not publish %s within %d ms", q, comm->world,
-                            theirs.c_str(), timeout_ms);
-            usleep(2000);
-        }
-    }
-    return csgn_comm_connect(comm, all.data());
-}
-
-void *csgn_comm_mailbox(const csgn_comm *comm, size_t *bytes) {
-    if (bytes) *bytes = kMailboxBytes;
-    return comm ? comm->box_local : nullptr;
-}
-
-uint32_t csgn_comm_pending(const csgn_comm *comm) { return comm ? (uint32_t)(comm->seq - comm->published) : 0; }
-
-void csgn_comm_slot_tag(uint64_t seq, uint32_t *slot, uint64_t *tag) {
-    if (slot) *slot = peer_slot(seq);
-    if (tag) *tag = peer_tag(seq);
-}
-
-int csgn_comm_free(csgn_comm *comm) {
-    if (!comm) return CSGN_OK;
-    if (!comm->rendezvous_file.empty()) remove(comm->rendezvous_file.c_str());
-    if (g.inited) {
-        cudaStreamSynchronize(g.stream);
-        for (int q = 0; q < comm->world; ++q)
-            if (comm->ipc_opened[q]) cudaIpcCloseMemHandle(comm->box[q]);
-        if (comm->box_local) cudaFree(comm->box_local);
-        if (comm->d_status) cudaFree(comm->d_status);
-        if (comm->d_local_ring) cudaFree(comm->d_local_ring);
-    }
-    delete comm;
-    return CSGN_OK;
-}
-
-int csgn_decrypt_sharded_async(const csgn_buf *c, const csgn_key *key, csgn_comm *comm, uint32_t collect_n,
-                               uint32_t collect_lag, uint64_t *device_totals, uint64_t *device_local) {
-    NEED_INIT();
-    if (!c || !key) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
-    int rc = comm_ready(comm);
-    if (rc != CSGN_OK) return rc;
-    if (c->L != key->L)
-        return fail(CSGN_ERR_SHAPE_MISMATCH, "ciphertext has %u words per block, key expects %u", c->L, key->L);
-    if (c->n_blocks > kPeerCountMask) return fail(CSGN_ERR_INVALID_ARGUMENT, "shard too large for a 40-bit count");
-    PeerPush pp;
-    rc = fill_push(comm, true, collect_n, collect_lag, device_totals, &pp);
-    if (rc != CSGN_OK) return rc;
-    await_upload(c);
-    cudaError_t e = launch_decrypt_count(c->d, c->n_blocks, c->L, key->d_mask,
-                                         key->h_mask.empty() ? nullptr : key->h_mask.data(), next_fold_scratch(), device_local,
-                                         g.stream, &pp);
-    if (e != cudaSuccess) return cuda_fail(e, "sharded decrypt kernel");
-    comm->seq += 1;
-    if (collect_n) comm->published = comm->seq;
-    return CSGN_OK;
-}
-
-int csgn_comm_collect_async(csgn_comm *comm, uint32_t n, uint32_t lag, uint64_t *device_totals) {
-    NEED_INIT();
-    int rc = comm_ready(comm);
-    if (rc != CSGN_OK) return rc;
-    if (n == 0) return CSGN_OK;
-    if (comm->seq == 0) return fail(CSGN_ERR_INVALID_ARGUMENT, "collect before any push");
-    PeerPush pp;
-    rc = fill_push(comm, false, n, lag, device_totals, &pp);
-    if (rc != CSGN_OK) return rc;
-    cudaError_t e = launch_peer_exchange(pp, false, 0, nullptr, g.stream);
-    if (e != cudaSuccess) return cuda_fail(e, "collect kernel");
-    comm->published = comm->seq;
-    return CSGN_OK;
-}
-
-int csgn_decrypt_sharded(const csgn_buf *c, const csgn_key *key, csgn_comm *comm, uint8_t *bit, uint64_t *total) {
-    NEED_INIT();
-    if (!bit) return fail(CSGN_ERR_INVALID_ARGUMENT, "null output");
-    int rc = comm_ready(comm);
-    if (rc != CSGN_OK) return rc;
-    rc = csgn_decrypt_sharded_async(c, key, comm, 1, 0, comm->d_status + 1, nullptr);
-    if (rc != CSGN_OK) return rc;
-    CU(cudaMemcpyAsync(g.h_result, comm->d_status, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaStreamSynchronize(g.stream));
-    if (g.h_result[0] != 0 || g.h_result[1] == UINT64_MAX) {
-        cudaMemsetAsync(comm->d_status, 0, sizeof(uint64_t), g.stream);
-        return fail(CSGN_ERR_TIMEOUT, "sharded decrypt: a peer's count did not arrive within %llu ms",
-                    (unsigned long long)(comm->timeout_ns / 1000000ull));
-    }
-    *bit = (uint8_t)(g.h_result[1] & 1u);
-    if (total) *total = g.h_result[1];
     return CSGN_OK;
 }
 
