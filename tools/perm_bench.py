@@ -31,6 +31,7 @@ for N, T, nbuf in ((1247, 1000000, 6), (16383, 90000, 6), (1247, 10000000, 2)):
                        ("prefetch 2 buffers", {"CSGN_PERM_VARIANT": "4"}), ("prefetch 1 buffer", {"CSGN_PERM_VARIANT": "5"}),
                        ("prefetch 2 buffers waves=4", {"CSGN_PERM_VARIANT": "6"}), ("prefetch 1 buffer waves=4", {"CSGN_PERM_VARIANT": "7"}),
                        ("prefetch 1 buffer waves=2", {"CSGN_PERM_VARIANT": "5", "CSGN_PERM_WAVES": "2"}),
+                       ("register-fed (variant 8)", {"CSGN_PERM_VARIANT": "8"}),
                        ("runtime-W kernel", {"CSGN_PERM_VARIANT": "1"}), ("runtime-W waves=1", {"CSGN_PERM_VARIANT": "1", "CSGN_PERM_WAVES": "1"}),
                        ("gather", {"CSGN_PERM_GATHER": "1"})):
         for k in ("CSGN_PERM_ITEMS", "CSGN_PERM_WAVES", "CSGN_PERM_GATHER", "CSGN_PERM_VARIANT"): os.environ.pop(k, None)
