@@ -157,7 +157,7 @@ template <int WC, int TILES, bool HOIST, int MINB>
 __global__ void __launch_bounds__(WC *TILES, MINB)
 permute_fixed_kernel(const uint32_t *__restrict__ in, const uint64_t T, const uint32_t *__restrict__ slice_map,
                      uint32_t *__restrict__ out, const uint64_t n_groups) {
-    extern __shared__ __align__(16) uint32_t S[];
+    extern __shared__ __align__(128) uint32_t S[];
     constexpr uint32_t tile_words = kStride * WC + 4u;     // last 4 words = the zero slot (keeps tiles 16-byte aligned)
     const uint32_t g = threadIdx.x / WC, c = threadIdx.x - g * WC;
     uint32_t *tile = S + g * tile_words;
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(512, 2)
 permute_sliced_kernel(const uint32_t *__restrict__ in, const uint64_t T, const uint32_t W,
                       const uint32_t *__restrict__ slice_map, uint32_t *__restrict__ out,
                       const uint32_t tiles_per_cta, const uint64_t n_groups) {
-    extern __shared__ __align__(16) uint32_t S[];    // tiles_per_cta * (36*W + 4) words
+    extern __shared__ __align__(128) uint32_t S[];    // tiles_per_cta * (36*W + 4) words
     const uint32_t tile_words = kStride * W + 4u;
     const uint32_t items = tiles_per_cta * W;
     pdl_enter();
