@@ -217,7 +217,8 @@ int csgn_shard_range(uint64_t n_blocks, int rank, int world, uint64_t *first, ui
  * at most CSGN_COMM_MAX_PENDING pushes may stay unpublished, and a collect window
  * (n + lag) spans at most as many.  A rank that never arrives makes the collect time out
  * (CSGN_PEER_TIMEOUT_MS, default 30000): the totals read UINT64_MAX, blocking calls return
- * CSGN_ERR_TIMEOUT, the GPU is never left spinning. */
+ * CSGN_ERR_TIMEOUT, the GPU is never left spinning.  After a timeout the ranks no longer agree on
+ * the push sequence: free the communicator and build a new one. */
 typedef struct csgn_comm csgn_comm;
 #define CSGN_IPC_HANDLE_BYTES 64
 #define CSGN_COMM_MAX_PENDING 64

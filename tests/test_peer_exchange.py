@@ -154,3 +154,92 @@ def test_fused_exchange_across_gpus(engine):
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-4000:]
     assert r.stdout.count("groups of checks passed") == n, r.stdout[-4000:]
+
+
+# ---------------------------------------------------------------------------
+# the mailbox protocol as a model (CPU): ranks drift freely between collects, yet no slot is ever
+# overwritten before every rank that still has to read it has done so
+# ---------------------------------------------------------------------------
+def _simulate(world, program, rng, ring=256, max_steps=10**6):
+    """program: list of ("push",) / ("close", n, lag) executed by EVERY rank (the collective contract).
+    A close publishes the rank's unpublished pushes to every mailbox, then blocks until the window
+    [last-lag-n+1, last-lag] of every rank has arrived.  The scheduler picks a runnable rank at random.
+    Returns the number of stale reads (a collected word that is not the push it should be)."""
+    tag_of = lambda s_: (s_ // ring) % 0xFFFFFF + 1          # peer.cuh's tag (checked against the C function above)
+    box = [[[None] * world for _ in range(ring)] for _ in range(world)]       # box[q][slot][r] = (tag, seq)
+    pc = [0] * world                 # program counter per rank
+    seq = [0] * world                # next push
+    published = [0] * world
+    waiting = [None] * world         # (first, last) window a rank blocks on
+    stale = 0
+    for _ in range(max_steps):
+        runnable = []
+        for r in range(world):
+            if waiting[r] is not None:
+                first, last = waiting[r]
+                ok = all(box[r][s % ring][q] is not None and box[r][s % ring][q][0] == tag_of(s)
+                         for s in range(first, last + 1) for q in range(world))
+                if ok:
+                    runnable.append(r)
+            elif pc[r] < len(program):
+                runnable.append(r)
+        if not runnable:
+            break
+        r = runnable[int(rng.integers(len(runnable)))]
+        if waiting[r] is not None:                       # the collect completes: read the window
+            first, last = waiting[r]
+            for s in range(first, last + 1):
+                for q in range(world):
+                    if box[r][s % ring][q][1] != s:
+                        stale += 1
+            waiting[r] = None
+            pc[r] += 1
+            continue
+        op = program[pc[r]]
+        if op[0] == "push":
+            seq[r] += 1
+            pc[r] += 1
+        else:
+            _, n, lag = op
+            for s in range(published[r], seq[r]):        # publish: one word per (push, rank)
+                for q in range(world):
+                    box[q][s % ring][r] = (tag_of(s), s)
+            published[r] = seq[r]
+            last = seq[r] - 1 - lag
+            waiting[r] = (last - n + 1, last)
+    assert all(p == len(program) for p in pc), "deadlock in the model"
+    return stale
+
+
+def _random_program(rng, batches, max_pending, lagged):
+    prog, prev = [], 0
+    for _ in range(batches):
+        n = int(rng.integers(1, max_pending // 2 + 1))
+        prog += [("push",)] * n
+        if lagged and prev and prev + n <= max_pending:
+            prog.append(("close", prev, n))              # the previous batch: never waits for a slow peer
+        else:
+            prog.append(("close", n, 0))
+        prev = n
+    return prog
+
+
+def test_mailbox_protocol_model_never_reads_a_lapped_slot():
+    from csgn_b200 import engine
+    rng = np.random.default_rng(2025)
+    for world in (2, 3, 8):
+        for lagged in (False, True):
+            prog = _random_program(rng, 60, engine.COMM_MAX_PENDING, lagged)     # ~1000 pushes: the ring wraps 4 times
+            assert _simulate(world, prog, rng) == 0
+    class Greedy:                                        # always pick the lowest runnable rank
+        def integers(self, n):
+            return 0
+    # the model does catch a protocol that breaks the bound: batches of 6 on a ring of 8 (bound: fewer than 4).  Rank 0
+    # finishes its first collect and publishes batch 2 over slots rank 1 has not read yet; rank 1 then never sees the
+    # tags it waits for (on the GPU: the collect would time out)
+    with pytest.raises(AssertionError, match="deadlock"):
+        _simulate(2, ([("push",)] * 6 + [("close", 6, 0)]) * 3, Greedy(), ring=8)
+    assert _simulate(2, ([("push",)] * 3 + [("close", 3, 0)]) * 6, Greedy(), ring=8) == 0      # within the bound: clean
+    # deterministic adversary: rank 0 runs ahead as far as the contract allows, rank 1 lags -- still clean
+    prog = _random_program(rng, 40, engine.COMM_MAX_PENDING, True)
+    assert _simulate(4, prog, Greedy()) == 0
