@@ -56,7 +56,7 @@ UNIT = "blocks/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
@@ -152,21 +152,26 @@ class ClockSampler(threading.Thread):
             return
         while not self._stop_evt.is_set():
             try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
                 r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                for bit, name in self.NAMES.items():
-                    if r & bit and name != "gpu_idle":
-                        self.reasons.add(name)
+                self.samples.append((time.perf_counter(), mhz, r))
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.001)
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Median SM clock and the throttle reasons of the samples taken inside [t_begin, t_end] (perf_counter): the
+        thread is started a little before the timed region so that NVML is warm, and only what falls inside counts."""
         self._stop_evt.set()
         self.join(timeout=2)
-        med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples)}
+        inside = [x for x in self.samples if (t_begin is None or x[0] >= t_begin) and (t_end is None or x[0] <= t_end)]
+        reasons = set()
+        for _, _, r in inside:
+            for bit, name in self.NAMES.items():
+                if r & bit and name != "gpu_idle":
+                    reasons.add(name)
+        med = float(np.median([x[1] for x in inside])) if inside else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons), "samples": len(inside)}
 
 
 # ---------------------------------------------------------------------------
@@ -466,15 +471,16 @@ def run_ours(args):
     K = args.steps
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
     sampler = ClockSampler(local)
+    sampler.start()                      # before the barrier: NVML's first calls are slow
     barrier()
     launches0 = eng.launch_count()
-    sampler.start()
-    t_wall = time.perf_counter()
+    t_begin = time.perf_counter()
     for k in range(K):
         step_device(evs[k], final=(k == K - 1))
     barrier()
-    t_wall = time.perf_counter() - t_wall
-    clocks = sampler.stop()
+    t_end = time.perf_counter()
+    t_wall = t_end - t_begin
+    clocks = sampler.stop(t_begin, t_end)
     launches = eng.launch_count() - launches0
 
     total_ms = evs[0][0].elapsed_time(evs[K - 1][3])
@@ -724,13 +730,14 @@ def run_chain(args):
     K = args.steps
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
     sampler = ClockSampler(local)
+    sampler.start()
     barrier()
     launches0 = eng.launch_count()
-    sampler.start()
+    t_begin = time.perf_counter()
     for k in range(K):
         step(evs[k])
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, time.perf_counter())
     launches = eng.launch_count() - launches0
     phases = [sum(e[i].elapsed_time(e[i + 1]) for e in evs) for i in range(4)]
     t = torch.tensor([evs[0][0].elapsed_time(evs[K - 1][4])] + phases, dtype=torch.float64, device=dev)
