@@ -28,6 +28,7 @@ and the per-pair satisfied-block counts are summed by ONE NCCL all-reduce per st
 and SecretKey::decrypt) on the host cores, one replica per core.
 """
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -85,6 +86,8 @@ def parse_args():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = every rank multiplies t1 x t2 (default, the headline); strong = the t1 blocks of the "
                          "left operand are split over the ranks (SURVEY 8d, the cfg5 sweep)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the side measurements of permute and add (GPU and reference CPU) reported under other_kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -257,6 +260,75 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
+
+def other_kernels(eng, torch, ctx, vo, N, D, L, peak, with_cpu):
+    """Permute and add on products the bench already holds (reported beside the headline, each
+    against the HBM roofline at 16*L bytes per block, with the unmodified reference's public calls on a bounded
+    sample).  Never part of `value`; any failure here is reported, not raised."""
+    out = {}
+    try:
+        T = vo[0].n_blocks
+        nb = len(vo) // 2 * 2
+        perm_np = np.random.default_rng(3).permutation(N).astype(np.uint64)
+        perm = eng.Permutation(ctx, perm_np)
+
+        def timed(fn, reps):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) * 1e-3 / reps
+
+        def permute_pass():                      # every even product into its odd neighbour: nothing stays in L2
+            for i in range(0, nb, 2):
+                vo[i].permute_into(perm, vo[i + 1])
+        t = timed(permute_pass, 3) / (nb // 2)
+        gbs = T * 16 * L / t / 1e9
+        out["permute"] = {"blocks_per_s": T / t, "gbs_read_plus_write": gbs, "frac_of_peak": gbs / peak,
+                          "avg_launch_us": t * 1e6, "blocks_per_launch": T}
+
+        def add_pass():
+            for i in range(0, nb, 2):
+                s_ = vo[i] + vo[i + 1]           # csgn_concat into a fresh buffer
+                del s_
+        t = timed(add_pass, 3) / (nb // 2)
+        gbs = 2 * T * 16 * L / t / 1e9
+        out["add"] = {"blocks_per_s": 2 * T / t, "gbs_read_plus_write": gbs, "frac_of_peak": gbs / peak,
+                      "avg_launch_us": t * 1e6, "blocks_per_launch": 2 * T}
+        if with_cpu:
+            from oracle import pyoracle
+            if pyoracle.ref_available():
+                ref = pyoracle.Ref()
+                rng = np.random.default_rng(5)
+                Tp = 20000 if N < 4096 else 1500          # the reference unpacks 8 bytes per BIT: 43 us per block at N=1247
+                v = seeded_blocks(rng, Tp, N)
+                h = ref.ct(v, N, D)
+                t0 = time.perf_counter()
+                hp = ref.lib.ref_ct_permute(h, perm_np.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), N)
+                tp = time.perf_counter() - t0
+                ref.ct_free(hp)
+                Ta = 100000 if N < 4096 else 8000
+                h2 = ref.ct(seeded_blocks(rng, Ta, N), N, D)
+                t0 = time.perf_counter()
+                hs = ref.lib.ref_ct_add(h2, h)
+                ta = time.perf_counter() - t0
+                for x in (h, h2, hs):
+                    ref.ct_free(x)
+                out["permute"]["cpu_reference_blocks_per_s"] = Tp / tp
+                out["permute"]["cpu_sample"] = ("public applyPermutation on a %d-block ciphertext, %.2f s, one thread; the "
+                                                "reference walks every block but RETURNS only block 0 (src/Ciphertext.cpp:33-40)"
+                                                % (Tp, tp))
+                out["add"]["cpu_reference_blocks_per_s"] = (Ta + Tp) / ta
+                out["add"]["cpu_sample"] = "public operator+ of %d + %d blocks, %.3f s, one thread" % (Ta, Tp, ta)
+    except Exception as e:  # noqa: BLE001
+        out["error"] = "%s: %s" % (type(e).__name__, e)
+    return out
+
+
 
 def connect_exchange(args, world, dev):
     """(comm, description).  comm is None at N=1 and for --exchange nccl.  Every rank must take the same
@@ -635,6 +707,8 @@ def run_ours(args):
         }
         if e2e:
             line["e2e"] = e2e
+        if world == 1 and not args.no_extras:
+            line["other_kernels"] = other_kernels(eng, torch, ctx, vo, N, D, L, peak, not args.no_cpu_baseline)
         if world == 1 and not args.no_cpu_baseline:
             # the reference overflows its int counters above 131,080 blocks at N=16383 (SURVEY hazard 4): the CPU
             # sample always uses the workload's own sizes, whatever --t1/--t2 say

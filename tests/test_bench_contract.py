@@ -47,4 +47,6 @@ def test_our_arm_line():
     e2e = d["e2e"]
     assert e2e["value"] > 5e9 and e2e["h2d_bytes_per_step"] == 16 * 2000 * 160 and e2e["d2h_bytes_per_step"] == 128
     assert d["gpu_launches"] == 3 * 32                       # 16 multiplies + 16 folds per step, nothing else
+    extra = d["other_kernels"]                               # permute and add, reported beside the headline
+    assert "error" not in extra and extra["permute"]["blocks_per_s"] > 5e9 and extra["add"]["gbs_read_plus_write"] > 3000
     assert d["clocks"]["sm_mhz"] and not (set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"})
