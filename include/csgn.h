@@ -139,7 +139,8 @@ int csgn_decrypt_count_async(const csgn_buf *c, const csgn_key *key, uint64_t *d
 int csgn_decrypt_product(const csgn_buf *const *factors, uint32_t n_factors, const csgn_key *key, uint8_t *bit,
                          uint64_t *count);
 /* ---- batches of independent items -------------------------------------------------------------
- * n independent products / folds in ONE call.  The library forks its internal lane streams (CSGN_LANES, default 2)
+ * n independent products / folds in ONE call: what a caller of the reference writes as a loop over
+ * Ciphertext::operator* (src/Ciphertext.cpp:231-247) or SecretKey::decrypt (src/SecretKey.cpp:208-224).  The library forks its internal lane streams (CSGN_LANES, default 2)
  * from the current stream, enqueues item i on lane i % lanes and joins them back, so the tail of one kernel
  * overlaps the launch ramp and first-load latency of the next item's: +12 % over n single calls at the
  * 160 MB products of Context(1247,16) 1000x1000 (profiles/README.md).  Ordering seen by the caller is that
