@@ -168,13 +168,23 @@ class ClockSampler(threading.Thread):
         self._stop_evt.set()
         self.join(timeout=2)
         inside = [x for x in self.samples if (t_begin is None or x[0] >= t_begin) and (t_end is None or x[0] <= t_end)]
+        note = None
+        if not inside and self.samples and t_begin is not None:
+            # a timed region shorter than one NVML round trip (a few steps only): take the samples closest to it --
+            # the GPU ran the same kernels (warm-up, e2e) right before and after
+            mid = 0.5 * (t_begin + (t_end if t_end is not None else t_begin))
+            inside = sorted(self.samples, key=lambda x: abs(x[0] - mid))[:3]
+            note = "timed region shorter than the sampling period: the %d samples nearest to it" % len(inside)
         reasons = set()
         for _, _, r in inside:
             for bit, name in self.NAMES.items():
                 if r & bit and name != "gpu_idle":
                     reasons.add(name)
         med = float(np.median([x[1] for x in inside])) if inside else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons), "samples": len(inside)}
+        out = {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons), "samples": len(inside)}
+        if note:
+            out["note"] = note
+        return out
 
 
 # ---------------------------------------------------------------------------
