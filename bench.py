@@ -279,6 +279,8 @@ def other_kernels(eng, torch, ctx, vo, N, D, L, peak, with_cpu):
     try:
         T = vo[0].n_blocks
         nb = len(vo) // 2 * 2
+        if nb < 2:
+            return {"skipped": "needs two products to ping-pong between (--pairs >= 2)"}
         perm_np = np.random.default_rng(3).permutation(N).astype(np.uint64)
         perm = eng.Permutation(ctx, perm_np)
 
