@@ -144,3 +144,29 @@ def test_cpp_api_sharded_over_the_gpus_of_the_box(tmp_path):
         assert rc == 0, "rank %d:\n%s" % (r, out[-3000:])
         assert "sharded_demo rank %d/%d: all checks passed" % (r, world) in out
     assert not [f for f in os.listdir(tmp_path) if f.endswith(".handle")]      # every rank removed its handle file
+
+
+def test_host_classes_clean_under_sanitizers(tmp_path):
+    """The host-side classes (Context, Plaintext, Permutation, SecretKey key handling, encrypt, Timer, Helper) built with
+    -fsanitize=address,undefined and driven by the differential program: no report, same verdict (the
+    reference itself trips ASan/UBSan in several places -- App. B; this port must not).  CPU only; needs the reference's
+    headers to compile, so it runs where /root/reference is present."""
+    ref_hdr = os.path.join(build.REFERENCE, "src", "certFHE.h")
+    ref_lib = os.path.join(ROOT, "oracle", "_ref", "libcertfhe_ref.so")
+    if not (os.path.exists(ref_hdr) and os.path.exists(ref_lib)):
+        pytest.skip("needs /root/reference (headers) and oracle/_ref")
+    exe = str(tmp_path / "host_vs_reference_asan")
+    cmd = ["g++", "-O1", "-g", "-std=c++11", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-w",
+           "-I" + build.CERTFHE, "-I" + build.INCLUDE, '-DCSGN_REFERENCE_HEADER="%s"' % ref_hdr, "-o", exe,
+           os.path.join(ROOT, "tests", "cpp", "host_vs_reference.cpp"),
+           os.path.join(build.CERTFHE, "host_types.cpp"), os.path.join(build.CERTFHE, "device_types.cpp"),
+           "-L" + build.LIBDIR, "-lcsgn", "-L" + os.path.dirname(ref_lib), "-lcertfhe_ref", "-pthread",
+           "-Wl,-rpath," + build.LIBDIR, "-Wl,-rpath," + os.path.dirname(ref_lib)]
+    c = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert c.returncode == 0, c.stdout[-3000:]
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0:protect_shadow_gap=0:halt_on_error=1",
+               UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
+    r = subprocess.run([exe], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "identical to the reference" in r.stdout
+    assert "AddressSanitizer" not in r.stdout and "runtime error" not in r.stdout, r.stdout[-3000:]
