@@ -211,3 +211,44 @@ def test_oracle_matches_live_reference_on_random_parameters(oracle, ref):
         assert ref.decrypt(strict, N, D, pk) == oracle.decrypt(one, N, key)
 
     run()
+
+
+def test_oracle_c_code_clean_under_sanitizers(tmp_path):
+    """oracle/csgn_oracle.c rebuilt with -fsanitize=address,undefined and driven through every entry point on eight
+    geometries (odd L, L = 1, N % 64 == 0 included): the checker itself must not rely on undefined behaviour."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path / "libcsgn_oracle_asan.so")
+    c = subprocess.run(["gcc", "-O1", "-g", "-fPIC", "-shared", "-fsanitize=address,undefined", "-fno-omit-frame-pointer",
+                        "-o", so, os.path.join(root, "oracle", "csgn_oracle.c")], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    assert c.returncode == 0, c.stdout[-2000:]
+    libasan = subprocess.run(["gcc", "-print-file-name=libasan.so"], stdout=subprocess.PIPE, text=True).stdout.strip()
+    if not os.path.isabs(libasan) or not os.path.exists(libasan):
+        pytest.skip("libasan.so not found next to gcc")
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+from oracle.pyoracle import Oracle, random_blocks, random_key, words_per_block, srand
+o = Oracle(%r)
+rng = np.random.default_rng(1)
+for N, D in ((1247, 16), (16383, 64), (65, 2), (191, 5), (63, 4), (1, 1), (128, 4), (2048, 8)):
+    L = words_per_block(N)
+    a, b = random_blocks(rng, 7, N), random_blocks(rng, 5, N)
+    s = random_key(rng, N, D)
+    p = o.mul(a, b, L); o.concat(a, b); o.decrypt(p, N, s); o.count_satisfied(p, N, s); o.checksum(p); o.mul_checksum(a, b, L)
+    if N > 1:
+        srand(3); perm = o.perm_generate(N); o.permute_all(p, N, perm); o.permute_block(a[:L], N, perm)
+        o.key_permute(N, s, perm); o.perm_inverse(perm); o.perm_compose(perm, perm)
+    srand(5); e = o.encrypt(1, N, D, s); o.encrypt(0, N, D, s); o.keygen(N, D)
+    o.encrypt_batch(np.array([0, 1, 1, 0], dtype=np.uint8), N, s, 99); o.bits_text(e, N)
+print("oracle under ASan/UBSan: clean")
+''' % (root, so)
+    env = dict(os.environ, LD_PRELOAD=libasan, ASAN_OPTIONS="detect_leaks=0:protect_shadow_gap=0:halt_on_error=1",
+               UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "clean" in r.stdout, r.stdout[-3000:]
+    assert "AddressSanitizer" not in r.stdout and "runtime error" not in r.stdout, r.stdout[-3000:]
