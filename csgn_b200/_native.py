@@ -21,12 +21,15 @@ SIGNATURES = {
     "csgn_device_info": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int), _u64p, _u64p, ctypes.POINTER(ctypes.c_int)]),
     "csgn_set_stream": (ctypes.c_int, [_vp]),
     "csgn_get_stream": (_vp, []),
+    "csgn_set_auto_lanes": (ctypes.c_int, [ctypes.c_int]),
+    "csgn_get_auto_lanes": (ctypes.c_int, []),
     "csgn_sync": (ctypes.c_int, []),
     "csgn_launch_count": (_u64, []),
     "csgn_words_per_block": (ctypes.c_uint32, [_u64]),
     "csgn_host_alloc": (ctypes.c_int, [ctypes.c_size_t, _vpp]),
     "csgn_host_free": (ctypes.c_int, [_vp]),
     "csgn_buf_upload": (ctypes.c_int, [_vp, _u64, ctypes.c_uint32, _vpp]),
+    "csgn_buf_upload_copy": (ctypes.c_int, [_vp, _u64, ctypes.c_uint32, _vpp]),
     "csgn_buf_alloc": (ctypes.c_int, [_u64, ctypes.c_uint32, _vpp]),
     "csgn_buf_wrap": (ctypes.c_int, [_vp, _u64, ctypes.c_uint32, _vpp]),
     "csgn_buf_clone": (ctypes.c_int, [_vp, _vpp]),
@@ -47,6 +50,18 @@ SIGNATURES = {
     "csgn_decrypt_count": (ctypes.c_int, [_vp, _vp, _u64p]),
     "csgn_decrypt_count_async": (ctypes.c_int, [_vp, _vp, _vp]),
     "csgn_decrypt_product": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_uint32, _vp, ctypes.POINTER(ctypes.c_uint8), _u64p]),
+    "csgn_decrypt_deferred": (ctypes.c_int, [_vp, _vp, _vpp]),
+    "csgn_result_ready": (ctypes.c_int, [_vp]),
+    "csgn_result_wait": (ctypes.c_int, [_vp, _u64p]),
+    "csgn_result_free": (ctypes.c_int, [_vp]),
+    "csgn_mul_count_async": (ctypes.c_int, [_vp, _vp, _vp, _vpp, _vp]),
+    "csgn_mul_decrypt": (ctypes.c_int, [_vp, _vp, _vp, _vpp, ctypes.POINTER(ctypes.c_uint8), _u64p]),
+    "csgn_mul_count_batch_async": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.c_uint32, _vp,
+                                                  ctypes.POINTER(_vp), _vp]),
+    "csgn_mul_decrypt_deferred": (ctypes.c_int, [_vp, _vp, _vp, _vpp, _vpp]),
+    "csgn_mul_decrypt_sharded_async": (ctypes.c_int, [_vp, _vp, _vp, _vpp, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp]),
+    "csgn_mul_decrypt_sharded_batch_async": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.c_uint32, _vp,
+                                                            ctypes.POINTER(_vp), _vp, ctypes.c_uint32, _vp]),
     "csgn_mul_batch": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.c_uint32, ctypes.POINTER(_vp)]),
     "csgn_mul_into_batch": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.c_uint32, ctypes.POINTER(_vp)]),
     "csgn_decrypt_count_batch_async": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_uint32, _vp, _vp]),

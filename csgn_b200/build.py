@@ -58,13 +58,16 @@ def libcertfhe_path():
     return os.path.join(LIBDIR, "libcertFHE.so")
 
 
-def build_libcsgn(force=False, verbose=False):
+def build_libcsgn(force=False, verbose=False, variants=False):
+    """libcsgn.so: one kernel per shape.  variants=True builds libcsgn_variants.so instead, with the losing kernel
+    variants of the tuning sweeps compiled in (-DCSGN_BUILD_VARIANTS; select it with CSGN_LIBRARY=<path> for A/B runs)."""
     os.makedirs(LIBDIR, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
-    out = libcsgn_path()
+    out = os.path.join(LIBDIR, "libcsgn_variants.so") if variants else libcsgn_path()
     if force or _stale(out, deps):
-        _run([_nvcc()] + NVCC_ARCH + NVCC_FLAGS + ["-shared", "-o", out] + srcs, verbose)
+        extra = ["-DCSGN_BUILD_VARIANTS"] if variants else []
+        _run([_nvcc()] + NVCC_ARCH + NVCC_FLAGS + extra + ["-shared", "-o", out] + srcs, verbose)
     return out
 
 
@@ -159,3 +162,5 @@ def build_all(force=False, verbose=False):
 if __name__ == "__main__":
     build_all(force="--force" in sys.argv, verbose=True)
     print("built:", libcsgn_path())
+    if "--variants" in sys.argv:
+        print("built:", build_libcsgn(force="--force" in sys.argv, verbose=True, variants=True))

@@ -6,13 +6,16 @@
 #include <atomic>
 #include <cstdarg>
 
-#define CSGN_VERSION_STRING "csgn-b200 0.1 (sm_100a)"
+#ifdef CSGN_BUILD_VARIANTS
+#define CSGN_VERSION_STRING "csgn-b200 0.2 (sm_100a) +variants"
+#else
+#define CSGN_VERSION_STRING "csgn-b200 0.2 (sm_100a)"
+#endif
 
 namespace csgn {
 namespace detail {
 
 State g;
-unsigned g_launches_since_switch = 1u << 30;
 DeviceProps g_props;
 std::atomic<uint64_t> g_launches{0};
 thread_local std::string t_error;
@@ -34,14 +37,26 @@ int cuda_fail(cudaError_t e, const char *what) {
                 cudaGetErrorString(e), cudaGetErrorName(e));
 }
 
-// Every fold launch takes the next pair of scratch words (running count, CTA ticket) and leaves them
-// zeroed, so decrypts enqueued on different streams (csgn_set_stream between calls) may run concurrently.
-constexpr uint32_t kFoldSlots = 64;
-uint64_t *next_fold_scratch() {
-    uint64_t *p = g.d_scratch + 8 + 2 * (g.fold_slot % kFoldSlots);
-    g.fold_slot += 1;
-    return p;
+// One fold scratch word per stream: folds of one stream never overlap (a kernel touches global memory only after
+// griddepcontrol.wait, i.e. after its predecessor has completed), folds of different streams never share a word.
+uint64_t *fold_scratch() {
+    size_t i = 0;
+    for (; i < g.scratch_streams.size(); ++i)
+        if (g.scratch_streams[i] == g.stream) break;
+    if (i == g.scratch_streams.size()) {
+        if (i < kScratchSlots) {
+            g.scratch_streams.push_back(g.stream);
+        } else {
+            // more distinct streams than slots (a caller cycling through hundreds of its own): share the last word,
+            // ordering this stream after everything that may still use it
+            i = kScratchSlots - 1;
+            cudaDeviceSynchronize();
+        }
+    }
+    return g.d_scratch + 8 + 2 * i;
 }
+
+bool folds_overlap() { return g.in_batch || g.auto_lanes; }
 
 int dev_alloc(uint64_t words, uint64_t **out, cudaStream_t stream) {
     *out = nullptr;
@@ -118,27 +133,111 @@ bool give_upload_slot(uint64_t *d, uint64_t cap_words) {
     return true;
 }
 
-// Called for every operand of every operation: order the work stream after a pending upload of `b`
-// (first consumer only) and remember which stream touched the words last.
-void await_upload(const csgn_buf *b) {
-    if (!b) return;
-    if (b->ready) {
-        cudaStreamWaitEvent(g.stream, b->ready, 0);
-        g.event_pool.push_back(b->ready);
-        b->ready = nullptr;
-    }
-    b->last_stream = g.stream;
+uint64_t synced_tick(cudaStream_t st) {
+    for (const StreamMark &m : g.synced)
+        if (m.s == st) return m.tick;
+    return 0;
 }
 
-// Before storage is handed back (pool or upload cache) on the CURRENT stream: if the last operation on it ran on
-// another stream (the caller multiplexes streams and frees later), the current stream first waits for that one.
-void order_after_last_use(const csgn_buf *b) {
-    if (!b->last_stream || b->last_stream == g.stream) return;
+void note_synced(cudaStream_t st) {
+    for (StreamMark &m : g.synced)
+        if (m.s == st) {
+            m.tick = g.tick - 1;         // every use recorded so far has a smaller tick
+            return;
+        }
+    g.synced.push_back({st, g.tick - 1});
+}
+
+// Make `consumer` wait for everything `mark.s` had enqueued up to now (a superset of the marked use), unless that
+// use is on the same stream, is known to have completed, or `consumer` already waits for it.
+void wait_for_mark(cudaStream_t consumer, const StreamMark &mark) {
+    if (!mark.s || mark.s == consumer || synced_tick(mark.s) >= mark.tick) return;
+    for (State::Waited &w : g.waited)
+        if (w.consumer == consumer && w.producer == mark.s) {
+            if (w.tick >= mark.tick) return;
+            cudaEvent_t e = take_event();
+            if (!e) return;
+            if (cudaEventRecord(e, mark.s) == cudaSuccess) cudaStreamWaitEvent(consumer, e, 0);
+            else cudaGetLastError();     // the caller destroyed that stream: its work was enqueued before, nothing to order
+            g.event_pool.push_back(e);
+            w.tick = g.tick - 1;         // every use recorded so far has a smaller tick
+            return;
+        }
     cudaEvent_t e = take_event();
     if (!e) return;
-    if (cudaEventRecord(e, b->last_stream) == cudaSuccess) cudaStreamWaitEvent(g.stream, e, 0);
-    else cudaGetLastError();     // the caller destroyed that stream: its work was enqueued before, nothing to order
+    if (cudaEventRecord(e, mark.s) == cudaSuccess) cudaStreamWaitEvent(consumer, e, 0);
+    else cudaGetLastError();
     g.event_pool.push_back(e);
+    if (g.waited.size() < 256) g.waited.push_back({consumer, mark.s, g.tick - 1});
+}
+
+// A pending upload of `b`: the current stream waits for it unless it already does; once the copy is known to have
+// completed the event is recycled.
+void await_ready(const csgn_buf *b) {
+    if (!b->ready) return;
+    if (cudaEventQuery(b->ready) == cudaSuccess) {
+        g.event_pool.push_back(b->ready);
+        b->ready = nullptr;
+        b->ready_waited.clear();
+        return;
+    }
+    cudaGetLastError();      // cudaErrorNotReady is not an error
+    for (cudaStream_t st : b->ready_waited)
+        if (st == g.stream) return;
+    cudaStreamWaitEvent(g.stream, b->ready, 0);
+    b->ready_waited.push_back(g.stream);
+}
+
+void acquire_read(const csgn_buf *b) {
+    if (!b) return;
+    await_ready(b);
+    wait_for_mark(g.stream, b->writer);
+    const uint64_t now = g.tick++;
+    if (b->writer.s == g.stream) {       // same stream as the writer: stream order already covers later writers' needs
+        b->writer.tick = now;
+        return;
+    }
+    for (StreamMark &m : b->readers)
+        if (m.s == g.stream) {
+            m.tick = now;
+            return;
+        }
+    b->readers.push_back({g.stream, now});
+}
+
+void acquire_write(const csgn_buf *b) {
+    if (!b) return;
+    await_ready(b);
+    wait_for_mark(g.stream, b->writer);
+    for (const StreamMark &m : b->readers) wait_for_mark(g.stream, m);
+    b->readers.clear();
+    b->writer = {g.stream, g.tick++};
+}
+
+// Before storage is handed back (pool or upload cache) on the CURRENT stream: that stream first waits for every
+// other stream that used the words (the caller multiplexes streams, or the library's lanes did).
+void order_after_all_uses(const csgn_buf *b) {
+    wait_for_mark(g.stream, b->writer);
+    for (const StreamMark &m : b->readers) wait_for_mark(g.stream, m);
+}
+
+AutoLane::AutoLane(const csgn_buf *x, const csgn_buf *y) : home(g.stream) {
+    if (!g.auto_lanes || g.in_batch || g.in_auto || g.n_lanes < 2) return;
+    g.in_auto = true;
+    // ways: 0 = the caller's stream, 1.. = the library's side lanes
+    const csgn_buf *big = (y && (!x || y->n_blocks > x->n_blocks)) ? y : x;
+    cudaStream_t pick = nullptr;
+    if (big && big->writer.s && synced_tick(big->writer.s) < big->writer.tick) {
+        if (big->writer.s == home) pick = home;
+        for (int i = 1; i < g.n_lanes && !pick; ++i)
+            if (big->writer.s == g.lane[i]) pick = g.lane[i];
+    }
+    if (!pick) {
+        const uint32_t way = g.rr++ % (uint32_t)g.n_lanes;
+        pick = way == 0 ? home : g.lane[way];
+    }
+    g.stream = pick;
+    active = true;
 }
 
 int new_buf(uint64_t n_blocks, uint32_t L, uint64_t cap_words, csgn_buf **out, cudaStream_t stream) {
@@ -153,6 +252,7 @@ int new_buf(uint64_t n_blocks, uint32_t L, uint64_t cap_words, csgn_buf **out, c
         delete b;
         return rc;
     }
+    b->writer = {stream ? stream : g.stream, g.tick++};      // the allocation is ordered on that stream
     *out = b;
     return CSGN_OK;
 }
@@ -163,14 +263,7 @@ using namespace detail;
 
 const DeviceProps &device_props() { return g_props; }
 void set_device_props(const DeviceProps &p) { g_props = p; }
-// A caller that moves between streams from one call to the next (csgn_set_stream) is enqueueing independent
-// ciphertexts so that their kernels overlap; launchers that care (the decrypt fold) then prefer several shorter waves of
-// CTAs, which back-fill behind another stream's kernel, over one persistent wave, which is best for a kernel running alone.
-void count_launch(unsigned n) {
-    g_launches.fetch_add(n, std::memory_order_relaxed);
-    if (g_launches_since_switch < (1u << 30)) g_launches_since_switch += n;
-}
-bool streams_alternate() { return g_launches_since_switch < 8; }
+void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 uint64_t launches() { return g_launches.load(std::memory_order_relaxed); }
 
 // Tuning knobs (CSGN_MUL_*, CSGN_DEC_*, CSGN_PERM_*, CSGN_PDL ...) are looked up only when
@@ -188,6 +281,48 @@ long env_long(const char *name, long dflt) {
 }
 
 }  // namespace csgn
+
+// Pinned staging for csgn_buf_upload_copy: the caller's words are copied here by the host and go to the device
+// from here, so the call needs no synchronisation and the caller may reuse its array at once.
+namespace {
+struct StagingSlot {
+    void *p;
+    size_t cap;
+    cudaEvent_t done;     // the H2D copy that last read this slot
+};
+std::vector<StagingSlot> g_staging;
+size_t g_staging_bytes = 0;
+constexpr size_t kStagingMaxTotal = 512ull << 20, kStagingMaxOne = 64ull << 20;
+
+StagingSlot *take_staging(size_t bytes) {
+    StagingSlot *best = nullptr;
+    for (StagingSlot &sl : g_staging) {
+        if (sl.cap < bytes || (best && best->cap <= sl.cap)) continue;
+        if (cudaEventQuery(sl.done) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        best = &sl;
+    }
+    if (best) return best;
+    size_t cap = 64 << 10;
+    while (cap < bytes) cap <<= 1;
+    if (g_staging_bytes + cap > kStagingMaxTotal) return nullptr;
+    StagingSlot sl = {nullptr, cap, nullptr};
+    if (cudaHostAlloc(&sl.p, cap, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFreeHost(sl.p);
+        return nullptr;
+    }
+    g_staging.push_back(sl);
+    g_staging_bytes += cap;
+    return &g_staging.back();
+}
+}  // namespace
 
 using namespace csgn;
 using namespace csgn::detail;
@@ -248,9 +383,17 @@ int csgn_init(int device) {
     // streams again -- so the pool only reuses memory whose free has completed or is ordered by the caller's own events.
     int off = 0;
     CU(cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off));
-    CU(cudaMalloc(reinterpret_cast<void **>(&g.d_scratch), (8 + 2 * kFoldSlots) * sizeof(uint64_t)));
-    CU(cudaMemset(g.d_scratch, 0, (8 + 2 * kFoldSlots) * sizeof(uint64_t)));
+    CU(cudaMalloc(reinterpret_cast<void **>(&g.d_scratch), (8 + 2 * kScratchSlots) * sizeof(uint64_t)));
+    CU(cudaMemset(g.d_scratch, 0, (8 + 2 * kScratchSlots) * sizeof(uint64_t)));
     CU(cudaHostAlloc(reinterpret_cast<void **>(&g.h_result), 8 * sizeof(uint64_t), cudaHostAllocDefault));
+    CU(cudaMalloc(reinterpret_cast<void **>(&g.d_results), kResultSlots * sizeof(uint64_t)));
+    CU(cudaHostAlloc(reinterpret_cast<void **>(&g.h_results), kResultSlots * sizeof(uint64_t), cudaHostAllocDefault));
+    g.free_results.clear();
+    for (uint32_t i = kResultSlots; i > 0; --i) g.free_results.push_back(i - 1);
+    {
+        const char *e = std::getenv("CSGN_AUTO_LANES");
+        g.auto_lanes = e && *e && std::atoi(e) != 0;
+    }
     g.device = device;
     g.inited = true;
     return CSGN_OK;
@@ -259,15 +402,22 @@ int csgn_init(int device) {
 int csgn_shutdown(void) {
     if (!g.inited) return CSGN_OK;
     cudaSetDevice(g.device);
-    cudaStreamSynchronize(g.copy_stream);
-    cudaStreamSynchronize(g.stream);
+    cudaDeviceSynchronize();
     for (const State::UploadSlot &sl : g.upload_cache) {
         cudaFreeAsync(sl.d, g.stream);
         cudaEventDestroy(sl.freed);
     }
     cudaStreamSynchronize(g.stream);
+    for (StagingSlot &sl : g_staging) {
+        cudaFreeHost(sl.p);
+        cudaEventDestroy(sl.done);
+    }
+    g_staging.clear();
+    g_staging_bytes = 0;
     cudaFree(g.d_scratch);
     cudaFreeHost(g.h_result);
+    if (g.d_results) cudaFree(g.d_results);
+    if (g.h_results) cudaFreeHost(g.h_results);
     for (cudaEvent_t e : g.event_pool) cudaEventDestroy(e);
     for (int i = 0; i < State::kMaxLanes; ++i) {
         if (g.lane[i]) {
@@ -300,11 +450,17 @@ int csgn_device_info(int *sm_count, uint64_t *hbm_total, uint64_t *hbm_free, int
 
 int csgn_set_stream(void *cuda_stream) {
     NEED_INIT();
-    cudaStream_t next = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : g.own_stream;
-    if (next != g.stream) g_launches_since_switch = 0;
-    g.stream = next;
+    g.stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : g.own_stream;
     return CSGN_OK;
 }
+
+int csgn_set_auto_lanes(int on) {
+    NEED_INIT();
+    g.auto_lanes = on != 0;
+    return CSGN_OK;
+}
+
+int csgn_get_auto_lanes(void) { return g.inited && g.auto_lanes ? 1 : 0; }
 
 void *csgn_get_stream(void) { return g.inited ? static_cast<void *>(g.stream) : nullptr; }
 
@@ -312,6 +468,12 @@ int csgn_sync(void) {
     NEED_INIT();
     CU(cudaStreamSynchronize(g.copy_stream));   // uploads whose buffers nobody has consumed yet
     CU(cudaStreamSynchronize(g.stream));
+    note_synced(g.copy_stream);
+    note_synced(g.stream);
+    for (int i = 1; i < g.n_lanes; ++i) {       // work the library itself placed on its side lanes (automatic lanes)
+        CU(cudaStreamSynchronize(g.lane[i]));
+        note_synced(g.lane[i]);
+    }
     return CSGN_OK;
 }
 
@@ -345,6 +507,7 @@ int csgn_buf_upload(const uint64_t *host_words, uint64_t n_blocks, uint32_t L, c
     NEED_INIT();
     if (!out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null output handle");
     if (n_blocks && !host_words) return fail(CSGN_ERR_INVALID_ARGUMENT, "null host words");
+    if (L == 0) return fail(CSGN_ERR_INVALID_ARGUMENT, "words per block must be > 0");
     // Allocation and copy are ordered on the copy stream, so an upload overlaps whatever the work
     // stream is running; the first consumer on the work stream waits for the `ready` event.
     csgn_buf *b = nullptr;
@@ -356,6 +519,7 @@ int csgn_buf_upload(const uint64_t *host_words, uint64_t n_blocks, uint32_t L, c
         b->n_blocks = n_blocks;
         b->L = L;
         b->cap_words = cap;
+        b->writer = {g.copy_stream, g.tick++};
     } else {
         int rc = new_buf(n_blocks, L, 0, &b, g.copy_stream);
         if (rc != CSGN_OK) return rc;
@@ -367,6 +531,9 @@ int csgn_buf_upload(const uint64_t *host_words, uint64_t n_blocks, uint32_t L, c
         if (e == cudaSuccess) {
             b->ready = take_event();
             e = b->ready ? cudaEventRecord(b->ready, g.copy_stream) : cudaStreamSynchronize(g.copy_stream);
+            // the `ready` event is the precise ordering for the copy; the writer mark on the copy stream is dropped so
+            // that consumers do not also wait for LATER uploads queued behind this one
+            if (e == cudaSuccess) b->writer = StreamMark();
         }
         if (e != cudaSuccess) {
             csgn_buf_free(b);
@@ -375,6 +542,27 @@ int csgn_buf_upload(const uint64_t *host_words, uint64_t n_blocks, uint32_t L, c
     }
     *out = b;
     return CSGN_OK;
+}
+
+int csgn_buf_upload_copy(const uint64_t *host_words, uint64_t n_blocks, uint32_t L, csgn_buf **out) {
+    NEED_INIT();
+    if (L == 0) return fail(CSGN_ERR_INVALID_ARGUMENT, "words per block must be > 0");
+    if (n_blocks > (UINT64_MAX / 8) / L) return fail(CSGN_ERR_INVALID_ARGUMENT, "block count overflows");
+    const size_t bytes = (size_t)n_blocks * L * sizeof(uint64_t);
+    StagingSlot *sl = (bytes && bytes <= kStagingMaxOne && host_words) ? take_staging(bytes) : nullptr;
+    if (!sl) {
+        // too large for staging (or none free): copy straight from the caller's memory and wait for it
+        int rc = csgn_buf_upload(host_words, n_blocks, L, out);
+        if (rc != CSGN_OK) return rc;
+        CU(cudaStreamSynchronize(g.copy_stream));
+        note_synced(g.copy_stream);
+        return CSGN_OK;
+    }
+    memcpy(sl->p, host_words, bytes);
+    int rc = csgn_buf_upload(static_cast<const uint64_t *>(sl->p), n_blocks, L, out);
+    // whatever happened, later users of the slot wait for everything the copy stream holds so far
+    cudaEventRecord(sl->done, g.copy_stream);
+    return rc;
 }
 
 int csgn_buf_wrap(void *device_words, uint64_t n_blocks, uint32_t L, csgn_buf **out) {
@@ -389,6 +577,7 @@ int csgn_buf_wrap(void *device_words, uint64_t n_blocks, uint32_t L, csgn_buf **
     b->L = L;
     b->cap_words = 0;
     b->owns = false;
+    b->writer = {g.stream, g.tick++};   // whatever produced the words was enqueued on the caller's current stream
     *out = b;
     return CSGN_OK;
 }
@@ -397,9 +586,10 @@ int csgn_buf_clone(const csgn_buf *src, csgn_buf **out) {
     NEED_INIT();
     if (!src || !out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
     csgn_buf *b = nullptr;
+    AutoLane lane(src);
     int rc = new_buf(src->n_blocks, src->L, 0, &b);
     if (rc != CSGN_OK) return rc;
-    await_upload(src);
+    acquire_read(src);
     cudaError_t e = launch_concat(src->d, src->n_blocks * src->L, nullptr, 0, b->d, g.stream);
     if (e != cudaSuccess) {
         csgn_buf_free(b);
@@ -416,9 +606,10 @@ int csgn_buf_slice(const csgn_buf *src, uint64_t first_block, uint64_t n_blocks,
         return fail(CSGN_ERR_INVALID_ARGUMENT, "block range [%llu,+%llu) outside %llu blocks",
                     (unsigned long long)first_block, (unsigned long long)n_blocks, (unsigned long long)src->n_blocks);
     csgn_buf *b = nullptr;
+    AutoLane lane(src);
     int rc = new_buf(n_blocks, src->L, 0, &b);
     if (rc != CSGN_OK) return rc;
-    await_upload(src);
+    acquire_read(src);
     cudaError_t e = launch_concat(src->d + first_block * src->L, n_blocks * src->L, nullptr, 0, b->d, g.stream);
     if (e != cudaSuccess) {
         csgn_buf_free(b);
@@ -436,10 +627,11 @@ int csgn_buf_download_range(const csgn_buf *buf, uint64_t first_block, uint64_t 
                     (unsigned long long)first_block, (unsigned long long)n_blocks, (unsigned long long)buf->n_blocks);
     if (n_blocks == 0) return CSGN_OK;
     if (!host_words) return fail(CSGN_ERR_INVALID_ARGUMENT, "null host destination");
-    await_upload(buf);
+    acquire_read(buf);
     CU(cudaMemcpyAsync(host_words, buf->d + first_block * buf->L, n_blocks * buf->L * sizeof(uint64_t),
                        cudaMemcpyDeviceToHost, g.stream));
     CU(cudaStreamSynchronize(g.stream));
+    note_synced(g.stream);
     return CSGN_OK;
 }
 
@@ -451,8 +643,9 @@ int csgn_buf_download(const csgn_buf *buf, uint64_t *host_words) {
 int csgn_buf_free(csgn_buf *buf) {
     if (!buf) return CSGN_OK;
     if (g.inited) {
-        if (buf->ready) await_upload(buf);     // a never-consumed upload must land before its memory is recycled
-        else order_after_last_use(buf);
+        await_ready(buf);                      // a never-consumed upload must land before its memory is recycled
+        order_after_all_uses(buf);
+        if (buf->ready) g.event_pool.push_back(buf->ready);     // the current stream waits for it: safe to re-record
     }
     if (g.inited && buf->owns && !(buf->recycle && give_upload_slot(buf->d, buf->cap_words))) dev_free(buf->d);
     delete buf;
@@ -462,47 +655,188 @@ int csgn_buf_free(csgn_buf *buf) {
 uint64_t csgn_buf_blocks(const csgn_buf *buf) { return buf ? buf->n_blocks : 0; }
 uint32_t csgn_buf_words_per_block(const csgn_buf *buf) { return buf ? buf->L : 0; }
 void *csgn_buf_device_ptr(const csgn_buf *buf) {
-    if (buf && g.inited) await_upload(buf);   // whoever reads the pointer is ordered after the work stream
+    // Whoever uses the pointer does so on the caller's current stream, in ways the library cannot see: order that
+    // stream after everything the library has in flight on the words, and treat it as their writer from now on.
+    if (buf && g.inited) acquire_write(buf);
     return buf ? buf->d : nullptr;
 }
 
 // ---------------------------------------------------------------------------
 // K1 multiply
 // ---------------------------------------------------------------------------
-int csgn_mul_into(const csgn_buf *a, const csgn_buf *b, csgn_buf *out) {
-    NEED_INIT();
-    if (!a || !b || !out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
-    if (a->L != b->L || a->L != out->L)
-        return fail(CSGN_ERR_SHAPE_MISMATCH, "words per block differ (%u, %u, %u)", a->L, b->L, out->L);
+}  // extern "C"
+
+namespace csgn {
+namespace detail {
+
+int check_mul_operands(const csgn_buf *a, const csgn_buf *b) {
+    if (!a || !b) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
+    if (a->L != b->L) return fail(CSGN_ERR_SHAPE_MISMATCH, "words per block differ (%u vs %u)", a->L, b->L);
     if (b->n_blocks && a->n_blocks > UINT64_MAX / b->n_blocks)
         return fail(CSGN_ERR_INVALID_ARGUMENT, "product block count overflows");
+    return CSGN_OK;
+}
+
+int check_mul_out(const csgn_buf *a, const csgn_buf *b, const csgn_buf *out) {
+    if (out->L != a->L) return fail(CSGN_ERR_SHAPE_MISMATCH, "words per block differ (%u, %u, %u)", a->L, b->L, out->L);
     if (out->n_blocks != a->n_blocks * b->n_blocks)
         return fail(CSGN_ERR_SHAPE_MISMATCH, "output holds %llu blocks, product has %llu",
                     (unsigned long long)out->n_blocks, (unsigned long long)(a->n_blocks * b->n_blocks));
     if (out->d == a->d || out->d == b->d) return fail(CSGN_ERR_INVALID_ARGUMENT, "output aliases an operand");
-    await_upload(a);
-    await_upload(b);
-    await_upload(out);
-    cudaError_t e = launch_mul(a->d, a->n_blocks, b->d, b->n_blocks, a->L, out->d, g.stream);
-    if (e != cudaSuccess) return cuda_fail(e, "multiply kernel");
     return CSGN_OK;
+}
+
+// Multiply (out != null) and/or fold the product under `key` (key != null) on the current stream.  With a key the
+// count goes to device_count and/or into the peer exchange `pp`.  One launch where a fused kernel exists.
+int enqueue_mul(const csgn_buf *a, const csgn_buf *b, csgn_buf *out, const csgn_key *key, uint64_t *device_count,
+                const PeerPush *pp) {
+    acquire_read(a);
+    acquire_read(b);
+    if (out) acquire_write(out);
+    if (!key) {
+        cudaError_t e = launch_mul(a->d, a->n_blocks, b->d, b->n_blocks, a->L, out->d, g.stream);
+        return e == cudaSuccess ? CSGN_OK : cuda_fail(e, "multiply kernel");
+    }
+    const uint64_t *hm = key->h_mask.empty() ? nullptr : key->h_mask.data();
+    const uint64_t T = a->n_blocks * b->n_blocks;
+    if (T == 0 || !mul_fold_supported(a->L)) {
+        // no fused kernel for this shape (blocks of more than 512 units): multiply, then fold -- two launches;
+        // a count-only request multiplies into a temporary
+        csgn_buf *tmp = nullptr;
+        if (!out && T) {
+            int rc = new_buf(T, a->L, 0, &tmp);
+            if (rc != CSGN_OK) return rc;
+        }
+        csgn_buf *dst = out ? out : tmp;
+        cudaError_t e = T ? launch_mul(a->d, a->n_blocks, b->d, b->n_blocks, a->L, dst->d, g.stream) : cudaSuccess;
+        if (e == cudaSuccess)
+            e = launch_decrypt_count(dst ? dst->d : nullptr, T, a->L, key->d_mask, hm, fold_scratch(), device_count, g.stream,
+                                     pp, folds_overlap());
+        if (tmp) csgn_buf_free(tmp);
+        return e == cudaSuccess ? CSGN_OK : cuda_fail(e, "multiply + decrypt kernels");
+    }
+    MulFold mf;
+    mf.mask = key->d_mask;
+    mf.host_mask = hm;
+    mf.scratch = fold_scratch();
+    mf.count_out = device_count;
+    mf.peer = pp;
+    cudaError_t e = launch_mul(a->d, a->n_blocks, b->d, b->n_blocks, a->L, out ? out->d : nullptr, g.stream, &mf);
+    return e == cudaSuccess ? CSGN_OK : cuda_fail(e, "fused multiply-decrypt kernel");
+}
+
+// Resolve the `out` convention of the fused entry points: null = count only; *out null = allocate; else write into.
+int fused_out(const csgn_buf *a, const csgn_buf *b, csgn_buf **out, csgn_buf **dst, bool *allocated) {
+    *dst = nullptr;
+    *allocated = false;
+    if (!out) return CSGN_OK;
+    if (*out) {
+        *dst = *out;
+        return check_mul_out(a, b, *out);
+    }
+    int rc = new_buf(a->n_blocks * b->n_blocks, a->L, 0, dst);
+    if (rc == CSGN_OK) *allocated = true;
+    return rc;
+}
+
+int check_key(const csgn_buf *a, const csgn_key *key) {
+    if (!key) return fail(CSGN_ERR_INVALID_ARGUMENT, "null key");
+    if (a->L != key->L)
+        return fail(CSGN_ERR_SHAPE_MISMATCH, "ciphertext has %u words per block, key expects %u", a->L, key->L);
+    return CSGN_OK;
+}
+
+}  // namespace detail
+}  // namespace csgn
+
+extern "C" {
+
+int csgn_mul_into(const csgn_buf *a, const csgn_buf *b, csgn_buf *out) {
+    NEED_INIT();
+    int rc = check_mul_operands(a, b);
+    if (rc != CSGN_OK) return rc;
+    if (!out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
+    rc = check_mul_out(a, b, out);
+    if (rc != CSGN_OK) return rc;
+    AutoLane lane(out->owns ? a : nullptr, out->owns ? b : nullptr);     // a view's consumer is on the caller's stream
+    return enqueue_mul(a, b, out, nullptr, nullptr, nullptr);
 }
 
 int csgn_mul(const csgn_buf *a, const csgn_buf *b, csgn_buf **out) {
     NEED_INIT();
-    if (!a || !b || !out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
-    if (a->L != b->L) return fail(CSGN_ERR_SHAPE_MISMATCH, "words per block differ (%u vs %u)", a->L, b->L);
-    if (b->n_blocks && a->n_blocks > UINT64_MAX / b->n_blocks)
-        return fail(CSGN_ERR_INVALID_ARGUMENT, "product block count overflows");
-    csgn_buf *c = nullptr;
-    int rc = new_buf(a->n_blocks * b->n_blocks, a->L, 0, &c);
+    int rc = check_mul_operands(a, b);
     if (rc != CSGN_OK) return rc;
-    rc = csgn_mul_into(a, b, c);
+    if (!out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
+    AutoLane lane(a, b);
+    csgn_buf *c = nullptr;
+    rc = new_buf(a->n_blocks * b->n_blocks, a->L, 0, &c);
+    if (rc != CSGN_OK) return rc;
+    rc = enqueue_mul(a, b, c, nullptr, nullptr, nullptr);
     if (rc != CSGN_OK) {
         csgn_buf_free(c);
         return rc;
     }
     *out = c;
+    return CSGN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// fused multiply -> decrypt
+// ---------------------------------------------------------------------------
+int csgn_mul_count_async(const csgn_buf *a, const csgn_buf *b, const csgn_key *key, csgn_buf **out, uint64_t *device_count) {
+    NEED_INIT();
+    int rc = check_mul_operands(a, b);
+    if (rc == CSGN_OK) rc = check_key(a, key);
+    if (rc != CSGN_OK) return rc;
+    if (!device_count) return fail(CSGN_ERR_INVALID_ARGUMENT, "null count destination");
+    csgn_buf *dst = nullptr;
+    bool allocated = false;
+    rc = fused_out(a, b, out, &dst, &allocated);
+    if (rc != CSGN_OK) return rc;
+    rc = enqueue_mul(a, b, dst, key, device_count, nullptr);
+    if (rc != CSGN_OK) {
+        if (allocated) csgn_buf_free(dst);
+        return rc;
+    }
+    if (allocated) *out = dst;
+    return CSGN_OK;
+}
+
+int csgn_mul_decrypt(const csgn_buf *a, const csgn_buf *b, const csgn_key *key, csgn_buf **out, uint8_t *bit,
+                     uint64_t *count) {
+    NEED_INIT();
+    if (!bit && !count) return fail(CSGN_ERR_INVALID_ARGUMENT, "no output");
+    int rc = csgn_mul_count_async(a, b, key, out, g.d_scratch + 2);
+    if (rc != CSGN_OK) return rc;
+    CU(cudaMemcpyAsync(g.h_result, g.d_scratch + 2, sizeof(uint64_t), cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    note_synced(g.stream);
+    if (bit) *bit = (uint8_t)(g.h_result[0] & 1u);
+    if (count) *count = g.h_result[0];
+    return CSGN_OK;
+}
+
+int csgn_mul_count_batch_async(const csgn_buf *const *a, const csgn_buf *const *b, uint32_t n, const csgn_key *key,
+                               csgn_buf **out, uint64_t *device_counts) {
+    NEED_INIT();
+    if (n && (!a || !b || !device_counts)) return fail(CSGN_ERR_INVALID_ARGUMENT, "null argument");
+    std::vector<bool> ours(n, false);
+    if (out)
+        for (uint32_t i = 0; i < n; ++i) ours[i] = out[i] == nullptr;
+    LaneScope lanes(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        lanes.enter(i);
+        int rc = csgn_mul_count_async(a[i], b[i], key, out ? &out[i] : nullptr, device_counts + i);
+        if (rc != CSGN_OK) {
+            lanes.join();
+            for (uint32_t k = 0; k < i; ++k)
+                if (ours[k]) {
+                    csgn_buf_free(out[k]);
+                    out[k] = nullptr;
+                }
+            return rc;
+        }
+    }
     return CSGN_OK;
 }
 
@@ -513,11 +847,12 @@ int csgn_concat(const csgn_buf *a, const csgn_buf *b, csgn_buf **out) {
     NEED_INIT();
     if (!a || !b || !out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
     if (a->L != b->L) return fail(CSGN_ERR_SHAPE_MISMATCH, "words per block differ (%u vs %u)", a->L, b->L);
+    AutoLane lane(a, b);
     csgn_buf *c = nullptr;
     int rc = new_buf(a->n_blocks + b->n_blocks, a->L, 0, &c);
     if (rc != CSGN_OK) return rc;
-    await_upload(a);
-    await_upload(b);
+    acquire_read(a);
+    acquire_read(b);
     cudaError_t e = launch_concat(a->d, a->n_blocks * a->L, b->d, b->n_blocks * b->L, c->d, g.stream);
     if (e != cudaSuccess) {
         csgn_buf_free(c);
@@ -534,8 +869,9 @@ int csgn_append(csgn_buf *a, const csgn_buf *b) {
     if (a->L != b->L) return fail(CSGN_ERR_SHAPE_MISMATCH, "words per block differ (%u vs %u)", a->L, b->L);
     const uint64_t na = a->n_blocks * a->L, nb = b->n_blocks * b->L;
     if (nb == 0) return CSGN_OK;
-    await_upload(a);
-    await_upload(b);
+    AutoLane lane(a, nullptr);           // the grown ciphertext stays on the stream that built it
+    acquire_write(a);
+    if (b != a) acquire_read(b);
     if (na + nb <= a->cap_words) {
         // b == a is fine: source [0,na) and destination [na,2na) do not overlap
         cudaError_t e = launch_concat(a->d, na, b->d, nb, a->d, g.stream);
@@ -617,10 +953,10 @@ int csgn_decrypt_count_async(const csgn_buf *c, const csgn_key *key, uint64_t *d
     if (!c || !key || !device_count) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
     if (c->L != key->L)
         return fail(CSGN_ERR_SHAPE_MISMATCH, "ciphertext has %u words per block, key expects %u", c->L, key->L);
-    await_upload(c);
+    acquire_read(c);
     cudaError_t e = launch_decrypt_count(c->d, c->n_blocks, c->L, key->d_mask,
-                                         key->h_mask.empty() ? nullptr : key->h_mask.data(), next_fold_scratch(), device_count,
-                                         g.stream);
+                                         key->h_mask.empty() ? nullptr : key->h_mask.data(), fold_scratch(), device_count,
+                                         g.stream, nullptr, folds_overlap());
     if (e != cudaSuccess) return cuda_fail(e, "decrypt kernel");
     return CSGN_OK;
 }
@@ -632,6 +968,7 @@ int csgn_decrypt_count(const csgn_buf *c, const csgn_key *key, uint64_t *count) 
     if (rc != CSGN_OK) return rc;
     CU(cudaMemcpyAsync(g.h_result, g.d_scratch + 2, sizeof(uint64_t), cudaMemcpyDeviceToHost, g.stream));
     CU(cudaStreamSynchronize(g.stream));
+    note_synced(g.stream);
     *count = g.h_result[0];
     return CSGN_OK;
 }
@@ -642,6 +979,99 @@ int csgn_decrypt(const csgn_buf *c, const csgn_key *key, uint8_t *bit) {
     int rc = csgn_decrypt_count(c, key, &count);
     if (rc != CSGN_OK) return rc;
     *bit = (uint8_t)(count & 1u);
+    return CSGN_OK;
+}
+
+// ---- deferred results: the fold and the copy of its count are enqueued, the host reads later -------------
+namespace {
+
+int take_result(csgn_result **out) {
+    if (g.free_results.empty()) return fail(CSGN_ERR_OUT_OF_MEMORY, "more than %u decrypt results pending", kResultSlots);
+    csgn_result *r = new csgn_result;
+    r->slot = g.free_results.back();
+    g.free_results.pop_back();
+    r->h = g.h_results + r->slot;
+    r->d = g.d_results + r->slot;
+    r->done = take_event();
+    if (!r->done) {
+        g.free_results.push_back(r->slot);
+        delete r;
+        return fail(CSGN_ERR_CUDA, "cannot create an event");
+    }
+    *out = r;
+    return CSGN_OK;
+}
+
+int finish_result(csgn_result *r, int rc) {
+    cudaError_t e = cudaSuccess;
+    if (rc == CSGN_OK) {
+        e = cudaMemcpyAsync(r->h, r->d, sizeof(uint64_t), cudaMemcpyDeviceToHost, g.stream);
+        if (e == cudaSuccess) e = cudaEventRecord(r->done, g.stream);
+    }
+    if (rc != CSGN_OK || e != cudaSuccess) {
+        r->waited = true;
+        csgn_result_free(r);
+        return rc != CSGN_OK ? rc : cuda_fail(e, "result copy");
+    }
+    return CSGN_OK;
+}
+
+}  // namespace
+
+int csgn_decrypt_deferred(const csgn_buf *c, const csgn_key *key, csgn_result **out) {
+    NEED_INIT();
+    if (!c || !key || !out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
+    csgn_result *r = nullptr;
+    int rc = take_result(&r);
+    if (rc != CSGN_OK) return rc;
+    AutoLane lane(c);
+    rc = finish_result(r, csgn_decrypt_count_async(c, key, r->d));
+    if (rc == CSGN_OK) *out = r;
+    return rc;
+}
+
+int csgn_mul_decrypt_deferred(const csgn_buf *a, const csgn_buf *b, const csgn_key *key, csgn_buf **prod,
+                              csgn_result **out) {
+    NEED_INIT();
+    if (!out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
+    int rc = check_mul_operands(a, b);
+    if (rc != CSGN_OK) return rc;
+    csgn_result *r = nullptr;
+    rc = take_result(&r);
+    if (rc != CSGN_OK) return rc;
+    AutoLane lane((!prod || !*prod || (*prod)->owns) ? a : nullptr, (!prod || !*prod || (*prod)->owns) ? b : nullptr);
+    rc = finish_result(r, csgn_mul_count_async(a, b, key, prod, r->d));
+    if (rc == CSGN_OK) *out = r;
+    return rc;
+}
+
+int csgn_result_ready(const csgn_result *r) {
+    if (!r) return 0;
+    if (r->waited) return 1;
+    const cudaError_t e = cudaEventQuery(r->done);
+    if (e != cudaSuccess) cudaGetLastError();
+    return e == cudaSuccess ? 1 : 0;
+}
+
+int csgn_result_wait(csgn_result *r, uint64_t *count) {
+    NEED_INIT();
+    if (!r) return fail(CSGN_ERR_INVALID_ARGUMENT, "null result");
+    if (!r->waited) {
+        CU(cudaEventSynchronize(r->done));
+        r->waited = true;
+    }
+    if (count) *count = *r->h;
+    return CSGN_OK;
+}
+
+int csgn_result_free(csgn_result *r) {
+    if (!r) return CSGN_OK;
+    if (g.inited) {
+        if (!r->waited && r->done) cudaEventSynchronize(r->done);   // the slot is reused: its copy must have landed
+        if (r->done) g.event_pool.push_back(r->done);
+        g.free_results.push_back(r->slot);
+    }
+    delete r;
     return CSGN_OK;
 }
 
@@ -668,6 +1098,7 @@ int csgn_decrypt_product(const csgn_buf *const *factors, uint32_t n_factors, con
     std::vector<uint64_t> h(n_factors);
     cudaError_t e = cudaMemcpyAsync(h.data(), d_counts, n_factors * sizeof(uint64_t), cudaMemcpyDeviceToHost, g.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e == cudaSuccess) note_synced(g.stream);
     dev_free(d_counts);
     if (e != cudaSuccess) return cuda_fail(e, "product decrypt readback");
     uint64_t prod = 1;
@@ -751,6 +1182,7 @@ int csgn_decrypt_batch(const csgn_buf *const *c, uint32_t n, const csgn_key *key
     if (rc == CSGN_OK) {
         e = cudaMemcpyAsync(h.data(), d, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, g.stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+        if (e == cudaSuccess) note_synced(g.stream);
     }
     dev_free(d);
     if (rc != CSGN_OK) return rc;
@@ -870,8 +1302,9 @@ int csgn_permute_into(const csgn_buf *c, const csgn_perm *perm, csgn_buf *out) {
     if (out->n_blocks > c->n_blocks)
         return fail(CSGN_ERR_SHAPE_MISMATCH, "output holds more blocks than the input");
     if (out->d == c->d) return fail(CSGN_ERR_INVALID_ARGUMENT, "permute cannot run in place");
-    await_upload(c);
-    await_upload(out);
+    AutoLane lane(out->owns ? c : nullptr);
+    acquire_read(c);
+    acquire_write(out);
     cudaError_t e = launch_permute(c->d, out->n_blocks, c->L, (uint32_t)perm->N, perm->d_map, perm->d_slice_map, out->d,
                                    g.stream);
     if (e != cudaSuccess) return cuda_fail(e, "permute kernel");
@@ -882,6 +1315,7 @@ int csgn_permute(const csgn_buf *c, const csgn_perm *perm, int strict_ref_trunca
     NEED_INIT();
     if (!c || !perm || !out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
     if (c->n_blocks == 0) return fail(CSGN_ERR_INVALID_ARGUMENT, "cannot permute an empty ciphertext");
+    AutoLane lane(c);
     csgn_buf *r = nullptr;
     int rc = new_buf(strict_ref_truncate ? 1 : c->n_blocks, c->L, 0, &r);
     if (rc != CSGN_OK) return rc;
@@ -901,12 +1335,13 @@ int csgn_buf_checksum(const csgn_buf *buf, uint64_t *xor_out, uint64_t *sum_out,
     NEED_INIT();
     if (!buf) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
     uint64_t *acc = g.d_scratch + 4;
-    await_upload(buf);
+    acquire_read(buf);
     CU(cudaMemsetAsync(acc, 0, 3 * sizeof(uint64_t), g.stream));
     cudaError_t e = launch_checksum(buf->d, buf->n_blocks * buf->L, acc, g.stream);
     if (e != cudaSuccess) return cuda_fail(e, "checksum kernel");
     CU(cudaMemcpyAsync(g.h_result + 4, acc, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, g.stream));
     CU(cudaStreamSynchronize(g.stream));
+    note_synced(g.stream);
     if (xor_out) *xor_out = g.h_result[4];
     if (sum_out) *sum_out = g.h_result[5];
     if (wsum_out) *wsum_out = g.h_result[6];

@@ -211,14 +211,61 @@ int csgn_decrypt_sharded_async(const csgn_buf *c, const csgn_key *key, csgn_comm
     PeerPush pp;
     rc = fill_push(comm, true, collect_n, collect_lag, device_totals, &pp);
     if (rc != CSGN_OK) return rc;
-    await_upload(c);
+    acquire_read(c);
     cudaError_t e = launch_decrypt_count(c->d, c->n_blocks, c->L, key->d_mask,
-                                         key->h_mask.empty() ? nullptr : key->h_mask.data(), next_fold_scratch(), device_local,
-                                         g.stream, &pp);
+                                         key->h_mask.empty() ? nullptr : key->h_mask.data(), fold_scratch(), device_local,
+                                         g.stream, &pp, folds_overlap());
     if (e != cudaSuccess) return cuda_fail(e, "sharded decrypt kernel");
     comm->seq += 1;
     if (collect_n) comm->published = comm->seq;
     return CSGN_OK;
+}
+
+int csgn_mul_decrypt_sharded_async(const csgn_buf *a, const csgn_buf *b, const csgn_key *key, csgn_buf **out,
+                                   csgn_comm *comm, uint32_t collect_n, uint32_t collect_lag, uint64_t *device_totals,
+                                   uint64_t *device_local) {
+    NEED_INIT();
+    int rc = check_mul_operands(a, b);
+    if (rc == CSGN_OK) rc = check_key(a, key);
+    if (rc == CSGN_OK) rc = comm_ready(comm);
+    if (rc != CSGN_OK) return rc;
+    if (a->n_blocks * b->n_blocks > kPeerCountMask) return fail(CSGN_ERR_INVALID_ARGUMENT, "shard too large for a 40-bit count");
+    PeerPush pp;
+    rc = fill_push(comm, true, collect_n, collect_lag, device_totals, &pp);
+    if (rc != CSGN_OK) return rc;
+    csgn_buf *dst = nullptr;
+    bool allocated = false;
+    rc = fused_out(a, b, out, &dst, &allocated);
+    if (rc != CSGN_OK) return rc;
+    rc = enqueue_mul(a, b, dst, key, device_local, &pp);
+    if (rc != CSGN_OK) {
+        if (allocated) csgn_buf_free(dst);
+        return rc;
+    }
+    if (allocated) *out = dst;
+    comm->seq += 1;
+    if (collect_n) comm->published = comm->seq;
+    return CSGN_OK;
+}
+
+int csgn_mul_decrypt_sharded_batch_async(const csgn_buf *const *a, const csgn_buf *const *b, uint32_t n,
+                                         const csgn_key *key, csgn_buf **out, csgn_comm *comm, uint32_t collect_lag,
+                                         uint64_t *device_totals) {
+    NEED_INIT();
+    if (n == 0) return CSGN_OK;
+    if (!a || !b || !device_totals) return fail(CSGN_ERR_INVALID_ARGUMENT, "null argument");
+    if ((uint64_t)n + collect_lag > kPeerMaxPending)
+        return fail(CSGN_ERR_INVALID_ARGUMENT, "batch of %u folds trailing by %u exceeds %u", n, collect_lag, kPeerMaxPending);
+    {
+        LaneScope lanes(n - 1);
+        for (uint32_t i = 0; i + 1 < n; ++i) {
+            lanes.enter(i);
+            int rc = csgn_mul_decrypt_sharded_async(a[i], b[i], key, out ? &out[i] : nullptr, comm, 0, 0, nullptr, nullptr);
+            if (rc != CSGN_OK) return rc;
+        }
+    }   // joined: the closing launch is ordered after every push it publishes
+    return csgn_mul_decrypt_sharded_async(a[n - 1], b[n - 1], key, out ? &out[n - 1] : nullptr, comm, n, collect_lag,
+                                          device_totals, nullptr);
 }
 
 int csgn_comm_collect_async(csgn_comm *comm, uint32_t n, uint32_t lag, uint64_t *device_totals) {
@@ -245,6 +292,7 @@ int csgn_decrypt_sharded(const csgn_buf *c, const csgn_key *key, csgn_comm *comm
     if (rc != CSGN_OK) return rc;
     CU(cudaMemcpyAsync(g.h_result, comm->d_status, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, g.stream));
     CU(cudaStreamSynchronize(g.stream));
+    note_synced(g.stream);
     if (g.h_result[0] != 0 || g.h_result[1] == UINT64_MAX) {
         cudaMemsetAsync(comm->d_status, 0, sizeof(uint64_t), g.stream);
         return fail(CSGN_ERR_TIMEOUT, "sharded decrypt: a peer's count did not arrive within %llu ms",

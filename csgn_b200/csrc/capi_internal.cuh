@@ -20,6 +20,13 @@
 // ---------------------------------------------------------------------------
 // handles
 // ---------------------------------------------------------------------------
+// A use of a buffer on a stream: `tick` is the library's operation counter when the use was enqueued.  The use is
+// known to have completed once the host has synchronised that stream at a later tick (State::synced).
+struct StreamMark {
+    cudaStream_t s = nullptr;
+    uint64_t tick = 0;
+};
+
 struct csgn_buf {
     uint64_t *d = nullptr;     // device words, n_blocks * L valid
     uint64_t n_blocks = 0;
@@ -27,8 +34,25 @@ struct csgn_buf {
     uint64_t cap_words = 0;    // allocated words (>= n_blocks*L); 0 for views
     bool owns = true;
     bool recycle = false;      // storage of an upload: goes back to the upload cache, not to the pool
-    mutable cudaEvent_t ready = nullptr;  // an upload on the copy stream still in flight
-    mutable cudaStream_t last_stream = nullptr;  // the stream of the last operation that touched the words
+    // An upload on the copy stream that may still be in flight.  EVERY stream that consumes the buffer waits for it
+    // (ready_waited remembers which already did); the event goes back to the pool once it is known to have completed.
+    mutable cudaEvent_t ready = nullptr;
+    mutable std::vector<cudaStream_t> ready_waited;
+    // Cross-stream ordering (batch lanes, automatic lanes, callers that multiplex streams): the stream of the last
+    // write (allocation counts as one) and the streams that have read since.  A reader on another stream waits for the
+    // writer, a writer for the writer and all readers, a free for everybody -- through an event recorded on the
+    // other stream at that moment (no event is recorded on the fast path where everything stays on one stream).
+    mutable StreamMark writer;
+    mutable std::vector<StreamMark> readers;
+};
+
+// A decrypt whose count is read later (csgn_decrypt_deferred): device word, pinned host word, completion event.
+struct csgn_result {
+    uint64_t *h = nullptr;     // pinned host word the count is copied to
+    uint64_t *d = nullptr;     // device word the fold writes
+    cudaEvent_t done = nullptr;
+    bool waited = false;
+    uint32_t slot = 0;
 };
 
 struct csgn_key {
@@ -87,12 +111,33 @@ struct State {
     };
     std::vector<UploadSlot> upload_cache;
     uint64_t upload_cache_words = 0;
-    uint64_t *d_scratch = nullptr;   // [2] blocking-call result, [4..6] checksum, [8 + 2k, 9 + 2k] fold scratch of launch k mod 64
-    uint32_t fold_slot = 0;
+    uint64_t *d_scratch = nullptr;   // [2] blocking-call result, [4..6] checksum, [8 + 2k] fold scratch word of stream slot k
     uint64_t *h_result = nullptr;    // pinned, 8 words
+    // Fold scratch: one word per STREAM (kernels of one stream never overlap their folds, PDL included, because a
+    // kernel touches global memory only after griddepcontrol.wait); streams are given slots on first use.
+    std::vector<cudaStream_t> scratch_streams;
+    // Operation counter and, per stream, its value at the last host synchronisation of that stream.
+    uint64_t tick = 1;
+    std::vector<StreamMark> synced;
+    // (consumer, producer, tick): `consumer` already waits for everything `producer` had enqueued at `tick`
+    struct Waited {
+        cudaStream_t consumer, producer;
+        uint64_t tick;
+    };
+    std::vector<Waited> waited;
+    // Automatic lanes (csgn_set_auto_lanes): independent operations of the drop-in API go to alternating internal
+    // streams, ordered by the buffers they touch; in_batch: a LaneScope is active (it places the items itself).
+    bool auto_lanes = false;
+    bool in_batch = false;
+    bool in_auto = false;
+    uint32_t rr = 0;
+    // deferred results: pinned host words + device words, handed out by slot
+    uint64_t *h_results = nullptr, *d_results = nullptr;
+    std::vector<uint32_t> free_results;
 };
 extern State g;
-extern unsigned g_launches_since_switch;   // launches since the caller last changed streams (see streams_alternate)
+constexpr uint32_t kResultSlots = 4096;
+constexpr uint32_t kScratchSlots = 256;
 
 // Record the message of a failure for csgn_last_error() and return `code`.
 int fail(int code, const char *fmt, ...);
@@ -114,12 +159,18 @@ int cuda_fail(cudaError_t e, const char *what);
 int dev_alloc(uint64_t words, uint64_t **out, cudaStream_t stream = nullptr);   // stream-ordered, on the work stream by default
 void dev_free(void *p);
 cudaEvent_t take_event();
-// Called for every operand of every operation: orders the work stream after a pending upload of `b`
-// and remembers which stream touched the words last.
-void await_upload(const csgn_buf *b);
+// Called for every operand of every operation, before the launch on the current stream g.stream: order that stream
+// after a pending upload of `b` and after the uses of `b` on OTHER streams that conflict (read: the last writer;
+// write: the last writer and every reader since), and record this use.
+void acquire_read(const csgn_buf *b);
+void acquire_write(const csgn_buf *b);
+// The host has synchronised `s`: every use recorded on it so far is complete.
+void note_synced(cudaStream_t s);
 int new_buf(uint64_t n_blocks, uint32_t L, uint64_t cap_words, csgn_buf **out, cudaStream_t stream = nullptr);
-// The next pair of fold scratch words (running count, CTA ticket); every launch gets its own.
-uint64_t *next_fold_scratch();
+// The fold scratch word of the current stream.
+uint64_t *fold_scratch();
+// True inside a batch call or with automatic lanes: folds run next to other kernels (several shorter waves).
+bool folds_overlap();
 
 // Scope of one batch call: item i runs with the work stream set to way i % n, where way 0 is the caller's own stream
 // and ways 1.. are the library's side lanes, forked from the caller's stream on construction; join() makes the
@@ -128,7 +179,9 @@ struct LaneScope {
     cudaStream_t home;
     int used = 1;
     bool active;
-    explicit LaneScope(uint32_t n_items) : home(g.stream), active(g.n_lanes > 1 && n_items > 1) {
+    bool was_in_batch;
+    explicit LaneScope(uint32_t n_items) : home(g.stream), active(g.n_lanes > 1 && n_items > 1), was_in_batch(g.in_batch) {
+        g.in_batch = true;
         if (!active) return;
         used = (int)std::min<uint32_t>(n_items, (uint32_t)g.n_lanes);
         cudaEventRecord(g.fork_point, home);
@@ -138,9 +191,9 @@ struct LaneScope {
         if (!active) return;
         const uint32_t way = item % (uint32_t)used;
         g.stream = way == 0 ? home : g.lane[way];
-        g_launches_since_switch = 0;              // the items of a batch overlap: the launchers' multi-wave forms apply
     }
     void join() {
+        g.in_batch = was_in_batch;
         if (!active) return;
         g.stream = home;
         for (int i = 1; i < used; ++i) {
@@ -150,6 +203,33 @@ struct LaneScope {
         active = false;
     }
     ~LaneScope() { join(); }
+};
+
+// Argument checks and the enqueue shared by the multiply entry points (capi.cu) and the sharded ones (capi_comm.cu).
+int check_mul_operands(const csgn_buf *a, const csgn_buf *b);
+int check_mul_out(const csgn_buf *a, const csgn_buf *b, const csgn_buf *out);
+int check_key(const csgn_buf *a, const csgn_key *key);
+// `out` convention of the fused entry points: null = count only; *out null = allocate; else write into *out.
+int fused_out(const csgn_buf *a, const csgn_buf *b, csgn_buf **out, csgn_buf **dst, bool *allocated);
+// Multiply (out != null) and/or fold the product under `key` (key != null) on the current stream; with a key the
+// count goes to device_count and/or into the peer exchange `pp`.  One launch wherever a fused kernel exists.
+int enqueue_mul(const csgn_buf *a, const csgn_buf *b, csgn_buf *out, const csgn_key *key, uint64_t *device_count,
+                const csgn::PeerPush *pp);
+
+// Scope of one operation of the drop-in API under automatic lanes (csgn_set_auto_lanes): the operation runs on the
+// way where its largest operand was last written while that write may still be in flight (a chain stays on one
+// stream and keeps its programmatic-dependent-launch overlap), or -- operands at rest -- on the next way round-robin,
+// so that consecutive independent operations overlap.  Ordering comes from acquire_read / acquire_write.
+struct AutoLane {
+    cudaStream_t home;
+    bool active = false;
+    AutoLane(const csgn_buf *x, const csgn_buf *y = nullptr);
+    ~AutoLane() {
+        if (active) {
+            g.stream = home;
+            g.in_auto = false;
+        }
+    }
 };
 
 }  // namespace detail

@@ -64,7 +64,7 @@ int csgn_buf_save(const csgn_buf *buf, uint64_t N, uint64_t D, const char *path)
     bool ok = fwrite(&h, sizeof h, 1, f) == 1;
     Staging st;
     cudaError_t e = st.init();
-    await_upload(buf);
+    acquire_read(buf);
     const uint64_t total = buf->n_blocks * buf->L, per = kStageBytes / 8;
     uint64_t x = 0;
     // D2H of piece k+1 overlaps the fwrite of piece k

@@ -10,20 +10,24 @@
 //
 // Roofline: HBM READ bandwidth, 8*L bytes per block, one bit out.
 //
-// Shape of the kernel.  The ciphertext is read as one flat stream of 16-byte units
-// (L4 = L/2 per block), fully coalesced: a warp owns a chunk of 32 consecutive blocks
-// = 32*L4 units and walks it in L4 steps of 32 lanes x 16 bytes.  A lane marks its
-// unit "failing" when a key bit inside it is 0; __ballot_sync turns each step into
-// 32 bits of a per-chunk fail string kept in shared memory.  Block b of the chunk is
-// satisfied iff bits [b*L4, (b+1)*L4) of that string are all clear -- lane b checks
-// exactly that, so the per-block AND across lanes needs no shuffles, whatever L4 is.
-// The loads of a chunk are independent (unrolled, up to 10 x 16 B in flight per
-// lane).  Counts fold lane -> warp -> CTA -> one atomicAdd per CTA; the last CTA to
-// finish publishes the total and re-arms the scratch words, so a decrypt is ONE launch.
+// The ciphertext is read as one flat stream of units -- 16 bytes (uint4) when L is even and the
+// words are 16-byte aligned, 8 bytes (uint2) otherwise (odd L: N = 191, 4097 ...) -- fully coalesced.
+// Three shapes of the same fold, chosen by units per block (UPB):
+//   lanes  UPB <= 16          a warp step covers 32/UPB whole blocks; a lane always holds the same unit of
+//                             a block, its mask unit lives in registers, a block's verdict is UPB adjacent
+//                             bits of one ballot                                  (N=1247: UPB = 10)
+//   wide   UPB % 32 == 0      warp per block, UPB/32 coalesced loads per lane, one vote per block
+//                                                                                 (N=16383: UPB = 128)
+//   string any UPB <= 512     a warp owns 32 consecutive blocks and walks them in UPB coalesced steps; each
+//                             step's ballot is 32 bits of a per-chunk fail string in shared memory; block b
+//                             is satisfied iff bits [b*UPB, (b+1)*UPB) are clear -- lane b checks exactly that
+// plus a warp-per-block kernel for blocks longer than 512 units.  Counts fold lane -> warp -> CTA -> ONE
+// atomic per CTA (fold.cuh); the last CTA publishes the total, so a decrypt is ONE launch.
 #include "kernels.cuh"
 #include "launch.cuh"
 #include "bulk.cuh"
 #include "peer.cuh"
+#include "fold.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -33,86 +37,35 @@ namespace {
 
 constexpr int kDecThreads = 256;
 constexpr int kDecWarps = kDecThreads / 32;
-constexpr uint32_t kDecMaxL4 = 512;   // mask x2 + fail strings stay within 32 KB of shared memory
+constexpr uint32_t kDecMaxUnits = 512;   // mask x2 + fail strings stay within 32 KB of shared memory
 
-__device__ __forceinline__ uint4 ld_stream(const uint4 *p) { return __ldcs(p); }
+template <typename VT> __device__ __forceinline__ VT vzero();
+template <> __device__ __forceinline__ uint4 vzero<uint4>() { return make_uint4(0u, 0u, 0u, 0u); }
+template <> __device__ __forceinline__ uint2 vzero<uint2>() { return make_uint2(0u, 0u); }
+template <typename VT> __device__ __forceinline__ VT ld_stream(const VT *p) { return __ldcs(p); }
 
-__device__ __forceinline__ bool unit_fails(const uint4 v, const uint4 m) {
-    // some key bit inside this 16-byte unit is zero
-    return (((~v.x) & m.x) | ((~v.y) & m.y) | ((~v.z) & m.z) | ((~v.w) & m.w)) != 0u;
-}
-
-// Publish the CTA's count; the last CTA writes the grand total and resets scratch.  With a
-// PeerPush (sharded decrypt) the total also goes into the rank's local ring, and if this launch
-// closes a batch its last CTA publishes the batch to every rank's mailbox over NVLink and
-// collects the requested totals (peer.cuh).
-__device__ __forceinline__ void fold_and_publish(uint64_t lane_count, uint64_t *scratch, uint64_t *count_out,
-                                                 const PeerPush &pp) {
-    __shared__ uint64_t s_warp[32];
-    __shared__ int s_last;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) lane_count += __shfl_xor_sync(0xffffffffu, lane_count, off);
-    if (lane == 0) s_warp[warp] = lane_count;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint64_t cta = 0;
-        const int nw = (blockDim.x + 31) >> 5;
-        for (int w = 0; w < nw; ++w) cta += s_warp[w];
-        if (cta) atomicAdd(reinterpret_cast<unsigned long long *>(scratch), (unsigned long long)cta);
-        __threadfence();
-        const unsigned long long ticket = atomicAdd(reinterpret_cast<unsigned long long *>(scratch + 1), 1ull);
-        const bool last = ticket == (unsigned long long)gridDim.x - 1;
-        if (last) {
-            __threadfence();
-            const uint64_t total = atomicExch(reinterpret_cast<unsigned long long *>(scratch), 0ull);
-            scratch[1] = 0;
-            if (count_out) *count_out = total;
-            if (pp.world) pp.local_ring[peer_slot(pp.seq)] = total;
-        }
-        s_last = last ? 1 : 0;
-    }
-    if (pp.world && (pp.publish_n | pp.collect_n)) {      // grid-uniform: the barrier is not divergent
-        __syncthreads();
-        if (s_last) peer_publish_collect(pp);
-    }
-}
-
-// The key mask of a small block travels in the kernel parameters: after a multiply has
-// streamed through L2 a 160-byte mask in global memory is a DRAM miss at the head of
-// every CTA, while the parameter bank is always hot.
-constexpr int kParamMaskUnits = 16;  // up to 32 words per block (N <= 2048)
-struct ParamMask {
-    uint4 u[kParamMaskUnits];
-};
-
-// L4C > 0: units per block known at compile time (fully unrolled walk); 0: runtime.
-template <int L4C, int UNROLL, int MINB>
+// ---------------------------------------------------------------------------------------
+// string: any units-per-block up to kDecMaxUnits.  UPBC > 0: known at compile time; 0: runtime.
+// ---------------------------------------------------------------------------------------
+template <typename VT, int UPBC, int UNROLL, int MINB>
 __global__ void __launch_bounds__(kDecThreads, MINB)
-decrypt_count_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint32_t L4rt,
-                     const uint4 *__restrict__ M4, const __grid_constant__ ParamMask pmask, const uint32_t cpw,
-                     uint64_t *scratch, uint64_t *count_out, const __grid_constant__ PeerPush pp) {
-    extern __shared__ uint4 smem[];
-    const uint32_t L4 = L4C ? (uint32_t)L4C : L4rt;
-    uint4 *sM2 = smem;                                               // mask, twice over
-    uint32_t *sF = reinterpret_cast<uint32_t *>(smem + 2 * L4);      // fail strings
+decrypt_count_kernel(const VT *__restrict__ V, const uint64_t T, const uint32_t upb_rt, const VT *__restrict__ M,
+                     const uint32_t cpw, uint64_t *scratch, uint64_t *count_out, const __grid_constant__ PeerPush pp) {
+    extern __shared__ uint4 smem_raw[];
+    const uint32_t UPB = UPBC ? (uint32_t)UPBC : upb_rt;
+    VT *sM2 = reinterpret_cast<VT *>(smem_raw);                      // mask, twice over
+    uint32_t *sF = reinterpret_cast<uint32_t *>(sM2 + 2 * UPB);      // fail strings
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    if (M4 == nullptr) {
-        // mask in the parameters: staged BEFORE waiting for the previous kernel (parameters are not
-        // produced by it), so that under PDL this prologue overlaps the predecessor's tail
-        for (uint32_t i = threadIdx.x; i < 2 * L4; i += blockDim.x) sM2[i] = pmask.u[i < L4 ? i : i - L4];
-        __syncthreads();
-        pdl_enter();
-    } else {
-        pdl_enter();
-        for (uint32_t i = threadIdx.x; i < 2 * L4; i += blockDim.x) sM2[i] = M4[i < L4 ? i : i - L4];
-        __syncthreads();
-    }
+    // The key mask is not produced by the previous kernel of the stream: it is staged BEFORE the PDL wait, so this
+    // prologue (a DRAM miss after a multiply has streamed through L2) overlaps the predecessor's tail.
+    for (uint32_t i = threadIdx.x; i < 2 * UPB; i += blockDim.x) sM2[i] = M[i < UPB ? i : i - UPB];
+    __syncthreads();
+    pdl_enter();
 
-    uint32_t *sFw = sF + warp * L4;
-    const uint4 *mk = sM2 + (lane % L4);
-    const uint32_t step = 32u % L4;          // advance of the unit-in-block index per walk step
-    const uint64_t n_units = T * L4;
+    uint32_t *sFw = sF + warp * UPB;
+    const VT *mk = sM2 + (lane % UPB);
+    const uint32_t step = 32u % UPB;          // advance of the unit-in-block index per walk step
+    const uint64_t n_units = T * UPB;
     const uint64_t n_chunks = (T + 31) >> 5;
     uint64_t my_count = 0;
 
@@ -123,38 +76,38 @@ decrypt_count_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint3
     const uint64_t stride = cpw ? (uint64_t)kDecWarps : (uint64_t)gridDim.x * kDecWarps;
     const uint64_t last = cpw ? min(n_chunks, ((uint64_t)blockIdx.x + 1) * kDecWarps * cpw) : n_chunks;
     for (uint64_t chunk = first; chunk < last; chunk += stride) {
-        const uint4 *src = V4 + (chunk * 32u * L4 + lane);
+        const VT *src = V + (chunk * 32u * UPB + lane);
         const bool full = (chunk + 1) * 32u <= T;    // warp-uniform: no per-load bounds in the common case
-        uint32_t koff = 0;                           // (32*r) % L4
-        for (uint32_t r = 0; r < L4; r += UNROLL) {
-            uint4 v[UNROLL];
+        uint32_t koff = 0;                           // (32*r) % UPB
+        for (uint32_t r = 0; r < UPB; r += UNROLL) {
+            VT v[UNROLL];
             if (full) {
 #pragma unroll
                 for (int u = 0; u < UNROLL; ++u)
-                    if ((L4C && L4C % UNROLL == 0) || r + u < L4) v[u] = ld_stream(src + 32u * (r + u));
+                    if ((UPBC && UPBC % UNROLL == 0) || r + u < UPB) v[u] = ld_stream(src + 32u * (r + u));
             } else {
-                const uint64_t q_lane = chunk * 32u * L4 + lane;
+                const uint64_t q_lane = chunk * 32u * UPB + lane;
 #pragma unroll
                 for (int u = 0; u < UNROLL; ++u) {
                     const uint64_t q = q_lane + 32u * (r + u);
-                    v[u] = (r + u < L4 && q < n_units) ? ld_stream(V4 + q) : make_uint4(0u, 0u, 0u, 0u);
+                    v[u] = (r + u < UPB && q < n_units) ? ld_stream(V + q) : vzero<VT>();
                 }
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
-                if ((L4C && L4C % UNROLL == 0) || r + u < L4) {   // warp-uniform
+                if ((UPBC && UPBC % UNROLL == 0) || r + u < UPB) {   // warp-uniform
                     const bool f = unit_fails(v[u], mk[koff]);
                     const uint32_t bal = __ballot_sync(0xffffffffu, f);
                     if (lane == 0) sFw[r + u] = bal;
                     koff += step;
-                    if (koff >= L4) koff -= L4;
+                    if (koff >= UPB) koff -= UPB;
                 }
             }
         }
         __syncwarp();
-        // lane b <-> block b of the chunk: bits [b*L4, b*L4+L4) of the fail string
+        // lane b <-> block b of the chunk: bits [b*UPB, b*UPB+UPB) of the fail string
         const uint64_t blk = chunk * 32u + lane;
-        const uint32_t lo = lane * L4, hi = lo + L4;
+        const uint32_t lo = lane * UPB, hi = lo + UPB;
         uint32_t any = 0;
         for (uint32_t w = lo >> 5; w <= (hi - 1) >> 5; ++w) {
             const uint32_t first = max(lo, w << 5) - (w << 5);
@@ -170,24 +123,26 @@ decrypt_count_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint3
 
 
 // ---------------------------------------------------------------------------------------
-// Lane-aligned fold for short blocks (L4 <= 16, e.g. N=1247: L4 = 10).
+// lanes: short blocks (UPB <= 16 units, e.g. N=1247: 10 units of 16 bytes).
 //
-// A warp step covers BPS = 32 / L4 whole blocks with the first BPS*L4 lanes (30 of 32 at L4 = 10;
+// A warp step covers BPS = 32 / UPB whole blocks with the first BPS*UPB lanes (30 of 32 at UPB = 10;
 // the step is still one contiguous, sector-aligned run of 480 bytes).  A lane therefore always
-// sits on the SAME 16-byte unit of a block: its key-mask unit lives in four registers for the
-// whole launch, a block's verdict is L4 adjacent bits of one ballot, and every lane computes the
-// same count from it -- no fail string in shared memory, no __syncwarp, no per-unit mask lookup.
-// What is left per 480 bytes is one load, four logic ops, a vote and a handful of uniform
-// integer ops, so U independent loads per lane stay in flight with registers to spare.
+// sits on the SAME unit of a block: its key-mask unit lives in registers for the whole launch (taken
+// from the kernel parameters -- no global or shared load at all for the mask), a block's verdict is
+// UPB adjacent bits of one ballot, and every lane computes the same count from it -- no fail string in
+// shared memory, no __syncwarp, no per-unit mask lookup.  What is left per step is one load, a few
+// logic ops, a vote and a handful of uniform integer ops, so U independent loads per lane stay in
+// flight with registers to spare.
 // ---------------------------------------------------------------------------------------
-template <int L4, int U, int MINB>
+template <typename VT, int UPB, int U, int MINB>
 __global__ void __launch_bounds__(kDecThreads, MINB)
-decrypt_count_lanes_kernel(const uint4 *__restrict__ V4, const uint64_t T, const __grid_constant__ ParamMask pmask,
+decrypt_count_lanes_kernel(const VT *__restrict__ V, const uint64_t T, const __grid_constant__ ParamMask pmask,
                            uint64_t *scratch, uint64_t *count_out, const __grid_constant__ PeerPush pp) {
-    constexpr uint32_t BPS = 32u / L4, ACTIVE = BPS * L4, BLKMASK = (1u << L4) - 1u;
+    constexpr uint32_t BPS = 32u / UPB, ACTIVE = BPS * UPB;
+    constexpr uint32_t BLKMASK = UPB == 32 ? 0xffffffffu : (1u << UPB) - 1u;
     const uint32_t lane = threadIdx.x & 31u;
     const bool active = lane < ACTIVE;
-    const uint4 m = active ? pmask.u[lane % L4] : make_uint4(0u, 0u, 0u, 0u);   // parameters: nothing to wait for
+    const VT m = active ? reinterpret_cast<const VT *>(&pmask)[lane % UPB] : vzero<VT>();   // parameters: nothing to wait for
     pdl_enter();
 
     const uint64_t n_steps = (T + BPS - 1) / BPS;
@@ -195,35 +150,174 @@ decrypt_count_lanes_kernel(const uint4 *__restrict__ V4, const uint64_t T, const
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     uint32_t cnt = 0;                         // warp-uniform: satisfied blocks seen by this warp
     for (uint64_t base = warp_global * U; base < n_steps; base += n_warps * U) {
-        const uint4 *src = V4 + (base * ACTIVE + lane);
-        uint4 v[U];
+        const VT *src = V + (base * ACTIVE + lane);
+        VT v[U];
         if ((base + U) * BPS <= T) {          // warp-uniform: all U steps lie inside the ciphertext
 #pragma unroll
-            for (int u = 0; u < U; ++u) v[u] = active ? ld_stream(src + (uint32_t)u * ACTIVE) : make_uint4(0u, 0u, 0u, 0u);
+            for (int u = 0; u < U; ++u) v[u] = active ? ld_stream(src + (uint32_t)u * ACTIVE) : vzero<VT>();
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const uint32_t bal = __ballot_sync(0xffffffffu, unit_fails(v[u], m));
 #pragma unroll
-                for (uint32_t b = 0; b < BPS; ++b) cnt += ((bal >> (b * L4)) & BLKMASK) == 0u ? 1u : 0u;
+                for (uint32_t b = 0; b < BPS; ++b) cnt += ((bal >> (b * UPB)) & BLKMASK) == 0u ? 1u : 0u;
             }
         } else {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const uint64_t blk = (base + u) * BPS + lane / L4;        // this lane's block
-                v[u] = (active && blk < T) ? ld_stream(src + (uint32_t)u * ACTIVE) : make_uint4(0u, 0u, 0u, 0u);
+                const uint64_t blk = (base + u) * BPS + lane / UPB;        // this lane's block
+                v[u] = (active && blk < T) ? ld_stream(src + (uint32_t)u * ACTIVE) : vzero<VT>();
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const uint32_t bal = __ballot_sync(0xffffffffu, unit_fails(v[u], m));
 #pragma unroll
                 for (uint32_t b = 0; b < BPS; ++b)
-                    cnt += ((base + u) * BPS + b < T && ((bal >> (b * L4)) & BLKMASK) == 0u) ? 1u : 0u;
+                    cnt += ((base + u) * BPS + b < T && ((bal >> (b * UPB)) & BLKMASK) == 0u) ? 1u : 0u;
             }
         }
     }
     fold_and_publish(lane == 0 ? (uint64_t)cnt : 0ull, scratch, count_out, pp);
 }
 
+// ---------------------------------------------------------------------------------------
+// wide: UPB a multiple of 32 (e.g. N=16383: 128 units): a block is UPL = UPB/32 coalesced warp
+// loads; one warp folds BPI blocks per iteration (BPI*UPL independent 16-byte loads in
+// flight per lane) and votes once per block.
+// ---------------------------------------------------------------------------------------
+template <int UPL, int BPI>
+__global__ void __launch_bounds__(kDecThreads, 4)
+decrypt_count_wide_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint4 *__restrict__ M4,
+                          uint64_t *scratch, uint64_t *count_out, const __grid_constant__ PeerPush pp) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint4 m[UPL];
+#pragma unroll
+    for (int u = 0; u < UPL; ++u) m[u] = __ldg(M4 + 32 * u + lane);     // the key is not the predecessor's output
+    pdl_enter();
+    const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t n_groups = (T + BPI - 1) / BPI;
+    uint64_t my_count = 0;
+    for (uint64_t grp = warp_global; grp < n_groups; grp += n_warps) {
+        uint4 v[BPI][UPL];
+#pragma unroll
+        for (int b = 0; b < BPI; ++b) {
+            const uint64_t blk = grp * BPI + b;
+            const uint4 *row = V4 + blk * (32u * UPL) + lane;
+#pragma unroll
+            for (int u = 0; u < UPL; ++u) v[b][u] = (blk < T) ? ld_stream(row + 32 * u) : vzero<uint4>();
+        }
+#pragma unroll
+        for (int b = 0; b < BPI; ++b) {
+            bool f = false;
+#pragma unroll
+            for (int u = 0; u < UPL; ++u) f |= unit_fails(v[b][u], m[u]);
+            const bool bad = __any_sync(0xffffffffu, f);
+            if (lane == 0 && !bad && grp * BPI + b < T) ++my_count;
+        }
+    }
+    fold_and_publish(my_count, scratch, count_out, pp);
+}
+
+// Blocks longer than kDecMaxUnits units (N > 65536): one warp per block, 64-bit loads.
+__global__ void __launch_bounds__(kDecThreads)
+decrypt_count_generic_kernel(const uint64_t *__restrict__ V, const uint64_t T, const uint32_t L,
+                             const uint64_t *__restrict__ M, uint64_t *scratch, uint64_t *count_out,
+                             const __grid_constant__ PeerPush pp) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    uint64_t my_count = 0;
+    pdl_enter();
+    for (uint64_t blk = warp_global; blk < T; blk += n_warps) {
+        const uint64_t *row = V + blk * L;
+        bool f = false;
+        for (uint32_t w = lane; w < L; w += 32) {
+            const uint64_t m = __ldg(M + w);
+            f |= ((~__ldcs(row + w)) & m) != 0ull;
+        }
+        const bool bad = __any_sync(0xffffffffu, f);
+        if (lane == 0 && !bad) ++my_count;
+    }
+    fold_and_publish(my_count, scratch, count_out, pp);
+}
+
+// Persistent grid: exactly the CTAs that are resident at once (a partial second wave
+// costs far more than it balances), never more than there is work for.
+template <typename Kernel>
+uint32_t resident_grid(Kernel kernel, size_t smem, uint64_t work_ctas) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kDecThreads, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    per_sm = (int)std::min<long>(per_sm, env_long("CSGN_DEC_CTAS_PER_SM", per_sm));
+    const uint64_t cap = (uint64_t)device_props().sm_count * (uint64_t)std::max(per_sm, 1);
+    return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(work_ctas, cap));
+}
+
+// One persistent wave of resident CTAs is best for a fold running alone at sizes where ramp and tail matter
+// (160 MB: 26.4 vs 27.4 us); several shorter waves are better beyond a GiB (+3 %) and when the caller overlaps folds
+// of several streams (back-fill behind the other stream's kernel: 24.5 -> 23.5 us per fold in the bench).
+uint64_t fold_waves(uint64_t bytes, bool overlapped) {
+    const bool many = overlapped || bytes >= (1ull << 30);
+    return (uint64_t)std::max<long>(1, env_long("CSGN_DEC_WAVES", many ? 4 : 1));
+}
+
+template <typename VT, int UPBC, int UNROLL, int MINB>
+cudaError_t launch_string(const void *v, uint64_t T, uint32_t upb, const void *mask, uint64_t *scratch, uint64_t *count_out,
+                          const PeerPush &pp, cudaStream_t stream) {
+    const uint64_t n_chunks = (T + 31) / 32;
+    const size_t smem = (size_t)2 * upb * sizeof(VT) + (size_t)kDecWarps * upb * sizeof(uint32_t);
+    const uint32_t cpw = (uint32_t)env_long("CSGN_DEC_CPW", 0);
+    uint32_t grid;
+    if (cpw)
+        grid = (uint32_t)std::max<uint64_t>(1, (n_chunks + (uint64_t)kDecWarps * cpw - 1) / ((uint64_t)kDecWarps * cpw));
+    else
+        grid = resident_grid(decrypt_count_kernel<VT, UPBC, UNROLL, MINB>, smem, (n_chunks + kDecWarps - 1) / kDecWarps);
+    return launch_kernel(decrypt_count_kernel<VT, UPBC, UNROLL, MINB>, grid, kDecThreads, smem, stream,
+                         static_cast<const VT *>(v), T, upb, static_cast<const VT *>(mask), cpw, scratch, count_out, pp);
+}
+
+template <typename VT, int UPB, int U, int MINB>
+cudaError_t launch_lanes(const void *v, uint64_t T, const uint64_t *host_mask, uint64_t *scratch, uint64_t *count_out,
+                         const PeerPush &pp, bool overlapped, cudaStream_t stream) {
+    ParamMask pm;
+    memset(&pm, 0, sizeof pm);
+    memcpy(&pm, host_mask, (size_t)UPB * sizeof(VT));
+    constexpr uint32_t BPS = 32u / UPB;
+    const uint64_t n_steps = (T + BPS - 1) / BPS;
+    const uint64_t work_ctas = (n_steps + (uint64_t)kDecWarps * U - 1) / ((uint64_t)kDecWarps * U);
+    uint32_t grid = resident_grid(decrypt_count_lanes_kernel<VT, UPB, U, MINB>, 0, work_ctas);
+    grid = (uint32_t)std::min<uint64_t>(work_ctas, (uint64_t)grid * fold_waves(T * UPB * sizeof(VT), overlapped));
+    return launch_kernel(decrypt_count_lanes_kernel<VT, UPB, U, MINB>, grid, kDecThreads, 0, stream,
+                         static_cast<const VT *>(v), T, pm, scratch, count_out, pp);
+}
+
+template <int UPL, int BPI>
+cudaError_t launch_wide(const uint64_t *v, uint64_t T, const uint64_t *mask, uint64_t *scratch,
+                        uint64_t *count_out, const PeerPush &pp, bool overlapped, cudaStream_t stream) {
+    const uint64_t n_groups = (T + BPI - 1) / BPI;
+    const uint64_t work_ctas = (n_groups + kDecWarps - 1) / kDecWarps;
+    uint32_t grid = resident_grid(decrypt_count_wide_kernel<UPL, BPI>, 0, work_ctas);
+    grid = (uint32_t)std::min<uint64_t>(work_ctas, (uint64_t)grid * fold_waves(T * (uint64_t)UPL * 512u, overlapped));
+    return launch_kernel(decrypt_count_wide_kernel<UPL, BPI>, grid, kDecThreads, 0, stream,
+                         reinterpret_cast<const uint4 *>(v), T, reinterpret_cast<const uint4 *>(mask), scratch, count_out, pp);
+}
+
+// Push and/or publish + collect without a fold (an empty local shard still owes its peers a
+// word; a collect may also be issued on its own).  One CTA.
+__global__ void __launch_bounds__(kDecThreads)
+peer_exchange_kernel(const __grid_constant__ PeerPush pp, const int do_push, const uint64_t value, uint64_t *count_out) {
+    pdl_enter();
+    if (do_push && threadIdx.x == 0) {
+        if (count_out) *count_out = value;
+        pp.local_ring[peer_slot(pp.seq)] = value;
+    }
+    if (pp.publish_n | pp.collect_n) {
+        __syncthreads();
+        peer_publish_collect(pp);
+    }
+}
+
+#ifdef CSGN_BUILD_VARIANTS
 // ---------------------------------------------------------------------------------------
 // Bulk-ring variant of the same fold (small blocks, L4 <= 16, e.g. N=1247).
 //
@@ -349,147 +443,8 @@ cudaError_t launch_ring(const uint64_t *v, uint64_t T, uint32_t L4, const uint64
                          by_param ? nullptr : reinterpret_cast<const uint4 *>(mask), pm, scratch, count_out, pp);
 }
 
-// L4 a multiple of 32 (e.g. N=16383: L4=128): a block is UPL = L4/32 coalesced warp
-// loads; one warp folds BPI blocks per iteration (BPI*UPL independent 16-byte loads in
-// flight per lane) and votes once per block.
-template <int UPL, int BPI>
-__global__ void __launch_bounds__(kDecThreads, 4)
-decrypt_count_wide_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint4 *__restrict__ M4,
-                          uint64_t *scratch, uint64_t *count_out, const __grid_constant__ PeerPush pp) {
-    const uint32_t lane = threadIdx.x & 31u;
-    pdl_enter();
-    uint4 m[UPL];
-#pragma unroll
-    for (int u = 0; u < UPL; ++u) m[u] = __ldg(M4 + 32 * u + lane);
-    const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const uint64_t n_groups = (T + BPI - 1) / BPI;
-    uint64_t my_count = 0;
-    for (uint64_t grp = warp_global; grp < n_groups; grp += n_warps) {
-        uint4 v[BPI][UPL];
-#pragma unroll
-        for (int b = 0; b < BPI; ++b) {
-            const uint64_t blk = grp * BPI + b;
-            const uint4 *row = V4 + blk * (32u * UPL) + lane;
-#pragma unroll
-            for (int u = 0; u < UPL; ++u) v[b][u] = (blk < T) ? ld_stream(row + 32 * u) : make_uint4(0u, 0u, 0u, 0u);
-        }
-#pragma unroll
-        for (int b = 0; b < BPI; ++b) {
-            bool f = false;
-#pragma unroll
-            for (int u = 0; u < UPL; ++u) f |= unit_fails(v[b][u], m[u]);
-            const bool bad = __any_sync(0xffffffffu, f);
-            if (lane == 0 && !bad && grp * BPI + b < T) ++my_count;
-        }
-    }
-    fold_and_publish(my_count, scratch, count_out, pp);
-}
 
-// Any L (odd, or too long for the fail string), any alignment: one warp per block.
-__global__ void __launch_bounds__(kDecThreads)
-decrypt_count_generic_kernel(const uint64_t *__restrict__ V, const uint64_t T, const uint32_t L,
-                             const uint64_t *__restrict__ M, uint64_t *scratch, uint64_t *count_out,
-                             const __grid_constant__ PeerPush pp) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    uint64_t my_count = 0;
-    pdl_enter();
-    for (uint64_t blk = warp_global; blk < T; blk += n_warps) {
-        const uint64_t *row = V + blk * L;
-        bool f = false;
-        for (uint32_t w = lane; w < L; w += 32) {
-            const uint64_t m = __ldg(M + w);
-            f |= ((~__ldcs(row + w)) & m) != 0ull;
-        }
-        const bool bad = __any_sync(0xffffffffu, f);
-        if (lane == 0 && !bad) ++my_count;
-    }
-    fold_and_publish(my_count, scratch, count_out, pp);
-}
-
-// Persistent grid: exactly the CTAs that are resident at once (a partial second wave
-// costs far more than it balances), never more than there is work for.
-template <typename Kernel>
-uint32_t resident_grid(Kernel kernel, size_t smem, uint64_t work_ctas) {
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kDecThreads, smem) != cudaSuccess || per_sm < 1)
-        per_sm = 1;
-    per_sm = (int)std::min<long>(per_sm, env_long("CSGN_DEC_CTAS_PER_SM", per_sm));
-    const uint64_t cap = (uint64_t)device_props().sm_count * (uint64_t)std::max(per_sm, 1);
-    return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(work_ctas, cap));
-}
-
-template <int L4C, int UNROLL, int MINB>
-cudaError_t launch_fast(const uint64_t *v, uint64_t T, uint32_t L4, const uint64_t *mask, const uint64_t *host_mask,
-                        uint64_t *scratch, uint64_t *count_out, const PeerPush &pp, cudaStream_t stream) {
-    ParamMask pm;
-    memset(&pm, 0, sizeof pm);
-    const bool by_param = host_mask && L4 <= (uint32_t)kParamMaskUnits && !env_long("CSGN_DEC_GLOBAL_MASK", 0);
-    if (by_param) memcpy(&pm, host_mask, (size_t)L4 * sizeof(uint4));
-    const uint64_t n_chunks = (T + 31) / 32;
-    const size_t smem = (size_t)2 * L4 * sizeof(uint4) + (size_t)kDecWarps * L4 * sizeof(uint32_t);
-    const uint32_t cpw = (uint32_t)env_long("CSGN_DEC_CPW", 0);
-    uint32_t grid;
-    if (cpw)
-        grid = (uint32_t)std::max<uint64_t>(1, (n_chunks + (uint64_t)kDecWarps * cpw - 1) / ((uint64_t)kDecWarps * cpw));
-    else
-        grid = resident_grid(decrypt_count_kernel<L4C, UNROLL, MINB>, smem, (n_chunks + kDecWarps - 1) / kDecWarps);
-    return launch_kernel(decrypt_count_kernel<L4C, UNROLL, MINB>, grid, kDecThreads, smem, stream,
-                         reinterpret_cast<const uint4 *>(v), T, L4,
-                         by_param ? nullptr : reinterpret_cast<const uint4 *>(mask), pm, cpw, scratch, count_out, pp);
-}
-
-template <int L4, int U, int MINB>
-cudaError_t launch_lanes(const uint64_t *v, uint64_t T, const uint64_t *host_mask, uint64_t *scratch, uint64_t *count_out,
-                         const PeerPush &pp, cudaStream_t stream) {
-    ParamMask pm;
-    memset(&pm, 0, sizeof pm);
-    memcpy(&pm, host_mask, (size_t)L4 * sizeof(uint4));
-    constexpr uint32_t BPS = 32u / L4;
-    const uint64_t n_steps = (T + BPS - 1) / BPS;
-    const uint64_t work_ctas = (n_steps + (uint64_t)kDecWarps * U - 1) / ((uint64_t)kDecWarps * U);
-    // One persistent wave of resident CTAs is best for a fold running alone at sizes where ramp and tail matter
-    // (160 MB: 26.4 vs 27.4 us); four shorter waves are better beyond a GiB (+3 %) and when the caller overlaps folds
-    // of several streams (back-fill behind the other stream's kernel: 24.5 -> 23.5 us per fold in the bench).
-    const bool many = streams_alternate() || T * (uint64_t)L4 * 16u >= (1ull << 30);
-    const uint64_t waves = (uint64_t)std::max<long>(1, env_long("CSGN_DEC_WAVES", many ? 4 : 1));
-    uint32_t grid = resident_grid(decrypt_count_lanes_kernel<L4, U, MINB>, 0, work_ctas);
-    grid = (uint32_t)std::min<uint64_t>(work_ctas, (uint64_t)grid * waves);
-    return launch_kernel(decrypt_count_lanes_kernel<L4, U, MINB>, grid, kDecThreads, 0, stream,
-                         reinterpret_cast<const uint4 *>(v), T, pm, scratch, count_out, pp);
-}
-
-template <int UPL, int BPI>
-cudaError_t launch_wide(const uint64_t *v, uint64_t T, const uint64_t *mask, uint64_t *scratch,
-                        uint64_t *count_out, const PeerPush &pp, cudaStream_t stream) {
-    const uint64_t n_groups = (T + BPI - 1) / BPI;
-    const uint64_t work_ctas = (n_groups + kDecWarps - 1) / kDecWarps;
-    // as in launch_lanes: several shorter waves when folds overlap or the fold is a GiB and more
-    const bool many = streams_alternate() || T * (uint64_t)UPL * 512u >= (1ull << 30);
-    const uint64_t waves = (uint64_t)std::max<long>(1, env_long("CSGN_DEC_WAVES", many ? 4 : 1));
-    uint32_t grid = resident_grid(decrypt_count_wide_kernel<UPL, BPI>, 0, work_ctas);
-    grid = (uint32_t)std::min<uint64_t>(work_ctas, (uint64_t)grid * waves);
-    return launch_kernel(decrypt_count_wide_kernel<UPL, BPI>, grid, kDecThreads, 0, stream,
-                         reinterpret_cast<const uint4 *>(v), T, reinterpret_cast<const uint4 *>(mask), scratch, count_out, pp);
-}
-
-
-// Push and/or publish + collect without a fold (an empty local shard still owes its peers a
-// word; a collect may also be issued on its own).  One CTA.
-__global__ void __launch_bounds__(kDecThreads)
-peer_exchange_kernel(const __grid_constant__ PeerPush pp, const int do_push, const uint64_t value, uint64_t *count_out) {
-    pdl_enter();
-    if (do_push && threadIdx.x == 0) {
-        if (count_out) *count_out = value;
-        pp.local_ring[peer_slot(pp.seq)] = value;
-    }
-    if (pp.publish_n | pp.collect_n) {
-        __syncthreads();
-        peer_publish_collect(pp);
-    }
-}
+#endif  // CSGN_BUILD_VARIANTS
 
 }  // namespace
 
@@ -499,9 +454,17 @@ cudaError_t launch_peer_exchange(const PeerPush &pp, bool do_push, uint64_t valu
     return launch_kernel(peer_exchange_kernel, 1, kDecThreads, 0, stream, pp, do_push ? 1 : 0, value, count_out);
 }
 
+bool build_has_variants() {
+#ifdef CSGN_BUILD_VARIANTS
+    return true;
+#else
+    return false;
+#endif
+}
+
 cudaError_t launch_decrypt_count(const uint64_t *v, uint64_t T, uint32_t L, const uint64_t *mask,
                                  const uint64_t *host_mask, uint64_t *scratch, uint64_t *count_out,
-                                 cudaStream_t stream, const PeerPush *peer) {
+                                 cudaStream_t stream, const PeerPush *peer, bool overlapped) {
     PeerPush pp;
     if (peer) pp = *peer;
     else memset(&pp, 0, sizeof pp);
@@ -510,37 +473,78 @@ cudaError_t launch_decrypt_count(const uint64_t *v, uint64_t T, uint32_t L, cons
         return count_out ? cudaMemsetAsync(count_out, 0, sizeof(uint64_t), stream) : cudaSuccess;
     }
     const DeviceProps &dp = device_props();
-    const uint64_t ctas_per_sm = (uint64_t)env_long("CSGN_DEC_CTAS_PER_SM", 8);
-    const long wide = env_long("CSGN_DEC_WIDE", 1);
-    const bool aligned = ((reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(mask)) & 15u) == 0;
-    const uint32_t L4 = L / 2;
-    cudaError_t err;
-    if ((L & 1u) || !aligned || L4 > kDecMaxL4 || env_long("CSGN_DEC_GENERIC", 0)) {
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(mask)) & 15u) == 0;
+    const bool units16 = !(L & 1u) && aligned16;
+    const uint32_t upb = units16 ? L / 2 : L;          // units per block: 16-byte or 8-byte
+    cudaError_t err = cudaErrorInvalidValue;
+    bool done = false;
+#ifdef CSGN_BUILD_VARIANTS
+    const long variant = env_long("CSGN_DEC_VARIANT", 0);
+    if (units16 && upb == 10 && variant > 0) {
+        done = true;
+        switch (variant) {
+            case 5: err = launch_ring<10, 4>(v, T, upb, mask, host_mask, scratch, count_out, pp, stream); break;
+            case 6: err = launch_ring<10, 3>(v, T, upb, mask, host_mask, scratch, count_out, pp, stream); break;
+            case 7: err = launch_ring<10, 5>(v, T, upb, mask, host_mask, scratch, count_out, pp, stream); break;
+            case 8: err = launch_lanes<uint4, 10, 10, 4>(v, T, host_mask, scratch, count_out, pp, overlapped, stream); break;
+            case 9: err = launch_lanes<uint4, 10, 8, 4>(v, T, host_mask, scratch, count_out, pp, overlapped, stream); break;
+            case 11: err = launch_lanes<uint4, 10, 6, 6>(v, T, host_mask, scratch, count_out, pp, overlapped, stream); break;
+            case 12: err = launch_lanes<uint4, 10, 16, 3>(v, T, host_mask, scratch, count_out, pp, overlapped, stream); break;
+            case 1: err = launch_string<uint4, 10, 10, 4>(v, T, upb, mask, scratch, count_out, pp, stream); break;
+            case 2: err = launch_string<uint4, 10, 5, 5>(v, T, upb, mask, scratch, count_out, pp, stream); break;
+            case 3: err = launch_string<uint4, 10, 5, 6>(v, T, upb, mask, scratch, count_out, pp, stream); break;
+            case 4: err = launch_string<uint4, 10, 2, 8>(v, T, upb, mask, scratch, count_out, pp, stream); break;
+            case 13: err = launch_string<uint4, 10, 10, 3>(v, T, upb, mask, scratch, count_out, pp, stream); break;
+            default: done = false;
+        }
+    }
+#endif
+    const bool force_string = env_long("CSGN_DEC_STRING", 0) != 0;
+    if (done) {
+    } else if (upb > kDecMaxUnits || env_long("CSGN_DEC_GENERIC", 0)) {
         const uint64_t want = (T + kDecWarps - 1) / kDecWarps;
+        const uint64_t ctas_per_sm = (uint64_t)env_long("CSGN_DEC_CTAS_PER_SM", 8);
         const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, dp.sm_count * ctas_per_sm));
         err = launch_kernel(decrypt_count_generic_kernel, grid, kDecThreads, 0, stream, v, T, L, mask, scratch, count_out, pp);
+    } else if (upb <= 16 && host_mask && !force_string) {
+        // every short block shape has its own lane-aligned instantiation (no cliff between contexts)
+#define CSGN_LANES_CASE(VT, UPB, U) \
+    case UPB: err = launch_lanes<VT, UPB, U, 3>(v, T, host_mask, scratch, count_out, pp, overlapped, stream); break;
+        if (units16) {
+            switch (upb) {
+                CSGN_LANES_CASE(uint4, 1, 12) CSGN_LANES_CASE(uint4, 2, 12) CSGN_LANES_CASE(uint4, 3, 12)
+                CSGN_LANES_CASE(uint4, 4, 12) CSGN_LANES_CASE(uint4, 5, 12) CSGN_LANES_CASE(uint4, 6, 12)
+                CSGN_LANES_CASE(uint4, 7, 12) CSGN_LANES_CASE(uint4, 8, 12) CSGN_LANES_CASE(uint4, 9, 12)
+                CSGN_LANES_CASE(uint4, 10, 12) CSGN_LANES_CASE(uint4, 11, 12) CSGN_LANES_CASE(uint4, 12, 12)
+                CSGN_LANES_CASE(uint4, 13, 12) CSGN_LANES_CASE(uint4, 14, 12) CSGN_LANES_CASE(uint4, 15, 12)
+                CSGN_LANES_CASE(uint4, 16, 12)
+            }
+        } else {
+            switch (upb) {
+                CSGN_LANES_CASE(uint2, 1, 16) CSGN_LANES_CASE(uint2, 2, 16) CSGN_LANES_CASE(uint2, 3, 16)
+                CSGN_LANES_CASE(uint2, 4, 16) CSGN_LANES_CASE(uint2, 5, 16) CSGN_LANES_CASE(uint2, 6, 16)
+                CSGN_LANES_CASE(uint2, 7, 16) CSGN_LANES_CASE(uint2, 8, 16) CSGN_LANES_CASE(uint2, 9, 16)
+                CSGN_LANES_CASE(uint2, 10, 16) CSGN_LANES_CASE(uint2, 11, 16) CSGN_LANES_CASE(uint2, 12, 16)
+                CSGN_LANES_CASE(uint2, 13, 16) CSGN_LANES_CASE(uint2, 14, 16) CSGN_LANES_CASE(uint2, 15, 16)
+                CSGN_LANES_CASE(uint2, 16, 16)
+            }
+        }
+#undef CSGN_LANES_CASE
+    } else if (units16 && upb % 32 == 0 && upb <= 256 && !force_string && env_long("CSGN_DEC_WIDE", 1)) {
+        switch (upb / 32) {
+            case 1: err = launch_wide<1, 8>(v, T, mask, scratch, count_out, pp, overlapped, stream); break;
+            case 2: err = launch_wide<2, 4>(v, T, mask, scratch, count_out, pp, overlapped, stream); break;
+            case 3: err = launch_wide<3, 3>(v, T, mask, scratch, count_out, pp, overlapped, stream); break;
+            case 4: err = launch_wide<4, 2>(v, T, mask, scratch, count_out, pp, overlapped, stream); break;   // N=16383
+            case 5: err = launch_wide<5, 2>(v, T, mask, scratch, count_out, pp, overlapped, stream); break;
+            case 6: err = launch_wide<6, 2>(v, T, mask, scratch, count_out, pp, overlapped, stream); break;
+            case 7: err = launch_wide<7, 1>(v, T, mask, scratch, count_out, pp, overlapped, stream); break;
+            default: err = launch_wide<8, 1>(v, T, mask, scratch, count_out, pp, overlapped, stream); break;
+        }
+    } else if (units16) {
+        err = launch_string<uint4, 0, 4, 4>(v, T, upb, mask, scratch, count_out, pp, stream);
     } else {
-        const long variant = env_long("CSGN_DEC_VARIANT", 0);
-        if (L4 == 10 && variant == 5) err = launch_ring<10, 4>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
-        else if (L4 == 10 && variant == 6) err = launch_ring<10, 3>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
-        else if (L4 == 10 && variant == 7) err = launch_ring<10, 5>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
-        else if (L4 == 10 && host_mask && variant == 8) err = launch_lanes<10, 10, 4>(v, T, host_mask, scratch, count_out, pp, stream);
-        else if (L4 == 10 && host_mask && variant == 9) err = launch_lanes<10, 8, 4>(v, T, host_mask, scratch, count_out, pp, stream);
-        else if (L4 == 10 && host_mask && variant == 10) err = launch_lanes<10, 12, 3>(v, T, host_mask, scratch, count_out, pp, stream);
-        else if (L4 == 10 && host_mask && variant == 11) err = launch_lanes<10, 6, 6>(v, T, host_mask, scratch, count_out, pp, stream);
-        else if (L4 == 10 && host_mask && variant == 12) err = launch_lanes<10, 16, 3>(v, T, host_mask, scratch, count_out, pp, stream);
-        else if (L4 == 10 && variant == 1) err = launch_fast<10, 10, 4>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
-        else if (L4 == 10 && variant == 2) err = launch_fast<10, 5, 5>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
-        else if (L4 == 10 && variant == 3) err = launch_fast<10, 5, 6>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
-        else if (L4 == 10 && variant == 4) err = launch_fast<10, 2, 8>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
-        else if (L4 == 10 && host_mask && variant != 13)                                                               // N=1247
-            err = launch_lanes<10, 12, 3>(v, T, host_mask, scratch, count_out, pp, stream);
-        else if (L4 == 10) err = launch_fast<10, 10, 3>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
-        else if (L4 == 128 && wide) err = launch_wide<4, 2>(v, T, mask, scratch, count_out, pp, stream);  // N=16383
-        else if (L4 == 64 && wide) err = launch_wide<2, 4>(v, T, mask, scratch, count_out, pp, stream);
-        else if (L4 == 32 && wide) err = launch_wide<1, 8>(v, T, mask, scratch, count_out, pp, stream);
-        else if (L4 == 128) err = launch_fast<128, 8, 3>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
-        else err = launch_fast<0, 4, 4>(v, T, L4, mask, host_mask, scratch, count_out, pp, stream);
+        err = launch_string<uint2, 0, 8, 4>(v, T, upb, mask, scratch, count_out, pp, stream);
     }
     count_launch();
     return err;

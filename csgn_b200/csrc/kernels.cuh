@@ -20,15 +20,27 @@ const DeviceProps &device_props();
 void set_device_props(const DeviceProps &p);
 void count_launch(unsigned n = 1);
 uint64_t launches();
-// true while the caller keeps switching streams between calls (independent work meant to overlap)
-bool streams_alternate();
+// true when the library was built with -DCSGN_BUILD_VARIANTS (the losing kernel variants kept for A/B sweeps)
+bool build_has_variants();
 
 // Integer environment knob (tuning sweeps only); `dflt` when unset or malformed.
 long env_long(const char *name, long dflt);
 
+// Fused multiply -> fold: what launch_mul needs to also count the satisfied blocks of the product.
+struct MulFold {
+    const uint64_t *mask;        // key mask, L words, device
+    const uint64_t *host_mask;   // the same on the host (optional): small masks ride in the kernel parameters
+    uint64_t *scratch;           // the launch's fold scratch word (zero between launches)
+    uint64_t *count_out;         // device word for the total; may be null when `peer` is given
+    const PeerPush *peer;        // optional: sharded decrypt (push / publish / collect in the same kernel)
+};
 // K1  out[(i*T2+j)*L+k] = a[i*L+k] & b[j*L+k]        (reference src/Ciphertext.cpp:153-163)
+// With `fold` the same launch also decrypt-folds the product (src/SecretKey.cpp:131-140) while its units are in
+// registers; `out` may then be null (count only, nothing is stored).  cudaErrorNotSupported when a shape has no
+// fused kernel (mul_fold_supported(L) is false): the caller multiplies and folds in two launches.
 cudaError_t launch_mul(const uint64_t *a, uint64_t T1, const uint64_t *b, uint64_t T2, uint32_t L,
-                       uint64_t *out, cudaStream_t stream);
+                       uint64_t *out, cudaStream_t stream, const MulFold *fold = nullptr);
+bool mul_fold_supported(uint32_t L);
 
 // K2  out = a || b                                     (reference src/Ciphertext.cpp:107-122)
 // Either source may be null/empty; out may alias a (append in place) when a == out.
@@ -36,13 +48,14 @@ cudaError_t launch_concat(const uint64_t *a, uint64_t n_words_a, const uint64_t 
                           uint64_t *out, cudaStream_t stream);
 
 // K3  count of blocks with all_w((v[w] & M[w]) == M[w]) (reference src/SecretKey.cpp:126-140)
-// `scratch` is two zero-initialised uint64 (running count, CTA ticket) that the kernel
-// leaves zeroed again; the total is written to *count_out (device memory).
+// `scratch` is one zero-initialised uint64 (count | CTA ticket << 40, fold.cuh) that the kernel
+// leaves zeroed again; the total is written to *count_out (device memory).  `overlapped`: the caller runs
+// this fold next to other kernels (batch lanes), so several shorter waves of CTAs back-fill better than one.
 // `host_mask` (optional) is a host copy of the same L words: small masks ride in the
 // kernel parameters instead of being fetched from global memory.
 cudaError_t launch_decrypt_count(const uint64_t *v, uint64_t T, uint32_t L, const uint64_t *mask,
                                  const uint64_t *host_mask, uint64_t *scratch, uint64_t *count_out,
-                                 cudaStream_t stream, const PeerPush *peer = nullptr);
+                                 cudaStream_t stream, const PeerPush *peer = nullptr, bool overlapped = false);
 // `peer` (optional, sharded decrypt): the kernel's last CTA also pushes the count into every
 // rank's mailbox and, when peer->collect_n > 0, collects the batch's totals (peer.cuh);
 // count_out may then be null.  launch_peer_exchange does the push/collect without a fold.

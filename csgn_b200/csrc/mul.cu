@@ -1,4 +1,4 @@
-// mul.cu -- K1, ciphertext multiply: the all-pairs AND of T1 x T2 blocks.
+// mul.cu -- K1, ciphertext multiply: the all-pairs AND of T1 x T2 blocks -- and the fused multiply -> fold.
 //
 //   out[(i*T2+j)*L+k] = a[i*L+k] & b[j*L+k]     (reference src/Ciphertext.cpp:153-163;
 //                                                the 1x1 shortcut :124-131 is T1=T2=1)
@@ -6,50 +6,125 @@
 // Roofline: HBM WRITE bandwidth.  8*L bytes are written per output block, the
 // operands (8*L*(T1+T2) bytes in total) stay L2-resident, one 64-bit AND per 8 bytes.
 //
-// Shape of the kernel.  Output row i is the whole right operand, seen as one flat
-// stream of Q = T2*L/2 16-byte units, ANDed with block a_i repeated with period
-// L4 = L/2 units.  The CTA size is a multiple of L4, so a thread that walks the flat
-// stream with stride blockDim always meets the same 16-byte fragment of a_i:
+// A ciphertext is a flat stream of units: 16 bytes (uint4, UPB = L/2 units per block) when L is even and
+// the words are 16-byte aligned, 8 bytes (uint2, UPB = L) otherwise (odd L: N = 191, 4097 ...).
+//
+// Tiled kernel (mul_outer_kernel).  Output row i is the whole right operand, seen as one flat
+// stream of Q = T2*UPB units, ANDed with block a_i repeated with period UPB.  The CTA size is a multiple
+// of UPB, so a thread that walks the flat stream with stride blockDim always meets the same fragment of a_i:
 //   - a work item is (column tile of U*blockDim units) x (chunk of R rows);
 //   - the thread's U units of b are loaded ONCE into registers (coalesced);
-//   - the R blocks of a are staged in shared memory (R*L4*16 bytes);
-//   - per row: one LDS.128 for the thread's fragment of a_i, U ANDs, U coalesced
-//     128-bit streaming stores (st.global.cs -- nothing re-reads the product).
+//   - the R blocks of a are staged in shared memory;
+//   - per row: one shared load for the thread's fragment of a_i, U ANDs, U coalesced
+//     streaming stores (st.global.cs -- nothing re-reads the product).
 // b is re-read from L2 once per R rows, so L2 read traffic is 1/R of the write
 // stream; no integer division happens inside the row loop.
+//
+// Flat kernel (mul_flat_kernel), for products with a short right operand and very many rows (chains:
+// (a*b)*d with a fresh d): the whole of b sits in shared memory, the output is walked as ONE flat stream in
+// grid-stride steps -- at any moment the resident CTAs write one compact, advancing window of the product, the
+// access pattern of a memset -- and the a fragments a step needs are fetched one step ahead.
+//
+// Fused multiply -> fold (FOLD != 0): SecretKey::decrypt of the product (reference src/SecretKey.cpp:131-140,
+// the caller pattern tests/basic_operations.cpp:35-40) evaluated on the product units while they are still in
+// registers: the thread tests a_i & b_j against ITS unit of the key mask (its unit index within a block never
+// changes), the per-unit verdicts of a tile are OR-ed across the UPB adjacent threads that hold one block, and the
+// satisfied blocks are counted and folded into the grid total exactly as in decrypt.cu.  One pass over HBM (the
+// product is written, never read back); FOLD == 2 stores nothing at all (decrypt-only consumers).
 #include "kernels.cuh"
 #include "launch.cuh"
+#include "fold.cuh"
 
 #include <algorithm>
+#include <cstring>
 
 namespace csgn {
 namespace {
 
 constexpr int kMulMaxThreads = 512;
 constexpr uint32_t kMulMaxSmem = 32 * 1024;
+constexpr uint32_t kFlatMaxSmem = 64 * 1024;     // right operand resident in shared memory
+constexpr bool kFlatByDefault = false;           // chain shapes take the flat kernel without being asked (measured: profiles/)
 
-__device__ __forceinline__ uint4 and4(const uint4 a, const uint4 b) {
+__device__ __forceinline__ uint4 vand(const uint4 a, const uint4 b) {
     return make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w);
 }
+__device__ __forceinline__ uint2 vand(const uint2 a, const uint2 b) { return make_uint2(a.x & b.x, a.y & b.y); }
+template <typename VT> __device__ __forceinline__ VT vzero();
+template <> __device__ __forceinline__ uint4 vzero<uint4>() { return make_uint4(0u, 0u, 0u, 0u); }
+template <> __device__ __forceinline__ uint2 vzero<uint2>() { return make_uint2(0u, 0u); }
 
-// Store flavours (tuning): 0 = st.global.cs (evict-first), 1 = default write-back,
-// 2 = st.global.wt (write-through).
-template <int MODE>
-__device__ __forceinline__ void st_out(uint4 *p, const uint4 v) {
-    if (MODE == 0) __stcs(p, v);
-    else if (MODE == 1) *p = v;
-    else __stwt(p, v);
+// What a fused launch carries besides the operands (by value in the kernel parameters).
+struct FoldParams {
+    ParamMask pmask;            // the key mask, when it fits (always hot: parameter bank)
+    const void *mask;           // the key mask in global memory (any size)
+    uint64_t *scratch;          // the launch's fold scratch word
+    uint64_t *count_out;        // device word for the total (may be null with a PeerPush)
+    PeerPush pp;
+    int mask_in_params;
+};
+
+template <typename VT>
+__device__ __forceinline__ VT fold_mask_unit(const FoldParams &fo, const uint32_t k) {
+    return fo.mask_in_params ? reinterpret_cast<const VT *>(&fo.pmask)[k] : __ldg(static_cast<const VT *>(fo.mask) + k);
 }
 
-template <int U, int MODE>
+// OR of `fails` over the UPB adjacent threads that hold one block; the group's first thread gets the result and
+// counts the clear bits under `valid`.  Whole CTA.  sFail: blockDim.x words of shared memory.
+__device__ __forceinline__ uint32_t count_group_clear(const uint64_t fails, const uint64_t valid, const uint32_t UPB,
+                                                      const uint32_t k, uint64_t *sFail) {
+    uint32_t got = 0;
+    if ((UPB & 31u) == 0u) {
+        // groups are whole warps (the CTA size is a multiple of UPB, hence of 32): reduce in the warp first
+        const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)fails);
+        const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(fails >> 32));
+        if ((threadIdx.x & 31u) == 0u) sFail[threadIdx.x >> 5] = ((uint64_t)hi << 32) | lo;
+        __syncthreads();
+        if (k == 0) {
+            uint64_t f = 0;
+            const uint32_t w0 = threadIdx.x >> 5;
+            for (uint32_t i = 0; i < (UPB >> 5); ++i) f |= sFail[w0 + i];
+            got = (uint32_t)__popcll(~f & valid);
+        }
+    } else {
+        sFail[threadIdx.x] = fails;
+        __syncthreads();
+        if (k == 0) {
+            uint64_t f = 0;
+            for (uint32_t i = 0; i < UPB; ++i) f |= sFail[threadIdx.x + i];
+            got = (uint32_t)__popcll(~f & valid);
+        }
+    }
+    return got;
+}
+
+// CTA count (held by the groups' first threads; almost always zero) -> grid.  Whole CTA, once.
+__device__ __forceinline__ void publish_cta_count(const uint32_t cnt, unsigned long long *s_cnt, const FoldParams &fo) {
+    if (cnt) atomicAdd(s_cnt, (unsigned long long)cnt);
+    __syncthreads();
+    grid_publish(threadIdx.x == 0 ? (uint64_t)*s_cnt : 0ull, fo.scratch, fo.count_out, fo.pp);
+}
+
+// FOLD: 0 = multiply, 1 = multiply and count the satisfied product blocks, 2 = count only (nothing stored).
+template <typename VT, int U, int FOLD>
 __global__ void __launch_bounds__(kMulMaxThreads)
-mul_outer_kernel(const uint4 *__restrict__ A4, const uint4 *__restrict__ B4, uint4 *__restrict__ out4,
-                 const uint32_t L4, const uint64_t T1, const uint64_t Q, const uint32_t R,
-                 const uint32_t n_col_tiles, const uint64_t n_items, const uint32_t pf_chunks) {
-    extern __shared__ uint4 sA[];
+mul_outer_kernel(const VT *__restrict__ A, const VT *__restrict__ B, VT *__restrict__ out,
+                 const uint32_t UPB, const uint64_t T1, const uint64_t Q, const uint32_t R,
+                 const uint32_t n_col_tiles, const uint64_t n_items, const uint32_t pf_chunks,
+                 const __grid_constant__ FoldParams fo) {
+    extern __shared__ uint4 smem_raw[];
+    VT *sA = reinterpret_cast<VT *>(smem_raw);
+    // fused fold: one 64-bit fail word per thread, behind the staged rows (8-byte aligned: R*UPB units of 8 or 16 bytes)
+    uint64_t *sFail = reinterpret_cast<uint64_t *>(sA + (size_t)R * UPB);
+    __shared__ unsigned long long s_cnt;
     const uint32_t tpb = blockDim.x;
-    const uint32_t k4 = threadIdx.x % L4;
+    const uint32_t k = threadIdx.x % UPB;
     const uint64_t tile_q = (uint64_t)tpb * U;
+    VT m = vzero<VT>();
+    if (FOLD) {
+        m = fold_mask_unit<VT>(fo, k);             // the key is not the predecessor's output: before the PDL wait
+        if (threadIdx.x == 0) s_cnt = 0ull;
+    }
     pdl_enter();
 
     // In real use the left operand is DRAM-cold (the previous product flushed L2) and an
@@ -59,66 +134,190 @@ mul_outer_kernel(const uint4 *__restrict__ A4, const uint4 *__restrict__ B4, uin
     // the first pf_chunks chunks, which nobody is ahead of, are requested line by line by
     // the first CTAs.
     if (pf_chunks) {
-        const uint64_t a_bytes = T1 * L4 * 16u;
-        const uint64_t head_bytes = min(a_bytes, (uint64_t)pf_chunks * R * L4 * 16u);
+        const uint64_t a_bytes = T1 * UPB * sizeof(VT);
+        const uint64_t head_bytes = min(a_bytes, (uint64_t)pf_chunks * R * UPB * sizeof(VT));
         if (threadIdx.x == 0 && (uint64_t)blockIdx.x * 128u < head_bytes)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(A4) + (uint64_t)blockIdx.x * 128u));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(A) + (uint64_t)blockIdx.x * 128u));
         if (blockIdx.x % n_col_tiles == 0) {
             const uint64_t row0 = ((uint64_t)blockIdx.x / n_col_tiles + pf_chunks) * R;
             if (row0 < T1) {
-                const uint32_t bytes = (uint32_t)min((uint64_t)R, T1 - row0) * L4 * 16u;
+                const uint32_t bytes = (uint32_t)min((uint64_t)R, T1 - row0) * UPB * (uint32_t)sizeof(VT);
                 const uint32_t off = threadIdx.x * 128u;
                 if (off < bytes + 128u)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(A4 + row0 * L4) +
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(A + row0 * UPB) +
                                                                    min(off, bytes - 1u)));
             }
         }
     }
 
+    uint32_t cnt = 0;
     for (uint64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const uint32_t ct = (uint32_t)(item % n_col_tiles);
         const uint64_t row0 = (item / n_col_tiles) * R;
         const uint32_t nrows = (uint32_t)min((uint64_t)R, T1 - row0);
         const uint64_t q0 = (uint64_t)ct * tile_q + threadIdx.x;
 
-        uint4 b[U];
+        VT b[U];
+        uint32_t live_bits = 0;                     // bit u: unit u of this thread lies inside the row
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint64_t q = q0 + (uint64_t)u * tpb;
-            b[u] = (q < Q) ? __ldg(B4 + q) : make_uint4(0u, 0u, 0u, 0u);
+            const bool in = q < Q;
+            b[u] = in ? __ldg(B + q) : vzero<VT>();
+            live_bits |= in ? (1u << u) : 0u;
         }
 
-        __syncthreads();  // the previous item's readers of sA are done
-        const uint4 *a_chunk = A4 + row0 * L4;
-        for (uint32_t idx = threadIdx.x; idx < nrows * L4; idx += tpb) sA[idx] = __ldg(a_chunk + idx);
+        __syncthreads();  // the previous item's readers of sA (and sFail) are done
+        const VT *a_chunk = A + row0 * UPB;
+        for (uint32_t idx = threadIdx.x; idx < nrows * UPB; idx += tpb) sA[idx] = __ldg(a_chunk + idx);
         __syncthreads();
 
-        uint4 *o = out4 + row0 * Q + q0;
-        const uint4 *sa = sA + k4;
+        VT *o = out + row0 * Q + q0;
+        const VT *sa = sA + k;
+        uint64_t fails = 0;                         // row r, unit u -> bit (nrows-1-r)*U + u
         if ((uint64_t)(ct + 1) * tile_q <= Q) {
 #pragma unroll 4
-            for (uint32_t r = 0; r < nrows; ++r, o += Q, sa += L4) {
-                const uint4 a = *sa;
+            for (uint32_t r = 0; r < nrows; ++r, o += Q, sa += UPB) {
+                const VT a = *sa;
+                uint32_t rowbits = 0;
 #pragma unroll
-                for (int u = 0; u < U; ++u) st_out<MODE>(o + (uint64_t)u * tpb, and4(a, b[u]));
+                for (int u = 0; u < U; ++u) {
+                    const VT v = vand(a, b[u]);
+                    if (FOLD != 2) __stcs(o + (uint64_t)u * tpb, v);
+                    if (FOLD) rowbits |= unit_fails(v, m) ? (1u << u) : 0u;
+                }
+                if (FOLD) fails = (fails << U) | rowbits;
             }
         } else {
             // ragged last column tile: per-unit bounds, loop-invariant predicates
-            bool live[U];
+            for (uint32_t r = 0; r < nrows; ++r, o += Q, sa += UPB) {
+                const VT a = *sa;
+                uint32_t rowbits = 0;
 #pragma unroll
-            for (int u = 0; u < U; ++u) live[u] = q0 + (uint64_t)u * tpb < Q;
-            for (uint32_t r = 0; r < nrows; ++r, o += Q, sa += L4) {
-                const uint4 a = *sa;
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (live[u]) st_out<MODE>(o + (uint64_t)u * tpb, and4(a, b[u]));
+                for (int u = 0; u < U; ++u) {
+                    const VT v = vand(a, b[u]);
+                    if (FOLD != 2 && ((live_bits >> u) & 1u)) __stcs(o + (uint64_t)u * tpb, v);
+                    if (FOLD) rowbits |= unit_fails(v, m) ? (1u << u) : 0u;
+                }
+                if (FOLD) fails = (fails << U) | rowbits;
             }
         }
+        if (FOLD) {
+            // nrows*U <= 64 (launcher); live units repeated for every row
+            const uint32_t nb = nrows * U;
+            const uint64_t all_rows = nb >= 64u ? ~0ull : ((1ull << nb) - 1ull);
+            const uint64_t valid = (all_rows / ((1ull << U) - 1ull)) * (uint64_t)live_bits;
+            cnt += count_group_clear(fails, valid, UPB, k, sFail);
+        }
+    }
+    if (FOLD) publish_cta_count(cnt, &s_cnt, fo);
+}
+
+// Flat kernel: see the head of the file.  Requires UPB | blockDim, blockDim <= Q, Q units of b in shared memory.
+// Step s of the CTA covers units [s*W, (s+1)*W) of the output stream, W = blockDim*U; steps are dealt round-robin
+// over the grid.  (i, q) = (row, unit in row) of the thread's first unit advance by a precomputed (di, dq) per
+// step -- no division in the loop; the thread's U units are blockDim apart and wrap at most once each.
+template <typename VT, int U, int FOLD>
+__global__ void __launch_bounds__(kMulMaxThreads)
+mul_flat_kernel(const VT *__restrict__ A, const VT *__restrict__ B, VT *__restrict__ out, const uint32_t UPB,
+                const uint32_t Q, const uint64_t total_units, const uint64_t n_steps, const uint64_t di,
+                const uint32_t dq, const __grid_constant__ FoldParams fo) {
+    extern __shared__ uint4 smem_raw[];
+    VT *sB = reinterpret_cast<VT *>(smem_raw);
+    uint64_t *sFail = reinterpret_cast<uint64_t *>(sB + Q);
+    __shared__ unsigned long long s_cnt;
+    const uint32_t tpb = blockDim.x;
+    const uint32_t k = threadIdx.x % UPB;
+    const uint64_t W = (uint64_t)tpb * U;
+    VT m = vzero<VT>();
+    if (FOLD) {
+        m = fold_mask_unit<VT>(fo, k);
+        if (threadIdx.x == 0) s_cnt = 0ull;
+    }
+    pdl_enter();
+    for (uint32_t idx = threadIdx.x; idx < Q; idx += tpb) sB[idx] = __ldg(B + idx);
+
+    // (row, unit in row) of this thread's first unit in step blockIdx.x
+    uint64_t i;
+    uint32_t q;
+    {
+        const uint64_t g0 = (uint64_t)blockIdx.x * W + threadIdx.x;
+        i = g0 / Q;                                  // once per thread
+        q = (uint32_t)(g0 - i * Q);
+    }
+    const VT *Ak = A + k;
+    const uint64_t T1 = total_units / Q;
+
+    // a fragments of the current step; the next step's are requested before the current one is stored
+    VT a_cur[U];
+    {
+        uint64_t iu = i;
+        uint32_t qu = q;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            a_cur[u] = iu < T1 ? __ldg(Ak + iu * UPB) : vzero<VT>();
+            qu += tpb;
+            if (qu >= Q) { qu -= Q; ++iu; }
+        }
+    }
+    __syncthreads();
+
+    uint32_t cnt = 0;
+    uint64_t fails = 0;
+    uint32_t nbits = 0;
+    for (uint64_t s = blockIdx.x; s < n_steps; s += gridDim.x) {
+        // next step's position and fragments
+        uint64_t i_n = i + di;
+        uint32_t q_n = q + dq;
+        if (q_n >= Q) { q_n -= Q; ++i_n; }
+        VT a_nxt[U];
+        {
+            uint64_t iu = i_n;
+            uint32_t qu = q_n;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                a_nxt[u] = iu < T1 ? __ldg(Ak + iu * UPB) : vzero<VT>();
+                qu += tpb;
+                if (qu >= Q) { qu -= Q; ++iu; }
+            }
+        }
+        VT *o = out + (s * W + threadIdx.x);
+        uint64_t g = s * W + threadIdx.x;
+        uint32_t qu = q;
+        uint32_t stepbits = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool in = g < total_units;
+            const VT v = vand(a_cur[u], sB[qu]);
+            if (FOLD != 2 && in) __stcs(o, v);
+            if (FOLD) stepbits |= (!in || unit_fails(v, m)) ? (1u << u) : 0u;
+            o += tpb;
+            g += tpb;
+            qu += tpb;
+            if (qu >= Q) qu -= Q;
+        }
+        if (FOLD) {
+            fails = (fails << U) | stepbits;
+            nbits += U;
+            if (nbits + U > 64u) {                   // CTA-uniform: every thread runs the same steps
+                cnt += count_group_clear(fails, nbits >= 64u ? ~0ull : ((1ull << nbits) - 1ull), UPB, k, sFail);
+                __syncthreads();                     // sFail is reused by the next flush
+                fails = 0;
+                nbits = 0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) a_cur[u] = a_nxt[u];
+        i = i_n;
+        q = q_n;
+    }
+    if (FOLD) {
+        if (nbits) cnt += count_group_clear(fails, (1ull << nbits) - 1ull, UPB, k, sFail);
+        publish_cta_count(cnt, &s_cnt, fo);
     }
 }
 
-
-// Any L (odd included), any alignment: one 64-bit word per thread-iteration.
+// Blocks longer than kMulMaxThreads units (N > 65536), any alignment: one 64-bit word per thread-iteration.
 __global__ void __launch_bounds__(256)
 mul_outer_generic_kernel(const uint64_t *__restrict__ A, const uint64_t *__restrict__ B,
                          uint64_t *__restrict__ out, const uint32_t L, const uint64_t row_words,
@@ -133,42 +332,89 @@ mul_outer_generic_kernel(const uint64_t *__restrict__ A, const uint64_t *__restr
     }
 }
 
-template <int U, int MODE>
-cudaError_t launch_v4m(const uint64_t *a, uint64_t T1, const uint64_t *b, uint64_t T2, uint32_t L4,
-                       uint64_t *out, uint32_t tpb, uint32_t R, uint64_t grid_cap, cudaStream_t stream) {
-    const uint64_t Q = T2 * L4;
+void fill_fold_params(FoldParams &fo, const MulFold *fold, uint32_t upb, size_t unit_bytes) {
+    memset(&fo, 0, sizeof fo);
+    if (!fold) return;
+    fo.mask = fold->mask;
+    fo.scratch = fold->scratch;
+    fo.count_out = fold->count_out;
+    if (fold->peer) fo.pp = *fold->peer;
+    if (fold->host_mask && (size_t)upb * unit_bytes <= sizeof(ParamMask)) {
+        memcpy(&fo.pmask, fold->host_mask, (size_t)upb * unit_bytes);
+        fo.mask_in_params = 1;
+    }
+}
+
+template <typename VT, int U, int FOLD>
+cudaError_t launch_tiled_uf(const void *a, uint64_t T1, const void *b, uint64_t Q, uint32_t upb, void *out, uint32_t tpb,
+                            uint32_t R, uint64_t grid_cap, const MulFold *fold, cudaStream_t stream) {
     const uint64_t tile_q = (uint64_t)tpb * U;
     const uint64_t n_col_tiles = (Q + tile_q - 1) / tile_q;
     const uint64_t n_chunks = (T1 + R - 1) / R;
     const uint64_t n_items = n_col_tiles * n_chunks;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, grid_cap);
-    const size_t smem = (size_t)R * L4 * sizeof(uint4);
+    const size_t smem = (size_t)R * upb * sizeof(VT) + (FOLD ? (size_t)tpb * sizeof(uint64_t) : 0);
     // prefetch distance: the chunks that ~two waves of resident CTAs cover
-    const uint64_t ahead_items = (uint64_t)device_props().sm_count * (uint64_t)env_long("CSGN_MUL_PF_CTAS_PER_SM", 8);
-    const uint32_t pf_chunks =
-        env_long("CSGN_MUL_PF_CTAS_PER_SM", 8) > 0 ? (uint32_t)((ahead_items + n_col_tiles - 1) / n_col_tiles) : 0u;
-    return launch_kernel(mul_outer_kernel<U, MODE>, grid, tpb, smem, stream, reinterpret_cast<const uint4 *>(a),
-                         reinterpret_cast<const uint4 *>(b), reinterpret_cast<uint4 *>(out), L4, T1, Q, R,
-                         (uint32_t)n_col_tiles, n_items, pf_chunks);
+    const long pf_per_sm = env_long("CSGN_MUL_PF_CTAS_PER_SM", 8);
+    const uint64_t ahead_items = (uint64_t)device_props().sm_count * (uint64_t)std::max<long>(pf_per_sm, 0);
+    const uint32_t pf_chunks = pf_per_sm > 0 ? (uint32_t)((ahead_items + n_col_tiles - 1) / n_col_tiles) : 0u;
+    FoldParams fo;
+    fill_fold_params(fo, fold, upb, sizeof(VT));
+    return launch_kernel(mul_outer_kernel<VT, U, FOLD>, grid, tpb, smem, stream, static_cast<const VT *>(a),
+                         static_cast<const VT *>(b), static_cast<VT *>(out), upb, T1, Q, R, (uint32_t)n_col_tiles, n_items,
+                         pf_chunks, fo);
 }
 
-template <int U>
-cudaError_t launch_v4(const uint64_t *a, uint64_t T1, const uint64_t *b, uint64_t T2, uint32_t L4,
-                      uint64_t *out, uint32_t tpb, uint32_t R, uint64_t grid_cap, cudaStream_t stream) {
-    switch (env_long("CSGN_MUL_STORE", 0)) {
-        case 1: return launch_v4m<U, 1>(a, T1, b, T2, L4, out, tpb, R, grid_cap, stream);
-        case 2: return launch_v4m<U, 2>(a, T1, b, T2, L4, out, tpb, R, grid_cap, stream);
-        default: return launch_v4m<U, 0>(a, T1, b, T2, L4, out, tpb, R, grid_cap, stream);
+template <typename VT, int U>
+cudaError_t launch_tiled_u(int fold_mode, const void *a, uint64_t T1, const void *b, uint64_t Q, uint32_t upb, void *out,
+                           uint32_t tpb, uint32_t R, uint64_t grid_cap, const MulFold *fold, cudaStream_t stream) {
+    switch (fold_mode) {
+        case 1: return launch_tiled_uf<VT, U, 1>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream);
+        case 2: return launch_tiled_uf<VT, U, 2>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream);
+        default: return launch_tiled_uf<VT, U, 0>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream);
     }
 }
 
-// CTA size for the tiled kernel: a multiple of L4 in [192, cap].  A partial last warp costs
+template <typename VT, int U, int FOLD>
+cudaError_t launch_flat_uf(const void *a, uint64_t T1, const void *b, uint32_t Q, uint32_t upb, void *out, uint32_t tpb,
+                           uint32_t grid_cap, const MulFold *fold, cudaStream_t stream) {
+    const uint64_t total = T1 * (uint64_t)Q;
+    const uint64_t W = (uint64_t)tpb * U;
+    const uint64_t n_steps = (total + W - 1) / W;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(n_steps, grid_cap);
+    const uint64_t delta = (uint64_t)grid * W;
+    const size_t smem = (size_t)Q * sizeof(VT) + (FOLD ? (size_t)tpb * sizeof(uint64_t) : 0);
+    static size_t configured = 0;       // per instantiation
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(mul_flat_kernel<VT, U, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)kFlatMaxSmem + (int)(kMulMaxThreads * sizeof(uint64_t)));
+        if (e != cudaSuccess) return e;
+        configured = kFlatMaxSmem + kMulMaxThreads * sizeof(uint64_t);
+    }
+    FoldParams fo;
+    fill_fold_params(fo, fold, upb, sizeof(VT));
+    return launch_kernel(mul_flat_kernel<VT, U, FOLD>, grid, tpb, smem, stream, static_cast<const VT *>(a),
+                         static_cast<const VT *>(b), static_cast<VT *>(out), upb, Q, total, n_steps, delta / Q,
+                         (uint32_t)(delta % Q), fo);
+}
+
+template <typename VT, int U>
+cudaError_t launch_flat_u(int fold_mode, const void *a, uint64_t T1, const void *b, uint32_t Q, uint32_t upb, void *out,
+                          uint32_t tpb, uint32_t grid_cap, const MulFold *fold, cudaStream_t stream) {
+    switch (fold_mode) {
+        case 1: return launch_flat_uf<VT, U, 1>(a, T1, b, Q, upb, out, tpb, grid_cap, fold, stream);
+        case 2: return launch_flat_uf<VT, U, 2>(a, T1, b, Q, upb, out, tpb, grid_cap, fold, stream);
+        default: return launch_flat_uf<VT, U, 0>(a, T1, b, Q, upb, out, tpb, grid_cap, fold, stream);
+    }
+}
+
+// CTA size for the tiled kernel: a multiple of UPB in [192, cap].  A partial last warp costs
 // issue slots in every item; a ragged last column tile only makes that tile's items shorter
 // (items are scheduled dynamically), so it weighs a quarter.
-uint32_t pick_tpb(uint32_t L4, uint64_t Q, int U, uint32_t cap) {
+uint32_t pick_tpb(uint32_t upb, uint64_t Q, int U, uint32_t cap) {
     uint32_t best = 0;
     double best_cost = 1e30;
-    for (uint32_t t = (cap / L4) * L4; t >= L4 && t > 0; t -= L4) {
+    for (uint32_t t = (cap / upb) * upb; t >= upb && t > 0; t -= upb) {
         const uint64_t tile = (uint64_t)t * U;
         const uint64_t n_tiles = (Q + tile - 1) / tile;
         const double pad = (double)(n_tiles * tile) / (double)Q;
@@ -178,66 +424,119 @@ uint32_t pick_tpb(uint32_t L4, uint64_t Q, int U, uint32_t cap) {
             best_cost = cost;
             best = t;
         }
-        if (t < 192 + L4) break;
+        if (t < 192 + upb) break;
     }
     return best;
 }
 
+// The multiple of `upb` in [lo, hi] that wastes the fewest lanes of a partial warp (largest on ties).
+uint32_t pick_tpb_flat(uint32_t upb, uint32_t lo, uint32_t hi) {
+    uint32_t best = 0;
+    double best_cost = 1e30;
+    for (uint32_t t = (hi / upb) * upb; t >= upb && t >= lo; t -= upb) {
+        const double warp = (double)((t + 31) / 32 * 32) / (double)t;
+        if (warp < best_cost - 1e-9) {
+            best_cost = warp;
+            best = t;
+        }
+    }
+    return best;
+}
+
+template <typename VT>
+cudaError_t launch_units(int fold_mode, const void *a, uint64_t T1, const void *b, uint64_t T2, uint32_t upb, void *out,
+                         const MulFold *fold, cudaStream_t stream) {
+    const DeviceProps &dp = device_props();
+    const uint64_t Q = T2 * upb;
+    const uint32_t tpb_cap = (uint32_t)std::min<long>(kMulMaxThreads, env_long("CSGN_MUL_TPB", 512));
+    const uint64_t out_units = T1 * Q;
+    const bool huge = out_units * sizeof(VT) >= (1ull << 30);     // >= 1 GiB of output
+    const uint64_t grid_cap = (uint64_t)std::min<long>(1l << 23, env_long("CSGN_MUL_GRID", 1l << 23));
+
+    // ---- flat kernel: short right operand, very many rows (chain products) ----
+    const long flat_knob = env_long("CSGN_MUL_FLAT", -1);         // -1: heuristic, 0: never, 1: whenever legal
+    const bool flat_legal = Q * sizeof(VT) <= kFlatMaxSmem && Q >= upb && Q >= 64 && T1 >= 2;
+    const bool flat_wanted = flat_knob > 0 || (flat_knob < 0 && kFlatByDefault && huge && T1 >= 16 * (uint64_t)dp.sm_count);
+    if (flat_legal && flat_wanted) {
+        int U = (int)env_long("CSGN_MUL_FLAT_U", 4);
+        U = U >= 8 ? 8 : U >= 4 ? 4 : U >= 2 ? 2 : 1;
+        uint32_t tpb = pick_tpb_flat(upb, 128, (uint32_t)std::min<uint64_t>(Q, std::min<uint32_t>(tpb_cap, 384)));
+        if (tpb == 0) tpb = pick_tpb_flat(upb, upb, (uint32_t)std::min<uint64_t>(Q, tpb_cap));
+        if (tpb) {
+            const uint32_t per_sm = (uint32_t)std::max<long>(1, env_long("CSGN_MUL_FLAT_CTAS_PER_SM", 4));
+            const uint32_t cap = (uint32_t)std::min<uint64_t>(grid_cap, (uint64_t)dp.sm_count * per_sm);
+            cudaError_t err;
+            switch (U) {
+                case 8: err = launch_flat_u<VT, 8>(fold_mode, a, T1, b, (uint32_t)Q, upb, out, tpb, cap, fold, stream); break;
+                case 4: err = launch_flat_u<VT, 4>(fold_mode, a, T1, b, (uint32_t)Q, upb, out, tpb, cap, fold, stream); break;
+                case 2: err = launch_flat_u<VT, 2>(fold_mode, a, T1, b, (uint32_t)Q, upb, out, tpb, cap, fold, stream); break;
+                default: err = launch_flat_u<VT, 1>(fold_mode, a, T1, b, (uint32_t)Q, upb, out, tpb, cap, fold, stream); break;
+            }
+            return err;
+        }
+    }
+
+    // ---- tiled kernel.  Many small work items balance best, but an item must keep R >= 3 rows per
+    // load of its b tile or the L2 re-reads show.  Units per thread: 1 for rows up to 128 KB
+    // (chains: many rows of a few hundred blocks), 2 beyond, 4 for products of a GiB and more
+    // with long rows.
+    const uint64_t Q16 = Q * sizeof(VT) / 16;                     // thresholds were tuned in 16-byte units
+    int U = (int)env_long("CSGN_MUL_U", Q16 < 8192 ? 1 : (huge && Q16 >= 32768) ? 4 : 2);
+    U = U >= 8 ? 8 : U >= 4 ? 4 : U >= 2 ? 2 : 1;
+    while (U > 1 && (uint64_t)upb * U > Q) U >>= 1;
+    const uint32_t r_smem = std::max<uint32_t>(1, std::min<uint32_t>(64, kMulMaxSmem / (upb * (uint32_t)sizeof(VT))));
+    const uint64_t target_items =
+        (uint64_t)dp.sm_count * (uint64_t)env_long("CSGN_MUL_ITEMS_PER_SM", huge ? 128 : 32);
+    uint32_t tpb = 0;
+    uint64_t R = 1;
+    for (;; U >>= 1) {
+        tpb = pick_tpb(upb, Q, U, tpb_cap);
+        if (tpb == 0) tpb = upb;
+        const uint64_t n_col_tiles = (Q + (uint64_t)tpb * U - 1) / ((uint64_t)tpb * U);
+        R = (T1 * n_col_tiles + target_items - 1) / target_items;
+        if (R >= 3 || U == 1 || env_long("CSGN_MUL_U", 0) > 0) break;
+    }
+    R = (uint64_t)env_long("CSGN_MUL_R", (long)R);
+    uint32_t r_max = r_smem;
+    if (fold_mode) r_max = std::min<uint32_t>(r_max, 64u / (uint32_t)U);      // one 64-bit fail word per thread and item
+    R = std::max<uint64_t>(1, std::min<uint64_t>(R, std::min<uint64_t>(r_max, T1)));
+
+    switch (U) {
+        case 8: return launch_tiled_u<VT, 8>(fold_mode, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream);
+        case 4: return launch_tiled_u<VT, 4>(fold_mode, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream);
+        case 2: return launch_tiled_u<VT, 2>(fold_mode, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream);
+        default: return launch_tiled_u<VT, 1>(fold_mode, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream);
+    }
+}
+
 }  // namespace
 
+bool mul_fold_supported(uint32_t L) { return L != 0 && ((L & 1u) ? L : L / 2) <= (uint32_t)kMulMaxThreads; }
+
 cudaError_t launch_mul(const uint64_t *a, uint64_t T1, const uint64_t *b, uint64_t T2, uint32_t L,
-                       uint64_t *out, cudaStream_t stream) {
+                       uint64_t *out, cudaStream_t stream, const MulFold *fold) {
     if (T1 == 0 || T2 == 0 || L == 0) return cudaSuccess;
-    const DeviceProps &dp = device_props();
-    const bool aligned = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
-                           reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
-    const uint32_t L4 = L / 2;
-    if ((L & 1u) || !aligned || L4 > (uint32_t)kMulMaxThreads || env_long("CSGN_MUL_GENERIC", 0)) {
+    const int fold_mode = fold ? (out ? 1 : 2) : 0;
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
+                             reinterpret_cast<uintptr_t>(out) | (fold ? reinterpret_cast<uintptr_t>(fold->mask) : 0)) & 15u) == 0;
+    const bool units16 = !(L & 1u) && aligned16;
+    const uint32_t upb = units16 ? L / 2 : L;
+    if (upb > (uint32_t)kMulMaxThreads || env_long("CSGN_MUL_GENERIC", 0)) {
+        if (fold) return cudaErrorNotSupported;      // the caller multiplies, then folds (two launches)
+        const DeviceProps &dp = device_props();
         const uint64_t row_words = T2 * L, total = T1 * row_words;
         const uint64_t want = (total + 255) / 256;
         const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)dp.sm_count * 16);
         count_launch();
         return launch_kernel(mul_outer_generic_kernel, grid, 256, 0, stream, a, b, out, L, row_words, total);
     }
-
-    const uint64_t Q = T2 * L4;
     if (T2 == 1 && T1 > 1 && !env_long("CSGN_MUL_NOSWAP", 0)) {
         // a (T1 blocks) x one block is, as a word stream, that block x a (out[i] = a_i & b_0
         // either way) -- and the swapped form is one long row instead of T1 tiny ones
-        return launch_mul(b, 1, a, T1, L, out, stream);
+        return launch_mul(b, 1, a, T1, L, out, stream, fold);
     }
-    const uint32_t tpb_cap = (uint32_t)env_long("CSGN_MUL_TPB", 512);
-    // Tiled kernel.  Many small work items balance best, but an item must keep R >= 3 rows per
-    // load of its b tile or the L2 re-reads show.  Units per thread: 1 for rows up to 128 KB
-    // (chains: many rows of a few hundred blocks), 2 beyond, 4 for products of a GiB and more
-    // with long rows.
-    const bool huge = T1 * Q >= (1ull << 26);     // >= 1 GiB of output
-    int U = (int)env_long("CSGN_MUL_U", Q < 8192 ? 1 : (huge && Q >= 32768) ? 4 : 2);
-    U = U >= 8 ? 8 : U >= 4 ? 4 : U >= 2 ? 2 : 1;
-    while (U > 1 && (uint64_t)L4 * U > Q) U >>= 1;
-    const uint32_t r_max = std::max<uint32_t>(1, std::min<uint32_t>(64, kMulMaxSmem / (L4 * 16)));
-    const uint64_t target_items =
-        (uint64_t)dp.sm_count * (uint64_t)env_long("CSGN_MUL_ITEMS_PER_SM", huge ? 128 : 32);
-    uint32_t tpb = 0;
-    uint64_t R = 1;
-    for (;; U >>= 1) {
-        tpb = pick_tpb(L4, Q, U, tpb_cap);
-        if (tpb == 0) tpb = L4;
-        const uint64_t n_col_tiles = (Q + (uint64_t)tpb * U - 1) / ((uint64_t)tpb * U);
-        R = (T1 * n_col_tiles + target_items - 1) / target_items;
-        if (R >= 3 || U == 1 || env_long("CSGN_MUL_U", 0) > 0) break;
-    }
-    R = (uint64_t)env_long("CSGN_MUL_R", (long)R);
-    R = std::max<uint64_t>(1, std::min<uint64_t>(R, std::min<uint64_t>(r_max, T1)));
-    const uint64_t grid_cap = (uint64_t)env_long("CSGN_MUL_GRID", 1 << 30);
-
-    cudaError_t err;
-    switch (U) {
-        case 8: err = launch_v4<8>(a, T1, b, T2, L4, out, tpb, (uint32_t)R, grid_cap, stream); break;
-        case 4: err = launch_v4<4>(a, T1, b, T2, L4, out, tpb, (uint32_t)R, grid_cap, stream); break;
-        case 2: err = launch_v4<2>(a, T1, b, T2, L4, out, tpb, (uint32_t)R, grid_cap, stream); break;
-        default: err = launch_v4<1>(a, T1, b, T2, L4, out, tpb, (uint32_t)R, grid_cap, stream); break;
-    }
+    const cudaError_t err = units16 ? launch_units<uint4>(fold_mode, a, T1, b, T2, upb, out, fold, stream)
+                                    : launch_units<uint2>(fold_mode, a, T1, b, T2, upb, out, fold, stream);
     count_launch();
     return err;
 }

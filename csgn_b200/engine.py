@@ -52,6 +52,20 @@ def set_stream(cuda_stream_ptr):
     check(_lib().csgn_set_stream(_vp(cuda_stream_ptr or 0)))
 
 
+def set_auto_lanes(on):
+    """csgn_set_auto_lanes: the library spreads consecutive independent operations over its internal streams."""
+    check(_lib().csgn_set_auto_lanes(1 if on else 0))
+
+
+def version():
+    return _lib().csgn_version().decode()
+
+
+def has_variants():
+    """True when libcsgn.so was built with -DCSGN_BUILD_VARIANTS (the losing kernel variants kept for A/B sweeps)."""
+    return "+variants" in version()
+
+
 def device_info():
     sm, cc = ctypes.c_int(), ctypes.c_int()
     tot, fr = ctypes.c_uint64(), ctypes.c_uint64()
@@ -268,6 +282,49 @@ def mul_batch(a, b):
     return [Ciphertext(_vp(out[i]), a[i].ctx) for i in range(n)]
 
 
+def mul_count_batch_async(key, a, b, device_counts_ptr, out=None, arrays=None):
+    """csgn_mul_count_batch_async: the fused multiply -> decrypt of n independent pairs.  out = None: count only;
+    out = list of Ciphertexts: the products are written into them; out = "alloc": the library allocates them and
+    the list is returned.  `arrays` = (handle_array(a), handle_array(b), handle_array(out) or None) skips marshalling."""
+    if arrays is not None:
+        aa, ab, ao = arrays
+    else:
+        aa, ab = handle_array(a), handle_array(b)
+        ao = None if out is None else ((_vp * len(aa))() if out == "alloc" else handle_array(out))
+    rc = _LIB.csgn_mul_count_batch_async(aa, ab, len(aa), key._h, ao, device_counts_ptr)
+    if rc:
+        check(rc)
+    if arrays is None and out == "alloc":
+        return [Ciphertext(_vp(ao[i]), a[i].ctx) for i in range(len(aa))]
+    return None
+
+
+class Result:
+    """A decrypt whose count the host reads later (csgn_result)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    def ready(self):
+        return bool(_lib().csgn_result_ready(self._h))
+
+    def count(self):
+        c = ctypes.c_uint64()
+        check(_lib().csgn_result_wait(self._h, ctypes.byref(c)))
+        return int(c.value)
+
+    def bit(self):
+        return self.count() & 1
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _LIB is not None:
+            try:
+                _LIB.csgn_result_free(h)
+            except Exception:
+                pass
+
+
 class SecretKey:
     """Secret positions held as a device position mask (csgn_key)."""
 
@@ -294,6 +351,45 @@ class SecretKey:
         c = ctypes.c_uint64()
         check(_lib().csgn_decrypt_count(ct._h, self._h, ctypes.byref(c)))
         return int(c.value)
+
+    def decrypt_deferred(self, ct):
+        """csgn_decrypt_deferred: enqueue the fold and the copy of its count; read it later from the Result."""
+        h = _vp()
+        check(_lib().csgn_decrypt_deferred(ct._h, self._h, ctypes.byref(h)))
+        return Result(h)
+
+    def mul_decrypt(self, a, b, out=None):
+        """csgn_mul_decrypt: Dec(a*b) by the fused kernel.  out = None: count only -> (bit, count);
+        out = "alloc": -> (bit, count, product); out = Ciphertext: the product is written into it."""
+        bit, cnt = ctypes.c_uint8(), ctypes.c_uint64()
+        if out is None:
+            check(_lib().csgn_mul_decrypt(a._h, b._h, self._h, None, ctypes.byref(bit), ctypes.byref(cnt)))
+            return int(bit.value), int(cnt.value)
+        h = _vp() if isinstance(out, str) else _vp(out._h.value if isinstance(out._h, _vp) else out._h)
+        check(_lib().csgn_mul_decrypt(a._h, b._h, self._h, ctypes.byref(h), ctypes.byref(bit), ctypes.byref(cnt)))
+        if isinstance(out, str):
+            return int(bit.value), int(cnt.value), Ciphertext(h, a.ctx)
+        return int(bit.value), int(cnt.value)
+
+    def mul_count_async(self, a, b, device_count_ptr, out=None):
+        """csgn_mul_count_async into a device word; out as in mul_decrypt (None / Ciphertext)."""
+        if out is None:
+            rc = _LIB.csgn_mul_count_async(a._h, b._h, self._h, None, device_count_ptr)
+        else:
+            h = _vp(out._h.value if isinstance(out._h, _vp) else out._h)
+            rc = _LIB.csgn_mul_count_async(a._h, b._h, self._h, ctypes.byref(h), device_count_ptr)
+        if rc:
+            check(rc)
+
+    def mul_decrypt_deferred(self, a, b, want_product=False):
+        """csgn_mul_decrypt_deferred -> Result, or (Result, product)."""
+        r = _vp()
+        if not want_product:
+            check(_lib().csgn_mul_decrypt_deferred(a._h, b._h, self._h, None, ctypes.byref(r)))
+            return Result(r)
+        h = _vp()
+        check(_lib().csgn_mul_decrypt_deferred(a._h, b._h, self._h, ctypes.byref(h), ctypes.byref(r)))
+        return Result(r), Ciphertext(h, a.ctx)
 
     def encrypt_batch(self, bits, seed, first_block=0):
         """n fresh blocks on the GPU, block i encrypting bits[i] (csgn_encrypt_batch, Philox keyed by seed)."""
@@ -389,6 +485,26 @@ class PeerComm:
         launch publishes all of them and collects the len(cts) pushes that end `lag` pushes earlier."""
         arr = array or handle_array(cts)
         rc = _LIB.csgn_decrypt_sharded_batch_async(arr, len(arr), key._h, self._h, lag, device_totals_ptr)
+        if rc:
+            check(rc)
+
+    def mul_push(self, key, a, b, out=None, collect_n=0, device_totals_ptr=0, device_local_ptr=0, lag=0):
+        """csgn_mul_decrypt_sharded_async: multiply this rank's shard by the replicated b, fold and exchange in one
+        kernel.  out = None: count only; out = Ciphertext: the product shard is written into it."""
+        if out is None:
+            rc = _LIB.csgn_mul_decrypt_sharded_async(a._h, b._h, key._h, None, self._h, collect_n, lag,
+                                                     device_totals_ptr or None, device_local_ptr or None)
+        else:
+            h = _vp(out._h.value if isinstance(out._h, _vp) else out._h)
+            rc = _LIB.csgn_mul_decrypt_sharded_async(a._h, b._h, key._h, ctypes.byref(h), self._h, collect_n, lag,
+                                                     device_totals_ptr or None, device_local_ptr or None)
+        if rc:
+            check(rc)
+
+    def mul_push_batch(self, key, arrays, device_totals_ptr, lag=0):
+        """csgn_mul_decrypt_sharded_batch_async; arrays = (handle_array(a), handle_array(b), handle_array(out) or None)."""
+        aa, ab, ao = arrays
+        rc = _LIB.csgn_mul_decrypt_sharded_batch_async(aa, ab, len(aa), key._h, ao, self._h, lag, device_totals_ptr)
         if rc:
             check(rc)
 

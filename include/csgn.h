@@ -67,6 +67,17 @@ int csgn_device_info(int *sm_count, uint64_t *hbm_total, uint64_t *hbm_free, int
  * library's own stream. */
 int csgn_set_stream(void *cuda_stream);
 void *csgn_get_stream(void);
+/* Automatic lanes (off by default; CSGN_AUTO_LANES=1 or Library::setAutoLanes in C++).  The reference's API has no
+ * batch calls: a user writes a loop over Ciphertext::operator* (src/Ciphertext.cpp:231-247) and SecretKey::decrypt
+ * (src/SecretKey.cpp:208-224).  With automatic lanes the library itself places consecutive INDEPENDENT operations
+ * (csgn_mul, csgn_mul_into / csgn_permute_into with a library-owned output, csgn_concat, csgn_append, csgn_permute,
+ * csgn_buf_clone / _slice, csgn_decrypt_deferred, csgn_mul_decrypt_deferred) on alternating internal streams, so
+ * that the tail of one kernel overlaps the ramp of the next; operations that depend on each other through a buffer
+ * are ordered by per-buffer last-writer / reader tracking and stay on one stream.  Calls that hand device memory to
+ * the caller (csgn_buf_device_ptr, *_async with a caller-owned destination) run on, or are joined into, the current
+ * stream, and csgn_sync waits for the lanes as well. */
+int csgn_set_auto_lanes(int on);
+int csgn_get_auto_lanes(void);
 int csgn_sync(void);
 /* Kernels launched by this library since csgn_init (for bench.py's gpu_launches). */
 uint64_t csgn_launch_count(void);
@@ -81,8 +92,14 @@ int csgn_host_free(void *p);
 /* ---- ciphertext buffers (storage behind certFHE::Ciphertext, src/Ciphertext.h:17-21) */
 
 /* Deep-copies n_blocks*L host words to the device: the Ciphertext(V,Bitlen,len,ctx)
- * constructor / setValues (src/Ciphertext.cpp:344-358, :392-403). */
+ * constructor / setValues (src/Ciphertext.cpp:344-358, :392-403).  Asynchronous: `host_words` (ideally pinned) must
+ * stay valid and unchanged until the copy has run (csgn_sync, or any blocking call on a consumer of the buffer). */
 int csgn_buf_upload(const uint64_t *host_words, uint64_t n_blocks, uint32_t L, csgn_buf **out);
+/* The same with the reference constructor's ownership contract and no synchronisation: the words are copied into
+ * library-owned pinned staging by the host before the call returns (the caller may free or overwrite its array at
+ * once), and travel to the device from there, asynchronously.  Uploads beyond 64 MB copy straight from the caller's
+ * memory and wait. */
+int csgn_buf_upload_copy(const uint64_t *host_words, uint64_t n_blocks, uint32_t L, csgn_buf **out);
 /* Uninitialised device storage for n_blocks blocks. */
 int csgn_buf_alloc(uint64_t n_blocks, uint32_t L, csgn_buf **out);
 /* Non-owning view over caller-owned device memory (e.g. a torch tensor). */
@@ -138,6 +155,36 @@ int csgn_decrypt_count_async(const csgn_buf *c, const csgn_key *key, uint64_t *d
  * *count (optional) the product of the counts, saturated at UINT64_MAX. */
 int csgn_decrypt_product(const csgn_buf *const *factors, uint32_t n_factors, const csgn_key *key, uint8_t *bit,
                          uint64_t *count);
+/* A decrypt whose result the host reads later: the fold and the device-to-host copy of its count are enqueued and the
+ * call returns at once; csgn_result_wait blocks until the count has landed (and may be called again), csgn_result_ready
+ * polls, csgn_result_free releases the slot.  This is what lets a loop over SecretKey::decrypt run without one host
+ * synchronisation per ciphertext -- certFHE::Plaintext resolves its value on first use (csgn_b200/certfhe). */
+typedef struct csgn_result csgn_result;
+int csgn_decrypt_deferred(const csgn_buf *c, const csgn_key *key, csgn_result **out);
+int csgn_result_ready(const csgn_result *r);
+int csgn_result_wait(csgn_result *r, uint64_t *count);
+int csgn_result_free(csgn_result *r);
+
+/* ---- fused multiply -> decrypt (the caller pattern tests/basic_operations.cpp:35-40: operator*, then
+ * SecretKey::decrypt of the product).  ONE kernel writes the product a*b (src/Ciphertext.cpp:153-163) and evaluates
+ * the decrypt predicate (src/SecretKey.cpp:131-140) on the product words while they are still in registers: one pass
+ * over HBM (the product is written, never read back) instead of two.
+ * The `out` convention of every entry point below:  out == NULL  -> count only, nothing is stored (decrypt-only
+ * consumers);  *out == NULL -> the product is allocated by the library and returned in *out;  otherwise the product
+ * is written into *out, which must hold exactly T1*T2 blocks (a view from csgn_buf_wrap included).
+ * The count of satisfied product blocks goes to a device uint64 (decrypt = count & 1); no host synchronisation. */
+int csgn_mul_count_async(const csgn_buf *a, const csgn_buf *b, const csgn_key *key, csgn_buf **out, uint64_t *device_count);
+/* Blocking convenience: *bit = Dec(a*b), *count (optional) the satisfied-block count. */
+int csgn_mul_decrypt(const csgn_buf *a, const csgn_buf *b, const csgn_key *key, csgn_buf **out, uint8_t *bit,
+                     uint64_t *count);
+/* n independent pairs in one call, spread over the library's lanes (see "batches" below); out may be NULL (count only)
+ * or an array of n handles following the convention above entry by entry. */
+int csgn_mul_count_batch_async(const csgn_buf *const *a, const csgn_buf *const *b, uint32_t n, const csgn_key *key,
+                               csgn_buf **out, uint64_t *device_counts);
+/* Deferred form (see csgn_decrypt_deferred); `prod` follows the `out` convention. */
+int csgn_mul_decrypt_deferred(const csgn_buf *a, const csgn_buf *b, const csgn_key *key, csgn_buf **prod,
+                              csgn_result **out);
+
 /* ---- batches of independent items -------------------------------------------------------------
  * n independent products / folds in ONE call: what a caller of the reference writes as a loop over
  * Ciphertext::operator* (src/Ciphertext.cpp:231-247) or SecretKey::decrypt (src/SecretKey.cpp:208-224).  The library forks its internal lane streams (CSGN_LANES, default 2)
@@ -251,6 +298,15 @@ int csgn_decrypt_sharded_async(const csgn_buf *c, const csgn_key *key, csgn_comm
  * publishes all n and collects the n pushes that end collect_lag pushes earlier (0: this batch) into device_totals. */
 int csgn_decrypt_sharded_batch_async(const csgn_buf *const *c, uint32_t n, const csgn_key *key, csgn_comm *comm,
                                      uint32_t collect_lag, uint64_t *device_totals);
+/* Fused multiply -> sharded decrypt: multiply this rank's shard a (its block range of the left operand) by the
+ * replicated b, fold the product AND do the cross-GPU exchange in ONE kernel -- compute, reduction and collective
+ * tile by tile in a single launch.  Arguments as csgn_decrypt_sharded_async, `out` as in csgn_mul_count_async. */
+int csgn_mul_decrypt_sharded_async(const csgn_buf *a, const csgn_buf *b, const csgn_key *key, csgn_buf **out,
+                                   csgn_comm *comm, uint32_t collect_n, uint32_t collect_lag, uint64_t *device_totals,
+                                   uint64_t *device_local);
+int csgn_mul_decrypt_sharded_batch_async(const csgn_buf *const *a, const csgn_buf *const *b, uint32_t n,
+                                         const csgn_key *key, csgn_buf **out, csgn_comm *comm, uint32_t collect_lag,
+                                         uint64_t *device_totals);
 /* Enqueue a publish + collect on its own (one small launch): the n pushes ending lag pushes before
  * the most recent one. */
 int csgn_comm_collect_async(csgn_comm *comm, uint32_t n, uint32_t lag, uint64_t *device_totals);

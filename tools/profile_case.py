@@ -52,6 +52,9 @@ def main():
     comm.push(key, vo[0])
     comm.push(key, vo[1 % nbuf], 2, tot.data_ptr())
     vo[0].permute_into(perm, vo[1])
+    # the fused multiply -> decrypt (product written and folded in one launch), and its count-only form
+    key.mul_count_async(va, vb, cnt.data_ptr(), out=vo[2 % nbuf])
+    key.mul_count_async(va, vb, cnt.data_ptr())
     fresh = key.encrypt_batch(np.random.default_rng(9).integers(0, 2, size=T1 * T2).astype(np.uint8), seed=1)
     s = va + vb
     torch.cuda.synchronize()
