@@ -20,10 +20,11 @@
 // b is re-read from L2 once per R rows, so L2 read traffic is 1/R of the write
 // stream; no integer division happens inside the row loop.
 //
-// Flat kernel (mul_flat_kernel), for products with a short right operand and very many rows (chains:
-// (a*b)*d with a fresh d): the whole of b sits in shared memory, the output is walked as ONE flat stream in
-// grid-stride steps -- at any moment the resident CTAs write one compact, advancing window of the product, the
-// access pattern of a memset -- and the a fragments a step needs are fetched one step ahead.
+// Chains ((a*b)*d with a fresh, short d: 10^6 rows of a few thousand units) use the same kernel with few rows per
+// item, so that the resident CTAs write one compact, advancing window of the product (7.1 TB/s on a 20 GB product).
+// A flat kernel (b resident in shared memory, the output walked as ONE stream in grid-stride steps, a fragments
+// fetched a step ahead: mul_flat_kernel, built only with -DCSGN_BUILD_VARIANTS) was measured against it on both chain
+// shapes and never won (profiles/r2_sweep_chain.log): 6.4-6.5 TB/s at best.
 //
 // Fused multiply -> fold (FOLD != 0): SecretKey::decrypt of the product (reference src/SecretKey.cpp:131-140,
 // the caller pattern tests/basic_operations.cpp:35-40) evaluated on the product units while they are still in
@@ -43,8 +44,10 @@ namespace {
 
 constexpr int kMulMaxThreads = 512;
 constexpr uint32_t kMulMaxSmem = 32 * 1024;
+#ifdef CSGN_BUILD_VARIANTS
 constexpr uint32_t kFlatMaxSmem = 64 * 1024;     // right operand resident in shared memory
-constexpr bool kFlatByDefault = false;           // chain shapes take the flat kernel without being asked (measured: profiles/)
+constexpr bool kFlatByDefault = false;           // never: the tiled kernel with few rows per item wins on every chain shape
+#endif
 
 __device__ __forceinline__ uint4 vand(const uint4 a, const uint4 b) {
     return make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w);
@@ -213,6 +216,7 @@ mul_outer_kernel(const VT *__restrict__ A, const VT *__restrict__ B, VT *__restr
     if (FOLD) publish_cta_count(cnt, &s_cnt, fo);
 }
 
+#ifdef CSGN_BUILD_VARIANTS
 // Flat kernel: see the head of the file.  Requires UPB | blockDim, blockDim <= Q, Q units of b in shared memory.
 // Step s of the CTA covers units [s*W, (s+1)*W) of the output stream, W = blockDim*U; steps are dealt round-robin
 // over the grid.  (i, q) = (row, unit in row) of the thread's first unit advance by a precomputed (di, dq) per
@@ -317,6 +321,8 @@ mul_flat_kernel(const VT *__restrict__ A, const VT *__restrict__ B, VT *__restri
     }
 }
 
+#endif  // CSGN_BUILD_VARIANTS
+
 // Blocks longer than kMulMaxThreads units (N > 65536), any alignment: one 64-bit word per thread-iteration.
 __global__ void __launch_bounds__(256)
 mul_outer_generic_kernel(const uint64_t *__restrict__ A, const uint64_t *__restrict__ B,
@@ -375,6 +381,7 @@ cudaError_t launch_tiled_u(int fold_mode, const void *a, uint64_t T1, const void
     }
 }
 
+#ifdef CSGN_BUILD_VARIANTS
 template <typename VT, int U, int FOLD>
 cudaError_t launch_flat_uf(const void *a, uint64_t T1, const void *b, uint32_t Q, uint32_t upb, void *out, uint32_t tpb,
                            uint32_t grid_cap, const MulFold *fold, cudaStream_t stream) {
@@ -408,6 +415,8 @@ cudaError_t launch_flat_u(int fold_mode, const void *a, uint64_t T1, const void 
     }
 }
 
+#endif  // CSGN_BUILD_VARIANTS
+
 // CTA size for the tiled kernel: a multiple of UPB in [192, cap].  A partial last warp costs
 // issue slots in every item; a ragged last column tile only makes that tile's items shorter
 // (items are scheduled dynamically), so it weighs a quarter.
@@ -429,6 +438,7 @@ uint32_t pick_tpb(uint32_t upb, uint64_t Q, int U, uint32_t cap) {
     return best;
 }
 
+#ifdef CSGN_BUILD_VARIANTS
 // The multiple of `upb` in [lo, hi] that wastes the fewest lanes of a partial warp (largest on ties).
 uint32_t pick_tpb_flat(uint32_t upb, uint32_t lo, uint32_t hi) {
     uint32_t best = 0;
@@ -443,6 +453,8 @@ uint32_t pick_tpb_flat(uint32_t upb, uint32_t lo, uint32_t hi) {
     return best;
 }
 
+#endif  // CSGN_BUILD_VARIANTS
+
 template <typename VT>
 cudaError_t launch_units(int fold_mode, const void *a, uint64_t T1, const void *b, uint64_t T2, uint32_t upb, void *out,
                          const MulFold *fold, cudaStream_t stream) {
@@ -453,6 +465,7 @@ cudaError_t launch_units(int fold_mode, const void *a, uint64_t T1, const void *
     const bool huge = out_units * sizeof(VT) >= (1ull << 30);     // >= 1 GiB of output
     const uint64_t grid_cap = (uint64_t)std::min<long>(1l << 23, env_long("CSGN_MUL_GRID", 1l << 23));
 
+#ifdef CSGN_BUILD_VARIANTS
     // ---- flat kernel: short right operand, very many rows (chain products) ----
     const long flat_knob = env_long("CSGN_MUL_FLAT", -1);         // -1: heuristic, 0: never, 1: whenever legal
     const bool flat_legal = Q * sizeof(VT) <= kFlatMaxSmem && Q >= upb && Q >= 64 && T1 >= 2;
@@ -476,6 +489,8 @@ cudaError_t launch_units(int fold_mode, const void *a, uint64_t T1, const void *
         }
     }
 
+#endif  // CSGN_BUILD_VARIANTS
+
     // ---- tiled kernel.  Many small work items balance best, but an item must keep R >= 3 rows per
     // load of its b tile or the L2 re-reads show.  Units per thread: 1 for rows up to 128 KB
     // (chains: many rows of a few hundred blocks), 2 beyond, 4 for products of a GiB and more
@@ -496,6 +511,11 @@ cudaError_t launch_units(int fold_mode, const void *a, uint64_t T1, const void *
         R = (T1 * n_col_tiles + target_items - 1) / target_items;
         if (R >= 3 || U == 1 || env_long("CSGN_MUL_U", 0) > 0) break;
     }
+    // B200 sweeps (tools/r2_sweep.py rsel, profiles/r2_rsel.log).  Chains -- very many short rows -- write fastest when
+    // the resident CTAs cover a compact window of the product: few rows per item.  A fused item pays one cross-thread
+    // reduction however many rows it has, so it wants 12-16 of them on every shape measured.
+    if (huge && U == 1) R = std::min<uint64_t>(R, 4);
+    if (fold_mode) R = std::max<uint64_t>(12, std::min<uint64_t>(R, 16));
     R = (uint64_t)env_long("CSGN_MUL_R", (long)R);
     uint32_t r_max = r_smem;
     if (fold_mode) r_max = std::min<uint32_t>(r_max, 64u / (uint32_t)U);      // one 64-bit fail word per thread and item

@@ -185,6 +185,38 @@ def sec_shapes():
     print(json.dumps([{**r, **{"frac_" + k: v for k, v in f.items()}} for r, f in rows]))
 
 
+
+
+def sec_rsel():
+    """rows per item (R) for the plain and the fused multiply over the shapes the launcher has to choose for"""
+    shapes = [("cfg2 1000x1000", 1247, 16, 1000, 1000, 16), ("N=1247 10000x1000 (1.6 GB)", 1247, 16, 10000, 1000, 2),
+              ("N=1247 1000x10000 (1.6 GB)", 1247, 16, 1000, 10000, 2),
+              ("cfg5 300x300", 16383, 64, 300, 300, 12), ("cfg5 1000x1000 (2 GB)", 16383, 64, 1000, 1000, 2),
+              ("cfg5 2000x2000 (8.2 GB)", 16383, 64, 2000, 2000, 1), ("chain25 (4 GB)", 1247, 16, 1000000, 25, 2),
+              ("chain125 (20 GB)", 1247, 16, 1000000, 125, 1), ("N=191 3000x3000", 191, 4, 3000, 3000, 8),
+              ("N=4097 560x560", 4097, 16, 560, 560, 12), ("N=33000 200x200", 33000, 64, 200, 200, 12)]
+    for name, N, D, T1, T2, P in shapes:
+        ctx, L, va, vb, vo, key, cnt, keep = setup(N, D, T1, T2, P)
+        nb = T1 * T2 * L * 8
+        reps = 5 if nb < 1e9 else 2
+        print("# %s: %.1f MB per product, %d buffers" % (name, nb / 1e6, P))
+        for R in (0, 2, 3, 4, 6, 8, 12, 16, 24, 32, 64):
+            for U in ((0,) if R == 0 else (0, 1, 2, 4)):
+                kn = {}
+                if R:
+                    kn["CSGN_MUL_R"] = R
+                if U:
+                    kn["CSGN_MUL_U"] = U
+                setenv(**kn)
+                m = timed(lambda i: va[i].mul_into(vb[i], vo[i]), P, reps=reps)
+                f = timed(lambda i: key.mul_count_async(va[i], vb[i], cnt.data_ptr() + 8 * i, out=vo[i]), P, reps=reps)
+                print("  R=%-3s U=%-2s  multiply %9.2f us %.3f | fused %9.2f us %.3f" %
+                      (R or "dflt", U or "d", m[0], nb / m[0] / 1e3 / PEAK, f[0], nb / f[0] / 1e3 / PEAK), flush=True)
+        setenv()
+        del va, vb, vo, keep
+        torch.cuda.empty_cache()
+
+
 if __name__ == "__main__":
     for which in (sys.argv[1:] or ["fused", "chain", "shapes"]):
-        {"fused": sec_fused, "chain": sec_chain, "shapes": sec_shapes}[which]()
+        {"fused": sec_fused, "chain": sec_chain, "shapes": sec_shapes, "rsel": sec_rsel}[which]()
