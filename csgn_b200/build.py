@@ -152,11 +152,26 @@ def build_reference_demos(force=False, verbose=False):
     return outs
 
 
+def build_tools(force=False, verbose=False):
+    """tools/bin/cpp_e2e: the bench step through the C++ drop-in API (bench.py reports it as e2e_cpp)."""
+    src = os.path.join(ROOT, "tools", "cpp_e2e.cpp")
+    if not os.path.exists(src) or not os.path.exists(libcertfhe_path()):
+        return []
+    bindir = os.path.join(ROOT, "tools", "bin")
+    os.makedirs(bindir, exist_ok=True)
+    out = os.path.join(bindir, "cpp_e2e")
+    if force or _stale(out, [src, libcertfhe_path()] + glob.glob(os.path.join(CERTFHE, "*.h"))):
+        _run(["g++", "-O2", "-std=c++11", "-Wall", "-I" + CERTFHE, "-I" + INCLUDE, "-o", out, src, "-L" + LIBDIR,
+              "-lcertFHE", "-lcsgn", "-Wl,-rpath,$ORIGIN/../../csgn_b200/lib"], verbose)
+    return [out]
+
+
 def build_all(force=False, verbose=False):
     build_libcsgn(force, verbose)
     build_libcertfhe(force, verbose)
     build_cpp_tests(force, verbose)
     build_reference_demos(force, verbose)
+    build_tools(force, verbose)
 
 
 if __name__ == "__main__":

@@ -29,6 +29,7 @@
 struct csgn_buf;
 struct csgn_key;
 struct csgn_perm;
+struct csgn_result;
 
 namespace certFHE {
 
@@ -65,6 +66,22 @@ public:
     // 10^9-block chain that is only ever decrypted never touches 160 GB of HBM.
     static void setLazyProducts(bool lazy);
     static bool getLazyProducts();
+    // Fused products (ON by default; CSGN_FUSED_PRODUCTS=0 or setFusedProducts(false) gives one kernel per operator,
+    // as in the first release).  The reference's callers multiply and then decrypt (tests/basic_operations.cpp:35-40:
+    // `c = a * b; sk.decrypt(c)`).  With fused products operator* / *= only note their operands; the product is
+    // written by the first operation that needs its words -- and when that operation is SecretKey::decrypt, ONE
+    // kernel writes the product and evaluates the decrypt predicate on the product words while they are in registers
+    // (csgn_mul_decrypt_deferred): one pass over HBM instead of a write and a read.  The product is kept, so
+    // anything that follows (getValues, +, applyPermutation, another decrypt) sees the same words as before.
+    static void setFusedProducts(bool fused);
+    static bool getFusedProducts();
+    // Automatic lanes (ON by default in this API; CSGN_AUTO_LANES=0 or setAutoLanes(false) keeps one stream).  A loop
+    // over operator* / decrypt of independent ciphertexts is spread over the engine's internal streams, so that the
+    // tail of one kernel overlaps the ramp of the next (csgn_set_auto_lanes); operations that touch the same
+    // ciphertext stay ordered.  Together with the deferred Plaintext below this gives plain reference-style code the
+    // overlap that the batch entry points give.
+    static void setAutoLanes(bool on);
+    static bool getAutoLanes();
     // Multi-GPU, one process per GPU.  connectPeers joins the `world` processes of a job: every
     // rank publishes the handle of its mailbox under rendezvous_dir (csgn_comm_connect_dir; `job_tag` unique per
     // job) and maps the others' over NVLink.  initializeLibrary() does this by itself when the launcher exports
@@ -108,7 +125,13 @@ public:
 
 // ---- Plaintext (reference src/Plaintext.h:14-46) --------------------------------------
 class Plaintext {
-    unsigned char value;
+    mutable unsigned char value;
+    // SecretKey::decrypt returns at once: the fold and the copy of its count are enqueued on the GPU and the value is
+    // read when somebody asks for it (getValue, operator<<).  A loop of decrypts therefore costs one host
+    // synchronisation at the first read instead of one per ciphertext.  Copies share the pending result.
+    mutable std::shared_ptr<csgn_result> pending;
+    void resolve() const;
+    friend class SecretKey;
 
 public:
     Plaintext();
@@ -155,8 +178,12 @@ class Ciphertext {
     // Device-resident blocks.  Buffers are immutable once shared, so copies share them
     // (the reference deep-copies on every by-value return); += clones first if shared.
     mutable std::shared_ptr<csgn_buf> dev;
-    // Non-empty: the value is the product of these buffers, not multiplied out (lazy mode).
+    // Non-empty: the value is the product of these buffers, not written yet (fused mode: exactly two, written by the
+    // first operation that needs the words; lazy mode: any number, never written by decrypt / applyPermutation).
     mutable std::vector<std::shared_ptr<csgn_buf> > factors;
+    // Shared by the copies of one pending product: whichever copy writes the product first leaves it here, the
+    // others pick it up instead of multiplying again.
+    mutable std::shared_ptr<std::shared_ptr<csgn_buf> > product_slot;
     Context *certFHEcontext;   // context of encryption (null for a default-constructed object)
     mutable uint64_t *host_v;  // host mirror of the words / host staging before upload
     mutable uint64_t *host_bitlen;
@@ -169,7 +196,10 @@ class Ciphertext {
     void release();
     void upload_staged();
     void materialize() const;  // multiply pending factors out into `dev`
-    void collect_factors(std::vector<std::shared_ptr<csgn_buf> > &into) const;
+    // the same, with the decrypt fold of the product done by the kernel that writes it; returns the pending count
+    csgn_result *materialize_and_fold(const csgn_key *key, int *status) const;
+    void collect_factors(std::vector<std::shared_ptr<csgn_buf> > &into, bool flatten) const;
+    bool adopt_written_product() const;  // a copy has already written the pending product: take it
     friend class SecretKey;
 
 public:

@@ -23,7 +23,9 @@ void check(int status, const char *what) {
 }
 
 void ensure_engine() {
-    if (!csgn_is_initialized()) check(csgn_init(-1), "csgn_init");
+    if (csgn_is_initialized()) return;
+    check(csgn_init(-1), "csgn_init");
+    check(csgn_set_auto_lanes(Library::getAutoLanes() ? 1 : 0), "csgn_set_auto_lanes");
 }
 
 }  // namespace glue
@@ -36,12 +38,27 @@ inline uint64_t canonical_bits(uint64_t i, uint64_t L, uint64_t rem) {
 }
 
 void require_canonical_bitlen(const uint64_t *bitlen, uint64_t len, const Context &ctx) {
+    // block by block, no division per word: this runs in every Ciphertext(V, Bitlen, len, ctx)
     const uint64_t L = ctx.getDefaultN(), rem = ctx.getN() % 64;
-    for (uint64_t i = 0; i < len; ++i)
-        if (bitlen[i] != canonical_bits(i, L, rem))
-            throw Error("Ciphertext: bitlen[" + to_string(i) + "] = " + to_string(bitlen[i]) +
-                        " is not the canonical pattern for N = " + to_string(ctx.getN()) +
-                        " (the reference would mis-index such an object, src/SecretKey.cpp:133)");
+    const uint64_t last = rem ? rem : 64;
+    uint64_t bad = len;
+    for (uint64_t base = 0; base < len && bad == len; base += L) {
+        const uint64_t n = len - base < L ? len - base : L;
+        uint64_t diff = 0;
+        for (uint64_t k = 0; k + 1 < n; ++k) diff |= bitlen[base + k] ^ 64u;
+        if (n == L) diff |= bitlen[base + L - 1] ^ last;
+        else if (n) diff |= bitlen[base + n - 1] ^ 64u;
+        if (diff)
+            for (uint64_t k = 0; k < n; ++k)
+                if (bitlen[base + k] != canonical_bits(base + k, L, rem)) {
+                    bad = base + k;
+                    break;
+                }
+    }
+    if (bad != len)
+        throw Error("Ciphertext: bitlen[" + to_string(bad) + "] = " + to_string(bitlen[bad]) +
+                    " is not the canonical pattern for N = " + to_string(ctx.getN()) +
+                    " (the reference would mis-index such an object, src/SecretKey.cpp:133)");
 }
 
 uint64_t *copy_words(const uint64_t *src, uint64_t n) {
@@ -78,9 +95,10 @@ Ciphertext::Ciphertext(const uint64_t *V, const uint64_t *Bitlen, const uint64_t
     if (Bitlen) require_canonical_bitlen(Bitlen, len, context);
     glue::ensure_engine();
     csgn_buf *b = nullptr;
-    glue::check(csgn_buf_upload(V, len / L, (uint32_t)L, &b), "csgn_buf_upload");
+    // the caller may free V right after the constructor: the words are copied into library-owned pinned staging
+    // before this returns and travel to the device from there (no synchronisation)
+    glue::check(csgn_buf_upload_copy(V, len / L, (uint32_t)L, &b), "csgn_buf_upload_copy");
     dev = adopt(b);
-    glue::check(csgn_sync(), "csgn_sync");  // the caller may free V right after the constructor
 }
 
 Ciphertext::Ciphertext(const Ciphertext &o) : Ciphertext() {
@@ -97,14 +115,17 @@ Ciphertext::Ciphertext(const Ciphertext &o) : Ciphertext() {
     } else {
         dev = o.dev;
         factors = o.factors;
+        product_slot = o.product_slot;
     }
 }
 
 Ciphertext::Ciphertext(Ciphertext &&o) noexcept
-    : dev(std::move(o.dev)), factors(std::move(o.factors)), certFHEcontext(o.certFHEcontext), host_v(o.host_v),
+    : dev(std::move(o.dev)), factors(std::move(o.factors)), product_slot(std::move(o.product_slot)),
+      certFHEcontext(o.certFHEcontext), host_v(o.host_v),
       host_bitlen(o.host_bitlen), host_len(o.host_len), host_v_valid(o.host_v_valid), staged(o.staged),
       sharded(o.sharded) {
     o.factors.clear();
+    o.product_slot.reset();
     o.certFHEcontext = nullptr;
     o.host_v = o.host_bitlen = nullptr;
     o.host_len = 0;
@@ -128,6 +149,7 @@ void Ciphertext::invalidate_mirror() const {
 void Ciphertext::release() {
     dev.reset();
     factors.clear();
+    product_slot.reset();
     invalidate_mirror();
     staged = false;
 }
@@ -142,17 +164,24 @@ void Ciphertext::upload_staged() {
     if (host_bitlen) require_canonical_bitlen(host_bitlen, host_len, *certFHEcontext);
     glue::ensure_engine();
     csgn_buf *b = nullptr;
-    glue::check(csgn_buf_upload(host_v, host_len / L, (uint32_t)L, &b), "csgn_buf_upload");
+    glue::check(csgn_buf_upload_copy(host_v, host_len / L, (uint32_t)L, &b), "csgn_buf_upload_copy");
     dev = adopt(b);
-    glue::check(csgn_sync(), "csgn_sync");
     staged = false;  // host_v stays behind as a valid mirror
     host_v_valid = true;
+}
+
+bool Ciphertext::adopt_written_product() const {
+    if (!product_slot || !*product_slot) return false;
+    dev = *product_slot;
+    factors.clear();
+    product_slot.reset();
+    return true;
 }
 
 void Ciphertext::materialize() const {
     // multiply the pending factors out, left to right: ((f0*f1)*f2)... -- the reference's own
     // i-major block order, whatever the grouping (block order of a product is associative)
-    if (factors.empty()) return;
+    if (factors.empty() || adopt_written_product()) return;
     std::shared_ptr<csgn_buf> acc = factors[0];
     for (size_t i = 1; i < factors.size(); ++i) {
         csgn_buf *prod = nullptr;
@@ -161,10 +190,37 @@ void Ciphertext::materialize() const {
     }
     dev = acc;
     factors.clear();
+    if (product_slot) *product_slot = dev;
+    product_slot.reset();
 }
 
-void Ciphertext::collect_factors(std::vector<std::shared_ptr<csgn_buf> > &into) const {
+csgn_result *Ciphertext::materialize_and_fold(const csgn_key *key, int *status) const {
+    // ((f0*f1)*...)*f_last with the LAST multiply fused with the decrypt fold: the kernel that writes the product
+    // also counts its satisfied blocks (reference pattern tests/basic_operations.cpp:35-40; loops
+    // src/Ciphertext.cpp:153-163 + src/SecretKey.cpp:131-140)
+    std::shared_ptr<csgn_buf> acc = factors[0];
+    for (size_t i = 1; i + 1 < factors.size(); ++i) {
+        csgn_buf *prod = nullptr;
+        glue::check(csgn_mul(acc.get(), factors[i].get(), &prod), "csgn_mul");
+        acc = adopt(prod);
+    }
+    csgn_buf *prod = nullptr;
+    csgn_result *res = nullptr;
+    *status = csgn_mul_decrypt_deferred(acc.get(), factors.back().get(), key, &prod, &res);
+    if (*status != CSGN_OK) return nullptr;
+    dev = adopt(prod);
+    factors.clear();
+    if (product_slot) *product_slot = dev;
+    product_slot.reset();
+    return res;
+}
+
+void Ciphertext::collect_factors(std::vector<std::shared_ptr<csgn_buf> > &into, bool flatten) const {
+    // flatten (lazy mode): the factors of a pending product become factors of the new one.  Otherwise (fused mode)
+    // an operand that is itself a pending product is written now -- once, whoever uses it afterwards -- so that a
+    // pending product always has exactly two written factors.
     const_cast<Ciphertext *>(this)->upload_staged();
+    if (!flatten) materialize();
     if (!factors.empty()) into.insert(into.end(), factors.begin(), factors.end());
     else if (dev) into.push_back(dev);
 }
@@ -235,7 +291,7 @@ uint64_t Ciphertext::getBlocks() const {
         const uint64_t L = certFHEcontext ? certFHEcontext->getDefaultN() : 0;
         return L ? host_len / L : 0;
     }
-    if (!factors.empty()) {   // lazy product: the block counts multiply (saturating)
+    if (!factors.empty()) {   // pending product: the block counts multiply (saturating)
         uint64_t n = 1;
         for (size_t i = 0; i < factors.size(); ++i) {
             const uint64_t t = csgn_buf_blocks(factors[i].get());
@@ -336,6 +392,8 @@ Ciphertext &Ciphertext::operator=(Ciphertext &&o) noexcept {
     dev = std::move(o.dev);
     factors = std::move(o.factors);
     o.factors.clear();
+    product_slot = std::move(o.product_slot);
+    o.product_slot.reset();
     certFHEcontext = o.certFHEcontext;
     host_v = o.host_v;
     host_bitlen = o.host_bitlen;
@@ -410,11 +468,14 @@ Ciphertext Ciphertext::operator*(const Ciphertext &c) const {
     out.sharded = sharded;
     // the reference multiplies in the LEFT operand's context (src/Ciphertext.cpp:239)
     if (certFHEcontext) out.certFHEcontext = new Context(*certFHEcontext);
-    if (Library::getLazyProducts()) {
-        collect_factors(out.factors);
+    if (Library::getLazyProducts() || Library::getFusedProducts()) {
+        // the product is not written yet: decrypt folds it in the kernel that writes it (fused) or never writes it (lazy)
+        const bool flatten = Library::getLazyProducts();
+        collect_factors(out.factors, flatten);
         const size_t mine = out.factors.size();
-        c.collect_factors(out.factors);
+        c.collect_factors(out.factors, flatten);
         if (mine == 0 || out.factors.size() == mine) throw Error("Ciphertext::operator*: empty operand");
+        out.product_slot = std::make_shared<std::shared_ptr<csgn_buf> >();
         return out;
     }
     const csgn_buf *a = deviceBuffer(), *b = c.deviceBuffer();
@@ -427,14 +488,16 @@ Ciphertext Ciphertext::operator*(const Ciphertext &c) const {
 
 Ciphertext &Ciphertext::operator*=(const Ciphertext &c) {
     if (c.sharded) throw Error("Ciphertext::operator*=: the right operand of a product must be replicated");
-    if (Library::getLazyProducts()) {
+    if (Library::getLazyProducts() || Library::getFusedProducts()) {
+        const bool flatten = Library::getLazyProducts();
         std::vector<std::shared_ptr<csgn_buf> > f;
-        collect_factors(f);
+        collect_factors(f, flatten);
         const size_t mine = f.size();
-        c.collect_factors(f);
+        c.collect_factors(f, flatten);
         if (mine == 0 || f.size() == mine) throw Error("Ciphertext::operator*=: empty operand");
         dev.reset();
         factors.swap(f);
+        product_slot = std::make_shared<std::shared_ptr<csgn_buf> >();
         invalidate_mirror();
         return *this;
     }
@@ -468,6 +531,7 @@ void Ciphertext::applyPermutation_inplace(const Permutation &permutation) {
     Ciphertext permuted = applyPermutation(permutation);
     dev = std::move(permuted.dev);
     factors.swap(permuted.factors);
+    product_slot = std::move(permuted.product_slot);
     invalidate_mirror();
 }
 
@@ -480,9 +544,11 @@ Ciphertext Ciphertext::applyPermutation(const Permutation &permutation) {
     Ciphertext out;
     out.certFHEcontext = new Context(*certFHEcontext);
     out.sharded = sharded;
+    if (!factors.empty()) adopt_written_product();
     if (!factors.empty() && !strict) {
         // a permutation acts on each block, and a product block is an AND of factor blocks:
-        // pi(a_i & b_j) = pi(a_i) & pi(b_j) -- permute the factors, stay lazy
+        // pi(a_i & b_j) = pi(a_i) & pi(b_j) -- permute the factors, the product stays pending
+        out.product_slot = std::make_shared<std::shared_ptr<csgn_buf> >();
         for (size_t i = 0; i < factors.size(); ++i) {
             csgn_buf *pf = nullptr;
             glue::check(csgn_permute(factors[i].get(), map, 0, &pf), "csgn_permute");
@@ -643,21 +709,33 @@ void SecretKey::decryptBatch(Ciphertext *ciphertexts, uint64_t n, unsigned char 
     }
     std::vector<const csgn_buf *> bufs;
     std::vector<uint64_t> where;
+    std::vector<std::pair<uint64_t, Plaintext> > later;
     for (uint64_t i = 0; i < n; ++i) {
         Ciphertext &c = ciphertexts[i];
         c.upload_staged();
         if (c.sharded || !c.factors.empty() || (!c.dev && c.factors.empty())) {
-            bits[i] = decrypt(c).getValue();       // sharded, lazy or empty: the single-ciphertext path knows how
+            // sharded, pending or empty: the single-ciphertext path knows how; its value is read after everything
+            // has been enqueued
+            later.push_back(std::make_pair(i, decrypt(c)));
             continue;
         }
         bufs.push_back(c.dev.get());
         where.push_back(i);
     }
-    if (bufs.empty()) return;
-    std::vector<uint8_t> out(bufs.size());
-    glue::check(csgn_decrypt_batch(bufs.data(), (uint32_t)bufs.size(), device_key, out.data(), nullptr), "csgn_decrypt_batch");
-    for (size_t k = 0; k < bufs.size(); ++k) bits[where[k]] = out[k];
+    if (!bufs.empty()) {
+        std::vector<uint8_t> out(bufs.size());
+        glue::check(csgn_decrypt_batch(bufs.data(), (uint32_t)bufs.size(), device_key, out.data(), nullptr), "csgn_decrypt_batch");
+        for (size_t k = 0; k < bufs.size(); ++k) bits[where[k]] = out[k];
+    }
+    for (size_t k = 0; k < later.size(); ++k) bits[later[k].first] = later[k].second.getValue();
 }
+
+namespace {
+// a Plaintext whose value is read from `res` on first use
+std::shared_ptr<csgn_result> adopt_result(csgn_result *r) {
+    return std::shared_ptr<csgn_result>(r, [](csgn_result *p) { csgn_result_free(p); });
+}
+}  // namespace
 
 Plaintext SecretKey::decrypt(Ciphertext &ciphertext) {
     ciphertext.upload_staged();
@@ -675,15 +753,35 @@ Plaintext SecretKey::decrypt(Ciphertext &ciphertext) {
         glue::check(csgn_decrypt_sharded(local, device_key, glue::comm(), &bit, nullptr), "csgn_decrypt_sharded");
         return Plaintext(bit);
     }
-    if (!ciphertext.factors.empty()) {
-        // a product that was never multiplied out: Dec(f0*f1*...) = Dec(f0) & Dec(f1) & ...
+    if (!ciphertext.factors.empty() && Library::getLazyProducts()) {
+        // a product that is never multiplied out: Dec(f0*f1*...) = Dec(f0) & Dec(f1) & ...
         std::vector<const csgn_buf *> fs;
         for (size_t i = 0; i < ciphertext.factors.size(); ++i) fs.push_back(ciphertext.factors[i].get());
         glue::check(csgn_decrypt_product(fs.data(), (uint32_t)fs.size(), device_key, &bit, nullptr), "csgn_decrypt_product");
-    } else {
-        glue::check(csgn_decrypt(ciphertext.dev.get(), device_key, &bit), "csgn_decrypt");
+        return Plaintext(bit);
     }
-    return Plaintext(bit);
+    // The fold (fused with the multiply when the product has not been written yet) and the copy of its count are
+    // enqueued; the Plaintext reads the count on first use.  When every result slot is taken (thousands of unread
+    // Plaintexts) the call degrades to the blocking form.
+    csgn_result *res = nullptr;
+    if (!ciphertext.factors.empty()) ciphertext.adopt_written_product();
+    if (ciphertext.factors.size() >= 2) {
+        int rc = CSGN_OK;
+        res = ciphertext.materialize_and_fold(device_key, &rc);
+        if (rc != CSGN_OK && rc != CSGN_ERR_OUT_OF_MEMORY) glue::check(rc, "csgn_mul_decrypt_deferred");
+    }
+    if (!res) {
+        const csgn_buf *buf = ciphertext.deviceBuffer();
+        const int rc = csgn_decrypt_deferred(buf, device_key, &res);
+        if (rc == CSGN_ERR_OUT_OF_MEMORY) {
+            glue::check(csgn_decrypt(buf, device_key, &bit), "csgn_decrypt");
+            return Plaintext(bit);
+        }
+        glue::check(rc, "csgn_decrypt_deferred");
+    }
+    Plaintext out;
+    out.pending = adopt_result(res);
+    return out;
 }
 
 void SecretKey::applyPermutation_inplace(const Permutation &permutation) {

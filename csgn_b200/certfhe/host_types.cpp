@@ -17,12 +17,23 @@ bool g_strict_permute = false;
 bool g_strict_permute_set = false;
 bool g_lazy_products = false;
 bool g_lazy_products_set = false;
+bool g_fused_products = true;
+bool g_fused_products_set = false;
+bool g_auto_lanes = true;
+bool g_auto_lanes_set = false;
+
+bool env_flag(const char *name, bool dflt) {
+    const char *e = getenv(name);
+    if (!e || !*e) return dflt;
+    return strcmp(e, "0") != 0;
+}
 }  // namespace
 
 void Library::initializeLibrary() {
     // reference src/Helpers.cpp:8-12: the PRNG is seeded with the local time
     srand(time(NULL));
     glue::ensure_engine();
+    glue::check(csgn_set_auto_lanes(getAutoLanes() ? 1 : 0), "csgn_set_auto_lanes");
     // one process per GPU under a launcher: join the job's peers
     const char *ws = getenv("WORLD_SIZE"), *rk = getenv("RANK"), *dir = getenv("CSGN_RENDEZVOUS_DIR");
     if (ws && rk && dir && atoi(ws) >= 1 && !glue::comm()) {
@@ -94,6 +105,33 @@ bool Library::getLazyProducts() {
     return g_lazy_products;
 }
 
+void Library::setFusedProducts(bool fused) {
+    g_fused_products = fused;
+    g_fused_products_set = true;
+}
+
+bool Library::getFusedProducts() {
+    if (!g_fused_products_set) {
+        g_fused_products = env_flag("CSGN_FUSED_PRODUCTS", true);
+        g_fused_products_set = true;
+    }
+    return g_fused_products;
+}
+
+void Library::setAutoLanes(bool on) {
+    g_auto_lanes = on;
+    g_auto_lanes_set = true;
+    if (csgn_is_initialized()) glue::check(csgn_set_auto_lanes(on ? 1 : 0), "csgn_set_auto_lanes");
+}
+
+bool Library::getAutoLanes() {
+    if (!g_auto_lanes_set) {
+        g_auto_lanes = env_flag("CSGN_AUTO_LANES", true);
+        g_auto_lanes_set = true;
+    }
+    return g_auto_lanes;
+}
+
 void Library::synchronize() {
     glue::ensure_engine();
     glue::check(csgn_sync(), "csgn_sync");
@@ -163,8 +201,24 @@ void Context::setD(uint64_t d) {
 Plaintext::Plaintext() : value(0) {}
 Plaintext::Plaintext(const int v) : value((unsigned char)(v & 0x01)) {}  // src/Plaintext.cpp:30-33
 Plaintext::~Plaintext() {}
-unsigned char Plaintext::getValue() const { return value; }
-void Plaintext::setValue(unsigned char v) { value = v & 0x01; }
+
+void Plaintext::resolve() const {
+    if (!pending) return;
+    uint64_t count = 0;
+    glue::check(csgn_result_wait(pending.get(), &count), "csgn_result_wait");
+    value = (unsigned char)(count & 1u);      // the XOR over the blocks is the parity of the satisfied-block count
+    pending.reset();
+}
+
+unsigned char Plaintext::getValue() const {
+    resolve();
+    return value;
+}
+
+void Plaintext::setValue(unsigned char v) {
+    pending.reset();
+    value = v & 0x01;
+}
 
 ostream &operator<<(ostream &out, const Plaintext &c) {
     // reference src/Plaintext.cpp:10-19: the digit, then a newline

@@ -213,6 +213,80 @@ static void lazy_products() {
     EXPECT(x.getLen() == 2 * A.getLen() && seckey.decrypt(x).getValue() == 0);
 }
 
+// Fused products (the default): operator* notes its operands; SecretKey::decrypt of a product that has not been written
+// yet writes it AND folds it in one kernel.  Everything observable must equal the one-kernel-per-operator behaviour.
+static void fused_products() {
+    Context context(1247, 16);
+    SecretKey seckey(context);
+    srand(99);
+    auto sum_of = [&](int n, int &parity) {
+        Ciphertext acc;
+        parity = 0;
+        for (int i = 0; i < n; ++i) {
+            Plaintext p(rand() % 2);
+            parity ^= p.getValue();
+            Ciphertext e = seckey.encrypt(p);
+            if (i == 0) acc = e; else acc += e;
+        }
+        return acc;
+    };
+    int pa, pb, pd;
+    Ciphertext A = sum_of(37, pa), B = sum_of(23, pb), Dd = sum_of(11, pd);
+    Library::setFusedProducts(false);
+    Ciphertext eager = A * B;                                  // csgn_mul, now
+    Ciphertext eager3 = eager * Dd;
+    Library::setFusedProducts(true);
+    EXPECT(Library::getFusedProducts() && Library::getAutoLanes());
+    // decrypt first: the fused kernel writes the product and folds it; the words are there afterwards
+    Ciphertext f1 = A * B;
+    EXPECT(f1.getLen() == eager.getLen() && f1.getBlocks() == 37 * 23);
+    Plaintext p1 = seckey.decrypt(f1);                         // pending until read
+    Plaintext p1copy = p1;
+    EXPECT(memcmp(f1.getValues(), eager.getValues(), eager.getLen() * 8) == 0);
+    EXPECT(p1.getValue() == (pa & pb) && p1copy.getValue() == (pa & pb));
+    EXPECT(seckey.decrypt(f1).getValue() == (pa & pb));        // again, now a plain fold of the written product
+    // words first: a plain multiply, then a plain fold
+    Ciphertext f2 = A * B;
+    EXPECT(memcmp(f2.getValues(), eager.getValues(), eager.getLen() * 8) == 0);
+    EXPECT(seckey.decrypt(f2).getValue() == (pa & pb));
+    // copies of a pending product: whichever is used first writes it, the other picks it up
+    Ciphertext f3 = A * B, f3copy = f3;
+    EXPECT(seckey.decrypt(f3copy).getValue() == (pa & pb));
+    EXPECT(memcmp(f3.getValues(), eager.getValues(), eager.getLen() * 8) == 0);
+    // chains: the inner product is written once, the outer one is fused with its decrypt
+    Ciphertext inner = A * B;
+    Ciphertext c1 = inner * Dd, c2 = inner * A;
+    EXPECT(c1.getBlocks() == 37 * 23 * 11);
+    EXPECT(seckey.decrypt(c1).getValue() == (pa & pb & pd));
+    EXPECT(seckey.decrypt(c2).getValue() == (pa & pb & pa));
+    EXPECT(memcmp(c1.getValues(), eager3.getValues(), eager3.getLen() * 8) == 0);
+    Ciphertext acc = A;
+    acc *= B;
+    acc *= Dd;
+    EXPECT(seckey.decrypt(acc).getValue() == (pa & pb & pd));
+    EXPECT(memcmp(acc.getValues(), eager3.getValues(), eager3.getLen() * 8) == 0);
+    // a pending product in a sum, permuted, saved
+    Ciphertext s = (A * B) + Dd;
+    EXPECT(s.getLen() == eager.getLen() + Dd.getLen() && seckey.decrypt(s).getValue() == ((pa & pb) ^ pd));
+    Permutation pi(context);
+    SecretKey pk = seckey.applyPermutation(pi);
+    Ciphertext fp = (A * B).applyPermutation(pi);              // permutes the operands; still pending
+    EXPECT(pk.decrypt(fp).getValue() == (pa & pb));
+    EXPECT(memcmp(fp.getValues(), eager.applyPermutation(pi).getValues(), eager.getLen() * 8) == 0);
+    // many decrypts in flight, read afterwards (one synchronisation at the first read)
+    std::vector<Ciphertext> prods;
+    std::vector<Plaintext> plains;
+    for (int i = 0; i < 40; ++i) prods.push_back(i % 2 ? A * B : B * Dd);
+    for (int i = 0; i < 40; ++i) plains.push_back(seckey.decrypt(prods[i]));
+    for (int i = 0; i < 40; ++i) EXPECT(plains[i].getValue() == (i % 2 ? (pa & pb) : (pb & pd)));
+    std::ostringstream os;
+    os << plains[1];
+    EXPECT(os.str() == std::string(1, (char)('0' | (pa & pb))) + "\n");
+    Plaintext set = seckey.decrypt(prods[0]);
+    set.setValue(1);                                            // overrides a pending value
+    EXPECT(set.getValue() == 1);
+}
+
 static void misuse_is_loud() {
     Context context(1247, 16);
     uint64_t words[20] = {0}, bitlen[20];
@@ -246,9 +320,16 @@ int main() {
     random_circuits(191, 5, 3, 4);   // odd number of words per block
     random_circuits(128, 4, 4, 4);   // N % 64 == 0 (the reference overflows its arrays here)
     lazy_products();
+    fused_products();
     Library::setLazyProducts(true);
     random_circuits(1247, 16, 5, 4);  // the same circuits with products kept lazy
     Library::setLazyProducts(false);
+    Library::setFusedProducts(false);  // ... and with one kernel per operator on one stream (the first release)
+    Library::setAutoLanes(false);
+    random_circuits(1247, 16, 6, 4);
+    random_circuits(191, 5, 7, 2);
+    Library::setFusedProducts(true);
+    Library::setAutoLanes(true);
     misuse_is_loud();
     if (failures) {
         std::cerr << failures << " expectation(s) failed" << endl;

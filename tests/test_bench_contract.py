@@ -36,17 +36,35 @@ def test_reference_arm_line():
 
 @pytest.mark.gpu
 def test_our_arm_line():
-    d = _run(["--steps", "3", "--warmup", "3", "--no-cpu-baseline"], 900)
+    d = _run(["--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--sustain-s", "0.3"], 1200)
     assert BASE_KEYS <= set(d) and "impl" not in d
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] >= 3 and d["scaling"] == "weak" and d["dtype"] == "u64"
-    assert d["value"] > 5e9 and d["config"]["workload"].startswith("cfg2")
+    assert d["value"] > 1e10 and d["config"]["workload"].startswith("cfg2") and d["config"]["mode"].startswith("fused")
     roof = d["roofline"]
     assert roof["bound"] == "hbm" and roof["unit"] == "GB/s" and roof["peak"] > 1000
     assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9 and roof["achieved"] > 3000
     assert roof["algorithmic_bytes_per_launch"] == 160000000
     e2e = d["e2e"]
-    assert e2e["value"] > 5e9 and e2e["h2d_bytes_per_step"] == 16 * 2000 * 160 and e2e["d2h_bytes_per_step"] == 128
-    assert d["gpu_launches"] == 3 * 32                       # 16 multiplies + 16 folds per step, nothing else
+    assert e2e["value"] > 1e10 and e2e["h2d_bytes_per_step"] == 16 * 2000 * 160 and e2e["d2h_bytes_per_step"] == 128
+    assert d["gpu_launches"] == 3 * 16                       # one fused multiply->decrypt kernel per pair, nothing else
+    assert d["precheck"]["passed"] is True and len(d["precheck"]["cases"]) == 3
+    two = d["two_pass"]                                      # the round-1 step (separate kernels) on the same buffers
+    assert two["gpu_launches"] == 3 * 32 and 5e9 < two["value"] < d["value"]
+    assert d["sustained"]["seconds"] >= 0.3 and d["sustained"]["value"] > 1e10
     extra = d["other_kernels"]                               # permute and add, reported beside the headline
     assert "error" not in extra and extra["permute"]["blocks_per_s"] > 5e9 and extra["add"]["gbs_read_plus_write"] > 3000
+    ow = d["other_workloads"]                                # BASELINE.json configs[3] and [4]
+    for name in ("cfg5_300x300", "cfg5_2000x2000", "cfg4_chain"):
+        assert "error" not in ow[name], ow[name]
+    assert ow["cfg4_chain"]["blocks_per_gpu"] == 125000000 and ow["cfg4_chain"]["multiply_chain"]["frac_of_peak"] > 0.8
+    assert ow["cfg5_2000x2000"]["multiply"]["frac_of_peak"] > 0.8
+    cpp = d["e2e_cpp"]                                       # the same step through libcertFHE.so
+    assert cpp.get("checked") is True and cpp["value"] > 1e9, cpp
     assert d["clocks"]["sm_mhz"] and not (set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"})
+
+
+@pytest.mark.gpu
+def test_two_pass_mode_line():
+    d = _run(["--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--no-extras", "--mode", "two-pass"], 600)
+    assert d["config"]["mode"].startswith("two-pass") and d["gpu_launches"] == 3 * 32
+    assert set(d["kernels"]) >= {"multiply", "decrypt"} and d["value"] > 5e9
