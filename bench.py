@@ -860,8 +860,8 @@ def run_ours(args):
     # --- e2e: pinned host operands through the public C ABI ---------------------------
     e2e = None
     if not args.no_e2e:
-        a_ptrs = [host_a[p].data_ptr() for p in range(P)]
-        b_ptrs = [host_b[p].data_ptr() for p in range(P)]
+        uploader = eng.UploadBatch([host_a[p].data_ptr() for p in range(P)] + [host_b[p].data_ptr() for p in range(P)],
+                                   [T1] * P + [T2] * P, ctx)
         host_counts2 = [torch.zeros(P, dtype=torch.int64).pin_memory() for _ in range(2)]
         done_ev = [torch.cuda.Event(), torch.cuda.Event()]
         in_flight = [False, False]
@@ -884,26 +884,25 @@ def run_ours(args):
             # ago, so no rank waits for a slower one); the D2H enqueued after it carries step k-1's result.
             slot = e2e_no[0] & 1
             e2e_no[0] += 1
-            check(slot)                                                    # frees this slot's buffers (step k-2)
-            has = [eng.Ciphertext.from_host_ptr(a_ptrs[p], T1, ctx) for p in range(P)]   # H2D on the copy stream
-            hbs = [eng.Ciphertext.from_host_ptr(b_ptrs[p], T2, ctx) for p in range(P)]
+            check(slot)
+            ops = uploader.upload()                                        # csgn_buf_upload_batch: 2P operands, H2D on the copy stream
+            ha, hb = eng.handle_slice(ops, 0, P), eng.handle_slice(ops, P, P)
+            ho = (ctypes.c_void_p * P)()                                   # the library allocates the P products
             lag_now = e2e_lag and e2e_no[0] > 1
             dst = count_ptrs2[slot ^ 1] if lag_now else count_ptrs2[slot]
             if fused:
-                ha, hb = eng.handle_array(has), eng.handle_array(hbs)
-                ho = (ctypes.c_void_p * P)()                               # the library allocates the P products
                 if comm is None:
                     eng.mul_count_batch_async(key, None, None, dst, arrays=(ha, hb, ho))
                 else:
                     comm.mul_push_batch(key, (ha, hb, ho), dst, lag=P if lag_now else 0)
-                prods = [eng.Ciphertext(ctypes.c_void_p(ho[i]), ctx) for i in range(P)]
             else:
-                prods = eng.mul_batch(has, hbs)                            # csgn_mul_batch (allocates the P products)
+                eng.mul_batch_arrays(ha, hb, ho)                           # csgn_mul_batch
                 if comm is not None:
-                    comm.push_batch(key, prods, dst, lag=P if lag_now else 0)
+                    comm.push_batch(key, None, dst, lag=P if lag_now else 0, array=ho)
                 else:
-                    key.count_satisfied_batch_async(prods, dst)
-            del has, hbs, prods                                            # stream-ordered frees
+                    key.count_satisfied_batch_async(None, dst, array=ho)
+            eng.free_handles(ops)                                          # stream-ordered frees
+            eng.free_handles(ho)
             if world > 1 and comm is None:
                 dist.all_reduce(counts2[slot])
             if e2e_lag:
@@ -947,7 +946,7 @@ def run_ours(args):
         e2e = {"value": blocks_per_step * K / (float(e2e_ms.item()) * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(P * (T1 + T2) * L * 8), "d2h_bytes_per_step": int(P * 8),
                "ms_per_step": float(e2e_ms.item()) / K,
-               "path": ("csgn_buf_upload x2P (pinned host) -> %s; one D2H of the P counts per step, read and checked "
+               "path": ("csgn_buf_upload_batch (2P operands, pinned host) -> %s; one D2H of the P counts per step, read and checked "
                         "against the host-known truth on the host every step (one step behind the enqueue); per GPU"
                         % (("csgn_mul_decrypt_sharded_batch_async" if comm is not None else "csgn_mul_count_batch_async")
                            if fused else

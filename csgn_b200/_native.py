@@ -30,6 +30,8 @@ SIGNATURES = {
     "csgn_host_free": (ctypes.c_int, [_vp]),
     "csgn_buf_upload": (ctypes.c_int, [_vp, _u64, ctypes.c_uint32, _vpp]),
     "csgn_buf_upload_copy": (ctypes.c_int, [_vp, _u64, ctypes.c_uint32, _vpp]),
+    "csgn_buf_upload_batch": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp]),
+    "csgn_buf_free_batch": (ctypes.c_int, [_vp, ctypes.c_uint32]),
     "csgn_buf_alloc": (ctypes.c_int, [_u64, ctypes.c_uint32, _vpp]),
     "csgn_buf_wrap": (ctypes.c_int, [_vp, _u64, ctypes.c_uint32, _vpp]),
     "csgn_buf_clone": (ctypes.c_int, [_vp, _vpp]),

@@ -565,6 +565,80 @@ int csgn_buf_upload_copy(const uint64_t *host_words, uint64_t n_blocks, uint32_t
     return rc;
 }
 
+int csgn_buf_upload_batch(const uint64_t *const *host_words, const uint64_t *n_blocks, uint32_t n, uint32_t L,
+                          csgn_buf **out) {
+    NEED_INIT();
+    if (n == 0) return CSGN_OK;
+    if (!host_words || !n_blocks || !out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null argument");
+    if (L == 0) return fail(CSGN_ERR_INVALID_ARGUMENT, "words per block must be > 0");
+    // one slab for the n operands (each 256-byte aligned), copies back to back on the copy stream
+    constexpr uint64_t kAlignWords = 32;
+    std::vector<uint64_t> off(n);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (n_blocks[i] && !host_words[i]) return fail(CSGN_ERR_INVALID_ARGUMENT, "null host words (operand %u)", i);
+        if (n_blocks[i] > (UINT64_MAX / 16) / L) return fail(CSGN_ERR_INVALID_ARGUMENT, "block count overflows");
+        off[i] = total;
+        total += (n_blocks[i] * L + kAlignWords - 1) / kAlignWords * kAlignWords;
+    }
+    if (total == 0) total = kAlignWords;
+    csgn_slab *sl = new csgn_slab;
+    uint64_t cap = 0;
+    sl->d = total <= kUploadCacheMaxWords ? take_upload_slot(total, &cap) : nullptr;
+    if (sl->d) sl->cap_words = cap;
+    else {
+        int rc = dev_alloc(total, &sl->d, g.copy_stream);
+        if (rc != CSGN_OK) {
+            delete sl;
+            return rc;
+        }
+        sl->cap_words = total;
+    }
+    std::vector<void *> dsts, srcs;
+    std::vector<size_t> sizes;
+    for (uint32_t i = 0; i < n; ++i)
+        if (n_blocks[i]) {
+            dsts.push_back(sl->d + off[i]);
+            srcs.push_back(const_cast<uint64_t *>(host_words[i]));
+            sizes.push_back((size_t)n_blocks[i] * L * sizeof(uint64_t));
+        }
+    // operands that follow one another in host memory AND in the slab (rows of one pinned array whose size is a
+    // multiple of 256 bytes) travel as one copy: fewer, larger copies
+    cudaError_t e = cudaSuccess;
+    for (size_t i = 0; i < dsts.size() && e == cudaSuccess;) {
+        size_t j = i + 1, bytes = sizes[i];
+        while (j < dsts.size() && static_cast<char *>(srcs[i]) + bytes == static_cast<char *>(srcs[j]) &&
+               static_cast<char *>(dsts[i]) + bytes == static_cast<char *>(dsts[j])) {
+            bytes += sizes[j];
+            ++j;
+        }
+        e = cudaMemcpyAsync(dsts[i], srcs[i], bytes, cudaMemcpyHostToDevice, g.copy_stream);
+        i = j;
+    }
+    if (e != cudaSuccess) {
+        cudaStreamSynchronize(g.copy_stream);
+        dev_free(sl->d);
+        delete sl;
+        return cuda_fail(e, "cudaMemcpyAsync(H2D batch)");
+    }
+    // the views are ordered after the copies through their writer mark on the copy stream: the first consumer on a
+    // stream records ONE event there for the whole batch (wait_for_mark remembers what a stream already waits for)
+    const uint64_t tick = g.tick++;
+    for (uint32_t i = 0; i < n; ++i) {
+        csgn_buf *b = new csgn_buf;
+        b->d = sl->d + off[i];
+        b->n_blocks = n_blocks[i];
+        b->L = L;
+        b->cap_words = 0;
+        b->owns = false;
+        b->slab = sl;
+        b->writer = {g.copy_stream, tick};
+        out[i] = b;
+    }
+    sl->refs = n;
+    return CSGN_OK;
+}
+
 int csgn_buf_wrap(void *device_words, uint64_t n_blocks, uint32_t L, csgn_buf **out) {
     NEED_INIT();
     if (!out || L == 0) return fail(CSGN_ERR_INVALID_ARGUMENT, "bad view arguments");
@@ -640,8 +714,38 @@ int csgn_buf_download(const csgn_buf *buf, uint64_t *host_words) {
     return csgn_buf_download_range(buf, 0, buf->n_blocks, host_words);
 }
 
+namespace {
+// A view of a batched upload goes away: its uses are remembered by the slab (no CUDA call), and the last view's
+// release orders the current stream after all of them and hands the storage back -- one event for the whole batch.
+void release_slab_view(csgn_buf *buf) {
+    csgn_slab *sl = buf->slab;
+    auto note = [&](const StreamMark &m) {
+        if (!m.s) return;
+        for (StreamMark &u : sl->uses)
+            if (u.s == m.s) {
+                u.tick = std::max(u.tick, m.tick);
+                return;
+            }
+        sl->uses.push_back(m);
+    };
+    note(buf->writer);
+    for (const StreamMark &m : buf->readers) note(m);
+    if (--sl->refs != 0) return;
+    if (g.inited) {
+        for (const StreamMark &m : sl->uses) wait_for_mark(g.stream, m);
+        if (!give_upload_slot(sl->d, sl->cap_words)) dev_free(sl->d);
+    }
+    delete sl;
+}
+}  // namespace
+
 int csgn_buf_free(csgn_buf *buf) {
     if (!buf) return CSGN_OK;
+    if (buf->slab) {
+        release_slab_view(buf);
+        delete buf;
+        return CSGN_OK;
+    }
     if (g.inited) {
         await_ready(buf);                      // a never-consumed upload must land before its memory is recycled
         order_after_all_uses(buf);
@@ -649,6 +753,12 @@ int csgn_buf_free(csgn_buf *buf) {
     }
     if (g.inited && buf->owns && !(buf->recycle && give_upload_slot(buf->d, buf->cap_words))) dev_free(buf->d);
     delete buf;
+    return CSGN_OK;
+}
+
+int csgn_buf_free_batch(csgn_buf *const *bufs, uint32_t n) {
+    if (!bufs) return CSGN_OK;
+    for (uint32_t i = 0; i < n; ++i) csgn_buf_free(bufs[i]);
     return CSGN_OK;
 }
 

@@ -27,6 +27,14 @@ struct StreamMark {
     uint64_t tick = 0;
 };
 
+// Device storage shared by the buffers of one batched upload (csgn_buf_upload_batch): one allocation, one release.
+struct csgn_slab {
+    uint64_t *d = nullptr;
+    uint64_t cap_words = 0;
+    uint32_t refs = 0;
+    std::vector<StreamMark> uses;   // every use of the freed views that may still be in flight, by stream
+};
+
 struct csgn_buf {
     uint64_t *d = nullptr;     // device words, n_blocks * L valid
     uint64_t n_blocks = 0;
@@ -34,6 +42,7 @@ struct csgn_buf {
     uint64_t cap_words = 0;    // allocated words (>= n_blocks*L); 0 for views
     bool owns = true;
     bool recycle = false;      // storage of an upload: goes back to the upload cache, not to the pool
+    csgn_slab *slab = nullptr; // a view into a batched upload's shared storage (owns == false)
     // An upload on the copy stream that may still be in flight.  EVERY stream that consumes the buffer waits for it
     // (ready_waited remembers which already did); the event goes back to the pool once it is known to have completed.
     mutable cudaEvent_t ready = nullptr;

@@ -263,6 +263,41 @@ def handle_array(cts):
     return (_vp * len(cts))(*[c._h.value if isinstance(c._h, _vp) else c._h for c in cts])
 
 
+class UploadBatch:
+    """csgn_buf_upload_batch with its argument arrays built once: n operands go to the device in one call (one
+    shared allocation, copies issued back to back).  upload() returns a ctypes array of n csgn_buf handles -- pass slices of it
+    (handle_slice) to the batch entry points and release it with free_handles."""
+
+    def __init__(self, host_ptrs, n_blocks, ctx):
+        self.n, self.ctx = len(host_ptrs), ctx
+        self._ptrs = (_vp * self.n)(*host_ptrs)
+        self._nb = (ctypes.c_uint64 * self.n)(*n_blocks)
+
+    def upload(self):
+        out = (_vp * self.n)()
+        rc = _LIB.csgn_buf_upload_batch(self._ptrs, self._nb, self.n, self.ctx.L, out)
+        if rc:
+            check(rc)
+        return out
+
+
+def handle_slice(arr, first, n):
+    """entries [first, first+n) of a handle array, as an array the batch entry points accept (no copy)"""
+    return (_vp * n).from_buffer(arr, first * ctypes.sizeof(_vp))
+
+
+def free_handles(arr):
+    """csgn_buf_free_batch: release every handle of a ctypes handle array"""
+    _LIB.csgn_buf_free_batch(arr, len(arr))
+
+
+def mul_batch_arrays(aa, ab, ao):
+    """csgn_mul_batch on handle arrays: ao[i] (NULL on entry) receives the product aa[i] * ab[i]."""
+    rc = _LIB.csgn_mul_batch(aa, ab, len(aa), ao)
+    if rc:
+        check(rc)
+
+
 def mul_into_batch(a, b, out, arrays=None):
     """csgn_mul_into_batch: out[i] = a[i] * b[i]; the library overlaps the independent products on its lanes.
     `arrays` = (handle_array(a), handle_array(b), handle_array(out)) built beforehand skips the marshalling."""

@@ -100,6 +100,15 @@ int csgn_buf_upload(const uint64_t *host_words, uint64_t n_blocks, uint32_t L, c
  * once), and travel to the device from there, asynchronously.  Uploads beyond 64 MB copy straight from the caller's
  * memory and wait. */
 int csgn_buf_upload_copy(const uint64_t *host_words, uint64_t n_blocks, uint32_t L, csgn_buf **out);
+/* n uploads in one call (the operands of a batch of products): one device allocation shared by the n buffers, the
+ * copies issued back to back (operands adjacent in host memory travel as one copy), one ordering event per consuming
+ * stream instead of one per operand.  host_words[i]
+ * (ideally pinned) holds n_blocks[i]*L words and must stay valid until the copies have run, as for csgn_buf_upload.
+ * out[0..n) are ordinary read-only operands (not growable by csgn_append); the shared storage is released when the
+ * last of them is freed.  csgn_buf_free_batch frees n handles in one call. */
+int csgn_buf_upload_batch(const uint64_t *const *host_words, const uint64_t *n_blocks, uint32_t n, uint32_t L,
+                          csgn_buf **out);
+int csgn_buf_free_batch(csgn_buf *const *bufs, uint32_t n);
 /* Uninitialised device storage for n_blocks blocks. */
 int csgn_buf_alloc(uint64_t n_blocks, uint32_t L, csgn_buf **out);
 /* Non-owning view over caller-owned device memory (e.g. a torch tensor). */

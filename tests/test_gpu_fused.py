@@ -105,7 +105,10 @@ def test_fused_every_kernel_form(engine, oracle, knobs):
                                    dict(CSGN_MUL_FLAT=1, CSGN_MUL_FLAT_U=2, CSGN_MUL_GRID=7),
                                    dict(CSGN_MUL_FLAT=1, CSGN_MUL_FLAT_U=8), dict(CSGN_MUL_FLAT=1, CSGN_MUL_TPB=128)])
 def test_flat_multiply_matches_oracle(engine, oracle, knobs):
-    """The chain-shape kernel (whole right operand in shared memory, output walked as one flat stream)."""
+    """The chain-shape kernel (whole right operand in shared memory, output walked as one flat stream) -- a losing
+    variant, compiled only with -DCSGN_BUILD_VARIANTS."""
+    if not engine.has_variants():
+        pytest.skip("libcsgn.so was built without the tuning variants")
     rng = np.random.default_rng(5)
     for N in (1247, 16383, 191, 2048):
         L = words_per_block(N)
@@ -308,3 +311,48 @@ def test_buffer_used_on_many_streams_then_freed(engine, oracle):
     torch.cuda.synchronize()
     got = counts.cpu().tolist()
     assert got[:32] == [w for w in wants for _ in (0, 1)]
+
+
+def test_batched_upload_shared_storage(engine, oracle):
+    """csgn_buf_upload_batch: n ragged operands (an empty one included) in one shared allocation and copies issued back to back;
+    the views feed batch products on the library's lanes, are freed in any order, and the storage is recycled."""
+    import ctypes
+    import torch
+    N, D = 1247, 3
+    L = words_per_block(N)
+    rng = np.random.default_rng(47)
+    ctx = engine.Context(N, D)
+    s = random_key(rng, N, D)
+    key = engine.SecretKey(ctx, s)
+    sizes_a, sizes_b = [700, 1, 333, 64, 0, 1200], [50, 900, 31, 64, 5, 2]
+    hosts = [torch.from_numpy(planted(rng, max(t, 1), N, s)[:t * L].view(np.int64).copy()).pin_memory() for t in sizes_a + sizes_b]
+    P = len(sizes_a)
+    up = engine.UploadBatch([h.data_ptr() for h in hosts], sizes_a + sizes_b, ctx)
+    want = [oracle.mul(hosts[p].numpy().view(np.uint64), hosts[P + p].numpy().view(np.uint64), L) if sizes_a[p] else
+            np.zeros(0, dtype=np.uint64) for p in range(P)]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    counts = torch.zeros(P, dtype=torch.int64, device=dev)
+    for rep in range(4):
+        ops = up.upload()
+        # every view reads back what went in
+        for i in (0, 3, P + 1):
+            got = engine.Ciphertext(ctypes.c_void_p(ops[i]), ctx)
+            assert np.array_equal(got.getValues(), hosts[i].numpy().view(np.uint64)), (rep, i)
+            got._h = None                                   # the array below still owns the handle
+        live = [p for p in range(P) if sizes_a[p]]
+        ha = (ctypes.c_void_p * len(live))(*[ops[p] for p in live])
+        hb = (ctypes.c_void_p * len(live))(*[ops[P + p] for p in live])
+        ho = (ctypes.c_void_p * len(live))()
+        counts.zero_()
+        engine.mul_count_batch_async(key, None, None, counts.data_ptr(), arrays=(ha, hb, ho))
+        if rep % 2:
+            engine.free_handles(ops)                        # operands released while the kernels are still queued
+        prods = [engine.Ciphertext(ctypes.c_void_p(ho[i]), ctx) for i in range(len(live))]
+        for i, p in enumerate(live):
+            assert np.array_equal(prods[i].getValues(), want[p]), (rep, p)
+            assert int(counts[i].item()) == oracle.count_satisfied(want[p], N, s), (rep, p)
+        if not rep % 2:
+            for i in reversed(range(2 * P)):                # one by one, last first
+                engine._lib().csgn_buf_free(ctypes.c_void_p(ops[i]))
+        del prods
+    engine.sync()
