@@ -1372,6 +1372,20 @@ int csgn_perm_create(uint64_t N, const uint64_t *perm, csgn_perm **out) {
                 slices[(size_t)j * W + c] = 4u * (stride * sc + (31u - (uint32_t)(p & 31u)));
             }
     }
+    // The plane kernel keeps slice (c, j) at word j*W + c of the tile itself: the same gather, other offsets.
+    std::vector<uint32_t> planes;
+    if (permute_plane_supported(h->L) && h->L >= 32) {
+        const uint32_t W = 2 * h->L;
+        planes.assign((size_t)32 * W, 4u * 32u * W);      // default = the zero words behind the tile
+        for (uint32_t c = 0; c < W; ++c)
+            for (uint32_t j = 0; j < 32; ++j) {
+                const uint64_t i = 64ull * (c >> 1) + ((c & 1u) ? 31u - j : 63u - j);
+                if (i >= N) continue;
+                const uint64_t p = perm[i];
+                const uint32_t sc = 2u * (uint32_t)(p >> 6) + (((p & 63u) < 32u) ? 1u : 0u);
+                planes[(size_t)j * W + c] = 4u * ((31u - (uint32_t)(p & 31u)) * W + sc);
+            }
+    }
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&h->d_map), (size_t)N * sizeof(uint32_t));
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(h->d_map, map.data(), (size_t)N * sizeof(uint32_t), cudaMemcpyHostToDevice, g.stream);
@@ -1381,10 +1395,17 @@ int csgn_perm_create(uint64_t N, const uint64_t *perm, csgn_perm **out) {
             e = cudaMemcpyAsync(h->d_slice_map, slices.data(), slices.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
                                 g.stream);
     }
+    if (e == cudaSuccess && !planes.empty()) {
+        e = cudaMalloc(reinterpret_cast<void **>(&h->d_plane_map), planes.size() * sizeof(uint32_t));
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(h->d_plane_map, planes.data(), planes.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                g.stream);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
     if (e != cudaSuccess) {
         if (h->d_map) cudaFree(h->d_map);
         if (h->d_slice_map) cudaFree(h->d_slice_map);
+        if (h->d_plane_map) cudaFree(h->d_plane_map);
         delete h;
         return cuda_fail(e, "permutation upload");
     }
@@ -1398,6 +1419,7 @@ int csgn_perm_free(csgn_perm *perm) {
         cudaStreamSynchronize(g.stream);
         cudaFree(perm->d_map);
         if (perm->d_slice_map) cudaFree(perm->d_slice_map);
+        if (perm->d_plane_map) cudaFree(perm->d_plane_map);
     }
     delete perm;
     return CSGN_OK;
@@ -1415,8 +1437,8 @@ int csgn_permute_into(const csgn_buf *c, const csgn_perm *perm, csgn_buf *out) {
     AutoLane lane(out->owns ? c : nullptr);
     acquire_read(c);
     acquire_write(out);
-    cudaError_t e = launch_permute(c->d, out->n_blocks, c->L, (uint32_t)perm->N, perm->d_map, perm->d_slice_map, out->d,
-                                   g.stream);
+    cudaError_t e = launch_permute(c->d, out->n_blocks, c->L, (uint32_t)perm->N, perm->d_map, perm->d_slice_map,
+                                   perm->d_plane_map, out->d, g.stream);
     if (e != cudaSuccess) return cuda_fail(e, "permute kernel");
     return CSGN_OK;
 }

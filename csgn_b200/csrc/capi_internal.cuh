@@ -75,6 +75,7 @@ struct csgn_key {
 struct csgn_perm {
     uint32_t *d_map = nullptr;   // N entries: (src_word << 6) | right_shift
     uint32_t *d_slice_map = nullptr;  // 64*L entries for the bit-sliced kernel (permute.cu), or null
+    uint32_t *d_plane_map = nullptr;  // 64*L entries for the plane kernel (long blocks), or null
     uint64_t N = 0;
     uint32_t L = 0;
 };

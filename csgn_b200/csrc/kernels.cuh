@@ -65,9 +65,12 @@ cudaError_t launch_peer_exchange(const PeerPush &pp, bool do_push, uint64_t valu
 // K4  out_bit[i] = in_bit[perm[i]] for every block     (reference src/Ciphertext.cpp:24-69)
 // src_map[i] = (perm[i]>>6)<<6 | (63 - (perm[i]&63)): source word and right-shift.
 // slice_map (optional, 64*L entries; see permute.cu) enables the bit-sliced tile kernel.
+// plane_map (optional, 64*L entries): the same gather for the plane kernel (long blocks; slices kept in the tile's own
+// 32 x 2L array): byte offset (j_src*2L + c_src)*4, or 4*32*2L (zero words) for pad bits.
 cudaError_t launch_permute(const uint64_t *in, uint64_t T, uint32_t L, uint32_t N, const uint32_t *src_map,
-                           const uint32_t *slice_map, uint64_t *out, cudaStream_t stream);
+                           const uint32_t *slice_map, const uint32_t *plane_map, uint64_t *out, cudaStream_t stream);
 bool permute_sliced_supported(uint32_t L);
+bool permute_plane_supported(uint32_t L);
 // Words between consecutive slice rows of a tile in shared memory (32 slices + padding; 16-byte
 // aligned rows, conflict-free 128-bit stores).  The slice map's byte offsets are built with it.
 constexpr uint32_t kPermSliceStride = 36;

@@ -282,6 +282,123 @@ permute_prefetch_kernel(const uint32_t *__restrict__ in, const uint64_t T, const
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Plane kernel, for long blocks (W >= 64 32-bit words).  A tile of 32 blocks is 32 rows of W words; its 32*W slices
+// are kept in the SAME 32 x W array -- slice (column c, bit j) at word j*W + c, "plane j" -- so a tile costs 128*W
+// bytes of shared memory and nothing else (N = 16383: 64 KB; the padded slice rows of the kernels above need 74 KB
+// next to a 64 KB raw tile, which leaves one CTA of 512 threads per SM).  Three CTAs of 256 threads are then
+// resident per SM at N = 16383 and run out of phase: while one transposes (integer pipe), another gathers (shared
+// memory) and the third loads or stores (HBM) -- the three resources this kernel needs in nearly equal measure.
+//   BULK = true : the tile arrives by ONE bulk asynchronous copy (cp.async.bulk, byte-counted on an mbarrier) issued
+//                 as soon as the previous tile's gathers are done; phase A transposes each column in place.
+//   BULK = false: phase A loads its column from global memory into registers (32 coalesced 128-byte warp rows).
+// Thread t owns columns t, t+THREADS, ...; lanes are consecutive columns, so every row access is conflict-free and
+// only the gather (random planes and columns) sees bank conflicts.  plane_map[j*W + c] = BYTE offset (j_src*W +
+// c_src)*4 of the source slice of output (column c, bit j), or of the zero words behind the tile for pad bits.
+// (Keeping the thread's 32 gather offsets in registers, packed two to a word, was measured too: no faster -- the
+// map loads are not what the kernel waits for -- and it spills at three CTAs per SM.)
+template <int WC, int THREADS, int MINB, bool BULK>
+__global__ void __launch_bounds__(THREADS, MINB)
+permute_plane_kernel(const uint32_t *__restrict__ in, const uint64_t T, const uint32_t Wrt,
+                     const uint32_t *__restrict__ plane_map, uint32_t *__restrict__ out, const uint64_t n_tiles) {
+    extern __shared__ __align__(128) uint32_t S[];
+    const uint32_t W = WC ? (uint32_t)WC : Wrt;
+    uint32_t *tile = S;                                                   // 32*W words, 4 zero words, the mbarrier
+    uint64_t *bar = reinterpret_cast<uint64_t *>(S + 32u * W + 4u);
+    const uint32_t tile_addr = smem_u32(tile);
+    if (threadIdx.x < 4) tile[32u * W + threadIdx.x] = 0u;
+    if (BULK && threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_init_fence();
+    }
+    __syncthreads();
+    pdl_enter();
+
+    // a tile whose byte count is not a multiple of 16 (the ragged last tile of an odd-L ciphertext) is loaded by the
+    // threads themselves; it can only be the last tile, so the mbarrier's phase stays in step with `it`
+    auto bulk_bytes = [&](uint64_t t) -> uint32_t {
+        const uint32_t blocks = (uint32_t)min((uint64_t)32u, T - t * 32u);
+        const uint32_t bytes = blocks * W * 4u;
+        return (bytes & 15u) ? 0u : bytes;
+    };
+    if (BULK && threadIdx.x == 0 && blockIdx.x < n_tiles) {
+        const uint32_t bytes = bulk_bytes(blockIdx.x);
+        if (bytes) {
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(tile, in + (uint64_t)blockIdx.x * 32u * W, bytes, bar);
+        }
+    }
+
+    uint32_t it = 0;
+    for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const uint64_t blk0 = t * 32u;
+        const uint32_t blocks = (uint32_t)min((uint64_t)32u, T - blk0);
+        const bool full = blocks == 32u;
+        // ---- phase A: every column of the tile transposed into its 32 planes
+        if (BULK) {
+            if (bulk_bytes(t)) mbar_wait(bar, it & 1u);
+            else {
+                const uint32_t *src = in + blk0 * W;
+                for (uint32_t idx = threadIdx.x; idx < blocks * W; idx += THREADS) tile[idx] = __ldcs(src + idx);
+                __syncthreads();
+            }
+            for (uint32_t c = threadIdx.x; c < W; c += THREADS) {
+                uint32_t x[32];
+#pragma unroll
+                for (int b = 0; b < 32; ++b) x[b] = tile[(uint32_t)b * W + c];   // rows past the end: stale words, whose
+                transpose32(x);                                                  // bits only reach rows that are not stored
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tile[(uint32_t)j * W + c] = x[j];
+            }
+        } else {
+            for (uint32_t c = threadIdx.x; c < W; c += THREADS) {
+                const uint32_t *src = in + blk0 * W + c;
+                uint32_t x[32];
+                if (full) {
+#pragma unroll
+                    for (int b = 0; b < 32; ++b) x[b] = __ldcs(src + (uint32_t)b * W);
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 32; ++b) x[b] = ((uint32_t)b < blocks) ? __ldcs(src + (uint64_t)b * W) : 0u;
+                }
+                transpose32(x);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tile[(uint32_t)j * W + c] = x[j];
+            }
+        }
+        __syncthreads();
+        // ---- phase B: gather the 32 source planes of every output column, transpose back, store
+        for (uint32_t c = threadIdx.x; c < W; c += THREADS) {
+            const uint32_t *map = plane_map + c;
+            uint32_t y[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) y[j] = lds_u32(tile_addr + __ldg(map + (uint32_t)j * W));
+            transpose32(y);
+            uint32_t *dst = out + blk0 * W + c;
+            if (full) {
+#pragma unroll
+                for (int b = 0; b < 32; ++b) __stcs(dst + (uint32_t)b * W, y[b]);
+            } else {
+#pragma unroll
+                for (int b = 0; b < 32; ++b)
+                    if ((uint32_t)b < blocks) __stcs(dst + (uint64_t)b * W, y[b]);
+            }
+        }
+        __syncthreads();   // every gather is done: the planes may be overwritten
+        if (BULK && threadIdx.x == 0) {
+            const uint64_t nxt = t + gridDim.x;
+            if (nxt < n_tiles) {
+                const uint32_t bytes = bulk_bytes(nxt);
+                if (bytes) {
+                    proxy_fence_async();
+                    mbar_expect_tx(bar, bytes);
+                    bulk_g2s(tile, in + nxt * 32u * W, bytes, bar);
+                }
+            }
+        }
+    }
+}
+
 // Any W (runtime): work items (tile, column) strided over the CTA's threads.
 __global__ void __launch_bounds__(512, 2)
 permute_sliced_kernel(const uint32_t *__restrict__ in, const uint64_t T, const uint32_t W,
@@ -401,6 +518,24 @@ cudaError_t launch_prefetch(const uint64_t *in, uint64_t T, const uint32_t *slic
                          reinterpret_cast<const uint32_t *>(in), T, slice_map, reinterpret_cast<uint32_t *>(out), n_groups);
 }
 
+template <int WC, int THREADS, int MINB, bool BULK>
+cudaError_t launch_plane(const uint64_t *in, uint64_t T, uint32_t W, const uint32_t *plane_map, uint64_t *out, int waves,
+                         cudaStream_t stream) {
+    const size_t smem = ((size_t)32 * W + 4) * sizeof(uint32_t) + 16;
+    static int per_sm = 0;
+    static size_t cached_smem = 0;
+    if (per_sm == 0 || cached_smem != smem) {
+        cudaError_t e = resident_ctas(permute_plane_kernel<WC, THREADS, MINB, BULK>, THREADS, smem, &per_sm);
+        if (e != cudaSuccess) return e;
+        cached_smem = smem;
+    }
+    const uint64_t n_tiles = (T + 31) / 32;
+    const uint64_t cap = (uint64_t)device_props().sm_count * per_sm * (uint64_t)std::max<long>(1, env_long("CSGN_PERM_WAVES", waves));
+    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, cap));
+    return launch_kernel(permute_plane_kernel<WC, THREADS, MINB, BULK>, grid, THREADS, smem, stream,
+                         reinterpret_cast<const uint32_t *>(in), T, W, plane_map, reinterpret_cast<uint32_t *>(out), n_tiles);
+}
+
 cudaError_t launch_sliced(const uint64_t *in, uint64_t T, uint32_t W, const uint32_t *slice_map, uint64_t *out,
                           uint32_t tiles_per_cta, uint32_t tpb, size_t smem, cudaStream_t stream) {
     const DeviceProps &dp = device_props();
@@ -428,11 +563,48 @@ bool permute_sliced_supported(uint32_t L) {
     return need <= device_props().smem_optin && 2 * L >= 1;
 }
 
+bool permute_plane_supported(uint32_t L) {
+    return ((size_t)64 * L + 4) * sizeof(uint32_t) + 16 <= device_props().smem_optin;
+}
+
 cudaError_t launch_permute(const uint64_t *in, uint64_t T, uint32_t L, uint32_t N, const uint32_t *src_map,
-                           const uint32_t *slice_map, uint64_t *out, cudaStream_t stream) {
+                           const uint32_t *slice_map, const uint32_t *plane_map, uint64_t *out, cudaStream_t stream) {
     if (T == 0 || L == 0) return cudaSuccess;
     const DeviceProps &dp = device_props();
     const bool aligned4 = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 3u) == 0;
+    if (plane_map && aligned4 && permute_plane_supported(L) && !env_long("CSGN_PERM_GATHER", 0)) {
+        const uint32_t W = 2 * L;
+        const long pv = env_long("CSGN_PERM_PLANE", -1);      // sweep knob: which instantiation
+        const bool aligned16 = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
+        if (pv >= 0) {
+            cudaError_t r = cudaErrorNotSupported;
+            switch (pv) {
+                case 0: if (W == 512 && aligned16) r = launch_plane<512, 256, 3, true>(in, T, W, plane_map, out, 1, stream); break;
+                case 1: if (W == 512) r = launch_plane<512, 256, 3, false>(in, T, W, plane_map, out, 1, stream); break;
+                case 2: if (W == 512 && aligned16) r = launch_plane<512, 512, 1, true>(in, T, W, plane_map, out, 1, stream); break;
+                case 3: if (W == 512) r = launch_plane<512, 512, 2, false>(in, T, W, plane_map, out, 1, stream); break;
+                case 4: if (W == 512) r = launch_plane<512, 128, 6, false>(in, T, W, plane_map, out, 1, stream); break;
+                case 5: if (W == 512 && aligned16) r = launch_plane<512, 128, 6, true>(in, T, W, plane_map, out, 1, stream); break;
+                case 6: r = launch_plane<0, 256, 3, false>(in, T, W, plane_map, out, 1, stream); break;
+                case 7: if (aligned16) r = launch_plane<0, 256, 3, true>(in, T, W, plane_map, out, 1, stream); break;
+                case 8: r = launch_plane<0, 128, 4, false>(in, T, W, plane_map, out, 1, stream); break;
+                case 9: if (aligned16) r = launch_plane<0, 512, 1, true>(in, T, W, plane_map, out, 1, stream); break;
+                case 10: if (W == 512 && aligned16) r = launch_plane<512, 512, 2, true>(in, T, W, plane_map, out, 1, stream); break;
+                case 11: if (W == 512 && aligned16) r = launch_plane<512, 384, 2, true>(in, T, W, plane_map, out, 1, stream); break;
+                case 12: if (W == 256 && aligned16) r = launch_plane<256, 128, 6, true>(in, T, W, plane_map, out, 1, stream); break;
+                case 13: if (W == 256 && aligned16) r = launch_plane<256, 256, 3, true>(in, T, W, plane_map, out, 1, stream); break;
+                case 14: if (W == 256 && aligned16) r = launch_plane<256, 256, 4, true>(in, T, W, plane_map, out, 1, stream); break;
+                case 15: if (W == 256) r = launch_plane<256, 128, 6, false>(in, T, W, plane_map, out, 1, stream); break;
+                case 16: if (aligned16) r = launch_plane<0, 1024, 1, true>(in, T, W, plane_map, out, 1, stream); break;
+                case 17: if (aligned16) r = launch_plane<0, 128, 6, true>(in, T, W, plane_map, out, 1, stream); break;
+                default: break;
+            }
+            if (r != cudaErrorNotSupported) {
+                count_launch();
+                return r;
+            }
+        }
+    }
     if (slice_map && aligned4 && permute_sliced_supported(L) && !env_long("CSGN_PERM_GATHER", 0)) {
         const uint32_t W = 2 * L;
         const long variant = env_long("CSGN_PERM_VARIANT", 0);   // 1: the runtime-W kernel even for known shapes

@@ -336,6 +336,27 @@ def test_permute_every_kernel_variant(engine, oracle, N):
                     assert np.array_equal(ct.applyPermutation(p).getValues(), want), (N, T, variant, waves)
 
 
+@pytest.mark.parametrize("N", [16383, 8191, 4097, 33000, 2111])
+def test_permute_plane_kernel_forms(engine, oracle, N):
+    """The plane kernel (long blocks: the slices live in the tile's own 32 x W array) in every instantiation the
+    launcher may pick -- bulk-copy fed and register fed, 1..4 columns per thread, compile-time and runtime W --
+    on ragged and multi-wave sizes; odd L (N = 4097, 33000 is even L = 516; 2111 has L = 33) takes the cooperative
+    load for its ragged last tile."""
+    rng = np.random.default_rng(N + 11)
+    ctx = engine.Context(N, 4)
+    perm = rng.permutation(N).astype(np.uint64)
+    p = engine.Permutation(ctx, perm)
+    for T in (1, 31, 32, 33, 97, 700):
+        v = random_blocks(rng, T, N)
+        ct = engine.Ciphertext.from_host(v, ctx)
+        want = oracle.permute_all(v, N, perm)
+        assert np.array_equal(ct.applyPermutation(p).getValues(), want), (N, T, "default")
+        for form in range(18):
+            for waves in (1, 2):
+                with _Env(CSGN_PERM_PLANE=form, CSGN_PERM_WAVES=waves):
+                    assert np.array_equal(ct.applyPermutation(p).getValues(), want), (N, T, form, waves)
+
+
 def test_permutation_must_be_a_bijection(engine):
     ctx = engine.Context(65, 2)
     bad = np.arange(65, dtype=np.uint64)
@@ -386,8 +407,12 @@ def test_config2_1000x1000_full_size(engine, oracle):
     assert permuted.n_blocks == prod.n_blocks
     k2 = engine.SecretKey(ctx, oracle.key_permute(1247, s, perm))
     assert k2.count_satisfied(permuted) == count
-    sample = prod.download_range(123456, 64)
-    assert np.array_equal(permuted.download_range(123456, 64), oracle.permute_all(sample, 1247, perm))
+    # EVERY word of the permuted 1M-block product against the oracle's permutation of the product (the
+    # earlier check sampled 64 blocks); the oracle walks the 10^6 blocks bit by bit in a few seconds
+    want = oracle.permute_all(prod.getValues(), 1247, perm)
+    assert np.array_equal(permuted.getValues(), want)
+    assert permuted.checksum() == oracle.checksum(want)
+    del want
     assert np.array_equal(prod.applyPermutation(p, strict_ref_truncate=True).getValues(),
                           oracle.permute_block(prod.download_range(0, 1), 1247, perm))
     # with the real D=16 on raw random blocks nothing is satisfied: decrypt is 0
