@@ -572,37 +572,48 @@ cudaError_t launch_permute(const uint64_t *in, uint64_t T, uint32_t L, uint32_t 
     if (T == 0 || L == 0) return cudaSuccess;
     const DeviceProps &dp = device_props();
     const bool aligned4 = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 3u) == 0;
-    if (plane_map && aligned4 && permute_plane_supported(L) && !env_long("CSGN_PERM_GATHER", 0)) {
+    if (plane_map && aligned4 && permute_plane_supported(L) && !env_long("CSGN_PERM_GATHER", 0) &&
+        !env_long("CSGN_PERM_VARIANT", 0)) {
         const uint32_t W = 2 * L;
         const long pv = env_long("CSGN_PERM_PLANE", -1);      // sweep knob: which instantiation
         const bool aligned16 = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
-        if (pv >= 0) {
-            cudaError_t r = cudaErrorNotSupported;
-            switch (pv) {
-                case 0: if (W == 512 && aligned16) r = launch_plane<512, 256, 3, true>(in, T, W, plane_map, out, 1, stream); break;
-                case 1: if (W == 512) r = launch_plane<512, 256, 3, false>(in, T, W, plane_map, out, 1, stream); break;
-                case 2: if (W == 512 && aligned16) r = launch_plane<512, 512, 1, true>(in, T, W, plane_map, out, 1, stream); break;
-                case 3: if (W == 512) r = launch_plane<512, 512, 2, false>(in, T, W, plane_map, out, 1, stream); break;
-                case 4: if (W == 512) r = launch_plane<512, 128, 6, false>(in, T, W, plane_map, out, 1, stream); break;
-                case 5: if (W == 512 && aligned16) r = launch_plane<512, 128, 6, true>(in, T, W, plane_map, out, 1, stream); break;
-                case 6: r = launch_plane<0, 256, 3, false>(in, T, W, plane_map, out, 1, stream); break;
-                case 7: if (aligned16) r = launch_plane<0, 256, 3, true>(in, T, W, plane_map, out, 1, stream); break;
-                case 8: r = launch_plane<0, 128, 4, false>(in, T, W, plane_map, out, 1, stream); break;
-                case 9: if (aligned16) r = launch_plane<0, 512, 1, true>(in, T, W, plane_map, out, 1, stream); break;
-                case 10: if (W == 512 && aligned16) r = launch_plane<512, 512, 2, true>(in, T, W, plane_map, out, 1, stream); break;
-                case 11: if (W == 512 && aligned16) r = launch_plane<512, 384, 2, true>(in, T, W, plane_map, out, 1, stream); break;
-                case 12: if (W == 256 && aligned16) r = launch_plane<256, 128, 6, true>(in, T, W, plane_map, out, 1, stream); break;
-                case 13: if (W == 256 && aligned16) r = launch_plane<256, 256, 3, true>(in, T, W, plane_map, out, 1, stream); break;
-                case 14: if (W == 256 && aligned16) r = launch_plane<256, 256, 4, true>(in, T, W, plane_map, out, 1, stream); break;
-                case 15: if (W == 256) r = launch_plane<256, 128, 6, false>(in, T, W, plane_map, out, 1, stream); break;
-                case 16: if (aligned16) r = launch_plane<0, 1024, 1, true>(in, T, W, plane_map, out, 1, stream); break;
-                case 17: if (aligned16) r = launch_plane<0, 128, 6, true>(in, T, W, plane_map, out, 1, stream); break;
-                default: break;
-            }
-            if (r != cudaErrorNotSupported) {
-                count_launch();
-                return r;
-            }
+        // The shipped forms (B200 sweeps: tools/perm_plane_sweep.py, profiles/r2_perm_plane_sweep*.log):
+        //   W = 512 (N = 16383): 3 CTAs of 256 threads per SM, 4 waves   69 us / 90,000 blocks (was 75), 0.90 of the copy peak at 10^6
+        //   W = 256 (N = 8191) : 6 CTAs of 128 threads per SM            57 us / 160,000 blocks (was 66)
+        //   other 128 <= W <= 448: the runtime-W form, 6 CTAs of 128 threads
+        // pv selects one of them by hand (tests); the other instantiations of the sweeps need -DCSGN_BUILD_VARIANTS.
+        cudaError_t r = cudaErrorNotSupported;
+        switch (pv) {
+            case -1:
+                if (W == 512 && aligned16) r = launch_plane<512, 256, 3, true>(in, T, W, plane_map, out, 4, stream);
+                else if (W == 256 && aligned16) r = launch_plane<256, 128, 6, true>(in, T, W, plane_map, out, 4, stream);
+                else if (W >= 128 && W <= 448 && aligned16) r = launch_plane<0, 128, 6, true>(in, T, W, plane_map, out, 16, stream);
+                break;
+            case 0: if (W == 512 && aligned16) r = launch_plane<512, 256, 3, true>(in, T, W, plane_map, out, 4, stream); break;
+            case 6: r = launch_plane<0, 256, 3, false>(in, T, W, plane_map, out, 4, stream); break;
+            case 12: if (W == 256 && aligned16) r = launch_plane<256, 128, 6, true>(in, T, W, plane_map, out, 4, stream); break;
+            case 17: if (aligned16) r = launch_plane<0, 128, 6, true>(in, T, W, plane_map, out, 16, stream); break;
+#ifdef CSGN_BUILD_VARIANTS
+            case 1: if (W == 512) r = launch_plane<512, 256, 3, false>(in, T, W, plane_map, out, 1, stream); break;
+            case 2: if (W == 512 && aligned16) r = launch_plane<512, 512, 1, true>(in, T, W, plane_map, out, 1, stream); break;
+            case 3: if (W == 512) r = launch_plane<512, 512, 2, false>(in, T, W, plane_map, out, 1, stream); break;
+            case 4: if (W == 512) r = launch_plane<512, 128, 6, false>(in, T, W, plane_map, out, 1, stream); break;
+            case 5: if (W == 512 && aligned16) r = launch_plane<512, 128, 6, true>(in, T, W, plane_map, out, 1, stream); break;
+            case 7: if (aligned16) r = launch_plane<0, 256, 3, true>(in, T, W, plane_map, out, 1, stream); break;
+            case 8: r = launch_plane<0, 128, 4, false>(in, T, W, plane_map, out, 1, stream); break;
+            case 9: if (aligned16) r = launch_plane<0, 512, 1, true>(in, T, W, plane_map, out, 1, stream); break;
+            case 10: if (W == 512 && aligned16) r = launch_plane<512, 512, 2, true>(in, T, W, plane_map, out, 1, stream); break;
+            case 11: if (W == 512 && aligned16) r = launch_plane<512, 384, 2, true>(in, T, W, plane_map, out, 1, stream); break;
+            case 13: if (W == 256 && aligned16) r = launch_plane<256, 256, 3, true>(in, T, W, plane_map, out, 1, stream); break;
+            case 14: if (W == 256 && aligned16) r = launch_plane<256, 256, 4, true>(in, T, W, plane_map, out, 1, stream); break;
+            case 15: if (W == 256) r = launch_plane<256, 128, 6, false>(in, T, W, plane_map, out, 1, stream); break;
+            case 16: if (aligned16) r = launch_plane<0, 1024, 1, true>(in, T, W, plane_map, out, 1, stream); break;
+#endif
+            default: break;
+        }
+        if (r != cudaErrorNotSupported) {
+            count_launch();
+            return r;
         }
     }
     if (slice_map && aligned4 && permute_sliced_supported(L) && !env_long("CSGN_PERM_GATHER", 0)) {
@@ -616,18 +627,20 @@ cudaError_t launch_permute(const uint64_t *in, uint64_t T, uint32_t L, uint32_t 
             return launch_prefetch<40, 4, 1, 4, 2>(in, T, slice_map, out, stream);
         }
         if (W == 40 && (variant == 0 || variant == 8)) return launch_fixed<40, 4, true, 4, 4>(in, T, slice_map, out, stream);
+#ifdef CSGN_BUILD_VARIANTS
         if (W == 40 && variant == 4 && aligned16) return launch_prefetch<40, 4, 2, 3, 1>(in, T, slice_map, out, stream);
         if (W == 40 && variant == 5 && aligned16) return launch_prefetch<40, 4, 1, 4, 1>(in, T, slice_map, out, stream);
         if (W == 40 && variant == 6 && aligned16) return launch_prefetch<40, 4, 2, 3, 4>(in, T, slice_map, out, stream);
         if (W == 40 && variant == 7 && aligned16) return launch_prefetch<40, 4, 1, 4, 4>(in, T, slice_map, out, stream);
         if (W == 40 && variant == 2) return launch_fixed<40, 4, false, 6, 4>(in, T, slice_map, out, stream);
         if (W == 40 && variant == 3) return launch_fixed<40, 8, true, 2, 4>(in, T, slice_map, out, stream);
-        // N=16383: one 64 KB tile + 74 KB of slices = one CTA per SM; the prefetch still wins (74.9 vs 79.8 us / 90,000 blocks)
-        if (W == 512 && variant == 0 && aligned16) return launch_prefetch<512, 1, 1, 1, 2>(in, T, slice_map, out, stream);
-        if (W == 512 && (variant == 0 || variant == 8)) return launch_fixed<512, 1, false, 2, 16>(in, T, slice_map, out, stream);
+        // N=16383 before the plane kernel: one 64 KB tile + 74 KB of slices = one CTA per SM (74.9 us / 90,000 blocks)
+        if (W == 512 && variant == 9 && aligned16) return launch_prefetch<512, 1, 1, 1, 2>(in, T, slice_map, out, stream);
+        if (W == 512 && variant == 8) return launch_fixed<512, 1, false, 2, 16>(in, T, slice_map, out, stream);
         if (W == 512 && variant == 2) return launch_fixed<512, 1, true, 1, 16>(in, T, slice_map, out, stream);
         if (W == 512 && variant == 4 && aligned16) return launch_prefetch<512, 1, 1, 1, 4>(in, T, slice_map, out, stream);
         if (W == 512 && variant == 5 && aligned16) return launch_prefetch<512, 1, 1, 1, 16>(in, T, slice_map, out, stream);
+#endif
         const uint32_t tile_words = kStride * W + 4u;
         // several tiles per CTA when a block is short
         uint32_t tiles_per_cta = std::max<uint32_t>(1, (uint32_t)env_long("CSGN_PERM_ITEMS", 160) / W);
