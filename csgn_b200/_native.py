@@ -46,6 +46,10 @@ SIGNATURES = {
     "csgn_mul_into": (ctypes.c_int, [_vp, _vp, _vp]),
     "csgn_concat": (ctypes.c_int, [_vp, _vp, _vpp]),
     "csgn_append": (ctypes.c_int, [_vp, _vp]),
+    "csgn_concat_lazy": (ctypes.c_int, [_vp, _vp, _vpp]),
+    "csgn_buf_segments": (ctypes.c_int, [_vp]),
+    "csgn_buf_retained": (ctypes.c_int, [_vp]),
+    "csgn_buf_flatten": (ctypes.c_int, [_vp]),
     "csgn_key_create": (ctypes.c_int, [_u64, _vp, ctypes.c_uint32, _vpp]),
     "csgn_key_free": (ctypes.c_int, [_vp]),
     "csgn_decrypt": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(ctypes.c_uint8)]),

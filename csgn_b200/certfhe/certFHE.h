@@ -82,6 +82,13 @@ public:
     // overlap that the batch entry points give.
     static void setAutoLanes(bool on);
     static bool getAutoLanes();
+    // Zero-copy sums (ON by default; CSGN_ROPE_SUMS=0 or setRopeSums(false) copies both operands, as the first release
+    // did).  operator+ of two large ciphertexts returns a ciphertext that REFERS to the operands' device storage
+    // instead of copying 2 x their size (csgn_concat_lazy): decrypt, applyPermutation and a product with the sum on
+    // the left walk the parts; anything that needs one array (getValues, a product with the sum on the right, save)
+    // makes it dense once.  Small operands are copied -- a loop of `acc = acc + fresh` stays one array.
+    static void setRopeSums(bool on);
+    static bool getRopeSums();
     // Multi-GPU, one process per GPU.  connectPeers joins the `world` processes of a job: every
     // rank publishes the handle of its mailbox under rendezvous_dir (csgn_comm_connect_dir; `job_tag` unique per
     // job) and maps the others' over NVLink.  initializeLibrary() does this by itself when the launcher exports

@@ -427,7 +427,10 @@ Ciphertext Ciphertext::operator+(const Ciphertext &c) const {
     if (ctx) out.certFHEcontext = new Context(*ctx);
     if (a && b) {
         csgn_buf *sum = nullptr;
-        glue::check(csgn_concat(a, b, &sum), "csgn_concat");
+        // the reference copies both operands (src/Ciphertext.cpp:215-223, then again in the constructor); large
+        // operands are referred to instead (a lazy sum), small ones copied once
+        if (Library::getRopeSums()) glue::check(csgn_concat_lazy(a, b, &sum), "csgn_concat_lazy");
+        else glue::check(csgn_concat(a, b, &sum), "csgn_concat");
         out.dev = adopt(sum);
     } else if (a || b) {
         out.dev = a ? dev : c.dev;   // x + (empty) is x: share it
@@ -449,7 +452,8 @@ Ciphertext &Ciphertext::operator+=(const Ciphertext &c) {
         sharded = c.sharded;
         dev = rhs;
     } else {
-        if (dev.use_count() > 1 + (dev == rhs ? 1 : 0)) {   // shared with a copy: do not grow it under the other owner
+        if (dev.use_count() > 1 + (dev == rhs ? 1 : 0) || csgn_buf_retained(dev.get())) {
+            // shared with a copy, or part of a lazy sum: do not grow it under the other owner
             csgn_buf *mine = nullptr;
             glue::check(csgn_buf_clone(dev.get(), &mine), "csgn_buf_clone");
             dev = adopt(mine);

@@ -21,6 +21,8 @@ bool g_fused_products = true;
 bool g_fused_products_set = false;
 bool g_auto_lanes = true;
 bool g_auto_lanes_set = false;
+bool g_rope_sums = true;
+bool g_rope_sums_set = false;
 
 bool env_flag(const char *name, bool dflt) {
     const char *e = getenv(name);
@@ -130,6 +132,19 @@ bool Library::getAutoLanes() {
         g_auto_lanes_set = true;
     }
     return g_auto_lanes;
+}
+
+void Library::setRopeSums(bool on) {
+    g_rope_sums = on;
+    g_rope_sums_set = true;
+}
+
+bool Library::getRopeSums() {
+    if (!g_rope_sums_set) {
+        g_rope_sums = env_flag("CSGN_ROPE_SUMS", true);
+        g_rope_sums_set = true;
+    }
+    return g_rope_sums;
 }
 
 void Library::synchronize() {

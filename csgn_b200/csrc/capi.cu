@@ -257,6 +257,53 @@ int new_buf(uint64_t n_blocks, uint32_t L, uint64_t cap_words, csgn_buf **out, c
     return CSGN_OK;
 }
 
+// Copy the words of `src` (dense or a lazy sum) to dst on the current stream.
+int copy_words_into(const csgn_buf *src, uint64_t *dst) {
+    if (!is_rope(src)) {
+        acquire_read(src);
+        cudaError_t e = launch_concat(src->d, src->n_blocks * src->L, nullptr, 0, dst, g.stream);
+        return e == cudaSuccess ? CSGN_OK : cuda_fail(e, "copy kernel");
+    }
+    uint64_t off = 0;
+    for (size_t i = 0; i < src->segs.size(); i += 2) {          // two segments per launch (the copy kernel has two sources)
+        const csgn_buf *x = src->segs[i], *y = i + 1 < src->segs.size() ? src->segs[i + 1] : nullptr;
+        acquire_read(x);
+        if (y) acquire_read(y);
+        const uint64_t nx = x->n_blocks * x->L, ny = y ? y->n_blocks * y->L : 0;
+        cudaError_t e = launch_concat(x->d, nx, y ? y->d : nullptr, ny, dst + off, g.stream);
+        if (e != cudaSuccess) return cuda_fail(e, "copy kernel");
+        off += nx + ny;
+    }
+    return CSGN_OK;
+}
+
+void drop_segments(const csgn_buf *b) {
+    std::vector<csgn_buf *> segs;
+    segs.swap(b->segs);
+    for (csgn_buf *x : segs) csgn_buf_free(x);
+}
+
+int need_dense(const csgn_buf *b) {
+    if (!is_rope(b)) return CSGN_OK;
+    csgn_buf *m = const_cast<csgn_buf *>(b);
+    uint64_t *d = nullptr;
+    const uint64_t words = b->n_blocks * b->L;
+    int rc = dev_alloc(words, &d);
+    if (rc != CSGN_OK) return rc;
+    rc = copy_words_into(b, d);
+    if (rc != CSGN_OK) {
+        dev_free(d);
+        return rc;
+    }
+    m->d = d;
+    m->cap_words = words;
+    m->owns = true;
+    m->writer = {g.stream, g.tick++};
+    m->readers.clear();
+    drop_segments(b);          // the segments' storage is released in stream order, after the copies that read it
+    return CSGN_OK;
+}
+
 }  // namespace detail
 
 using namespace detail;
@@ -663,11 +710,10 @@ int csgn_buf_clone(const csgn_buf *src, csgn_buf **out) {
     AutoLane lane(src);
     int rc = new_buf(src->n_blocks, src->L, 0, &b);
     if (rc != CSGN_OK) return rc;
-    acquire_read(src);
-    cudaError_t e = launch_concat(src->d, src->n_blocks * src->L, nullptr, 0, b->d, g.stream);
-    if (e != cudaSuccess) {
+    rc = copy_words_into(src, b->d);       // a lazy sum is copied segment by segment
+    if (rc != CSGN_OK) {
         csgn_buf_free(b);
-        return cuda_fail(e, "clone kernel");
+        return rc;
     }
     *out = b;
     return CSGN_OK;
@@ -681,7 +727,9 @@ int csgn_buf_slice(const csgn_buf *src, uint64_t first_block, uint64_t n_blocks,
                     (unsigned long long)first_block, (unsigned long long)n_blocks, (unsigned long long)src->n_blocks);
     csgn_buf *b = nullptr;
     AutoLane lane(src);
-    int rc = new_buf(n_blocks, src->L, 0, &b);
+    int rc = need_dense(src);
+    if (rc != CSGN_OK) return rc;
+    rc = new_buf(n_blocks, src->L, 0, &b);
     if (rc != CSGN_OK) return rc;
     acquire_read(src);
     cudaError_t e = launch_concat(src->d + first_block * src->L, n_blocks * src->L, nullptr, 0, b->d, g.stream);
@@ -701,6 +749,10 @@ int csgn_buf_download_range(const csgn_buf *buf, uint64_t first_block, uint64_t 
                     (unsigned long long)first_block, (unsigned long long)n_blocks, (unsigned long long)buf->n_blocks);
     if (n_blocks == 0) return CSGN_OK;
     if (!host_words) return fail(CSGN_ERR_INVALID_ARGUMENT, "null host destination");
+    {
+        int rc = need_dense(buf);
+        if (rc != CSGN_OK) return rc;
+    }
     acquire_read(buf);
     CU(cudaMemcpyAsync(host_words, buf->d + first_block * buf->L, n_blocks * buf->L * sizeof(uint64_t),
                        cudaMemcpyDeviceToHost, g.stream));
@@ -741,6 +793,15 @@ void release_slab_view(csgn_buf *buf) {
 
 int csgn_buf_free(csgn_buf *buf) {
     if (!buf) return CSGN_OK;
+    if (buf->refs > 1) {            // a lazy sum still refers to it: the last reference releases the storage
+        --buf->refs;
+        return CSGN_OK;
+    }
+    if (is_rope(buf)) {
+        drop_segments(buf);
+        delete buf;
+        return CSGN_OK;
+    }
     if (buf->slab) {
         release_slab_view(buf);
         delete buf;
@@ -767,7 +828,10 @@ uint32_t csgn_buf_words_per_block(const csgn_buf *buf) { return buf ? buf->L : 0
 void *csgn_buf_device_ptr(const csgn_buf *buf) {
     // Whoever uses the pointer does so on the caller's current stream, in ways the library cannot see: order that
     // stream after everything the library has in flight on the words, and treat it as their writer from now on.
-    if (buf && g.inited) acquire_write(buf);
+    if (buf && g.inited) {
+        if (need_dense(buf) != CSGN_OK) return nullptr;
+        acquire_write(buf);
+    }
     return buf ? buf->d : nullptr;
 }
 
@@ -792,7 +856,8 @@ int check_mul_out(const csgn_buf *a, const csgn_buf *b, const csgn_buf *out) {
     if (out->n_blocks != a->n_blocks * b->n_blocks)
         return fail(CSGN_ERR_SHAPE_MISMATCH, "output holds %llu blocks, product has %llu",
                     (unsigned long long)out->n_blocks, (unsigned long long)(a->n_blocks * b->n_blocks));
-    if (out->d == a->d || out->d == b->d) return fail(CSGN_ERR_INVALID_ARGUMENT, "output aliases an operand");
+    if (out->d && (out->d == a->d || out->d == b->d)) return fail(CSGN_ERR_INVALID_ARGUMENT, "output aliases an operand");
+    if (out->refs > 1) return fail(CSGN_ERR_INVALID_ARGUMENT, "output is part of a lazy sum (csgn_concat_lazy): clone it first");
     return CSGN_OK;
 }
 
@@ -800,6 +865,24 @@ int check_mul_out(const csgn_buf *a, const csgn_buf *b, const csgn_buf *out) {
 // count goes to device_count and/or into the peer exchange `pp`.  One launch where a fused kernel exists.
 int enqueue_mul(const csgn_buf *a, const csgn_buf *b, csgn_buf *out, const csgn_key *key, uint64_t *device_count,
                 const PeerPush *pp) {
+    int rc0 = need_dense(b);                       // a lazy RIGHT operand interleaves with every row: one dense array
+    if (rc0 == CSGN_OK && out) rc0 = need_dense(out);
+    if (rc0 == CSGN_OK && (key || !out)) rc0 = need_dense(a);
+    if (rc0 != CSGN_OK) return rc0;
+    if (is_rope(a)) {
+        // (A1 || A2 || ...) * B = (A1*B) || (A2*B) || ...  (output is i-major, src/Ciphertext.cpp:159): one launch per
+        // segment of the left operand, each into its own row range of the dense product -- the sum is never copied
+        acquire_read(b);
+        acquire_write(out);
+        uint64_t row = 0;
+        for (const csgn_buf *x : a->segs) {
+            acquire_read(x);
+            cudaError_t e = launch_mul(x->d, x->n_blocks, b->d, b->n_blocks, a->L, out->d + row * b->n_blocks * a->L, g.stream);
+            if (e != cudaSuccess) return cuda_fail(e, "multiply kernel");
+            row += x->n_blocks;
+        }
+        return CSGN_OK;
+    }
     acquire_read(a);
     acquire_read(b);
     if (out) acquire_write(out);
@@ -961,6 +1044,16 @@ int csgn_concat(const csgn_buf *a, const csgn_buf *b, csgn_buf **out) {
     csgn_buf *c = nullptr;
     int rc = new_buf(a->n_blocks + b->n_blocks, a->L, 0, &c);
     if (rc != CSGN_OK) return rc;
+    if (is_rope(a) || is_rope(b)) {
+        rc = copy_words_into(a, c->d);
+        if (rc == CSGN_OK) rc = copy_words_into(b, c->d + a->n_blocks * a->L);
+        if (rc != CSGN_OK) {
+            csgn_buf_free(c);
+            return rc;
+        }
+        *out = c;
+        return CSGN_OK;
+    }
     acquire_read(a);
     acquire_read(b);
     cudaError_t e = launch_concat(a->d, a->n_blocks * a->L, b->d, b->n_blocks * b->L, c->d, g.stream);
@@ -972,14 +1065,66 @@ int csgn_concat(const csgn_buf *a, const csgn_buf *b, csgn_buf **out) {
     return CSGN_OK;
 }
 
+// a || b without moving a word: the result refers to the operands' storage.
+namespace {
+constexpr size_t kRopeMaxSegments = 32;
+constexpr uint64_t kRopeMinWords = (1ull << 20) / 8;      // below 1 MiB a copy is cheaper than one more segment to walk
+void add_segments(csgn_buf *r, const csgn_buf *x) {
+    if (is_rope(x)) {
+        for (csgn_buf *sgm : x->segs) {
+            ++sgm->refs;
+            r->segs.push_back(sgm);
+        }
+    } else if (x->n_blocks) {
+        csgn_buf *m = const_cast<csgn_buf *>(x);
+        ++m->refs;
+        r->segs.push_back(m);
+    }
+}
+}  // namespace
+
+int csgn_concat_lazy(const csgn_buf *a, const csgn_buf *b, csgn_buf **out) {
+    NEED_INIT();
+    if (!a || !b || !out) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
+    if (a->L != b->L) return fail(CSGN_ERR_SHAPE_MISMATCH, "words per block differ (%u vs %u)", a->L, b->L);
+    const size_t na = is_rope(a) ? a->segs.size() : 1, nb = is_rope(b) ? b->segs.size() : 1;
+    const uint64_t wa = a->n_blocks * a->L, wb = b->n_blocks * b->L;
+    // small operands, and sums that would grow a long tail of segments, are copied (csgn_concat)
+    if (wa < kRopeMinWords || wb < kRopeMinWords || na + nb > kRopeMaxSegments) return csgn_concat(a, b, out);
+    csgn_buf *r = new csgn_buf;
+    r->L = a->L;
+    r->n_blocks = a->n_blocks + b->n_blocks;
+    r->cap_words = 0;
+    add_segments(r, a);
+    add_segments(r, b);
+    *out = r;
+    return CSGN_OK;
+}
+
+int csgn_buf_segments(const csgn_buf *buf) { return !buf ? 0 : is_rope(buf) ? (int)buf->segs.size() : 1; }
+int csgn_buf_retained(const csgn_buf *buf) { return buf && buf->refs > 1 ? 1 : 0; }
+
+int csgn_buf_flatten(csgn_buf *buf) {
+    NEED_INIT();
+    if (!buf) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
+    AutoLane lane(buf);
+    return need_dense(buf);
+}
+
 int csgn_append(csgn_buf *a, const csgn_buf *b) {
     NEED_INIT();
     if (!a || !b) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
     if (!a->owns) return fail(CSGN_ERR_INVALID_ARGUMENT, "cannot grow a non-owning view");
+    if (a->refs > 1) return fail(CSGN_ERR_INVALID_ARGUMENT, "cannot grow a buffer that is part of a lazy sum: clone it first");
     if (a->L != b->L) return fail(CSGN_ERR_SHAPE_MISMATCH, "words per block differ (%u vs %u)", a->L, b->L);
     const uint64_t na = a->n_blocks * a->L, nb = b->n_blocks * b->L;
     if (nb == 0) return CSGN_OK;
     AutoLane lane(a, nullptr);           // the grown ciphertext stays on the stream that built it
+    {
+        int rc = need_dense(a);
+        if (rc == CSGN_OK) rc = need_dense(b);
+        if (rc != CSGN_OK) return rc;
+    }
     acquire_write(a);
     if (b != a) acquire_read(b);
     if (na + nb <= a->cap_words) {
@@ -1063,9 +1208,27 @@ int csgn_decrypt_count_async(const csgn_buf *c, const csgn_key *key, uint64_t *d
     if (!c || !key || !device_count) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
     if (c->L != key->L)
         return fail(CSGN_ERR_SHAPE_MISMATCH, "ciphertext has %u words per block, key expects %u", c->L, key->L);
+    const uint64_t *hm = key->h_mask.empty() ? nullptr : key->h_mask.data();
+    if (is_rope(c)) {
+        // the count of a concatenation is the sum of its parts' counts (src/SecretKey.cpp:139 XORs block by block):
+        // one fold per segment into a scratch word each, then a one-warp sum -- the sum is never copied together
+        const uint32_t n = (uint32_t)c->segs.size();
+        uint64_t *part = nullptr;
+        int rc = dev_alloc(n, &part);
+        if (rc != CSGN_OK) return rc;
+        cudaError_t e = cudaSuccess;
+        for (uint32_t i = 0; i < n && e == cudaSuccess; ++i) {
+            const csgn_buf *x = c->segs[i];
+            acquire_read(x);
+            e = launch_decrypt_count(x->d, x->n_blocks, x->L, key->d_mask, hm, fold_scratch(), part + i, g.stream, nullptr,
+                                     folds_overlap());
+        }
+        if (e == cudaSuccess) e = launch_sum_words(part, n, device_count, g.stream);
+        dev_free(part);
+        return e == cudaSuccess ? CSGN_OK : cuda_fail(e, "decrypt kernel");
+    }
     acquire_read(c);
-    cudaError_t e = launch_decrypt_count(c->d, c->n_blocks, c->L, key->d_mask,
-                                         key->h_mask.empty() ? nullptr : key->h_mask.data(), fold_scratch(), device_count,
+    cudaError_t e = launch_decrypt_count(c->d, c->n_blocks, c->L, key->d_mask, hm, fold_scratch(), device_count,
                                          g.stream, nullptr, folds_overlap());
     if (e != cudaSuccess) return cuda_fail(e, "decrypt kernel");
     return CSGN_OK;
@@ -1433,8 +1596,28 @@ int csgn_permute_into(const csgn_buf *c, const csgn_perm *perm, csgn_buf *out) {
                     out->L, perm->L);
     if (out->n_blocks > c->n_blocks)
         return fail(CSGN_ERR_SHAPE_MISMATCH, "output holds more blocks than the input");
-    if (out->d == c->d) return fail(CSGN_ERR_INVALID_ARGUMENT, "permute cannot run in place");
+    if (out->d && out->d == c->d) return fail(CSGN_ERR_INVALID_ARGUMENT, "permute cannot run in place");
+    if (out->refs > 1) return fail(CSGN_ERR_INVALID_ARGUMENT, "output is part of a lazy sum (csgn_concat_lazy): clone it first");
     AutoLane lane(out->owns ? c : nullptr);
+    {
+        int rc = need_dense(out);
+        if (rc != CSGN_OK) return rc;
+    }
+    if (is_rope(c)) {
+        // a permutation acts on every block by itself: each segment goes straight to its place in the dense result
+        acquire_write(out);
+        uint64_t done = 0;
+        for (const csgn_buf *x : c->segs) {
+            if (done >= out->n_blocks) break;
+            const uint64_t n = std::min<uint64_t>(x->n_blocks, out->n_blocks - done);
+            acquire_read(x);
+            cudaError_t e = launch_permute(x->d, n, c->L, (uint32_t)perm->N, perm->d_map, perm->d_slice_map, perm->d_plane_map,
+                                           out->d + done * c->L, g.stream);
+            if (e != cudaSuccess) return cuda_fail(e, "permute kernel");
+            done += n;
+        }
+        return CSGN_OK;
+    }
     acquire_read(c);
     acquire_write(out);
     cudaError_t e = launch_permute(c->d, out->n_blocks, c->L, (uint32_t)perm->N, perm->d_map, perm->d_slice_map,
@@ -1467,6 +1650,10 @@ int csgn_buf_checksum(const csgn_buf *buf, uint64_t *xor_out, uint64_t *sum_out,
     NEED_INIT();
     if (!buf) return fail(CSGN_ERR_INVALID_ARGUMENT, "null handle");
     uint64_t *acc = g.d_scratch + 4;
+    {
+        int rc = need_dense(buf);
+        if (rc != CSGN_OK) return rc;
+    }
     acquire_read(buf);
     CU(cudaMemsetAsync(acc, 0, 3 * sizeof(uint64_t), g.stream));
     cudaError_t e = launch_checksum(buf->d, buf->n_blocks * buf->L, acc, g.stream);

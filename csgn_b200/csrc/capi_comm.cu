@@ -208,6 +208,8 @@ int csgn_decrypt_sharded_async(const csgn_buf *c, const csgn_key *key, csgn_comm
     if (c->L != key->L)
         return fail(CSGN_ERR_SHAPE_MISMATCH, "ciphertext has %u words per block, key expects %u", c->L, key->L);
     if (c->n_blocks > kPeerCountMask) return fail(CSGN_ERR_INVALID_ARGUMENT, "shard too large for a 40-bit count");
+    rc = need_dense(c);          // the fold that publishes to the peers reads one array
+    if (rc != CSGN_OK) return rc;
     PeerPush pp;
     rc = fill_push(comm, true, collect_n, collect_lag, device_totals, &pp);
     if (rc != CSGN_OK) return rc;

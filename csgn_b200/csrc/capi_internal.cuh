@@ -43,6 +43,11 @@ struct csgn_buf {
     bool owns = true;
     bool recycle = false;      // storage of an upload: goes back to the upload cache, not to the pool
     csgn_slab *slab = nullptr; // a view into a batched upload's shared storage (owns == false)
+    // Lazy sum (csgn_concat_lazy): the value is the concatenation of these buffers, each kept alive by a reference,
+    // and d == nullptr until some operation needs one dense array (flatten).  decrypt, permute and a product with the
+    // sum as LEFT operand walk the segments instead.
+    mutable std::vector<csgn_buf *> segs;
+    uint32_t refs = 1;         // the caller's handle + one per lazy sum that refers to this buffer
     // An upload on the copy stream that may still be in flight.  EVERY stream that consumes the buffer waits for it
     // (ready_waited remembers which already did); the event goes back to the pool once it is known to have completed.
     mutable cudaEvent_t ready = nullptr;
@@ -177,6 +182,10 @@ void acquire_write(const csgn_buf *b);
 // The host has synchronised `s`: every use recorded on it so far is complete.
 void note_synced(cudaStream_t s);
 int new_buf(uint64_t n_blocks, uint32_t L, uint64_t cap_words, csgn_buf **out, cudaStream_t stream = nullptr);
+// A lazy sum becomes one dense array on the current stream (no-op for a dense buffer).  Every entry point that needs
+// `b->d` calls this first; the segment-aware ones (decrypt, permute, product with a lazy LEFT operand, concat) do not.
+int need_dense(const csgn_buf *b);
+inline bool is_rope(const csgn_buf *b) { return b && !b->segs.empty(); }
 // The fold scratch word of the current stream.
 uint64_t *fold_scratch();
 // True inside a batch call or with automatic lanes: folds run next to other kernels (several shorter waves).

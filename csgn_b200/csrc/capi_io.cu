@@ -55,6 +55,10 @@ int csgn_buf_save(const csgn_buf *buf, uint64_t N, uint64_t D, const char *path)
     if (csgn_words_per_block(N) != buf->L)
         return fail(CSGN_ERR_SHAPE_MISMATCH, "N = %llu gives %u words per block, buffer has %u", (unsigned long long)N,
                     csgn_words_per_block(N), buf->L);
+    {
+        int rc = need_dense(buf);
+        if (rc != CSGN_OK) return rc;
+    }
     FILE *f = fopen(path, "wb");
     if (!f) return fail(CSGN_ERR_INVALID_ARGUMENT, "cannot open %s for writing", path);
     FileHeader h;

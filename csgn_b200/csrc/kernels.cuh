@@ -47,6 +47,9 @@ bool mul_fold_supported(uint32_t L);
 cudaError_t launch_concat(const uint64_t *a, uint64_t n_words_a, const uint64_t *b, uint64_t n_words_b,
                           uint64_t *out, cudaStream_t stream);
 
+// out[0] = sum of in[0..n): the partial counts of a ciphertext held as several segments (a lazy sum)
+cudaError_t launch_sum_words(const uint64_t *in, uint32_t n, uint64_t *out, cudaStream_t stream);
+
 // K3  count of blocks with all_w((v[w] & M[w]) == M[w]) (reference src/SecretKey.cpp:126-140)
 // `scratch` is one zero-initialised uint64 (count | CTA ticket << 40, fold.cuh) that the kernel
 // leaves zeroed again; the total is written to *count_out (device memory).  `overlapped`: the caller runs

@@ -64,7 +64,23 @@ checksum_kernel(const uint64_t *__restrict__ v, const uint64_t n_words, uint64_t
     }
 }
 
+// out[0] = in[0] + ... + in[n-1]   (the partial counts of a ciphertext held as several segments)
+__global__ void __launch_bounds__(32)
+sum_words_kernel(const uint64_t *__restrict__ in, const uint32_t n, uint64_t *out) {
+    pdl_enter();
+    uint64_t s = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += 32) s += in[i];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (threadIdx.x == 0) *out = s;
+}
+
 }  // namespace
+
+cudaError_t launch_sum_words(const uint64_t *in, uint32_t n, uint64_t *out, cudaStream_t stream) {
+    count_launch();
+    return launch_kernel(sum_words_kernel, 1, 32, 0, stream, in, n, out);
+}
 
 cudaError_t launch_concat(const uint64_t *a, uint64_t n_words_a, const uint64_t *b, uint64_t n_words_b,
                           uint64_t *out, cudaStream_t stream) {

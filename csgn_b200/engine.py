@@ -248,6 +248,20 @@ class Ciphertext:
         check(_lib().csgn_append(self._h, other._h))
         return self
 
+    def add_lazy(self, other):
+        """csgn_concat_lazy: self || other without copying (a rope of the operands' storage)."""
+        h = _vp()
+        check(_lib().csgn_concat_lazy(self._h, other._h, ctypes.byref(h)))
+        return Ciphertext(h, self.ctx)
+
+    @property
+    def segments(self):
+        return int(_lib().csgn_buf_segments(self._h))
+
+    def flatten(self):
+        check(_lib().csgn_buf_flatten(self._h))
+        return self
+
     def applyPermutation(self, perm, strict_ref_truncate=False):
         h = _vp()
         check(_lib().csgn_permute(self._h, perm._h, 1 if strict_ref_truncate else 0, ctypes.byref(h)))

@@ -141,6 +141,18 @@ int csgn_concat(const csgn_buf *a, const csgn_buf *b, csgn_buf **out);
 /* operator+= (src/Ciphertext.cpp:249-281): a = a || b, growing a's storage
  * geometrically so that a chain of += copies each block O(1) times. */
 int csgn_append(csgn_buf *a, const csgn_buf *b);
+/* The same sum WITHOUT moving a word ("add as a zero-copy rope"): the result refers to the storage of
+ * a and b -- each kept alive by a reference, so the caller may free its own handles at once -- and is one logical
+ * ciphertext of a.blocks + b.blocks blocks.  decrypt folds segment by segment and sums the counts, permute and a
+ * product with the sum as LEFT operand ((A1||A2)*B = (A1*B)||(A2*B)) write each segment's share straight into the
+ * dense result; everything else (download, right operand, save, csgn_buf_device_ptr ...) first makes it one dense
+ * array, once, inside the library (csgn_buf_flatten does it by hand).  Operands below 1 MiB, and sums that would
+ * exceed 32 segments, are copied as by csgn_concat.  A buffer that a lazy sum refers to (csgn_buf_retained) cannot be
+ * grown or overwritten in place: csgn_append / *_into refuse it; clone it first. */
+int csgn_concat_lazy(const csgn_buf *a, const csgn_buf *b, csgn_buf **out);
+int csgn_buf_segments(const csgn_buf *buf);   /* 1 for a dense buffer */
+int csgn_buf_retained(const csgn_buf *buf);   /* 1 while some lazy sum refers to it */
+int csgn_buf_flatten(csgn_buf *buf);
 
 /* Secret key as the per-word position mask M[s>>6] |= 1<<(63-(s&63)); the block
  * predicate of SecretKey::decrypt (src/SecretKey.cpp:131-137) is all_w((v&M)==M). */

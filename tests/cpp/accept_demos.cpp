@@ -287,6 +287,47 @@ static void fused_products() {
     EXPECT(set.getValue() == 1);
 }
 
+// Zero-copy sums (the default): operator+ of large ciphertexts refers to the operands instead of copying them.
+static void rope_sums() {
+    Context context(1247, 16);
+    SecretKey seckey(context);
+    srand(123);
+    std::vector<unsigned char> bx(9000), by(8000), bz(3);
+    int px = 0, py = 0, pz = 0;
+    for (size_t i = 0; i < bx.size(); ++i) { bx[i] = rand() & 1; px ^= bx[i]; }
+    for (size_t i = 0; i < by.size(); ++i) { by[i] = rand() & 1; py ^= by[i]; }
+    for (size_t i = 0; i < bz.size(); ++i) { bz[i] = rand() & 1; pz ^= bz[i]; }
+    Ciphertext x = seckey.encryptBatch(bx.data(), bx.size(), 1), y = seckey.encryptBatch(by.data(), by.size(), 2);
+    Ciphertext z = seckey.encryptBatch(bz.data(), bz.size(), 3);
+    Library::setRopeSums(false);
+    Ciphertext copied = x + y;                              // csgn_concat: both operands copied
+    Library::setRopeSums(true);
+    EXPECT(Library::getRopeSums());
+    Ciphertext sum = x + y;                                 // refers to x and y
+    EXPECT(sum.getLen() == copied.getLen() && sum.getBlocks() == 17000);
+    EXPECT(seckey.decrypt(sum).getValue() == (px ^ py));
+    Permutation pi(context);
+    SecretKey pk = seckey.applyPermutation(pi);
+    Ciphertext psum = sum.applyPermutation(pi);
+    EXPECT(pk.decrypt(psum).getValue() == (px ^ py));
+    EXPECT(memcmp(psum.getValues(), copied.applyPermutation(pi).getValues(), copied.getLen() * 8) == 0);
+    Ciphertext left = sum * z, right = z * sum;             // sum on the left: per part; on the right: made dense once
+    EXPECT(seckey.decrypt(left).getValue() == ((px ^ py) & pz));
+    EXPECT(memcmp(left.getValues(), (copied * z).getValues(), left.getLen() * 8) == 0);
+    EXPECT(memcmp(right.getValues(), (z * copied).getValues(), right.getLen() * 8) == 0);
+    // growing an operand afterwards must not change the sum
+    Ciphertext sum2 = x + y;
+    x += z;
+    EXPECT(x.getBlocks() == 9003 && sum2.getBlocks() == 17000);
+    EXPECT(memcmp(sum2.getValues(), copied.getValues(), copied.getLen() * 8) == 0);
+    EXPECT(seckey.decrypt(x).getValue() == (px ^ pz));
+    // a sum of sums, grown in place afterwards
+    Ciphertext big = (sum2 + copied) + sum2;
+    EXPECT(big.getBlocks() == 51000 && seckey.decrypt(big).getValue() == (px ^ py));
+    big += z;
+    EXPECT(big.getBlocks() == 51003 && seckey.decrypt(big).getValue() == (px ^ py ^ pz));
+}
+
 static void misuse_is_loud() {
     Context context(1247, 16);
     uint64_t words[20] = {0}, bitlen[20];
@@ -321,6 +362,7 @@ int main() {
     random_circuits(128, 4, 4, 4);   // N % 64 == 0 (the reference overflows its arrays here)
     lazy_products();
     fused_products();
+    rope_sums();
     Library::setLazyProducts(true);
     random_circuits(1247, 16, 5, 4);  // the same circuits with products kept lazy
     Library::setLazyProducts(false);

@@ -356,3 +356,77 @@ def test_batched_upload_shared_storage(engine, oracle):
                 engine._lib().csgn_buf_free(ctypes.c_void_p(ops[i]))
         del prods
     engine.sync()
+
+
+def test_lazy_sum_rope(engine, oracle):
+    """csgn_concat_lazy (add as a zero-copy rope): decrypt, permute and a product with the sum on the
+    left walk the segments; everything else flattens once; the operands may be freed at once; growing or overwriting
+    a buffer that a sum refers to is refused."""
+    N, D = 1247, 3
+    L = words_per_block(N)
+    rng = np.random.default_rng(53)
+    ctx = engine.Context(N, D)
+    s = random_key(rng, N, D)
+    key = engine.SecretKey(ctx, s)
+    parts = [planted(rng, t, N, s, 0.2) for t in (7000, 9001, 8000)]
+    whole = np.concatenate(parts)
+    small = planted(rng, 3, N, s, 0.7)
+    perm = rng.permutation(N).astype(np.uint64)
+    p = engine.Permutation(ctx, perm)
+
+    def build():
+        cts = [engine.Ciphertext.from_host(x, ctx) for x in parts]
+        r = cts[0].add_lazy(cts[1]).add_lazy(cts[2])
+        assert r.segments == 3 and r.n_blocks == 24001
+        del cts                                     # the sum keeps the storage alive
+        return r
+
+    r = build()
+    assert key.count_satisfied(r) == oracle.count_satisfied(whole, N, s)
+    assert r.segments == 3                          # decrypt did not copy the parts together
+    assert np.array_equal(r.applyPermutation(p).getValues(), oracle.permute_all(whole, N, perm))
+    strict = r.applyPermutation(p, strict_ref_truncate=True)
+    assert np.array_equal(strict.getValues(), oracle.permute_block(whole[:L], N, perm))
+    cs = engine.Ciphertext.from_host(small, ctx)
+    assert np.array_equal((r * cs).getValues(), oracle.mul(whole, small, L))          # lazy LEFT operand: per segment
+    assert r.segments == 3
+    bit, cnt, prod = key.mul_decrypt(cs, cs, out="alloc")
+    assert cnt == oracle.count_satisfied(oracle.mul(small, small, L), N, s)
+    bit, cnt = key.mul_decrypt(r, cs)                                                   # fused: flattens the left operand
+    assert cnt == oracle.count_satisfied(oracle.mul(whole, small, L), N, s) and r.segments == 1
+    r = build()
+    assert np.array_equal((cs * r).getValues(), oracle.mul(small, whole, L))          # lazy RIGHT operand: flattened once
+    assert r.segments == 1 and np.array_equal(r.getValues(), whole)
+    r = build()
+    assert np.array_equal(r.getValues(), whole) and r.segments == 1                    # download flattens
+    r = build()
+    assert r.checksum() == oracle.checksum(whole)
+    # sums of sums, and the copy for small operands / long tails
+    a, b = engine.Ciphertext.from_host(parts[0], ctx), engine.Ciphertext.from_host(parts[1], ctx)
+    ab, ba = a.add_lazy(b), b.add_lazy(a)
+    four = ab.add_lazy(ba)
+    assert four.segments == 4
+    assert key.count_satisfied(four) == 2 * oracle.count_satisfied(np.concatenate(parts[:2]), N, s)
+    assert np.array_equal(four.clone().getValues(), np.concatenate([parts[0], parts[1], parts[1], parts[0]]))
+    assert a.add_lazy(cs).segments == 1             # a small operand is copied
+    assert np.array_equal(a.add_lazy(cs).getValues(), np.concatenate([parts[0], small]))
+    tail = a
+    for _ in range(40):
+        tail = tail.add_lazy(b)
+    assert tail.segments <= 32 and tail.n_blocks == 7000 + 40 * 9001
+    assert key.count_satisfied(tail) == oracle.count_satisfied(parts[0], N, s) + 40 * oracle.count_satisfied(parts[1], N, s)
+    del tail
+    # a buffer that a sum refers to cannot be grown or overwritten in place
+    with pytest.raises(engine.CsgnError):
+        a += cs
+    nine = engine.Ciphertext.empty(9, ctx)
+    big9 = engine.Ciphertext.from_host(planted(rng, 7000, N, s), ctx)
+    keep = big9.add_lazy(big9)                      # big9 is now referred to
+    with pytest.raises(engine.CsgnError):
+        big9.permute_into(p, big9)
+    with pytest.raises(engine.CsgnError):
+        engine.Ciphertext.from_host(planted(rng, 70, N, s), ctx).mul_into(engine.Ciphertext.from_host(planted(rng, 100, N, s), ctx), big9)
+    del keep, nine
+    del ab, ba, four
+    a += cs                                         # released: growable again
+    assert np.array_equal(a.getValues(), np.concatenate([parts[0], small]))
