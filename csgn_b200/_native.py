@@ -82,6 +82,12 @@ SIGNATURES = {
     "csgn_buf_checksum": (ctypes.c_int, [_vp, _u64p, _u64p, _u64p]),
     "csgn_buf_save": (ctypes.c_int, [_vp, _u64, _u64, ctypes.c_char_p]),
     "csgn_buf_load": (ctypes.c_int, [ctypes.c_char_p, _u64p, _u64p, _vpp]),
+    "csgn_buf_save_shard": (ctypes.c_int, [_vp, _u64, _u64, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, _u64]),
+    "csgn_buf_load_shard": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vpp]),
+    "csgn_key_positions_save": (ctypes.c_int, [ctypes.c_char_p, _u64, _u64, _vp, _u64]),
+    "csgn_key_positions_load": (ctypes.c_int, [ctypes.c_char_p, _vp, _vp, _vp, _u64, _vp]),
+    "csgn_perm_entries_save": (ctypes.c_int, [ctypes.c_char_p, _vp, _u64]),
+    "csgn_perm_entries_load": (ctypes.c_int, [ctypes.c_char_p, _vp, _u64, _vp]),
     "csgn_shard_range": (ctypes.c_int, [_u64, ctypes.c_int, ctypes.c_int, _u64p, _u64p]),
     "csgn_comm_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vpp, _vp]),
     "csgn_comm_connect": (ctypes.c_int, [_vp, _vp]),

@@ -176,6 +176,10 @@ public:
     Permutation operator+(const Permutation &permB) const;  // (this o permB)[i] = this[permB[i]]
     Permutation &operator+=(const Permutation &permB);
 
+    // Extension: binary file (64-byte header + the entries, checksummed; csgn_perm_entries_save / _load).
+    void save(const std::string &path) const;
+    static Permutation load(const std::string &path);
+
     // engine side
     csgn_perm *deviceMap(uint64_t N) const;
 };
@@ -242,6 +246,10 @@ public:
     // through pinned staging (csgn_buf_save / csgn_buf_load).  The reference has no serialisation.
     void save(const std::string &path) const;
     static Ciphertext load(const std::string &path);
+    // A sharded ciphertext as one file per rank, `<prefix>.shard<rank>of<world>` (csgn_buf_save_shard): every rank
+    // writes / reads its own blocks, no collective.  loadSharded returns a ciphertext marked sharded.
+    void saveSharded(const std::string &prefix) const;
+    static Ciphertext loadSharded(const std::string &prefix);
     // This rank's contiguous block range (csgn_shard_range) of a ciphertext that every rank holds in full.
     // The result is marked sharded: * with a replicated right operand, applyPermutation and + of two sharded
     // ciphertexts stay shard-local; getValues()/getLen()/operator<< see the local blocks only.
@@ -286,6 +294,11 @@ public:
     uint64_t *getKey() const;  // internal array: do not delete
     void setKey(uint64_t *s, uint64_t len);
     long size();
+
+    // Extension: binary file (64-byte header with N, D + the secret positions, checksummed;
+    // csgn_key_positions_save / _load).  The file holds the secret: protect it like the key.
+    void save(const std::string &path) const;
+    static SecretKey load(const std::string &path);
 };
 
 // ---- Timer (reference src/Timer.h:13-74) -------------------------------------------------

@@ -10,6 +10,7 @@
 #include "certFHE.h"
 #include "engine_glue.h"
 
+#include <cstdlib>
 #include <ctime>
 #include <utility>
 #include <vector>
@@ -531,6 +532,27 @@ Ciphertext Ciphertext::load(const std::string &path) {
     return out;
 }
 
+void Ciphertext::saveSharded(const std::string &prefix) const {
+    const csgn_buf *buf = deviceBuffer();
+    if (!buf || !certFHEcontext) throw Error("Ciphertext::saveSharded: empty ciphertext or no Context");
+    glue::check(csgn_buf_save_shard(buf, certFHEcontext->getN(), certFHEcontext->getD(), prefix.c_str(), Library::getRank(),
+                                    Library::getWorldSize(), 0),
+                "csgn_buf_save_shard");
+}
+
+Ciphertext Ciphertext::loadSharded(const std::string &prefix) {
+    glue::ensure_engine();
+    uint64_t n = 0, d = 0;
+    csgn_buf *buf = nullptr;
+    glue::check(csgn_buf_load_shard(prefix.c_str(), Library::getRank(), Library::getWorldSize(), &n, &d, nullptr, &buf),
+                "csgn_buf_load_shard");
+    Ciphertext out;
+    out.dev = adopt(buf);
+    out.certFHEcontext = new Context(n, d);
+    out.sharded = true;
+    return out;
+}
+
 void Ciphertext::applyPermutation_inplace(const Permutation &permutation) {
     Ciphertext permuted = applyPermutation(permutation);
     dev = std::move(permuted.dev);
@@ -645,6 +667,27 @@ void SecretKey::setKey(uint64_t *key, uint64_t len) {
 long SecretKey::size() {
     // reference src/SecretKey.cpp:269-276
     return (long)(sizeof(void *) + sizeof(long) + sizeof(uint64_t) * (uint64_t)length);
+}
+
+void SecretKey::save(const std::string &path) const {
+    glue::check(csgn_key_positions_save(path.c_str(), certFHEContext->getN(), certFHEContext->getD(), s, (uint64_t)length),
+                "csgn_key_positions_save");
+}
+
+SecretKey SecretKey::load(const std::string &path) {
+    uint64_t n = 0, d = 0, count = 0;
+    glue::check(csgn_key_positions_load(path.c_str(), &n, &d, nullptr, 0, &count), "csgn_key_positions_load");
+    std::vector<uint64_t> pos(count ? count : 1);
+    glue::check(csgn_key_positions_load(path.c_str(), &n, &d, pos.data(), count, &count), "csgn_key_positions_load");
+    // the constructor reseeds rand() from the clock and draws a key (src/SecretKey.cpp:308-337): let it do that on a
+    // scratch generator state, so that the caller's rand() sequence continues exactly where it was
+    char scratch[128];
+    char *caller_state = initstate(1u, scratch, sizeof scratch);
+    SecretKey key((Context(n, d)));
+    setstate(caller_state);
+    key.setKey(pos.data(), count);
+    for (size_t i = 0; i < pos.size(); ++i) ((volatile uint64_t *)pos.data())[i] = 0;
+    return key;
 }
 
 uint64_t *SecretKey::encrypt(unsigned char bit, uint64_t n, uint64_t d, uint64_t *key) {

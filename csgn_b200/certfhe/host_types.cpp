@@ -270,6 +270,18 @@ Permutation::Permutation(const uint64_t size) : Permutation() {
 
 Permutation::Permutation(const Context &context) : Permutation(context.getN()) {}
 
+void Permutation::save(const std::string &path) const {
+    glue::check(csgn_perm_entries_save(path.c_str(), permutation, length), "csgn_perm_entries_save");
+}
+
+Permutation Permutation::load(const std::string &path) {
+    uint64_t count = 0;
+    glue::check(csgn_perm_entries_load(path.c_str(), nullptr, 0, &count), "csgn_perm_entries_load");
+    std::vector<uint64_t> p(count ? count : 1);
+    glue::check(csgn_perm_entries_load(path.c_str(), p.data(), count, &count), "csgn_perm_entries_load");
+    return Permutation(p.data(), count);
+}
+
 Permutation::Permutation(const Permutation &p) : Permutation(p.permutation, p.length) {}
 
 Permutation::~Permutation() {

@@ -213,6 +213,19 @@ class Ciphertext:
         check(_lib().csgn_buf_load(str(path).encode(), ctypes.byref(n), ctypes.byref(d), ctypes.byref(h)))
         return cls(h, Context(n.value, d.value))
 
+    def save_shard(self, prefix, rank, world, first_block=0):
+        """csgn_buf_save_shard: this rank's local blocks as `<prefix>.shard<rank>of<world>`."""
+        check(_lib().csgn_buf_save_shard(self._h, self.ctx.N, self.ctx.D, str(prefix).encode(), int(rank), int(world),
+                                         int(first_block)))
+
+    @classmethod
+    def load_shard(cls, prefix, rank, world):
+        """-> (ciphertext of the rank's local blocks, first global block as recorded at save time)"""
+        h, n, d, first = _vp(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        check(_lib().csgn_buf_load_shard(str(prefix).encode(), int(rank), int(world), ctypes.byref(n), ctypes.byref(d),
+                                         ctypes.byref(first), ctypes.byref(h)))
+        return cls(h, Context(n.value, d.value)), first.value
+
     def clone(self):
         h = _vp()
         check(_lib().csgn_buf_clone(self._h, ctypes.byref(h)))
@@ -477,6 +490,19 @@ class SecretKey:
     def size(self):
         return 16 + 8 * int(self.s.size)
 
+    def save(self, path):
+        """csgn_key_positions_save: header (N, D, count, checksum) + the secret positions."""
+        check(_lib().csgn_key_positions_save(str(path).encode(), self.ctx.N, self.ctx.D, self.s.ctypes.data_as(_vp), self.s.size))
+
+    @classmethod
+    def load(cls, path):
+        n, d, cnt = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        check(_lib().csgn_key_positions_load(str(path).encode(), ctypes.byref(n), ctypes.byref(d), None, 0, ctypes.byref(cnt)))
+        pos = np.empty(cnt.value, dtype=np.uint64)
+        check(_lib().csgn_key_positions_load(str(path).encode(), ctypes.byref(n), ctypes.byref(d), pos.ctypes.data_as(_vp),
+                                             pos.size, ctypes.byref(cnt)))
+        return cls(Context(n.value, d.value), pos)
+
 
 IPC_HANDLE_BYTES = 64
 COMM_MAX_PENDING = 64
@@ -575,6 +601,20 @@ class Permutation:
         self.p = _host_words(perm)
         self._h = _vp()
         check(_lib().csgn_perm_create(ctx.N, self.p.ctypes.data_as(_vp), ctypes.byref(self._h)))
+
+    def save(self, path):
+        """csgn_perm_entries_save: header (length, checksum) + the entries."""
+        check(_lib().csgn_perm_entries_save(str(path).encode(), self.p.ctypes.data_as(_vp), self.p.size))
+
+    @classmethod
+    def load(cls, path, ctx):
+        cnt = ctypes.c_uint64()
+        check(_lib().csgn_perm_entries_load(str(path).encode(), None, 0, ctypes.byref(cnt)))
+        perm = np.empty(cnt.value, dtype=np.uint64)
+        check(_lib().csgn_perm_entries_load(str(path).encode(), perm.ctypes.data_as(_vp), perm.size, ctypes.byref(cnt)))
+        if cnt.value != ctx.N:
+            raise ValueError("permutation of %d entries, context has N = %d" % (cnt.value, ctx.N))
+        return cls(ctx, perm)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None

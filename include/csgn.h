@@ -257,6 +257,22 @@ int csgn_buf_checksum(const csgn_buf *buf, uint64_t *xor_out, uint64_t *sum_out,
  * can be written or read; the checksum is verified on load. */
 int csgn_buf_save(const csgn_buf *buf, uint64_t N, uint64_t D, const char *path);
 int csgn_buf_load(const char *path, uint64_t *N, uint64_t *D, csgn_buf **out);
+/* A ciphertext sharded over the job's GPUs (8e) as one file per rank, `<prefix>.shard<rank>of<world>`: the ordinary
+ * file of the rank's local blocks, with the shard's identity and first global block in the header.  No collective:
+ * every rank writes / reads its own file; loading checks that the file was written as this rank of this world. */
+int csgn_buf_save_shard(const csgn_buf *buf, uint64_t N, uint64_t D, const char *prefix, int rank, int world,
+                        uint64_t first_block);
+int csgn_buf_load_shard(const char *prefix, int rank, int world, uint64_t *N, uint64_t *D, uint64_t *first_block,
+                        csgn_buf **out);
+/* SecretKey and Permutation files (SURVEY.md 8f-3 names all three types; upstream has only SecretKey::size(),
+ * src/SecretKey.cpp:269-276, and the Permutation state of src/Permutation.cpp:139-171 to persist).  Host only -- no
+ * device is touched and csgn_init is not needed.  64-byte header {magic "CSGNSK01" / "CSGNPM01", N, D, count, xor of
+ * the entries} + count uint64 entries; positions / entries are validated on save and load.  *_load with a null
+ * destination only reports the count (and N, D). */
+int csgn_key_positions_save(const char *path, uint64_t N, uint64_t D, const uint64_t *positions, uint64_t n);
+int csgn_key_positions_load(const char *path, uint64_t *N, uint64_t *D, uint64_t *positions, uint64_t capacity, uint64_t *n);
+int csgn_perm_entries_save(const char *path, const uint64_t *perm, uint64_t n);
+int csgn_perm_entries_load(const char *path, uint64_t *perm, uint64_t capacity, uint64_t *n);
 
 /* ---- sharding (one process per GPU) ------------------------------------------ */
 

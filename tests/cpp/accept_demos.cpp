@@ -328,6 +328,40 @@ static void rope_sums() {
     EXPECT(big.getBlocks() == 51003 && seckey.decrypt(big).getValue() == (px ^ py ^ pz));
 }
 
+// SecretKey / Permutation files, and a ciphertext as one file per rank (here: the single rank of this process).
+static void files() {
+    Context context(1247, 16);
+    SecretKey seckey(context);
+    srand(321);
+    Permutation pi(context);
+    std::vector<unsigned char> bits(5000);
+    int parity = 0;
+    for (size_t i = 0; i < bits.size(); ++i) { bits[i] = rand() & 1; parity ^= bits[i]; }
+    Ciphertext c = seckey.encryptBatch(bits.data(), bits.size(), 9);
+    seckey.save("/tmp/csgn_accept.sk");
+    pi.save("/tmp/csgn_accept.pm");
+    srand(5);
+    const int before = rand();
+    srand(5);
+    SecretKey k2 = SecretKey::load("/tmp/csgn_accept.sk");
+    EXPECT(rand() == before);                                   // loading a key leaves the caller's rand() sequence alone
+    Permutation p2 = Permutation::load("/tmp/csgn_accept.pm");
+    EXPECT(k2.getLength() == seckey.getLength() && memcmp(k2.getKey(), seckey.getKey(), 16 * 8) == 0);
+    EXPECT(p2.getLength() == 1247 && memcmp(p2.getPermutation(), pi.getPermutation(), 1247 * 8) == 0);
+    EXPECT(k2.decrypt(c).getValue() == parity);
+    EXPECT(k2.applyPermutation(p2).decrypt(*new Ciphertext(c.applyPermutation(p2))).getValue() == parity);
+    c.saveSharded("/tmp/csgn_accept.ct");
+    Ciphertext back = Ciphertext::loadSharded("/tmp/csgn_accept.ct");
+    EXPECT(back.isSharded() && back.getBlocks() == 5000);
+    EXPECT(memcmp(back.getValues(), c.getValues(), c.getLen() * 8) == 0);
+    bool threw = false;
+    try { Ciphertext::load("/tmp/csgn_accept.ct.shard0of1"); } catch (const Error &) { threw = true; }
+    EXPECT(threw);
+    remove("/tmp/csgn_accept.sk");
+    remove("/tmp/csgn_accept.pm");
+    remove("/tmp/csgn_accept.ct.shard0of1");
+}
+
 static void misuse_is_loud() {
     Context context(1247, 16);
     uint64_t words[20] = {0}, bitlen[20];
@@ -363,6 +397,7 @@ int main() {
     lazy_products();
     fused_products();
     rope_sums();
+    files();
     Library::setLazyProducts(true);
     random_circuits(1247, 16, 5, 4);  // the same circuits with products kept lazy
     Library::setLazyProducts(false);

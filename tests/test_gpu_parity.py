@@ -548,6 +548,53 @@ def test_save_load_round_trip(engine, oracle, tmp_path):
         engine.Ciphertext.load(tmp_path / "other.bin")
 
 
+def test_sharded_files_and_key_permutation_files(engine, oracle, tmp_path):
+    """one ciphertext file per rank (csgn_buf_save_shard), SecretKey and Permutation files; what comes
+    back decrypts and permutes exactly as what went in."""
+    N, D = 1247, 4
+    L = words_per_block(N)
+    rng = np.random.default_rng(91)
+    ctx = engine.Context(N, D)
+    s = random_key(rng, N, D)
+    key = engine.SecretKey(ctx, s)
+    perm = rng.permutation(N).astype(np.uint64)
+    p = engine.Permutation(ctx, perm)
+    v = random_blocks(rng, 10007, N)
+    mask = np.zeros(L, dtype=np.uint64)
+    for pos in s:
+        mask[int(pos) >> 6] |= np.uint64(1 << (63 - (int(pos) & 63)))
+    v.reshape(-1, L)[rng.choice(10007, 300, replace=False)] |= mask
+    world = 3
+    prefix = tmp_path / "big.csgn"
+    for rank in range(world):                                      # every "rank" writes its own block range
+        first, count = engine.shard_range(10007, rank, world)
+        engine.Ciphertext.from_host(v[first * L:(first + count) * L], ctx).save_shard(prefix, rank, world, first)
+    parts, total = [], 0
+    for rank in range(world):
+        ct, first = engine.Ciphertext.load_shard(prefix, rank, world)
+        assert first == total and (ct.ctx.N, ct.ctx.D) == (N, D)
+        total += ct.n_blocks
+        parts.append(ct)
+    assert total == 10007
+    assert np.array_equal(np.concatenate([c.getValues() for c in parts]), v)
+    assert sum(key.count_satisfied(c) for c in parts) == oracle.count_satisfied(v, N, s)
+    with pytest.raises(engine.CsgnError, match="not written as shard"):       # another world size: another file set
+        os.replace(str(prefix) + ".shard1of3", str(prefix) + ".shard1of4")
+        engine.Ciphertext.load_shard(prefix, 1, 4)
+    with pytest.raises(engine.CsgnError, match="one shard of a sharded"):      # a shard is not a whole ciphertext
+        engine.Ciphertext.load(str(prefix) + ".shard0of3")
+    # the key and the permutation through their files
+    key.save(tmp_path / "k.sk")
+    p.save(tmp_path / "p.pm")
+    key2 = engine.SecretKey.load(tmp_path / "k.sk")
+    p2 = engine.Permutation.load(tmp_path / "p.pm", ctx)
+    assert (key2.ctx.N, key2.ctx.D) == (N, D) and np.array_equal(key2.s, s) and np.array_equal(p2.p, perm)
+    whole = engine.Ciphertext.from_host(v, ctx)
+    assert key2.count_satisfied(whole) == oracle.count_satisfied(v, N, s)
+    assert np.array_equal(whole.applyPermutation(p2).getValues(), oracle.permute_all(v, N, perm))
+
+
+
 def test_sharded_path_world_size_1_nccl(engine, oracle):
     """The N>1 code path (block-range shard, shard-local multiply chain, NCCL all-reduce of the count)
     at world size 1 on the one GPU this box has -- same calls bench.py makes under torchrun."""
