@@ -862,29 +862,34 @@ def run_ours(args):
     if not args.no_e2e:
         uploader = eng.UploadBatch([host_a[p].data_ptr() for p in range(P)] + [host_b[p].data_ptr() for p in range(P)],
                                    [T1] * P + [T2] * P, ctx)
-        host_counts2 = [torch.zeros(P, dtype=torch.int64).pin_memory() for _ in range(2)]
-        done_ev = [torch.cuda.Event(), torch.cuda.Event()]
-        in_flight = [False, False]
+        # results travel back through a ring of pinned host buffers; each D2H gets an event and is checked on the host
+        # one step LATER (after the next step has been enqueued), so the GPU never idles while the host reads
+        host_ring = [torch.zeros(P, dtype=torch.int64).pin_memory() for _ in range(4)]
+        ring_ev = [torch.cuda.Event() for _ in range(4)]
+        pending_checks = []                                                # [(event, host buffer)], oldest first
         e2e_no = [0]
+        d2h_no = [0]
         e2e_lag = comm is not None and args.collect == "lagged"
 
-        def check(slot):
-            """the host reads step `slot`'s result (waits for its D2H) and compares it with the host-known truth"""
-            if in_flight[slot]:
-                done_ev[slot].synchronize()
-                in_flight[slot] = False
-                if not torch.equal(host_counts2[slot], expected_host):
-                    raise SystemExit("e2e result differs from the host-known truth: %s vs %s" % (host_counts2[slot], expected_host))
+        def fetch(src):
+            """enqueue the D2H of one step's P counts"""
+            i = d2h_no[0] % 4
+            d2h_no[0] += 1
+            host_ring[i].copy_(src, non_blocking=True)
+            ring_ev[i].record(stream)
+            pending_checks.append((ring_ev[i], host_ring[i]))
+
+        def check_oldest():
+            ev, buf = pending_checks.pop(0)
+            ev.synchronize()
+            if not torch.equal(buf, expected_host):
+                raise SystemExit("e2e result differs from the host-known truth: %s vs %s" % (buf, expected_host))
 
         def step_e2e(final=False):
-            # Depth-2 pipeline: step k is enqueued in full (uploads, kernels, D2H of its counts) BEFORE the host waits
-            # for step k-1's result, so the GPU never idles while the host reads and checks.  Every step's result is
-            # still read and verified on the host; the timed region ends after the last one has been.
             # N > 1 with the lagged collect: the launch closing step k collects step k-1's sums (they arrived long
             # ago, so no rank waits for a slower one); the D2H enqueued after it carries step k-1's result.
             slot = e2e_no[0] & 1
             e2e_no[0] += 1
-            check(slot)
             ops = uploader.upload()                                        # csgn_buf_upload_batch: 2P operands, H2D on the copy stream
             ha, hb = eng.handle_slice(ops, 0, P), eng.handle_slice(ops, P, P)
             ho = (ctypes.c_void_p * P)()                                   # the library allocates the P products
@@ -906,32 +911,22 @@ def run_ours(args):
             if world > 1 and comm is None:
                 dist.all_reduce(counts2[slot])
             if e2e_lag:
-                if lag_now:                                                # step k-1's sums, collected by step k's closing launch
-                    host_counts2[slot ^ 1].copy_(counts2[slot ^ 1], non_blocking=True)
-                    done_ev[slot ^ 1].record(stream)
-                    in_flight[slot ^ 1] = True
+                if lag_now:
+                    fetch(counts2[slot ^ 1])                               # step k-1's sums, collected by step k's closing launch
                 if final:                                                  # nothing follows: fetch this step's sums too
                     comm.collect(P, count_ptrs2[slot])
-                    host_counts2[slot].copy_(counts2[slot], non_blocking=True)
-                    done_ev[slot].record(stream)
-                    in_flight[slot] = True
-                elif e2e_no[0] == 1:
-                    pass                                                   # the first step's sums arrive with the second
+                    fetch(counts2[slot])
             else:
-                host_counts2[slot].copy_(counts2[slot], non_blocking=True)
-                done_ev[slot].record(stream)
-                in_flight[slot] = True
-                check(slot ^ 1)
-
-        def drain_e2e():
-            check(0)
-            check(1)
+                fetch(counts2[slot])
+            while len(pending_checks) > 1:                                 # everything but the newest: already behind the queue
+                check_oldest()
 
         def run_e2e(n):
             e2e_no[0] = 0
             for i in range(n):
                 step_e2e(final=(i == n - 1))
-            drain_e2e()
+            while pending_checks:
+                check_oldest()
 
         run_e2e(max(3, args.warmup))
         barrier()

@@ -27,6 +27,11 @@ int comm_ready(const csgn_comm *comm) {
 
 // Parameters of a launch that pushes (with_push) and, when collect_n > 0, closes the batch:
 // publishes everything unpublished and collects pushes last-lag-collect_n+1 .. last-lag.
+// How a batch of sharded folds is closed: 1 = by a small exchange kernel of its own after all n items have run on
+// the lanes; 0 = by the last item's kernel (its last CTA publishes and collects), which then runs after the join,
+// alone.  Measured on 2 and 8 B200 (profiles/README.md); CSGN_PEER_CLOSE_KERNEL overrides under CSGN_TUNING.
+constexpr long kCloseWithOwnKernel = 1;
+
 int fill_push(const csgn_comm *comm, bool with_push, uint32_t collect_n, uint32_t lag, uint64_t *totals, PeerPush *pp) {
     memset(pp, 0, sizeof *pp);
     const uint64_t last = with_push ? comm->seq : comm->seq - 1;       // most recent push after this launch
@@ -258,6 +263,19 @@ int csgn_mul_decrypt_sharded_batch_async(const csgn_buf *const *a, const csgn_bu
     if (!a || !b || !device_totals) return fail(CSGN_ERR_INVALID_ARGUMENT, "null argument");
     if ((uint64_t)n + collect_lag > kPeerMaxPending)
         return fail(CSGN_ERR_INVALID_ARGUMENT, "batch of %u folds trailing by %u exceeds %u", n, collect_lag, kPeerMaxPending);
+    if (env_long("CSGN_PEER_CLOSE_KERNEL", kCloseWithOwnKernel)) {
+        // every item runs on the lanes, overlapped with its neighbours; the batch is then closed by ONE small kernel
+        // on the caller's stream that publishes the n counts over NVLink and collects the sums
+        {
+            LaneScope lanes(n);
+            for (uint32_t i = 0; i < n; ++i) {
+                lanes.enter(i);
+                int rc = csgn_mul_decrypt_sharded_async(a[i], b[i], key, out ? &out[i] : nullptr, comm, 0, 0, nullptr, nullptr);
+                if (rc != CSGN_OK) return rc;
+            }
+        }
+        return csgn_comm_collect_async(comm, n, collect_lag, device_totals);
+    }
     {
         LaneScope lanes(n - 1);
         for (uint32_t i = 0; i + 1 < n; ++i) {
@@ -313,6 +331,17 @@ int csgn_decrypt_sharded_batch_async(const csgn_buf *const *c, uint32_t n, const
     if (!c || !device_totals) return fail(CSGN_ERR_INVALID_ARGUMENT, "null argument");
     if ((uint64_t)n + collect_lag > kPeerMaxPending)
         return fail(CSGN_ERR_INVALID_ARGUMENT, "batch of %u folds trailing by %u exceeds %u", n, collect_lag, kPeerMaxPending);
+    if (env_long("CSGN_PEER_CLOSE_KERNEL", kCloseWithOwnKernel)) {
+        {
+            LaneScope lanes(n);
+            for (uint32_t i = 0; i < n; ++i) {
+                lanes.enter(i);
+                int rc = csgn_decrypt_sharded_async(c[i], key, comm, 0, 0, nullptr, nullptr);
+                if (rc != CSGN_OK) return rc;
+            }
+        }
+        return csgn_comm_collect_async(comm, n, collect_lag, device_totals);
+    }
     {
         LaneScope lanes(n - 1);
         for (uint32_t i = 0; i + 1 < n; ++i) {
