@@ -57,7 +57,8 @@ def test_libcertfhe_exports_the_reference_api():
         assert w in syms, w
     # it computes nothing itself: the evaluation entry points are undefined here and come from libcsgn
     undef = subprocess.run(["nm", "-D", "--undefined-only", path], stdout=subprocess.PIPE, text=True).stdout
-    for f in ("csgn_mul", "csgn_concat", "csgn_append", "csgn_decrypt", "csgn_permute", "csgn_buf_upload"):
+    for f in ("csgn_mul", "csgn_mul_decrypt_deferred", "csgn_concat", "csgn_concat_lazy", "csgn_append", "csgn_decrypt_deferred",
+              "csgn_permute", "csgn_buf_upload_copy"):
         assert re.search(r"\bU %s\b" % f, undef), f
     ldd = subprocess.run(["ldd", path], stdout=subprocess.PIPE, text=True).stdout
     assert "libcsgn.so" in ldd and "not found" not in ldd
