@@ -109,7 +109,11 @@ __device__ __forceinline__ void publish_cta_count(const uint32_t cnt, unsigned l
 }
 
 // FOLD: 0 = multiply, 1 = multiply and count the satisfied product blocks, 2 = count only (nothing stored).
-template <typename VT, int U, int FOLD>
+// ALIGN (fused kernels, blocks of up to 16 units): a warp uses its first (32/UPB)*UPB lanes, so that the UPB threads
+// holding one block are always lanes of ONE warp -- the per-block OR of the fail bits is then two redux.sync per item
+// and needs no shared memory and no barrier.  (N = 1247: 30 of 32 lanes; the idle lanes cost issue slots of a kernel
+// that is bound by HBM, not by issue.)
+template <typename VT, int U, int FOLD, int ALIGN>
 __global__ void __launch_bounds__(kMulMaxThreads)
 mul_outer_kernel(const VT *__restrict__ A, const VT *__restrict__ B, VT *__restrict__ out,
                  const uint32_t UPB, const uint64_t T1, const uint64_t Q, const uint32_t R,
@@ -120,8 +124,14 @@ mul_outer_kernel(const VT *__restrict__ A, const VT *__restrict__ B, VT *__restr
     // fused fold: one 64-bit fail word per thread, behind the staged rows (8-byte aligned: R*UPB units of 8 or 16 bytes)
     uint64_t *sFail = reinterpret_cast<uint64_t *>(sA + (size_t)R * UPB);
     __shared__ unsigned long long s_cnt;
-    const uint32_t tpb = blockDim.x;
-    const uint32_t k = threadIdx.x % UPB;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lanes_used = ALIGN ? (32u / UPB) * UPB : 32u;             // ALIGN: whole blocks per warp
+    const bool active = !ALIGN || lane < lanes_used;
+    // this thread's unit inside a row step, and the units one row step of the CTA covers
+    const uint32_t my_unit = ALIGN ? (threadIdx.x >> 5) * lanes_used + lane : threadIdx.x;
+    const uint32_t tpb = ALIGN ? (blockDim.x >> 5) * lanes_used : blockDim.x;
+    const uint32_t k = my_unit % UPB;
+    const uint32_t gmask = ALIGN ? ((UPB >= 32u ? 0xffffffffu : ((1u << UPB) - 1u)) << (lane / UPB * UPB)) : 0u;
     const uint64_t tile_q = (uint64_t)tpb * U;
     VT m = vzero<VT>();
     if (FOLD) {
@@ -158,27 +168,29 @@ mul_outer_kernel(const VT *__restrict__ A, const VT *__restrict__ B, VT *__restr
         const uint32_t ct = (uint32_t)(item % n_col_tiles);
         const uint64_t row0 = (item / n_col_tiles) * R;
         const uint32_t nrows = (uint32_t)min((uint64_t)R, T1 - row0);
-        const uint64_t q0 = (uint64_t)ct * tile_q + threadIdx.x;
+        const uint64_t q0 = (uint64_t)ct * tile_q + my_unit;
 
         VT b[U];
         uint32_t live_bits = 0;                     // bit u: unit u of this thread lies inside the row
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint64_t q = q0 + (uint64_t)u * tpb;
-            const bool in = q < Q;
+            const bool in = active && q < Q;
             b[u] = in ? __ldg(B + q) : vzero<VT>();
             live_bits |= in ? (1u << u) : 0u;
         }
 
         __syncthreads();  // the previous item's readers of sA (and sFail) are done
         const VT *a_chunk = A + row0 * UPB;
-        for (uint32_t idx = threadIdx.x; idx < nrows * UPB; idx += tpb) sA[idx] = __ldg(a_chunk + idx);
+        for (uint32_t idx = threadIdx.x; idx < nrows * UPB; idx += blockDim.x) sA[idx] = __ldg(a_chunk + idx);
         __syncthreads();
 
         VT *o = out + row0 * Q + q0;
         const VT *sa = sA + k;
         uint64_t fails = 0;                         // row r, unit u -> bit (nrows-1-r)*U + u
-        if ((uint64_t)(ct + 1) * tile_q <= Q) {
+        if (ALIGN && !active) {
+            // idle lanes of a lane-aligned warp: nothing to load, store or vote
+        } else if ((uint64_t)(ct + 1) * tile_q <= Q) {
 #pragma unroll 4
             for (uint32_t r = 0; r < nrows; ++r, o += Q, sa += UPB) {
                 const VT a = *sa;
@@ -210,7 +222,15 @@ mul_outer_kernel(const VT *__restrict__ A, const VT *__restrict__ B, VT *__restr
             const uint32_t nb = nrows * U;
             const uint64_t all_rows = nb >= 64u ? ~0ull : ((1ull << nb) - 1ull);
             const uint64_t valid = (all_rows / ((1ull << U) - 1ull)) * (uint64_t)live_bits;
-            cnt += count_group_clear(fails, valid, UPB, k, sFail);
+            if (ALIGN) {
+                if (active) {
+                    uint64_t f = (uint64_t)__reduce_or_sync(gmask, (uint32_t)fails);
+                    if (nb > 32u) f |= (uint64_t)__reduce_or_sync(gmask, (uint32_t)(fails >> 32)) << 32;   // CTA-uniform
+                    if (k == 0) cnt += (uint32_t)__popcll(~f & valid);
+                }
+            } else {
+                cnt += count_group_clear(fails, valid, UPB, k, sFail);
+            }
         }
     }
     if (FOLD) publish_cta_count(cnt, &s_cnt, fo);
@@ -351,29 +371,34 @@ void fill_fold_params(FoldParams &fo, const MulFold *fold, uint32_t upb, size_t 
     }
 }
 
-template <typename VT, int U, int FOLD>
+template <typename VT, int U, int FOLD, int ALIGN = 0>
 cudaError_t launch_tiled_uf(const void *a, uint64_t T1, const void *b, uint64_t Q, uint32_t upb, void *out, uint32_t tpb,
                             uint32_t R, uint64_t grid_cap, const MulFold *fold, cudaStream_t stream) {
-    const uint64_t tile_q = (uint64_t)tpb * U;
+    // ALIGN: tpb threads (a multiple of 32) cover (tpb/32) * (32/upb)*upb units per row step
+    const uint64_t tile_q = (uint64_t)(ALIGN ? (tpb / 32u) * ((32u / upb) * upb) : tpb) * U;
     const uint64_t n_col_tiles = (Q + tile_q - 1) / tile_q;
     const uint64_t n_chunks = (T1 + R - 1) / R;
     const uint64_t n_items = n_col_tiles * n_chunks;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, grid_cap);
-    const size_t smem = (size_t)R * upb * sizeof(VT) + (FOLD ? (size_t)tpb * sizeof(uint64_t) : 0);
+    const size_t smem = (size_t)R * upb * sizeof(VT) + ((FOLD && !ALIGN) ? (size_t)tpb * sizeof(uint64_t) : 0);
     // prefetch distance: the chunks that ~two waves of resident CTAs cover
     const long pf_per_sm = env_long("CSGN_MUL_PF_CTAS_PER_SM", 8);
     const uint64_t ahead_items = (uint64_t)device_props().sm_count * (uint64_t)std::max<long>(pf_per_sm, 0);
     const uint32_t pf_chunks = pf_per_sm > 0 ? (uint32_t)((ahead_items + n_col_tiles - 1) / n_col_tiles) : 0u;
     FoldParams fo;
     fill_fold_params(fo, fold, upb, sizeof(VT));
-    return launch_kernel(mul_outer_kernel<VT, U, FOLD>, grid, tpb, smem, stream, static_cast<const VT *>(a),
+    return launch_kernel(mul_outer_kernel<VT, U, FOLD, ALIGN>, grid, tpb, smem, stream, static_cast<const VT *>(a),
                          static_cast<const VT *>(b), static_cast<VT *>(out), upb, T1, Q, R, (uint32_t)n_col_tiles, n_items,
                          pf_chunks, fo);
 }
 
 template <typename VT, int U>
-cudaError_t launch_tiled_u(int fold_mode, const void *a, uint64_t T1, const void *b, uint64_t Q, uint32_t upb, void *out,
-                           uint32_t tpb, uint32_t R, uint64_t grid_cap, const MulFold *fold, cudaStream_t stream) {
+cudaError_t launch_tiled_u(int fold_mode, bool align, const void *a, uint64_t T1, const void *b, uint64_t Q, uint32_t upb,
+                           void *out, uint32_t tpb, uint32_t R, uint64_t grid_cap, const MulFold *fold, cudaStream_t stream) {
+    if (align) {
+        if (fold_mode == 1) return launch_tiled_uf<VT, U, 1, 1>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream);
+        return launch_tiled_uf<VT, U, 2, 1>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream);
+    }
     switch (fold_mode) {
         case 1: return launch_tiled_uf<VT, U, 1>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream);
         case 2: return launch_tiled_uf<VT, U, 2>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream);
@@ -460,7 +485,10 @@ cudaError_t launch_units(int fold_mode, const void *a, uint64_t T1, const void *
                          const MulFold *fold, cudaStream_t stream) {
     const DeviceProps &dp = device_props();
     const uint64_t Q = T2 * upb;
-    const uint32_t tpb_cap = (uint32_t)std::min<long>(kMulMaxThreads, env_long("CSGN_MUL_TPB", 512));
+    // The fused kernels hold more registers (54-64 against 34-40): CTAs of 256 threads keep four of them resident per
+    // SM, which is what hides an item's load phase behind the other CTAs' stores (B200, tools/fused_tpb_sweep.py: 22.4 us
+    // per 10^6-block product with 500-thread CTAs, 21.7 with 256 -- the plain multiply's time).
+    const uint32_t tpb_cap = (uint32_t)std::min<long>(kMulMaxThreads, env_long("CSGN_MUL_TPB", fold_mode ? 256 : 512));
     const uint64_t out_units = T1 * Q;
     const bool huge = out_units * sizeof(VT) >= (1ull << 30);     // >= 1 GiB of output
     const uint64_t grid_cap = (uint64_t)std::min<long>(1l << 23, env_long("CSGN_MUL_GRID", 1l << 23));
@@ -502,30 +530,53 @@ cudaError_t launch_units(int fold_mode, const void *a, uint64_t T1, const void *
     const uint32_t r_smem = std::max<uint32_t>(1, std::min<uint32_t>(64, kMulMaxSmem / (upb * (uint32_t)sizeof(VT))));
     const uint64_t target_items =
         (uint64_t)dp.sm_count * (uint64_t)env_long("CSGN_MUL_ITEMS_PER_SM", huge ? 128 : 32);
+    // Fused kernels for blocks of up to 16 units run lane-aligned (whole blocks per warp: the fold is two redux.sync
+    // per item, no shared memory, no barrier); their CTA is a whole number of warps.
+    const bool align = fold_mode != 0 && upb <= 16 && env_long("CSGN_MUL_ALIGN", 1) != 0;
+    const uint32_t lanes_used = align ? (32u / upb) * upb : 32u;
     uint32_t tpb = 0;
     uint64_t R = 1;
     for (;; U >>= 1) {
-        tpb = pick_tpb(upb, Q, U, tpb_cap);
-        if (tpb == 0) tpb = upb;
-        const uint64_t n_col_tiles = (Q + (uint64_t)tpb * U - 1) / ((uint64_t)tpb * U);
+        uint64_t step_units;            // units one row step of the CTA covers
+        if (align) {
+            // the warp count that pads the last column tile least (largest on ties), 8..16 warps
+            double best = 1e30;
+            const uint32_t max_warps = std::max<uint32_t>(1, std::min<uint32_t>(16, tpb_cap / 32));
+            for (uint32_t w = max_warps; w >= std::min<uint32_t>(8, max_warps); --w) {
+                const uint64_t tile = (uint64_t)w * lanes_used * U, nt = (Q + tile - 1) / tile;
+                const double pad = (double)(nt * tile) / (double)Q;
+                if (pad < best - 1e-9) {
+                    best = pad;
+                    tpb = w * 32;
+                }
+                if (w == 1) break;
+            }
+            step_units = (uint64_t)(tpb / 32) * lanes_used;
+        } else {
+            tpb = pick_tpb(upb, Q, U, tpb_cap);
+            if (tpb == 0) tpb = upb;
+            step_units = tpb;
+        }
+        const uint64_t n_col_tiles = (Q + step_units * U - 1) / (step_units * U);
         R = (T1 * n_col_tiles + target_items - 1) / target_items;
         if (R >= 3 || U == 1 || env_long("CSGN_MUL_U", 0) > 0) break;
     }
     // B200 sweeps (tools/r2_sweep.py rsel, profiles/r2_rsel.log).  Chains -- very many short rows -- write fastest when
-    // the resident CTAs cover a compact window of the product: few rows per item.  A fused item pays one cross-thread
-    // reduction however many rows it has, so it wants 12-16 of them on every shape measured.
+    // the resident CTAs cover a compact window of the product: few rows per item.  A fused item of the shared-memory
+    // fold pays one cross-thread reduction and a barrier however many rows it has, so it wants 12-16 of them on every
+    // shape measured; the lane-aligned fold costs two warp instructions per item and keeps the multiply's choice.
     if (huge && U == 1) R = std::min<uint64_t>(R, 4);
-    if (fold_mode) R = std::max<uint64_t>(12, std::min<uint64_t>(R, 16));
+    if (fold_mode) R = std::max<uint64_t>(8, std::min<uint64_t>(R, 16));
     R = (uint64_t)env_long("CSGN_MUL_R", (long)R);
     uint32_t r_max = r_smem;
     if (fold_mode) r_max = std::min<uint32_t>(r_max, 64u / (uint32_t)U);      // one 64-bit fail word per thread and item
     R = std::max<uint64_t>(1, std::min<uint64_t>(R, std::min<uint64_t>(r_max, T1)));
 
     switch (U) {
-        case 8: return launch_tiled_u<VT, 8>(fold_mode, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream);
-        case 4: return launch_tiled_u<VT, 4>(fold_mode, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream);
-        case 2: return launch_tiled_u<VT, 2>(fold_mode, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream);
-        default: return launch_tiled_u<VT, 1>(fold_mode, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream);
+        case 8: return launch_tiled_u<VT, 8>(fold_mode, align, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream);
+        case 4: return launch_tiled_u<VT, 4>(fold_mode, align, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream);
+        case 2: return launch_tiled_u<VT, 2>(fold_mode, align, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream);
+        default: return launch_tiled_u<VT, 1>(fold_mode, align, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream);
     }
 }
 

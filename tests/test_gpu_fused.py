@@ -90,10 +90,17 @@ def test_fused_mul_decrypt_matches_oracle(engine, oracle, N, D):
                                    dict(CSGN_MUL_FLAT=1), dict(CSGN_MUL_FLAT=1, CSGN_MUL_FLAT_U=1),
                                    dict(CSGN_MUL_FLAT=1, CSGN_MUL_FLAT_U=8, CSGN_MUL_GRID=5),
                                    dict(CSGN_MUL_FLAT=1, CSGN_MUL_FLAT_U=2, CSGN_MUL_TPB=64),
-                                   dict(CSGN_MUL_FLAT=1, CSGN_MUL_FLAT_CTAS_PER_SM=1)])
+                                   dict(CSGN_MUL_FLAT=1, CSGN_MUL_FLAT_CTAS_PER_SM=1),
+                                   # the shared-memory fold instead of the lane-aligned one, and the lane-aligned one at
+                                   # every unroll, tiny and maximal row counts, odd CTA sizes, a 3-CTA grid
+                                   dict(CSGN_MUL_ALIGN=0), dict(CSGN_MUL_ALIGN=0, CSGN_MUL_U=4, CSGN_MUL_R=16),
+                                   dict(CSGN_MUL_ALIGN=1, CSGN_MUL_U=1, CSGN_MUL_R=1), dict(CSGN_MUL_ALIGN=1, CSGN_MUL_U=2, CSGN_MUL_R=32),
+                                   dict(CSGN_MUL_ALIGN=1, CSGN_MUL_U=4, CSGN_MUL_R=16, CSGN_MUL_GRID=3),
+                                   dict(CSGN_MUL_ALIGN=1, CSGN_MUL_U=8, CSGN_MUL_R=8, CSGN_MUL_TPB=288),
+                                   dict(CSGN_MUL_ALIGN=1, CSGN_MUL_U=1, CSGN_MUL_R=64, CSGN_MUL_TPB=64)])
 def test_fused_every_kernel_form(engine, oracle, knobs):
     rng = np.random.default_rng(77)
-    for N, D in ((1247, 2), (16383, 3), (191, 1)):
+    for N, D in ((1247, 2), (16383, 3), (191, 1), (700, 2), (1000, 3), (330, 1)):      # 11 / 16 (8 units) / 6 words per block
         for T1, T2 in ((61, 97), (5, 700), (200, 1), (2000, 13), (700, 41)):
             if N == 16383:
                 T1, T2 = max(1, T1 // 4), max(1, T2 // 4)

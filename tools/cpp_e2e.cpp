@@ -40,24 +40,53 @@ uint64_t count_satisfied(const std::vector<uint64_t> &w, uint64_t L, const std::
     return n;
 }
 
+double g_host[5];   // host seconds spent in: constructors, operator*, decrypt, destructors, getValue (CPP_E2E_BREAKDOWN=1)
+
 double run(int steps, std::vector<Pair> &pairs, const std::vector<uint64_t> &bitlen, const Context &ctx, SecretKey &sk,
            bool *ok) {
     const uint64_t len = pairs[0].a.size();
     std::vector<Plaintext> plain(pairs.size());
+    const bool breakdown = getenv("CPP_E2E_BREAKDOWN") != nullptr;
+    typedef std::chrono::steady_clock clk;
+    for (int i = 0; i < 5; ++i) g_host[i] = 0;
     Library::synchronize();
-    const auto t0 = std::chrono::steady_clock::now();
+    const auto t0 = clk::now();
     for (int s = 0; s < steps; ++s) {
         for (size_t p = 0; p < pairs.size(); ++p) {
-            Ciphertext a(pairs[p].a.data(), bitlen.data(), len, ctx);
-            Ciphertext b(pairs[p].b.data(), bitlen.data(), len, ctx);
-            Ciphertext c = a * b;
-            plain[p] = sk.decrypt(c);
+            if (!breakdown) {
+                Ciphertext a(pairs[p].a.data(), bitlen.data(), len, ctx);
+                Ciphertext b(pairs[p].b.data(), bitlen.data(), len, ctx);
+                Ciphertext c = a * b;
+                plain[p] = sk.decrypt(c);
+                continue;
+            }
+            const auto u0 = clk::now();
+            Ciphertext *a = new Ciphertext(pairs[p].a.data(), bitlen.data(), len, ctx);
+            Ciphertext *b = new Ciphertext(pairs[p].b.data(), bitlen.data(), len, ctx);
+            const auto u1 = clk::now();
+            Ciphertext *c = new Ciphertext(*a * *b);
+            const auto u2 = clk::now();
+            plain[p] = sk.decrypt(*c);
+            const auto u3 = clk::now();
+            delete a; delete b; delete c;
+            const auto u4 = clk::now();
+            g_host[0] += std::chrono::duration<double>(u1 - u0).count();
+            g_host[1] += std::chrono::duration<double>(u2 - u1).count();
+            g_host[2] += std::chrono::duration<double>(u3 - u2).count();
+            g_host[3] += std::chrono::duration<double>(u4 - u3).count();
         }
+        const auto v0 = clk::now();
         for (size_t p = 0; p < pairs.size(); ++p)
             if (plain[p].getValue() != pairs[p].want) *ok = false;
+        g_host[4] += std::chrono::duration<double>(clk::now() - v0).count();
     }
     Library::synchronize();
-    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    const double t = std::chrono::duration<double>(clk::now() - t0).count();
+    if (breakdown)
+        fprintf(stderr, "host us per pair: constructors %.1f, operator* %.1f, decrypt %.1f, destructors %.1f; getValue per step %.1f us; "
+                        "wall per step %.1f us\n", 1e6 * g_host[0] / (steps * pairs.size()), 1e6 * g_host[1] / (steps * pairs.size()),
+                1e6 * g_host[2] / (steps * pairs.size()), 1e6 * g_host[3] / (steps * pairs.size()), 1e6 * g_host[4] / steps, 1e6 * t / steps);
+    return t;
 }
 
 }  // namespace

@@ -101,7 +101,9 @@ def sec_fused():
     line("fused batch of %d (per product)" % P, (t[0] / P, t[1] / P), nb)
     t = timed(lambda i: eng.mul_count_batch_async(key, None, None, cnt.data_ptr(), arrays=(arr[0], arr[1], None)), 1, reps=5)
     line("fused count-only batch of %d (per product)" % P, (t[0] / P, t[1] / P), nb)
-    combos = [dict(CSGN_MUL_GRID=148 * 4), dict(CSGN_MUL_GRID=148 * 8), dict(CSGN_MUL_GRID=148 * 16),
+    combos = [dict(CSGN_MUL_ALIGN=0), dict(CSGN_MUL_R=3), dict(CSGN_MUL_R=4), dict(CSGN_MUL_R=6), dict(CSGN_MUL_R=8), dict(CSGN_MUL_R=12),
+              dict(CSGN_MUL_R=16), dict(CSGN_MUL_R=4, CSGN_MUL_U=1), dict(CSGN_MUL_R=8, CSGN_MUL_U=1), dict(CSGN_MUL_R=4, CSGN_MUL_TPB=384),
+              dict(CSGN_MUL_R=4, CSGN_MUL_TPB=256), dict(CSGN_MUL_R=8, CSGN_MUL_TPB=256), dict(CSGN_MUL_GRID=148 * 4), dict(CSGN_MUL_GRID=148 * 8), dict(CSGN_MUL_GRID=148 * 16),
               dict(CSGN_MUL_ITEMS_PER_SM=16), dict(CSGN_MUL_ITEMS_PER_SM=64), dict(CSGN_MUL_U=4), dict(CSGN_MUL_U=1),
               dict(CSGN_MUL_R=8), dict(CSGN_MUL_R=16), dict(CSGN_MUL_R=32), dict(CSGN_MUL_TPB=320), dict(CSGN_MUL_TPB=256)]
     for g_ in (148 * 3, 148 * 4, 148 * 5, 148 * 6, 148 * 8):
@@ -217,6 +219,6 @@ def sec_rsel():
         torch.cuda.empty_cache()
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) >= 1 and os.path.basename(sys.argv[0]) == "r2_sweep.py":
     for which in (sys.argv[1:] or ["fused", "chain", "shapes"]):
         {"fused": sec_fused, "chain": sec_chain, "shapes": sec_shapes, "rsel": sec_rsel}[which]()
