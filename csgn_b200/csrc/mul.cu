@@ -525,48 +525,60 @@ cudaError_t launch_units(int fold_mode, const void *a, uint64_t T1, const void *
     // with long rows.
     const uint64_t Q16 = Q * sizeof(VT) / 16;                     // thresholds were tuned in 16-byte units
     int U = (int)env_long("CSGN_MUL_U", Q16 < 8192 ? 1 : (huge && Q16 >= 32768) ? 4 : 2);
+    if (fold_mode && env_long("CSGN_MUL_U", 0) <= 0) U = std::min(U, 2);      // fused: more rows per item beat more units per thread
     U = U >= 8 ? 8 : U >= 4 ? 4 : U >= 2 ? 2 : 1;
     while (U > 1 && (uint64_t)upb * U > Q) U >>= 1;
     const uint32_t r_smem = std::max<uint32_t>(1, std::min<uint32_t>(64, kMulMaxSmem / (upb * (uint32_t)sizeof(VT))));
     const uint64_t target_items =
         (uint64_t)dp.sm_count * (uint64_t)env_long("CSGN_MUL_ITEMS_PER_SM", huge ? 128 : 32);
     // Fused kernels for blocks of up to 16 units run lane-aligned (whole blocks per warp: the fold is two redux.sync
-    // per item, no shared memory, no barrier); their CTA is a whole number of warps.
-    const bool align = fold_mode != 0 && upb <= 16 && env_long("CSGN_MUL_ALIGN", 1) != 0;
+    // per item, no shared memory, no barrier); their CTA is a whole number of warps -- unless the row is so short that
+    // whole warps would pad the column tiles by more than a few percent (chains: 250 or 1250 units per row).
+    bool align = fold_mode != 0 && upb <= 16 && env_long("CSGN_MUL_ALIGN", 1) != 0;
     const uint32_t lanes_used = align ? (32u / upb) * upb : 32u;
     uint32_t tpb = 0;
     uint64_t R = 1;
+    uint64_t step_units = 0;            // units one row step of the CTA covers
     for (;; U >>= 1) {
-        uint64_t step_units;            // units one row step of the CTA covers
+        uint32_t tpb_free = pick_tpb(upb, Q, U, tpb_cap);
+        if (tpb_free == 0) tpb_free = upb;
+        tpb = tpb_free;
+        step_units = tpb_free;
         if (align) {
-            // the warp count that pads the last column tile least (largest on ties), 8..16 warps
+            // the warp count (4 .. cap/32, nearest to 8 on ties) that pads the last column tile least
             double best = 1e30;
-            const uint32_t max_warps = std::max<uint32_t>(1, std::min<uint32_t>(16, tpb_cap / 32));
-            for (uint32_t w = max_warps; w >= std::min<uint32_t>(8, max_warps); --w) {
+            uint32_t best_w = 0;
+            const uint32_t max_warps = std::max<uint32_t>(1, tpb_cap / 32);
+            for (uint32_t w = std::min<uint32_t>(4, max_warps); w <= max_warps; ++w) {
                 const uint64_t tile = (uint64_t)w * lanes_used * U, nt = (Q + tile - 1) / tile;
-                const double pad = (double)(nt * tile) / (double)Q;
-                if (pad < best - 1e-9) {
+                const double pad = (double)(nt * tile) / (double)Q * (32.0 / lanes_used);
+                const bool closer = best_w == 0 || (w > 8 ? w - 8 : 8 - w) < (best_w > 8 ? best_w - 8 : 8 - best_w);
+                if (pad < best - 1e-9 || (pad < best + 1e-9 && closer)) {
                     best = pad;
-                    tpb = w * 32;
+                    best_w = w;
                 }
-                if (w == 1) break;
             }
-            step_units = (uint64_t)(tpb / 32) * lanes_used;
-        } else {
-            tpb = pick_tpb(upb, Q, U, tpb_cap);
-            if (tpb == 0) tpb = upb;
-            step_units = tpb;
+            const uint64_t tile_f = (uint64_t)tpb_free * U, nt_f = (Q + tile_f - 1) / tile_f;
+            const double pad_free = (double)(nt_f * tile_f) / (double)Q * ((double)((tpb_free + 31) / 32 * 32) / tpb_free);
+            if (env_long("CSGN_MUL_ALIGN", 1) < 2 && best > 1.04 * pad_free) align = false;      // 2: lane-aligned whatever it pads
+            else {
+                tpb = best_w * 32;
+                step_units = (uint64_t)best_w * lanes_used;
+            }
         }
         const uint64_t n_col_tiles = (Q + step_units * U - 1) / (step_units * U);
         R = (T1 * n_col_tiles + target_items - 1) / target_items;
-        if (R >= 3 || U == 1 || env_long("CSGN_MUL_U", 0) > 0) break;
+        if (R >= 3 || U == 1 || fold_mode || env_long("CSGN_MUL_U", 0) > 0) break;
     }
-    // B200 sweeps (tools/r2_sweep.py rsel, profiles/r2_rsel.log).  Chains -- very many short rows -- write fastest when
-    // the resident CTAs cover a compact window of the product: few rows per item.  A fused item of the shared-memory
-    // fold pays one cross-thread reduction and a barrier however many rows it has, so it wants 12-16 of them on every
-    // shape measured; the lane-aligned fold costs two warp instructions per item and keeps the multiply's choice.
-    if (huge && U == 1) R = std::min<uint64_t>(R, 4);
-    if (fold_mode) R = std::max<uint64_t>(8, std::min<uint64_t>(R, 16));
+    // B200 sweeps (tools/r2_sweep.py rsel, profiles/r2_rsel*.log).  Chains -- very many short rows -- write fastest when
+    // the resident CTAs cover a compact window of the product: few rows per item.  A fused item carries fixed work (its
+    // slice of b, the staged rows, two barriers, the fold) that only pays off over ~56 KB of product: 8 rows of a
+    // 7.7 KB column tile at N=1247, two dozen rows where a tile row is short (chains, N=191).
+    if (huge && U == 1 && !fold_mode) R = std::min<uint64_t>(R, 4);
+    if (fold_mode) {
+        const uint64_t row_bytes = step_units * (uint64_t)U * sizeof(VT);
+        R = std::max<uint64_t>(6, (56 * 1024 + row_bytes - 1) / row_bytes);
+    }
     R = (uint64_t)env_long("CSGN_MUL_R", (long)R);
     uint32_t r_max = r_smem;
     if (fold_mode) r_max = std::min<uint32_t>(r_max, 64u / (uint32_t)U);      // one 64-bit fail word per thread and item
