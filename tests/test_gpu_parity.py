@@ -771,3 +771,14 @@ def test_batch_entry_points(engine, oracle):
         engine.mul_batch([a[0], a[1]], [b[0], bad])
     with pytest.raises(engine.CsgnError, match="words per block"):
         key.decrypt_batch([a[0], bad])
+
+
+def test_sanitize_case_sweep_runs_clean():
+    """tools/sanitize_case.py -- the script meant for compute-sanitizer (closed on this pool) -- as a plain run: every
+    kernel form at ragged sizes, each result against the oracle, in a fresh process."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitize_case.py")], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0 and "sanitize_case OK" in r.stdout, r.stdout[-3000:]

@@ -4,8 +4,10 @@
 
 Touches every kernel (tiled and generic multiply; all decrypt forms incl. the lane-aligned kernel, the bulk-copy ring and
 the fused publish + collect of a sharded decrypt at world size 1; concat/append; every form of the bit-sliced permute incl.
-the bulk-copy prefetch, and the gather permute; batched encryption; the batch entry points; checksum) at sizes with ragged
-tails, and checks results against the oracle so that a silent corruption cannot pass."""
+the bulk-copy prefetch, and the gather permute; batched encryption; the batch entry points; checksum; round 2: the fused
+multiply->decrypt in every fold form, the rows fold, the plane permute forms, deferred results, lazy sums, batched uploads)
+at sizes with ragged tails, and checks results against the oracle so that a silent corruption cannot pass.  compute-sanitizer is
+closed on this pool; the script runs plain in the GPU suite (tests/test_gpu_parity.py) as an oracle-checked sweep."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -67,5 +69,69 @@ for N in (1247, 16383, 191, 2048):
         plain = rng.integers(0, 2, size=41).astype(np.uint8)
         fresh = key.encrypt_batch(plain, seed=7)
         assert np.array_equal(fresh.getValues(), o.encrypt_batch(plain, N, s, 7)); n_checks += 1
+# ---- round-2 kernels: fused multiply->decrypt (lane-aligned and shared-memory fold), rows fold, plane permute, lazy sums
+import ctypes  # noqa: E402
+for N, D in ((1247, 2), (700, 2), (16383, 3), (191, 1), (33000, 2), (4097, 2), (8191, 2)):
+    L = words_per_block(N)
+    ctx = eng.Context(N, D)
+    s = random_key(rng, N, D)
+    key = eng.SecretKey(ctx, s)
+    mask = np.zeros(L, dtype=np.uint64)
+    for pos in s:
+        mask[int(pos) >> 6] |= np.uint64(1 << (63 - (int(pos) & 63)))
+    for T1, T2 in ((61, 97), (5, 130), (200, 1)) if L <= 64 else ((9, 14), (33, 5)):
+        a, b = random_blocks(rng, T1, N), random_blocks(rng, T2, N)
+        a.reshape(-1, L)[::3] |= mask
+        b.reshape(-1, L)[::2] |= mask
+        ca, cb = eng.Ciphertext.from_host(a, ctx), eng.Ciphertext.from_host(b, ctx)
+        want_words = o.mul(a, b, L)
+        want = o.count_satisfied(want_words, N, s)
+        for env in ({}, {"CSGN_MUL_ALIGN": "0"}, {"CSGN_MUL_ALIGN": "2", "CSGN_MUL_R": "3"}, {"CSGN_MUL_U": "1", "CSGN_MUL_R": "64"},
+                    {"CSGN_MUL_TPB": "96", "CSGN_MUL_U": "4"}):
+            os.environ.update(env)
+            bit, cnt, prod = key.mul_decrypt(ca, cb, out="alloc")
+            assert cnt == want and np.array_equal(prod.getValues(), want_words); n_checks += 1
+            assert key.mul_decrypt(ca, cb) == (want & 1, want); n_checks += 1
+            for k in env: del os.environ[k]
+        assert key.count_satisfied(prod) == want; n_checks += 1                     # rows / wide / lanes / string fold by shape
+        for bpi in ("1", "2", "4"):
+            os.environ["CSGN_DEC_ROWS_BPI"] = bpi
+            os.environ["CSGN_DEC_ROWS_MIN"] = "17"
+            assert key.count_satisfied(prod) == want; n_checks += 1
+        del os.environ["CSGN_DEC_ROWS_BPI"], os.environ["CSGN_DEC_ROWS_MIN"]
+        perm = rng.permutation(N).astype(np.uint64)
+        p = eng.Permutation(ctx, perm)
+        wantp = o.permute_all(want_words, N, perm)
+        for form in ("-1", "0", "6", "12", "17"):
+            os.environ["CSGN_PERM_PLANE"] = form
+            assert np.array_equal(prod.applyPermutation(p).getValues(), wantp); n_checks += 1
+        del os.environ["CSGN_PERM_PLANE"]
+        res = key.decrypt_deferred(prod)
+        assert res.count() == want; n_checks += 1
+# lazy sums: segments walked by decrypt / permute / left-operand product, flattened by everything else
+N, D = 1247, 2
+L = words_per_block(N)
+ctx = eng.Context(N, D)
+s = random_key(rng, N, D)
+key = eng.SecretKey(ctx, s)
+parts = [random_blocks(rng, t, N) for t in (7001, 6900)]
+whole = np.concatenate(parts)
+cts = [eng.Ciphertext.from_host(x, ctx) for x in parts]
+rope = cts[0].add_lazy(cts[1])
+assert rope.segments == 2 and key.count_satisfied(rope) == o.count_satisfied(whole, N, s); n_checks += 1
+perm = rng.permutation(N).astype(np.uint64)
+assert np.array_equal(rope.applyPermutation(eng.Permutation(ctx, perm)).getValues(), o.permute_all(whole, N, perm)); n_checks += 1
+small = eng.Ciphertext.from_host(random_blocks(rng, 3, N), ctx)
+assert np.array_equal((rope * small).getValues(), o.mul(whole, small.getValues(), L)); n_checks += 1
+assert np.array_equal(rope.getValues(), whole) and rope.segments == 1; n_checks += 1
+# batched upload: shared storage, views freed in any order
+hosts = [np.ascontiguousarray(random_blocks(rng, t, N)) for t in (40, 1, 77)]
+up = eng.UploadBatch([h.ctypes.data for h in hosts], [40, 1, 77], ctx)
+ops = up.upload()
+eng.sync()
+for i in (2, 0, 1):
+    view = eng.Ciphertext(ctypes.c_void_p(ops[i]), ctx)
+    assert np.array_equal(view.getValues(), hosts[i]); n_checks += 1
+    del view
 eng.sync()
 print("sanitize_case OK:", n_checks, "checks,", eng.launch_count(), "launches")
