@@ -560,7 +560,7 @@ cudaError_t launch_units(int fold_mode, const void *a, uint64_t T1, const void *
             }
             const uint64_t tile_f = (uint64_t)tpb_free * U, nt_f = (Q + tile_f - 1) / tile_f;
             const double pad_free = (double)(nt_f * tile_f) / (double)Q * ((double)((tpb_free + 31) / 32 * 32) / tpb_free);
-            if (env_long("CSGN_MUL_ALIGN", 1) < 2 && best > 1.04 * pad_free) align = false;      // 2: lane-aligned whatever it pads
+            if (env_long("CSGN_MUL_ALIGN", 1) < 2 && best > 1.06 * pad_free) align = false;      // 2: lane-aligned whatever it pads
             else {
                 tpb = best_w * 32;
                 step_units = (uint64_t)best_w * lanes_used;
