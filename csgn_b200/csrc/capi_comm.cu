@@ -2,6 +2,10 @@
 // does the cross-GPU exchange itself (csrc/peer.cuh has the device side and the protocol).
 #include "capi_internal.cuh"
 
+#include <errno.h>
+#include <signal.h>
+#include <unistd.h>
+
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -150,7 +154,10 @@ int csgn_comm_connect_dir(csgn_comm *comm, const unsigned char *handle, const ch
     const std::string mine = path_of(comm->rank), tmp = mine + ".tmp";
     FILE *f = fopen(tmp.c_str(), "wb");
     if (!f) return fail(CSGN_ERR_INVALID_ARGUMENT, "cannot write %s", tmp.c_str());
-    const bool ok = fwrite(handle, 1, CSGN_IPC_HANDLE_BYTES, f) == CSGN_IPC_HANDLE_BYTES;
+    // the file carries the writer's pid after the handle: a file left behind by a crashed job with the same tag names a
+    // process that no longer exists and is ignored, whatever its age
+    const uint64_t my_pid = (uint64_t)getpid();
+    const bool ok = fwrite(handle, 1, CSGN_IPC_HANDLE_BYTES, f) == CSGN_IPC_HANDLE_BYTES && fwrite(&my_pid, sizeof my_pid, 1, f) == 1;
     if (fclose(f) != 0 || !ok || rename(tmp.c_str(), mine.c_str()) != 0)
         return fail(CSGN_ERR_INVALID_ARGUMENT, "cannot publish %s", mine.c_str());
     comm->rendezvous_file = mine;
@@ -161,12 +168,15 @@ int csgn_comm_connect_dir(csgn_comm *comm, const unsigned char *handle, const ch
         const std::string theirs = path_of(q);
         for (long waited_ms = 0;; waited_ms += 2) {
             struct stat st;
-            if (stat(theirs.c_str(), &st) == 0 && st.st_size == CSGN_IPC_HANDLE_BYTES && st.st_mtime >= started - 120) {
+            if (stat(theirs.c_str(), &st) == 0 && st.st_size == CSGN_IPC_HANDLE_BYTES + (off_t)sizeof(uint64_t) &&
+                st.st_mtime >= started - 120) {
                 FILE *g2 = fopen(theirs.c_str(), "rb");
-                const bool got = g2 && fread(all.data() + (size_t)q * CSGN_IPC_HANDLE_BYTES, 1, CSGN_IPC_HANDLE_BYTES, g2) ==
-                                           CSGN_IPC_HANDLE_BYTES;
+                uint64_t their_pid = 0;
+                bool got = g2 && fread(all.data() + (size_t)q * CSGN_IPC_HANDLE_BYTES, 1, CSGN_IPC_HANDLE_BYTES, g2) ==
+                                     CSGN_IPC_HANDLE_BYTES && fread(&their_pid, sizeof their_pid, 1, g2) == 1;
                 if (g2) fclose(g2);
-                if (got) break;
+                // alive? (kill with signal 0 only probes; EPERM also means "exists")
+                if (got && their_pid != 0 && (kill((pid_t)their_pid, 0) == 0 || errno == EPERM)) break;
             }
             if (waited_ms >= timeout_ms)
                 return fail(CSGN_ERR_TIMEOUT, "rank %d of %d did not publish %s within %d ms", q, comm->world,

@@ -112,6 +112,7 @@ class ShardedCiphertext:
                 device = "cuda" if nccl else "cpu"
             c = torch.tensor([key.count_satisfied(self.local)], dtype=torch.int64, device=device)
         else:
-            c = counts_out
+            c = counts_out                          # caller's tensor: element 0 receives the local count, then the sum
+            c.view(-1)[0] = key.count_satisfied(self.local)
         allreduce_counts(c)
         return int(parity(c)[0].item())

@@ -83,6 +83,10 @@ def _worker(rank, world, port, results):
         key = OracleKey(s, o)
         bit = P2.decrypt(key)
         assert bit == o.decrypt(full, N, s)
+        # the same into a caller's tensor (the local count must be written before the all-reduce)
+        mine = torch.full((1,), 12345, dtype=torch.int64)
+        assert P2.decrypt(key, counts_out=mine) == bit
+        assert int(mine.item()) == o.count_satisfied(full, N, s)
         # batched form: P counts, one collective
         counts = torch.tensor([key.count_satisfied(P1.local), key.count_satisfied(P2.local)], dtype=torch.int64)
         sharding.allreduce_counts(counts)
