@@ -171,14 +171,15 @@ def measured_peak_gbs():
 def ncu_traffic(kernel, workload, fold=None):
     """dram bytes (read + write) per launch of the dominant kernel, from the committed ncu --set full
     capture of this workload (profiles/<round>_<workload>_ncu_summary.json), or None.  `fold`: the FOLD template
-    argument (the last one) of mul_outer_kernel<VT, U, FOLD>."""
+    argument (the third) of mul_outer_kernel<VT, U, FOLD, ALIGN>."""
     import re
     for tag in ("r2", "r1c", "r1b", "r1"):                      # the latest capture first
         try:
             with open(os.path.join(ROOT, "profiles", "%s_%s_ncu_summary.json" % (tag, workload))) as f:
                 for name, k in json.load(f)["kernels"].items():
                     m = re.search(kernel + r"<([^>]*)>", name)
-                    if kernel in name and (fold is None or (m and m.group(1).split(",")[-1].strip() == str(fold))):
+                    targs = [x.strip() for x in m.group(1).split(",")] if m else []
+                    if kernel in name and (fold is None or (len(targs) >= 3 and targs[2] == str(fold))):
                         return k["dram_traffic_bytes_per_launch"]
         except Exception:
             pass

@@ -525,7 +525,9 @@ cudaError_t launch_units(int fold_mode, const void *a, uint64_t T1, const void *
     // with long rows.
     const uint64_t Q16 = Q * sizeof(VT) / 16;                     // thresholds were tuned in 16-byte units
     int U = (int)env_long("CSGN_MUL_U", Q16 < 8192 ? 1 : (huge && Q16 >= 32768) ? 4 : 2);
-    if (fold_mode && env_long("CSGN_MUL_U", 0) <= 0) U = std::min(U, 2);      // fused: more rows per item beat more units per thread
+    // lane-aligned fused kernels (blocks of up to 16 units): 4 units per thread cost 79 registers -- three resident CTAs
+    // instead of four -- and measured slower than 2 units with more rows per item; long blocks keep 4 (63 registers)
+    if (fold_mode && upb <= 16 && env_long("CSGN_MUL_U", 0) <= 0) U = std::min(U, 2);
     U = U >= 8 ? 8 : U >= 4 ? 4 : U >= 2 ? 2 : 1;
     while (U > 1 && (uint64_t)upb * U > Q) U >>= 1;
     const uint32_t r_smem = std::max<uint32_t>(1, std::min<uint32_t>(64, kMulMaxSmem / (upb * (uint32_t)sizeof(VT))));
