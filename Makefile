@@ -5,6 +5,8 @@
 #                            (tester_basic_operations, tester_permutations, tester_timings -- the targets of the
 #                            reference's CMakeLists.txt:45-52); nothing is copied, the sources are compiled in place
 #   make cpp-tests           tests/cpp/accept_demos and sharded_demo
+#   make tools               tools/bin/cpp_e2e (the bench step through the C++ API; bench.py reports it as e2e_cpp)
+#   make variants            libcsgn_variants.so: the losing kernel variants of the tuning sweeps compiled in
 #   make clean
 #
 # nvcc cross-compiles for sm_100a without a GPU.  There is no CPU build of the kernels: no B200, no library.
@@ -44,7 +46,16 @@ cpp-tests: all
 	  $(CXX) -O2 -std=c++11 -Wall -Icsgn_b200/certfhe -Iinclude -o tests/cpp/bin/$$n tests/cpp/$$n.cpp -L$(LIBDIR) -lcertFHE -lcsgn \
 	    '-Wl,-rpath,$$ORIGIN/../../../csgn_b200/lib' || exit 1; done
 
-clean:
-	rm -rf $(LIBDIR)/*.so build tests/cpp/bin
+tools: all
+	@mkdir -p tools/bin
+	$(CXX) -O2 -std=c++11 -Wall -Icsgn_b200/certfhe -Iinclude -o tools/bin/cpp_e2e tools/cpp_e2e.cpp -L$(LIBDIR) -lcertFHE -lcsgn \
+	    '-Wl,-rpath,$$ORIGIN/../../csgn_b200/lib'
 
-.PHONY: all testers cpp-tests clean
+variants: $(CSRC) $(CHDR)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVCCFLAGS) -DCSGN_BUILD_VARIANTS -shared -o $(LIBDIR)/libcsgn_variants.so $(CSRC)
+
+clean:
+	rm -rf $(LIBDIR)/*.so build tests/cpp/bin tools/bin
+
+.PHONY: all testers cpp-tests tools variants clean
