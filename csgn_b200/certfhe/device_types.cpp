@@ -39,27 +39,20 @@ inline uint64_t canonical_bits(uint64_t i, uint64_t L, uint64_t rem) {
 }
 
 void require_canonical_bitlen(const uint64_t *bitlen, uint64_t len, const Context &ctx) {
-    // block by block, no division per word: this runs in every Ciphertext(V, Bitlen, len, ctx)
+    // This runs in every Ciphertext(V, Bitlen, len, ctx), over as many words as V has: the first block is compared
+    // with the canonical pattern, every later word with the word one block before it -- one long loop without a
+    // division or a branch, which the compiler vectorises (the pattern has period L).
     const uint64_t L = ctx.getDefaultN(), rem = ctx.getN() % 64;
-    const uint64_t last = rem ? rem : 64;
-    uint64_t bad = len;
-    for (uint64_t base = 0; base < len && bad == len; base += L) {
-        const uint64_t n = len - base < L ? len - base : L;
-        uint64_t diff = 0;
-        for (uint64_t k = 0; k + 1 < n; ++k) diff |= bitlen[base + k] ^ 64u;
-        if (n == L) diff |= bitlen[base + L - 1] ^ last;
-        else if (n) diff |= bitlen[base + n - 1] ^ 64u;
-        if (diff)
-            for (uint64_t k = 0; k < n; ++k)
-                if (bitlen[base + k] != canonical_bits(base + k, L, rem)) {
-                    bad = base + k;
-                    break;
-                }
-    }
-    if (bad != len)
-        throw Error("Ciphertext: bitlen[" + to_string(bad) + "] = " + to_string(bitlen[bad]) +
-                    " is not the canonical pattern for N = " + to_string(ctx.getN()) +
-                    " (the reference would mis-index such an object, src/SecretKey.cpp:133)");
+    uint64_t diff = 0;
+    const uint64_t head = len < L ? len : L;
+    for (uint64_t k = 0; k < head; ++k) diff |= bitlen[k] ^ canonical_bits(k, L, rem);
+    for (uint64_t i = L; i < len; ++i) diff |= bitlen[i] ^ bitlen[i - L];
+    if (!diff) return;
+    for (uint64_t i = 0; i < len; ++i)
+        if (bitlen[i] != canonical_bits(i, L, rem))
+            throw Error("Ciphertext: bitlen[" + to_string(i) + "] = " + to_string(bitlen[i]) +
+                        " is not the canonical pattern for N = " + to_string(ctx.getN()) +
+                        " (the reference would mis-index such an object, src/SecretKey.cpp:133)");
 }
 
 uint64_t *copy_words(const uint64_t *src, uint64_t n) {
