@@ -34,6 +34,32 @@ def test_reference_arm_line():
     assert d["gpu_launches"] == 0 and d["config"]["workload"].startswith("cfg2")
 
 
+def test_bench_numpy_restatement_matches_the_oracle():
+    """bench.py checks the GPU with its OWN numpy restatement (precheck, host-known truth); that restatement is pinned
+    to the oracle here, on CPU, for three contexts incl. odd L."""
+    import importlib.util
+    import numpy as np
+    from oracle.pyoracle import Oracle, random_blocks, random_key
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    o = Oracle()
+    rng = np.random.default_rng(31)
+    for N, D in ((1247, 3), (191, 2), (16383, 4), (128, 2)):
+        L = bench.words_per_block(N)
+        s = random_key(rng, N, D)
+        mask = bench.np_key_mask(N, s)
+        a = bench.planted_blocks(rng, 23, N, mask, k=7)
+        b = bench.planted_blocks(rng, 9, N, mask, k=4)
+        assert not np.any(a.reshape(-1, L)[:, -1] & ~np.uint64(((1 << 64) - 1) << ((64 - N % 64) % 64) & ((1 << 64) - 1)))   # pad bits stay zero
+        prod = bench.np_mul(a, b, L)
+        assert np.array_equal(prod, o.mul(a, b, L))
+        assert bench.np_count(a, L, mask) == o.count_satisfied(a, N, s) >= 7
+        assert bench.np_count(prod, L, mask) == o.count_satisfied(prod, N, s) == bench.np_count(a, L, mask) * bench.np_count(b, L, mask)
+        perm = rng.permutation(N).astype(np.uint64)
+        assert np.array_equal(bench.np_permute(prod, N, perm), o.permute_all(prod, N, perm))
+
+
 @pytest.mark.gpu
 def test_our_arm_line():
     d = _run(["--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--sustain-s", "0.3"], 1200)

@@ -25,6 +25,9 @@ def test_secret_key_file_round_trip(lib, tmp_path):
     path = str(tmp_path / "k.sk").encode()
     assert lib.csgn_key_positions_save(path, N, D, pos.ctypes.data_as(_vp), pos.size) == 0, _err(lib)
     assert os.path.getsize(path) == 64 + 8 * D
+    raw = np.fromfile(path, dtype=np.uint64)                 # the format, field by field (include/csgn.h)
+    assert raw[:1].tobytes() == b"CSGNSK01" and [int(x) for x in raw[1:5]] == [N, D, 0, D]
+    assert int(raw[5]) == int(np.bitwise_xor.reduce(pos)) and not raw[6:8].any() and np.array_equal(raw[8:], pos)
     n, d, cnt = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
     assert lib.csgn_key_positions_load(path, ctypes.byref(n), ctypes.byref(d), None, 0, ctypes.byref(cnt)) == 0   # size query
     assert (n.value, d.value, cnt.value) == (N, D, D)
@@ -53,6 +56,8 @@ def test_permutation_file_round_trip(lib, tmp_path):
     perm = np.random.default_rng(2).permutation(n).astype(np.uint64)
     path = str(tmp_path / "p.pm").encode()
     assert lib.csgn_perm_entries_save(path, perm.ctypes.data_as(_vp), n) == 0, _err(lib)
+    raw = np.fromfile(path, dtype=np.uint64)
+    assert raw[:1].tobytes() == b"CSGNPM01" and [int(x) for x in raw[1:5]] == [n, 0, 0, n] and np.array_equal(raw[8:], perm)
     cnt = ctypes.c_uint64()
     assert lib.csgn_perm_entries_load(path, None, 0, ctypes.byref(cnt)) == 0 and cnt.value == n
     got = np.zeros(n, dtype=np.uint64)
