@@ -262,6 +262,66 @@ decrypt_count_rows_kernel(const VT *__restrict__ V, const uint64_t T, const uint
     fold_and_publish(my_count, scratch, count_out, pp);
 }
 
+// ---------------------------------------------------------------------------------------
+// Odd L (half of all contexts): a block is not a whole number of 16-byte units, but TWO consecutive blocks are -- a
+// "double block" of 2L words = L units, 16-byte aligned whenever the ciphertext is.  A warp folds BPI double blocks per
+// iteration exactly as the rows kernel does, with two verdicts per double block: a unit's low word belongs to the first
+// block when its word index 2u is below L, its high word when 2u+1 is (the middle unit straddles the two blocks).  The
+// key-mask words of a unit come from L1.  An odd last block is folded by the grid's first warp with 8-byte loads.
+// ---------------------------------------------------------------------------------------
+template <int BPI>
+__global__ void __launch_bounds__(kDecThreads, 4)
+decrypt_count_pairs_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint32_t L, const uint64_t *__restrict__ M,
+                           uint64_t *scratch, uint64_t *count_out, const __grid_constant__ PeerPush pp) {
+    const uint32_t lane = threadIdx.x & 31u;
+    pdl_enter();
+    const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t n_pairs = T >> 1;
+    const uint64_t n_groups = (n_pairs + BPI - 1) / BPI;
+    const uint32_t steps = (L + 31u) >> 5;
+    uint64_t my_count = 0;
+    for (uint64_t grp = warp_global; grp < n_groups; grp += n_warps) {
+        const uint64_t pair0 = grp * BPI;
+        const uint4 *row = V4 + pair0 * L + lane;
+        bool f0[BPI], f1[BPI];
+#pragma unroll
+        for (int b = 0; b < BPI; ++b) f0[b] = f1[b] = false;
+#pragma unroll(8 / BPI)
+        for (uint32_t s = 0; s < steps; ++s) {
+            const uint32_t u = s * 32u + lane;
+            const bool in = u < L;
+            const bool lo_first = 2u * u < L, hi_first = 2u * u + 1u < L;
+            const uint64_t m_lo = in ? __ldg(M + (lo_first ? 2u * u : 2u * u - L)) : 0ull;
+            const uint64_t m_hi = in ? __ldg(M + (hi_first ? 2u * u + 1u : 2u * u + 1u - L)) : 0ull;
+            uint4 v[BPI];
+#pragma unroll
+            for (int b = 0; b < BPI; ++b)
+                v[b] = (in && pair0 + b < n_pairs) ? ld_stream(row + (uint64_t)b * L + s * 32u) : vzero<uint4>();
+#pragma unroll
+            for (int b = 0; b < BPI; ++b) {
+                const uint64_t lo = (uint64_t)v[b].x | ((uint64_t)v[b].y << 32), hi = (uint64_t)v[b].z | ((uint64_t)v[b].w << 32);
+                const bool fl = (~lo & m_lo) != 0ull, fh = (~hi & m_hi) != 0ull;
+                f0[b] |= (lo_first && fl) || (hi_first && fh);
+                f1[b] |= (!lo_first && fl) || (!hi_first && fh);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < BPI; ++b) {
+            const bool bad0 = __any_sync(0xffffffffu, f0[b]), bad1 = __any_sync(0xffffffffu, f1[b]);
+            if (lane == 0 && pair0 + b < n_pairs) my_count += (bad0 ? 0u : 1u) + (bad1 ? 0u : 1u);
+        }
+    }
+    if ((T & 1ull) && warp_global == 0) {
+        const uint64_t *last = reinterpret_cast<const uint64_t *>(V4) + (T - 1) * L;
+        bool f = false;
+        for (uint32_t w = lane; w < L; w += 32) f |= (~__ldcs(last + w) & __ldg(M + w)) != 0ull;
+        const bool bad = __any_sync(0xffffffffu, f);
+        if (lane == 0 && !bad) ++my_count;
+    }
+    fold_and_publish(my_count, scratch, count_out, pp);
+}
+
 // Blocks longer than kDecMaxUnits units (N > 65536): one warp per block, 64-bit loads.
 __global__ void __launch_bounds__(kDecThreads)
 decrypt_count_generic_kernel(const uint64_t *__restrict__ V, const uint64_t T, const uint32_t L,
@@ -355,6 +415,17 @@ cudaError_t launch_rows(const uint64_t *v, uint64_t T, uint32_t upb, const uint6
     grid = (uint32_t)std::min<uint64_t>(work_ctas, (uint64_t)grid * fold_waves(T * (uint64_t)upb * sizeof(VT), overlapped));
     return launch_kernel(decrypt_count_rows_kernel<VT, BPI>, grid, kDecThreads, 0, stream, reinterpret_cast<const VT *>(v), T,
                          upb, reinterpret_cast<const VT *>(mask), scratch, count_out, pp);
+}
+
+template <int BPI>
+cudaError_t launch_pairs(const uint64_t *v, uint64_t T, uint32_t L, const uint64_t *mask, uint64_t *scratch,
+                         uint64_t *count_out, const PeerPush &pp, bool overlapped, cudaStream_t stream) {
+    const uint64_t n_groups = std::max<uint64_t>(1, (T / 2 + BPI - 1) / BPI);
+    const uint64_t work_ctas = (n_groups + kDecWarps - 1) / kDecWarps;
+    uint32_t grid = resident_grid(decrypt_count_pairs_kernel<BPI>, 0, work_ctas);
+    grid = (uint32_t)std::min<uint64_t>(work_ctas, (uint64_t)grid * fold_waves(T * (uint64_t)L * 8u, overlapped));
+    return launch_kernel(decrypt_count_pairs_kernel<BPI>, grid, kDecThreads, 0, stream, reinterpret_cast<const uint4 *>(v), T, L,
+                         mask, scratch, count_out, pp);
 }
 
 // Push and/or publish + collect without a fold (an empty local shard still owes its peers a
@@ -556,6 +627,16 @@ cudaError_t launch_decrypt_count(const uint64_t *v, uint64_t T, uint32_t L, cons
 #endif
     const bool force_string = env_long("CSGN_DEC_STRING", 0) != 0;
     if (done) {
+    } else if ((L & 1u) && L >= (uint32_t)env_long("CSGN_DEC_PAIRS_MIN", 129) && !force_string &&
+               !env_long("CSGN_DEC_GENERIC", 0) && (reinterpret_cast<uintptr_t>(v) & 15u) == 0) {
+        // long odd-L blocks: double blocks of 2L words, 16-byte loads (B200, tools/oddl_probe.py: N = 12351, L = 193:
+        // 0.59 -> 0.66 of the copy peak; below ~5 steps per double block the fail-string kernel on 8-byte units is
+        // faster -- N = 4097, L = 65: 0.64 against 0.53 -- because a 65-unit row costs three load steps, the last for one lane)
+        const uint32_t steps = (L + 31u) / 32u;
+        const long bpi = env_long("CSGN_DEC_ROWS_BPI", steps >= 8 ? 1 : steps >= 4 ? 2 : 4);
+        if (bpi >= 4) err = launch_pairs<4>(v, T, L, mask, scratch, count_out, pp, overlapped, stream);
+        else if (bpi >= 2) err = launch_pairs<2>(v, T, L, mask, scratch, count_out, pp, overlapped, stream);
+        else err = launch_pairs<1>(v, T, L, mask, scratch, count_out, pp, overlapped, stream);
     } else if (upb > kDecMaxUnits || env_long("CSGN_DEC_GENERIC", 0)) {
         const uint64_t want = (T + kDecWarps - 1) / kDecWarps;
         const uint64_t ctas_per_sm = (uint64_t)env_long("CSGN_DEC_CTAS_PER_SM", 8);

@@ -65,6 +65,9 @@ struct FoldParams {
     uint64_t *count_out;        // device word for the total (may be null with a PeerPush)
     PeerPush pp;
     int mask_in_params;
+    // Odd L multiplied with 16-byte units (plain multiply, even T2): the right operand is read as T2/2 double blocks of
+    // 2L words, and each row of A -- dbl_words = L 8-byte words in memory -- is staged as the double block a_i || a_i.
+    uint32_t dbl_words;
 };
 
 template <typename VT>
@@ -146,18 +149,19 @@ mul_outer_kernel(const VT *__restrict__ A, const VT *__restrict__ B, VT *__restr
     // the chunk of item j + pf_chunks*n_col_tiles (done by the column-0 CTA of each chunk);
     // the first pf_chunks chunks, which nobody is ahead of, are requested line by line by
     // the first CTAs.
+    const uint32_t a_row_bytes = fo.dbl_words ? fo.dbl_words * 8u : UPB * (uint32_t)sizeof(VT);   // a row of A in memory
     if (pf_chunks) {
-        const uint64_t a_bytes = T1 * UPB * sizeof(VT);
-        const uint64_t head_bytes = min(a_bytes, (uint64_t)pf_chunks * R * UPB * sizeof(VT));
+        const uint64_t a_bytes = T1 * a_row_bytes;
+        const uint64_t head_bytes = min(a_bytes, (uint64_t)pf_chunks * R * a_row_bytes);
         if (threadIdx.x == 0 && (uint64_t)blockIdx.x * 128u < head_bytes)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(A) + (uint64_t)blockIdx.x * 128u));
         if (blockIdx.x % n_col_tiles == 0) {
             const uint64_t row0 = ((uint64_t)blockIdx.x / n_col_tiles + pf_chunks) * R;
             if (row0 < T1) {
-                const uint32_t bytes = (uint32_t)min((uint64_t)R, T1 - row0) * UPB * (uint32_t)sizeof(VT);
+                const uint32_t bytes = (uint32_t)min((uint64_t)R, T1 - row0) * a_row_bytes;
                 const uint32_t off = threadIdx.x * 128u;
                 if (off < bytes + 128u)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(A + row0 * UPB) +
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(A) + row0 * a_row_bytes +
                                                                    min(off, bytes - 1u)));
             }
         }
@@ -181,8 +185,21 @@ mul_outer_kernel(const VT *__restrict__ A, const VT *__restrict__ B, VT *__restr
         }
 
         __syncthreads();  // the previous item's readers of sA (and sFail) are done
-        const VT *a_chunk = A + row0 * UPB;
-        for (uint32_t idx = threadIdx.x; idx < nrows * UPB; idx += blockDim.x) sA[idx] = __ldg(a_chunk + idx);
+        if (sizeof(VT) == 16 && fo.dbl_words) {
+            // a_i || a_i: unit u of the double block is words (2u mod L, (2u+1) mod L) of a_i
+            const uint32_t Lw = fo.dbl_words;
+            const uint64_t *a64 = reinterpret_cast<const uint64_t *>(A) + row0 * Lw;
+            for (uint32_t idx = threadIdx.x; idx < nrows * UPB; idx += blockDim.x) {
+                const uint32_t r = idx / UPB, u = idx - r * UPB;
+                const uint32_t w0 = 2u * u < Lw ? 2u * u : 2u * u - Lw, w1 = 2u * u + 1u < Lw ? 2u * u + 1u : 2u * u + 1u - Lw;
+                const uint64_t x0 = __ldg(a64 + (uint64_t)r * Lw + w0), x1 = __ldg(a64 + (uint64_t)r * Lw + w1);
+                reinterpret_cast<uint2 *>(sA)[2 * idx] = make_uint2((uint32_t)x0, (uint32_t)(x0 >> 32));
+                reinterpret_cast<uint2 *>(sA)[2 * idx + 1] = make_uint2((uint32_t)x1, (uint32_t)(x1 >> 32));
+            }
+        } else {
+            const VT *a_chunk = A + row0 * UPB;
+            for (uint32_t idx = threadIdx.x; idx < nrows * UPB; idx += blockDim.x) sA[idx] = __ldg(a_chunk + idx);
+        }
         __syncthreads();
 
         VT *o = out + row0 * Q + q0;
@@ -358,8 +375,9 @@ mul_outer_generic_kernel(const uint64_t *__restrict__ A, const uint64_t *__restr
     }
 }
 
-void fill_fold_params(FoldParams &fo, const MulFold *fold, uint32_t upb, size_t unit_bytes) {
+void fill_fold_params(FoldParams &fo, const MulFold *fold, uint32_t upb, size_t unit_bytes, uint32_t dbl_words = 0) {
     memset(&fo, 0, sizeof fo);
+    fo.dbl_words = dbl_words;
     if (!fold) return;
     fo.mask = fold->mask;
     fo.scratch = fold->scratch;
@@ -373,7 +391,7 @@ void fill_fold_params(FoldParams &fo, const MulFold *fold, uint32_t upb, size_t 
 
 template <typename VT, int U, int FOLD, int ALIGN = 0>
 cudaError_t launch_tiled_uf(const void *a, uint64_t T1, const void *b, uint64_t Q, uint32_t upb, void *out, uint32_t tpb,
-                            uint32_t R, uint64_t grid_cap, const MulFold *fold, cudaStream_t stream) {
+                            uint32_t R, uint64_t grid_cap, const MulFold *fold, cudaStream_t stream, uint32_t dbl_words = 0) {
     // ALIGN: tpb threads (a multiple of 32) cover (tpb/32) * (32/upb)*upb units per row step
     const uint64_t tile_q = (uint64_t)(ALIGN ? (tpb / 32u) * ((32u / upb) * upb) : tpb) * U;
     const uint64_t n_col_tiles = (Q + tile_q - 1) / tile_q;
@@ -386,7 +404,7 @@ cudaError_t launch_tiled_uf(const void *a, uint64_t T1, const void *b, uint64_t 
     const uint64_t ahead_items = (uint64_t)device_props().sm_count * (uint64_t)std::max<long>(pf_per_sm, 0);
     const uint32_t pf_chunks = pf_per_sm > 0 ? (uint32_t)((ahead_items + n_col_tiles - 1) / n_col_tiles) : 0u;
     FoldParams fo;
-    fill_fold_params(fo, fold, upb, sizeof(VT));
+    fill_fold_params(fo, fold, upb, sizeof(VT), dbl_words);
     return launch_kernel(mul_outer_kernel<VT, U, FOLD, ALIGN>, grid, tpb, smem, stream, static_cast<const VT *>(a),
                          static_cast<const VT *>(b), static_cast<VT *>(out), upb, T1, Q, R, (uint32_t)n_col_tiles, n_items,
                          pf_chunks, fo);
@@ -394,7 +412,8 @@ cudaError_t launch_tiled_uf(const void *a, uint64_t T1, const void *b, uint64_t 
 
 template <typename VT, int U>
 cudaError_t launch_tiled_u(int fold_mode, bool align, const void *a, uint64_t T1, const void *b, uint64_t Q, uint32_t upb,
-                           void *out, uint32_t tpb, uint32_t R, uint64_t grid_cap, const MulFold *fold, cudaStream_t stream) {
+                           void *out, uint32_t tpb, uint32_t R, uint64_t grid_cap, const MulFold *fold, cudaStream_t stream,
+                           uint32_t dbl_words = 0) {
     if (align) {
         if (fold_mode == 1) return launch_tiled_uf<VT, U, 1, 1>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream);
         return launch_tiled_uf<VT, U, 2, 1>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream);
@@ -402,7 +421,7 @@ cudaError_t launch_tiled_u(int fold_mode, bool align, const void *a, uint64_t T1
     switch (fold_mode) {
         case 1: return launch_tiled_uf<VT, U, 1>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream);
         case 2: return launch_tiled_uf<VT, U, 2>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream);
-        default: return launch_tiled_uf<VT, U, 0>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream);
+        default: return launch_tiled_uf<VT, U, 0>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream, dbl_words);
     }
 }
 
@@ -482,7 +501,7 @@ uint32_t pick_tpb_flat(uint32_t upb, uint32_t lo, uint32_t hi) {
 
 template <typename VT>
 cudaError_t launch_units(int fold_mode, const void *a, uint64_t T1, const void *b, uint64_t T2, uint32_t upb, void *out,
-                         const MulFold *fold, cudaStream_t stream) {
+                         const MulFold *fold, cudaStream_t stream, uint32_t dbl_words = 0) {
     const DeviceProps &dp = device_props();
     const uint64_t Q = T2 * upb;
     // The fused kernels hold more registers (54-64 against 34-40): CTAs of 256 threads keep four of them resident per
@@ -587,10 +606,10 @@ cudaError_t launch_units(int fold_mode, const void *a, uint64_t T1, const void *
     R = std::max<uint64_t>(1, std::min<uint64_t>(R, std::min<uint64_t>(r_max, T1)));
 
     switch (U) {
-        case 8: return launch_tiled_u<VT, 8>(fold_mode, align, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream);
-        case 4: return launch_tiled_u<VT, 4>(fold_mode, align, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream);
-        case 2: return launch_tiled_u<VT, 2>(fold_mode, align, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream);
-        default: return launch_tiled_u<VT, 1>(fold_mode, align, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream);
+        case 8: return launch_tiled_u<VT, 8>(fold_mode, align, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream, dbl_words);
+        case 4: return launch_tiled_u<VT, 4>(fold_mode, align, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream, dbl_words);
+        case 2: return launch_tiled_u<VT, 2>(fold_mode, align, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream, dbl_words);
+        default: return launch_tiled_u<VT, 1>(fold_mode, align, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream, dbl_words);
     }
 }
 
@@ -620,8 +639,14 @@ cudaError_t launch_mul(const uint64_t *a, uint64_t T1, const uint64_t *b, uint64
         // either way) -- and the swapped form is one long row instead of T1 tiny ones
         return launch_mul(b, 1, a, T1, L, out, stream, fold);
     }
-    const cudaError_t err = units16 ? launch_units<uint4>(fold_mode, a, T1, b, T2, upb, out, fold, stream)
-                                    : launch_units<uint2>(fold_mode, a, T1, b, T2, upb, out, fold, stream);
+    // Odd L (half of all contexts): a block is not a whole number of 16-byte units, but TWO blocks are.  With an even
+    // number of right-operand blocks the plain multiply reads b as T2/2 double blocks of 2L words and stages every row of
+    // a as a_i || a_i -- the same words out, with 16-byte loads and stores instead of 8-byte ones.
+    const bool dbl = (L & 1u) && !fold && (T2 % 2 == 0) && L <= (uint32_t)kMulMaxThreads && env_long("CSGN_MUL_DOUBLE", 1) &&
+                     ((reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+    const cudaError_t err = dbl       ? launch_units<uint4>(0, a, T1, b, T2 / 2, L, out, nullptr, stream, L)
+                            : units16 ? launch_units<uint4>(fold_mode, a, T1, b, T2, upb, out, fold, stream)
+                                      : launch_units<uint2>(fold_mode, a, T1, b, T2, upb, out, fold, stream);
     count_launch();
     return err;
 }

@@ -217,6 +217,12 @@ def test_decrypt_every_block_shape(engine, oracle, L):
             assert key.count_satisfied(ct) == want, (L, T, "string")
         with _Env(CSGN_DEC_GENERIC=1):
             assert key.count_satisfied(ct) == want, (L, T, "generic")
+        if L % 2 and L >= 17:               # odd L: the double-block kernel, every blocks-per-iteration form; and without it
+            for bpi in (1, 2, 4):
+                with _Env(CSGN_DEC_ROWS_BPI=bpi, CSGN_DEC_PAIRS_MIN=17):
+                    assert key.count_satisfied(ct) == want, (L, T, "pairs", bpi)
+            with _Env(CSGN_DEC_PAIRS_MIN=100000):
+                assert key.count_satisfied(ct) == want, (L, T, "8-byte units")
         if T > 3:
             # a 16-byte-misaligned view of an even-L ciphertext takes the 8-byte-unit kernels
             import torch
@@ -437,3 +443,23 @@ def test_lazy_sum_rope(engine, oracle):
     del ab, ba, four
     a += cs                                         # released: growable again
     assert np.array_equal(a.getValues(), np.concatenate([parts[0], small]))
+
+
+@pytest.mark.parametrize("N", [191, 4097, 2111, 32950, 1950, 12351])
+def test_multiply_odd_L_as_double_blocks(engine, oracle, N):
+    """Odd L with an even number of right-operand blocks: the multiply runs on 16-byte units over double blocks (every row
+    of a staged as a_i || a_i).  Same words as the 8-byte-unit kernel and the oracle, ragged tiles and tiny shapes included."""
+    L = words_per_block(N)
+    assert L % 2 == 1
+    rng = np.random.default_rng(N + 3)
+    ctx = engine.Context(N, 2)
+    shapes = [(1, 2), (7, 2), (2, 8), (37, 54), (300, 200), (3, 1000), (129, 66), (1000, 4)] if L <= 64 else [(1, 2), (9, 14), (40, 6), (3, 70)]
+    for T1, T2 in shapes:
+        a, b = random_blocks(rng, T1, N), random_blocks(rng, T2, N)
+        ca, cb = engine.Ciphertext.from_host(a, ctx), engine.Ciphertext.from_host(b, ctx)
+        want = oracle.mul(a, b, L)
+        assert np.array_equal((ca * cb).getValues(), want), (N, T1, T2)
+        for knobs in (dict(CSGN_MUL_DOUBLE=0), dict(CSGN_MUL_U=1, CSGN_MUL_R=1), dict(CSGN_MUL_U=4, CSGN_MUL_R=7, CSGN_MUL_GRID=3),
+                      dict(CSGN_MUL_TPB=96, CSGN_MUL_U=2)):
+            with _Env(**knobs):
+                assert np.array_equal((ca * cb).getValues(), want), (N, T1, T2, knobs)
