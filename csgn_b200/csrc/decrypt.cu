@@ -123,6 +123,92 @@ decrypt_count_kernel(const VT *__restrict__ V, const uint64_t T, const uint32_t 
 
 
 // ---------------------------------------------------------------------------------------
+// string over DOUBLE blocks, for odd L of 17 words and more: two consecutive blocks are L 16-byte units, so the walk
+// above runs on 16-byte loads over the T/2 double blocks; a unit's low word belongs to the first block of its pair when
+// its word index 2k is below L, its high word when 2k+1 is -- two ballots per step, two fail strings per warp, two
+// verdicts per lane.  An odd last block is folded by the grid's first warp with 8-byte loads.
+// ---------------------------------------------------------------------------------------
+template <int UNROLL, int MINB>
+__global__ void __launch_bounds__(kDecThreads, MINB)
+decrypt_count_string_pairs_kernel(const uint4 *__restrict__ V, const uint64_t T, const uint32_t L,
+                                  const uint64_t *__restrict__ M, uint64_t *scratch, uint64_t *count_out,
+                                  const __grid_constant__ PeerPush pp) {
+    extern __shared__ uint4 smem_raw[];
+    const uint32_t UPB = L;                                          // units per double block
+    uint4 *sM2 = smem_raw;                                           // the double block's mask units, twice over
+    uint32_t *sF = reinterpret_cast<uint32_t *>(sM2 + 2 * UPB);      // fail strings: first blocks, second blocks
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < 2 * UPB; i += blockDim.x) {
+        const uint32_t u = i < UPB ? i : i - UPB;
+        const uint64_t lo = M[2u * u < L ? 2u * u : 2u * u - L], hi = M[2u * u + 1u < L ? 2u * u + 1u : 2u * u + 1u - L];
+        sM2[i] = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+    }
+    __syncthreads();
+    pdl_enter();
+
+    uint32_t *sF0 = sF + warp * 2u * UPB, *sF1 = sF0 + UPB;
+    const uint32_t k0 = lane % UPB;
+    const uint32_t step = 32u % UPB;
+    const uint64_t n_pairs = T >> 1;
+    const uint64_t n_units = n_pairs * UPB;
+    const uint64_t n_chunks = (n_pairs + 31) >> 5;
+    uint64_t my_count = 0;
+    for (uint64_t chunk = (uint64_t)blockIdx.x * kDecWarps + warp; chunk < n_chunks; chunk += (uint64_t)gridDim.x * kDecWarps) {
+        const uint64_t q_lane = chunk * 32u * UPB + lane;
+        const bool full = (chunk + 1) * 32u <= n_pairs;
+        uint32_t koff = 0;
+        for (uint32_t r = 0; r < UPB; r += UNROLL) {
+            uint4 v[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const uint64_t q = q_lane + 32u * (r + u);
+                v[u] = (r + u < UPB && (full || q < n_units)) ? ld_stream(V + q) : vzero<uint4>();
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if (r + u < UPB) {                                   // warp-uniform
+                    uint32_t k = k0 + koff;
+                    if (k >= UPB) k -= UPB;
+                    const uint4 m = sM2[k];
+                    const bool fl = ((~v[u].x & m.x) | (~v[u].y & m.y)) != 0u, fh = ((~v[u].z & m.z) | (~v[u].w & m.w)) != 0u;
+                    const bool lo_first = 2u * k < L, hi_first = 2u * k + 1u < L;
+                    const uint32_t b0 = __ballot_sync(0xffffffffu, (lo_first && fl) || (hi_first && fh));
+                    const uint32_t b1 = __ballot_sync(0xffffffffu, (!lo_first && fl) || (!hi_first && fh));
+                    if (lane == 0) {
+                        sF0[r + u] = b0;
+                        sF1[r + u] = b1;
+                    }
+                    koff += step;
+                    if (koff >= UPB) koff -= UPB;
+                }
+            }
+        }
+        __syncwarp();
+        // lane b <-> double block b of the chunk: bits [b*UPB, b*UPB+UPB) of each fail string
+        const uint64_t pair = chunk * 32u + lane;
+        const uint32_t lo = lane * UPB, hi = lo + UPB;
+        uint32_t any0 = 0, any1 = 0;
+        for (uint32_t w = lo >> 5; w <= (hi - 1) >> 5; ++w) {
+            const uint32_t first = max(lo, w << 5) - (w << 5);
+            const uint32_t last = min(hi, (w + 1) << 5) - (w << 5);   // exclusive, 1..32
+            const uint32_t m = (last - first == 32u) ? 0xffffffffu : (((1u << (last - first)) - 1u) << first);
+            any0 |= sF0[w] & m;
+            any1 |= sF1[w] & m;
+        }
+        if (pair < n_pairs) my_count += (any0 == 0u ? 1u : 0u) + (any1 == 0u ? 1u : 0u);
+        __syncwarp();                        // before the next chunk overwrites the strings
+    }
+    if ((T & 1ull) && blockIdx.x == 0 && warp == 0) {
+        const uint64_t *last = reinterpret_cast<const uint64_t *>(V) + (T - 1) * L;
+        bool f = false;
+        for (uint32_t w = lane; w < L; w += 32) f |= (~__ldcs(last + w) & __ldg(M + w)) != 0ull;
+        const bool bad = __any_sync(0xffffffffu, f);
+        if (lane == 0 && !bad) ++my_count;
+    }
+    fold_and_publish(my_count, scratch, count_out, pp);
+}
+
+// ---------------------------------------------------------------------------------------
 // lanes: short blocks (UPB <= 16 units, e.g. N=1247: 10 units of 16 bytes).
 //
 // A warp step covers BPS = 32 / UPB whole blocks with the first BPS*UPB lanes (30 of 32 at UPB = 10;
@@ -380,6 +466,16 @@ cudaError_t launch_string(const void *v, uint64_t T, uint32_t upb, const void *m
                          static_cast<const VT *>(v), T, upb, static_cast<const VT *>(mask), cpw, scratch, count_out, pp);
 }
 
+template <int UNROLL, int MINB>
+cudaError_t launch_string_pairs(const uint64_t *v, uint64_t T, uint32_t L, const uint64_t *mask, uint64_t *scratch,
+                                uint64_t *count_out, const PeerPush &pp, cudaStream_t stream) {
+    const uint64_t n_chunks = std::max<uint64_t>(1, (T / 2 + 31) / 32);
+    const size_t smem = (size_t)2 * L * sizeof(uint4) + (size_t)kDecWarps * 2 * L * sizeof(uint32_t);
+    const uint32_t grid = resident_grid(decrypt_count_string_pairs_kernel<UNROLL, MINB>, smem, (n_chunks + kDecWarps - 1) / kDecWarps);
+    return launch_kernel(decrypt_count_string_pairs_kernel<UNROLL, MINB>, grid, kDecThreads, smem, stream,
+                         reinterpret_cast<const uint4 *>(v), T, L, mask, scratch, count_out, pp);
+}
+
 template <typename VT, int UPB, int U, int MINB>
 cudaError_t launch_lanes(const void *v, uint64_t T, const uint64_t *host_mask, uint64_t *scratch, uint64_t *count_out,
                          const PeerPush &pp, bool overlapped, cudaStream_t stream) {
@@ -627,16 +723,21 @@ cudaError_t launch_decrypt_count(const uint64_t *v, uint64_t T, uint32_t L, cons
 #endif
     const bool force_string = env_long("CSGN_DEC_STRING", 0) != 0;
     if (done) {
-    } else if ((L & 1u) && L >= (uint32_t)env_long("CSGN_DEC_PAIRS_MIN", 129) && !force_string &&
+    } else if ((L & 1u) && L >= (uint32_t)env_long("CSGN_DEC_PAIRS_MIN", 49) && !force_string &&
                !env_long("CSGN_DEC_GENERIC", 0) && (reinterpret_cast<uintptr_t>(v) & 15u) == 0) {
-        // long odd-L blocks: double blocks of 2L words, 16-byte loads (B200, tools/oddl_probe.py: N = 12351, L = 193:
-        // 0.59 -> 0.66 of the copy peak; below ~5 steps per double block the fail-string kernel on 8-byte units is
-        // faster -- N = 4097, L = 65: 0.64 against 0.53 -- because a 65-unit row costs three load steps, the last for one lane)
+        // odd L of 49 words and more: double blocks of 2L words folded warp-per-double-block on 16-byte loads (B200,
+        // tools/oddl_probe.py, fraction of the copy peak against the 8-byte-unit kernel: L = 65 0.65 / 0.64, L = 97
+        // 0.66 / 0.58, L = 193 0.70 / 0.59); shorter odd blocks take the fail-string walk over double blocks below
+        // (L = 19 0.75 / 0.65, L = 33 0.73 / 0.70)
         const uint32_t steps = (L + 31u) / 32u;
         const long bpi = env_long("CSGN_DEC_ROWS_BPI", steps >= 8 ? 1 : steps >= 4 ? 2 : 4);
         if (bpi >= 4) err = launch_pairs<4>(v, T, L, mask, scratch, count_out, pp, overlapped, stream);
         else if (bpi >= 2) err = launch_pairs<2>(v, T, L, mask, scratch, count_out, pp, overlapped, stream);
         else err = launch_pairs<1>(v, T, L, mask, scratch, count_out, pp, overlapped, stream);
+    } else if ((L & 1u) && L >= 17 && L <= kDecMaxUnits && !env_long("CSGN_DEC_GENERIC", 0) && env_long("CSGN_DEC_STRING_PAIRS", 1) &&
+               (reinterpret_cast<uintptr_t>(v) & 15u) == 0) {
+        // odd L of 17..48 words: the fail-string walk on 16-byte units over double blocks
+        err = launch_string_pairs<4, 4>(v, T, L, mask, scratch, count_out, pp, stream);
     } else if (upb > kDecMaxUnits || env_long("CSGN_DEC_GENERIC", 0)) {
         const uint64_t want = (T + kDecWarps - 1) / kDecWarps;
         const uint64_t ctas_per_sm = (uint64_t)env_long("CSGN_DEC_CTAS_PER_SM", 8);

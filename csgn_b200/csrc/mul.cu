@@ -517,7 +517,7 @@ cudaError_t launch_units(int fold_mode, const void *a, uint64_t T1, const void *
     const long flat_knob = env_long("CSGN_MUL_FLAT", -1);         // -1: heuristic, 0: never, 1: whenever legal
     const bool flat_legal = Q * sizeof(VT) <= kFlatMaxSmem && Q >= upb && Q >= 64 && T1 >= 2;
     const bool flat_wanted = flat_knob > 0 || (flat_knob < 0 && kFlatByDefault && huge && T1 >= 16 * (uint64_t)dp.sm_count);
-    if (flat_legal && flat_wanted) {
+    if (flat_legal && flat_wanted && dbl_words == 0) {      // the flat kernel has no double-block staging
         int U = (int)env_long("CSGN_MUL_FLAT_U", 4);
         U = U >= 8 ? 8 : U >= 4 ? 4 : U >= 2 ? 2 : 1;
         uint32_t tpb = pick_tpb_flat(upb, 128, (uint32_t)std::min<uint64_t>(Q, std::min<uint32_t>(tpb_cap, 384)));

@@ -222,6 +222,10 @@ def test_decrypt_every_block_shape(engine, oracle, L):
                 with _Env(CSGN_DEC_ROWS_BPI=bpi, CSGN_DEC_PAIRS_MIN=17):
                     assert key.count_satisfied(ct) == want, (L, T, "pairs", bpi)
             with _Env(CSGN_DEC_PAIRS_MIN=100000):
+                assert key.count_satisfied(ct) == want, (L, T, "string over double blocks")
+            with _Env(CSGN_DEC_PAIRS_MIN=17):
+                assert key.count_satisfied(ct) == want, (L, T, "rows over double blocks")
+            with _Env(CSGN_DEC_PAIRS_MIN=100000, CSGN_DEC_STRING_PAIRS=0):
                 assert key.count_satisfied(ct) == want, (L, T, "8-byte units")
         if T > 3:
             # a 16-byte-misaligned view of an even-L ciphertext takes the 8-byte-unit kernels

@@ -19,7 +19,7 @@ def timed(fn, n, reps=5):
         e1.record(); torch.cuda.synchronize()
         res.append(e0.elapsed_time(e1) * 1e3 / (reps * n))
     return float(np.median(res))
-for N, T in ((4097, 560), (191, 3000), (1985, 800), (12351, 320)):
+for N, T in ((4097, 560), (2111, 780), (1215, 1000), (6200, 460), (12351, 320)):
     ctx = eng.Context(N, 16); L = ctx.L; P = 8
     A = [torch.randint(-2**62, 2**62, (T * L,), dtype=torch.int64, device=dev, generator=g) for _ in range(P)]
     B = [torch.randint(-2**62, 2**62, (T * L,), dtype=torch.int64, device=dev, generator=g) for _ in range(P)]
@@ -29,8 +29,9 @@ for N, T in ((4097, 560), (191, 3000), (1985, 800), (12351, 320)):
     key = eng.SecretKey(ctx, np.random.default_rng(7).permutation(N)[:16].astype(np.uint64))
     cnt = torch.zeros(P, dtype=torch.int64, device=dev)
     nb = T * T * L * 8
-    for label, env in (("double blocks", {}), ("8-byte units", {"CSGN_MUL_DOUBLE": "0", "CSGN_DEC_PAIRS_MIN": "100000"})):
-        for k in ("CSGN_MUL_DOUBLE", "CSGN_DEC_PAIRS_MIN"): os.environ.pop(k, None)
+    for label, env in (("double blocks", {}), ("string pairs", {"CSGN_DEC_PAIRS_MIN": "100000"}), ("rows pairs", {"CSGN_DEC_PAIRS_MIN": "17"}),
+                       ("8-byte units", {"CSGN_MUL_DOUBLE": "0", "CSGN_DEC_PAIRS_MIN": "100000", "CSGN_DEC_STRING_PAIRS": "0"})):
+        for k in ("CSGN_MUL_DOUBLE", "CSGN_DEC_PAIRS_MIN", "CSGN_DEC_STRING_PAIRS"): os.environ.pop(k, None)
         os.environ.update(env)
         m = timed(lambda i: va[i].mul_into(vb[i], vo[i]), P)
         d = timed(lambda i: key.count_satisfied_async(vo[i], cnt.data_ptr() + 8 * i), P)
