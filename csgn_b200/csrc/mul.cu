@@ -111,12 +111,28 @@ __device__ __forceinline__ void publish_cta_count(const uint32_t cnt, unsigned l
     grid_publish(threadIdx.x == 0 ? (uint64_t)*s_cnt : 0ull, fo.scratch, fo.count_out, fo.pp);
 }
 
+// Fail bit(s) of product unit `v` (unit u of the thread) under mask unit `m`: bit u, and for double blocks bit u for the
+// first block of the pair, bit 32+u for the second.
+template <typename VT, int DBLF>
+__device__ __forceinline__ uint64_t fail_bits(const VT v, const VT m, const int u, const bool lo_first, const bool hi_first) {
+    if constexpr (DBLF != 0 && sizeof(VT) == 16) {
+        const bool fl = ((~v.x & m.x) | (~v.y & m.y)) != 0u, fh = ((~v.z & m.z) | (~v.w & m.w)) != 0u;
+        const bool first = (lo_first && fl) || (hi_first && fh), second = (!lo_first && fl) || (!hi_first && fh);
+        return (first ? (1ull << u) : 0ull) | (second ? (1ull << (32 + u)) : 0ull);
+    } else {
+        return unit_fails(v, m) ? (1ull << u) : 0ull;
+    }
+}
+
 // FOLD: 0 = multiply, 1 = multiply and count the satisfied product blocks, 2 = count only (nothing stored).
 // ALIGN (fused kernels, blocks of up to 16 units): a warp uses its first (32/UPB)*UPB lanes, so that the UPB threads
 // holding one block are always lanes of ONE warp -- the per-block OR of the fail bits is then two redux.sync per item
 // and needs no shared memory and no barrier.  (N = 1247: 30 of 32 lanes; the idle lanes cost issue slots of a kernel
 // that is bound by HBM, not by issue.)
-template <typename VT, int U, int FOLD, int ALIGN>
+// DBLF (fused, odd L on 16-byte units): a "block" of UPB = L units is TWO blocks; a unit's low word belongs to the first
+// when its word index 2k is below L, its high word when 2k+1 is.  The fail bits of the two halves travel in the low and
+// the high 32 bits of the thread's fail word (rows x units <= 32), so one OR across the group still serves both.
+template <typename VT, int U, int FOLD, int ALIGN, int DBLF = 0>
 __global__ void __launch_bounds__(kMulMaxThreads)
 mul_outer_kernel(const VT *__restrict__ A, const VT *__restrict__ B, VT *__restrict__ out,
                  const uint32_t UPB, const uint64_t T1, const uint64_t Q, const uint32_t R,
@@ -137,8 +153,19 @@ mul_outer_kernel(const VT *__restrict__ A, const VT *__restrict__ B, VT *__restr
     const uint32_t gmask = ALIGN ? ((UPB >= 32u ? 0xffffffffu : ((1u << UPB) - 1u)) << (lane / UPB * UPB)) : 0u;
     const uint64_t tile_q = (uint64_t)tpb * U;
     VT m = vzero<VT>();
+    bool lo_first = true, hi_first = true;         // DBLF: which block of the pair this unit's words belong to
     if (FOLD) {
-        m = fold_mask_unit<VT>(fo, k);             // the key is not the predecessor's output: before the PDL wait
+        if constexpr (DBLF != 0 && sizeof(VT) == 16) {
+            const uint32_t Lw = fo.dbl_words;
+            const uint64_t *M64 = static_cast<const uint64_t *>(fo.mask);
+            lo_first = 2u * k < Lw;
+            hi_first = 2u * k + 1u < Lw;
+            const uint64_t mlo = __ldg(M64 + (lo_first ? 2u * k : 2u * k - Lw));
+            const uint64_t mhi = __ldg(M64 + (hi_first ? 2u * k + 1u : 2u * k + 1u - Lw));
+            m = make_uint4((uint32_t)mlo, (uint32_t)(mlo >> 32), (uint32_t)mhi, (uint32_t)(mhi >> 32));
+        } else {
+            m = fold_mask_unit<VT>(fo, k);         // the key is not the predecessor's output: before the PDL wait
+        }
         if (threadIdx.x == 0) s_cnt = 0ull;
     }
     pdl_enter();
@@ -211,12 +238,12 @@ mul_outer_kernel(const VT *__restrict__ A, const VT *__restrict__ B, VT *__restr
 #pragma unroll 4
             for (uint32_t r = 0; r < nrows; ++r, o += Q, sa += UPB) {
                 const VT a = *sa;
-                uint32_t rowbits = 0;
+                uint64_t rowbits = 0;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const VT v = vand(a, b[u]);
                     if (FOLD != 2) __stcs(o + (uint64_t)u * tpb, v);
-                    if (FOLD) rowbits |= unit_fails(v, m) ? (1u << u) : 0u;
+                    if (FOLD) rowbits |= fail_bits<VT, DBLF>(v, m, u, lo_first, hi_first);
                 }
                 if (FOLD) fails = (fails << U) | rowbits;
             }
@@ -224,12 +251,12 @@ mul_outer_kernel(const VT *__restrict__ A, const VT *__restrict__ B, VT *__restr
             // ragged last column tile: per-unit bounds, loop-invariant predicates
             for (uint32_t r = 0; r < nrows; ++r, o += Q, sa += UPB) {
                 const VT a = *sa;
-                uint32_t rowbits = 0;
+                uint64_t rowbits = 0;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const VT v = vand(a, b[u]);
                     if (FOLD != 2 && ((live_bits >> u) & 1u)) __stcs(o + (uint64_t)u * tpb, v);
-                    if (FOLD) rowbits |= unit_fails(v, m) ? (1u << u) : 0u;
+                    if (FOLD) rowbits |= fail_bits<VT, DBLF>(v, m, u, lo_first, hi_first);
                 }
                 if (FOLD) fails = (fails << U) | rowbits;
             }
@@ -238,7 +265,8 @@ mul_outer_kernel(const VT *__restrict__ A, const VT *__restrict__ B, VT *__restr
             // nrows*U <= 64 (launcher); live units repeated for every row
             const uint32_t nb = nrows * U;
             const uint64_t all_rows = nb >= 64u ? ~0ull : ((1ull << nb) - 1ull);
-            const uint64_t valid = (all_rows / ((1ull << U) - 1ull)) * (uint64_t)live_bits;
+            uint64_t valid = (all_rows / ((1ull << U) - 1ull)) * (uint64_t)live_bits;
+            if (DBLF) valid |= valid << 32;              // both halves of every double block (nb <= 32, launcher)
             if (ALIGN) {
                 if (active) {
                     uint64_t f = (uint64_t)__reduce_or_sync(gmask, (uint32_t)fails);
@@ -383,13 +411,13 @@ void fill_fold_params(FoldParams &fo, const MulFold *fold, uint32_t upb, size_t 
     fo.scratch = fold->scratch;
     fo.count_out = fold->count_out;
     if (fold->peer) fo.pp = *fold->peer;
-    if (fold->host_mask && (size_t)upb * unit_bytes <= sizeof(ParamMask)) {
+    if (dbl_words == 0 && fold->host_mask && (size_t)upb * unit_bytes <= sizeof(ParamMask)) {   // (double blocks read the L-word mask from global memory)
         memcpy(&fo.pmask, fold->host_mask, (size_t)upb * unit_bytes);
         fo.mask_in_params = 1;
     }
 }
 
-template <typename VT, int U, int FOLD, int ALIGN = 0>
+template <typename VT, int U, int FOLD, int ALIGN = 0, int DBLF = 0>
 cudaError_t launch_tiled_uf(const void *a, uint64_t T1, const void *b, uint64_t Q, uint32_t upb, void *out, uint32_t tpb,
                             uint32_t R, uint64_t grid_cap, const MulFold *fold, cudaStream_t stream, uint32_t dbl_words = 0) {
     // ALIGN: tpb threads (a multiple of 32) cover (tpb/32) * (32/upb)*upb units per row step
@@ -405,7 +433,7 @@ cudaError_t launch_tiled_uf(const void *a, uint64_t T1, const void *b, uint64_t 
     const uint32_t pf_chunks = pf_per_sm > 0 ? (uint32_t)((ahead_items + n_col_tiles - 1) / n_col_tiles) : 0u;
     FoldParams fo;
     fill_fold_params(fo, fold, upb, sizeof(VT), dbl_words);
-    return launch_kernel(mul_outer_kernel<VT, U, FOLD, ALIGN>, grid, tpb, smem, stream, static_cast<const VT *>(a),
+    return launch_kernel(mul_outer_kernel<VT, U, FOLD, ALIGN, DBLF>, grid, tpb, smem, stream, static_cast<const VT *>(a),
                          static_cast<const VT *>(b), static_cast<VT *>(out), upb, T1, Q, R, (uint32_t)n_col_tiles, n_items,
                          pf_chunks, fo);
 }
@@ -418,6 +446,13 @@ cudaError_t launch_tiled_u(int fold_mode, bool align, const void *a, uint64_t T1
         if (fold_mode == 1) return launch_tiled_uf<VT, U, 1, 1>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream);
         return launch_tiled_uf<VT, U, 2, 1>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream);
     }
+    if constexpr (sizeof(VT) == 16 && U <= 2) {
+        if (dbl_words && fold_mode == 1)
+            return launch_tiled_uf<VT, U, 1, 0, 1>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream, dbl_words);
+        if (dbl_words && fold_mode == 2)
+            return launch_tiled_uf<VT, U, 2, 0, 1>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream, dbl_words);
+    }
+    if (dbl_words && fold_mode) return cudaErrorNotSupported;       // the launcher caps U at 2 for fused double blocks
     switch (fold_mode) {
         case 1: return launch_tiled_uf<VT, U, 1>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream);
         case 2: return launch_tiled_uf<VT, U, 2>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream);
@@ -547,6 +582,7 @@ cudaError_t launch_units(int fold_mode, const void *a, uint64_t T1, const void *
     // lane-aligned fused kernels (blocks of up to 16 units): 4 units per thread cost 79 registers -- three resident CTAs
     // instead of four -- and measured slower than 2 units with more rows per item; long blocks keep 4 (63 registers)
     if (fold_mode && upb <= 16 && env_long("CSGN_MUL_U", 0) <= 0) U = std::min(U, 2);
+    if (fold_mode && dbl_words) U = std::min(U, 2);                            // fused double blocks: rows x units <= 32
     U = U >= 8 ? 8 : U >= 4 ? 4 : U >= 2 ? 2 : 1;
     while (U > 1 && (uint64_t)upb * U > Q) U >>= 1;
     const uint32_t r_smem = std::max<uint32_t>(1, std::min<uint32_t>(64, kMulMaxSmem / (upb * (uint32_t)sizeof(VT))));
@@ -555,7 +591,7 @@ cudaError_t launch_units(int fold_mode, const void *a, uint64_t T1, const void *
     // Fused kernels for blocks of up to 16 units run lane-aligned (whole blocks per warp: the fold is two redux.sync
     // per item, no shared memory, no barrier); their CTA is a whole number of warps -- unless the row is so short that
     // whole warps would pad the column tiles by more than a few percent (chains: 250 or 1250 units per row).
-    bool align = fold_mode != 0 && upb <= 16 && env_long("CSGN_MUL_ALIGN", 1) != 0;
+    bool align = fold_mode != 0 && upb <= 16 && dbl_words == 0 && env_long("CSGN_MUL_ALIGN", 1) != 0;
     const uint32_t lanes_used = align ? (32u / upb) * upb : 32u;
     uint32_t tpb = 0;
     uint64_t R = 1;
@@ -602,7 +638,7 @@ cudaError_t launch_units(int fold_mode, const void *a, uint64_t T1, const void *
     }
     R = (uint64_t)env_long("CSGN_MUL_R", (long)R);
     uint32_t r_max = r_smem;
-    if (fold_mode) r_max = std::min<uint32_t>(r_max, 64u / (uint32_t)U);      // one 64-bit fail word per thread and item
+    if (fold_mode) r_max = std::min<uint32_t>(r_max, (dbl_words ? 32u : 64u) / (uint32_t)U);   // one 64-bit fail word per thread and item
     R = std::max<uint64_t>(1, std::min<uint64_t>(R, std::min<uint64_t>(r_max, T1)));
 
     switch (U) {
@@ -642,9 +678,11 @@ cudaError_t launch_mul(const uint64_t *a, uint64_t T1, const uint64_t *b, uint64
     // Odd L (half of all contexts): a block is not a whole number of 16-byte units, but TWO blocks are.  With an even
     // number of right-operand blocks the plain multiply reads b as T2/2 double blocks of 2L words and stages every row of
     // a as a_i || a_i -- the same words out, with 16-byte loads and stores instead of 8-byte ones.
-    const bool dbl = (L & 1u) && !fold && (T2 % 2 == 0) && L <= (uint32_t)kMulMaxThreads && env_long("CSGN_MUL_DOUBLE", 1) &&
-                     ((reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
-    const cudaError_t err = dbl       ? launch_units<uint4>(0, a, T1, b, T2 / 2, L, out, nullptr, stream, L)
+    // The fused kernel does the same, with two verdicts per double block.
+    const bool dbl = (L & 1u) && (T2 % 2 == 0) && L <= (uint32_t)kMulMaxThreads && env_long("CSGN_MUL_DOUBLE", 1) &&
+                     ((reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0 &&
+                     (!fold || (L > 16 && (reinterpret_cast<uintptr_t>(fold->mask) & 7u) == 0));   // short odd blocks fuse lane-aligned on 8-byte units
+    const cudaError_t err = dbl       ? launch_units<uint4>(fold_mode, a, T1, b, T2 / 2, L, out, fold, stream, L)
                             : units16 ? launch_units<uint4>(fold_mode, a, T1, b, T2, upb, out, fold, stream)
                                       : launch_units<uint2>(fold_mode, a, T1, b, T2, upb, out, fold, stream);
     count_launch();

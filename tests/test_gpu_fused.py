@@ -467,3 +467,21 @@ def test_multiply_odd_L_as_double_blocks(engine, oracle, N):
                       dict(CSGN_MUL_TPB=96, CSGN_MUL_U=2)):
             with _Env(**knobs):
                 assert np.array_equal((ca * cb).getValues(), want), (N, T1, T2, knobs)
+
+
+@pytest.mark.parametrize("N,D", [(191, 2), (4097, 3), (2111, 1), (1950, 2), (12351, 2), (32950, 2)])
+def test_fused_odd_L_as_double_blocks(engine, oracle, N, D):
+    """Odd L with an even right operand: the fused multiply -> decrypt on 16-byte units over double blocks -- product
+    words and count (two verdicts per double block), count-only form, against the oracle and against the 8-byte kernel."""
+    L = words_per_block(N)
+    assert L % 2 == 1
+    rng = np.random.default_rng(N + 17)
+    shapes = [(1, 2), (7, 2), (2, 8), (37, 54), (300, 200), (3, 1000), (129, 66)] if L <= 64 else [(1, 2), (9, 14), (40, 6), (3, 70)]
+    seen = 0
+    for T1, T2 in shapes:
+        seen += check_fused(engine, oracle, N, D, T1, T2, rng, tag="double blocks")
+        for knobs in (dict(CSGN_MUL_DOUBLE=0), dict(CSGN_MUL_U=1, CSGN_MUL_R=1), dict(CSGN_MUL_U=2, CSGN_MUL_R=16, CSGN_MUL_GRID=3),
+                      dict(CSGN_MUL_TPB=96, CSGN_MUL_U=1, CSGN_MUL_R=32)):
+            with _Env(**knobs):
+                seen += check_fused(engine, oracle, N, D, T1, T2, rng, tag=str(knobs))
+    assert seen > 0
