@@ -588,18 +588,21 @@ cudaError_t launch_permute(const uint64_t *in, uint64_t T, uint32_t L, uint32_t 
                 if (W == 512 && aligned16) r = launch_plane<512, 256, 3, true>(in, T, W, plane_map, out, 4, stream);
                 else if (W == 256 && aligned16) r = launch_plane<256, 128, 6, true>(in, T, W, plane_map, out, 4, stream);
                 else if (W >= 128 && W <= 448 && aligned16) r = launch_plane<0, 128, 6, true>(in, T, W, plane_map, out, 16, stream);
+                // (CTA sizes that waste fewer threads per column pass -- 192 for W = 130, 256 ... -- were measured:
+                //  six small CTAs per SM beat them on four of five contexts, tools/perm_cta_probe.py)
                 break;
             case 0: if (W == 512 && aligned16) r = launch_plane<512, 256, 3, true>(in, T, W, plane_map, out, 4, stream); break;
             case 6: r = launch_plane<0, 256, 3, false>(in, T, W, plane_map, out, 4, stream); break;
             case 12: if (W == 256 && aligned16) r = launch_plane<256, 128, 6, true>(in, T, W, plane_map, out, 4, stream); break;
             case 17: if (aligned16) r = launch_plane<0, 128, 6, true>(in, T, W, plane_map, out, 16, stream); break;
+            case 18: if (aligned16) r = launch_plane<0, 192, 4, true>(in, T, W, plane_map, out, 16, stream); break;
+            case 7: if (aligned16) r = launch_plane<0, 256, 3, true>(in, T, W, plane_map, out, 16, stream); break;
 #ifdef CSGN_BUILD_VARIANTS
             case 1: if (W == 512) r = launch_plane<512, 256, 3, false>(in, T, W, plane_map, out, 1, stream); break;
             case 2: if (W == 512 && aligned16) r = launch_plane<512, 512, 1, true>(in, T, W, plane_map, out, 1, stream); break;
             case 3: if (W == 512) r = launch_plane<512, 512, 2, false>(in, T, W, plane_map, out, 1, stream); break;
             case 4: if (W == 512) r = launch_plane<512, 128, 6, false>(in, T, W, plane_map, out, 1, stream); break;
             case 5: if (W == 512 && aligned16) r = launch_plane<512, 128, 6, true>(in, T, W, plane_map, out, 1, stream); break;
-            case 7: if (aligned16) r = launch_plane<0, 256, 3, true>(in, T, W, plane_map, out, 1, stream); break;
             case 8: r = launch_plane<0, 128, 4, false>(in, T, W, plane_map, out, 1, stream); break;
             case 9: if (aligned16) r = launch_plane<0, 512, 1, true>(in, T, W, plane_map, out, 1, stream); break;
             case 10: if (W == 512 && aligned16) r = launch_plane<512, 512, 2, true>(in, T, W, plane_map, out, 1, stream); break;

@@ -351,7 +351,7 @@ def test_permute_plane_kernel_forms(engine, oracle, N):
         ct = engine.Ciphertext.from_host(v, ctx)
         want = oracle.permute_all(v, N, perm)
         assert np.array_equal(ct.applyPermutation(p).getValues(), want), (N, T, "default")
-        for form in range(18):
+        for form in range(19):
             for waves in (1, 2):
                 with _Env(CSGN_PERM_PLANE=form, CSGN_PERM_WAVES=waves):
                     assert np.array_equal(ct.applyPermutation(p).getValues(), want), (N, T, form, waves)
