@@ -189,9 +189,10 @@ def ncu_traffic(kernel, workload, fold=None):
 class ClockSampler(threading.Thread):
     """SM clock, board power and throttle reasons during the timed region (NVML, ~1 ms period)."""
 
-    def __init__(self, index):
+    def __init__(self, index, period_s=0.0005, with_power=False):
         super().__init__(daemon=True)
         self.index, self.samples, self.max_mhz = index, [], None
+        self.period_s, self.with_power = period_s, with_power
         self._stop_evt = threading.Event()
         self.ok = False
         try:
@@ -217,8 +218,8 @@ class ClockSampler(threading.Thread):
                 mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
                 r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 mw = None
-                if i % 8 == 7:                   # board power: every eighth sample (each NVML call costs ~1 ms, and the
-                    try:                         # headline's timed region is only a few milliseconds long)
+                if self.with_power:              # board power: only the slow samplers (sustained run, side workloads) --
+                    try:                         # NVML calls take a driver lock, and the headline's region is 7 ms long
                         mw = self.nv.nvmlDeviceGetPowerUsage(self.h)
                     except Exception:
                         mw = None
@@ -226,7 +227,7 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
             i += 1
-            time.sleep(0.0005)
+            time.sleep(self.period_s)
 
     def stop(self, t_begin=None, t_end=None):
         """Median SM clock and the throttle reasons of the samples taken inside [t_begin, t_end] (perf_counter): the
@@ -531,7 +532,7 @@ def other_workloads(eng, torch, dist, dev, rank, world, comm, peak, chain_d):
             vo = [eng.Ciphertext.from_tensor(outs[p], ctx) for p in range(P)]
             cnt = torch.zeros(P, dtype=torch.int64, device=dev)
             reps = 3 if prod_bytes < 1e9 else 1
-            sampler = ClockSampler(dev.index)
+            sampler = ClockSampler(dev.index, period_s=0.01, with_power=True)
             sampler.start()
             sync_all()
             t0 = time.perf_counter()
@@ -591,7 +592,7 @@ def other_workloads(eng, torch, dist, dev, rank, world, comm, peak, chain_d):
             else:
                 key.mul_count_async(vx, vd, tot.data_ptr(), out=vy)
 
-        sampler = ClockSampler(dev.index)
+        sampler = ClockSampler(dev.index, period_s=0.01, with_power=True)
         sampler.start()
         sync_all()
         t0 = time.perf_counter()
@@ -1017,7 +1018,7 @@ def run_ours(args):
     if extras and args.sustain_s > 0:
         # the same step loop for >= sustain_s seconds: does the figure survive sustained streaming?
         per_chunk = max(50, int(0.25 / max(1e-6, main["total_ms"] * 1e-3 / K)))
-        sampler = ClockSampler(local)
+        sampler = ClockSampler(local, period_s=0.005, with_power=True)
         sampler.start()
         barrier()
         step_no[0] = 0

@@ -132,7 +132,9 @@ __device__ __forceinline__ uint64_t fail_bits(const VT v, const VT m, const int 
 // DBLF (fused, odd L on 16-byte units): a "block" of UPB = L units is TWO blocks; a unit's low word belongs to the first
 // when its word index 2k is below L, its high word when 2k+1 is.  The fail bits of the two halves travel in the low and
 // the high 32 bits of the thread's fail word (rows x units <= 32), so one OR across the group still serves both.
-template <typename VT, int U, int FOLD, int ALIGN, int DBLF = 0>
+// DBLA: the rows of A are staged doubled (a_i || a_i) -- set for every double-block launch, fused or not; a template
+// argument so that the ordinary kernels carry none of it (the chain-shape multiply lost 7 % to a run-time test here).
+template <typename VT, int U, int FOLD, int ALIGN, int DBLF = 0, int DBLA = 0>
 __global__ void __launch_bounds__(kMulMaxThreads)
 mul_outer_kernel(const VT *__restrict__ A, const VT *__restrict__ B, VT *__restrict__ out,
                  const uint32_t UPB, const uint64_t T1, const uint64_t Q, const uint32_t R,
@@ -176,7 +178,7 @@ mul_outer_kernel(const VT *__restrict__ A, const VT *__restrict__ B, VT *__restr
     // the chunk of item j + pf_chunks*n_col_tiles (done by the column-0 CTA of each chunk);
     // the first pf_chunks chunks, which nobody is ahead of, are requested line by line by
     // the first CTAs.
-    const uint32_t a_row_bytes = fo.dbl_words ? fo.dbl_words * 8u : UPB * (uint32_t)sizeof(VT);   // a row of A in memory
+    const uint32_t a_row_bytes = DBLA ? fo.dbl_words * 8u : UPB * (uint32_t)sizeof(VT);   // a row of A in memory
     if (pf_chunks) {
         const uint64_t a_bytes = T1 * a_row_bytes;
         const uint64_t head_bytes = min(a_bytes, (uint64_t)pf_chunks * R * a_row_bytes);
@@ -212,7 +214,7 @@ mul_outer_kernel(const VT *__restrict__ A, const VT *__restrict__ B, VT *__restr
         }
 
         __syncthreads();  // the previous item's readers of sA (and sFail) are done
-        if (sizeof(VT) == 16 && fo.dbl_words) {
+        if constexpr (DBLA != 0 && sizeof(VT) == 16) {
             // a_i || a_i: unit u of the double block is words (2u mod L, (2u+1) mod L) of a_i
             const uint32_t Lw = fo.dbl_words;
             const uint64_t *a64 = reinterpret_cast<const uint64_t *>(A) + row0 * Lw;
@@ -417,7 +419,7 @@ void fill_fold_params(FoldParams &fo, const MulFold *fold, uint32_t upb, size_t 
     }
 }
 
-template <typename VT, int U, int FOLD, int ALIGN = 0, int DBLF = 0>
+template <typename VT, int U, int FOLD, int ALIGN = 0, int DBLF = 0, int DBLA = 0>
 cudaError_t launch_tiled_uf(const void *a, uint64_t T1, const void *b, uint64_t Q, uint32_t upb, void *out, uint32_t tpb,
                             uint32_t R, uint64_t grid_cap, const MulFold *fold, cudaStream_t stream, uint32_t dbl_words = 0) {
     // ALIGN: tpb threads (a multiple of 32) cover (tpb/32) * (32/upb)*upb units per row step
@@ -433,7 +435,7 @@ cudaError_t launch_tiled_uf(const void *a, uint64_t T1, const void *b, uint64_t 
     const uint32_t pf_chunks = pf_per_sm > 0 ? (uint32_t)((ahead_items + n_col_tiles - 1) / n_col_tiles) : 0u;
     FoldParams fo;
     fill_fold_params(fo, fold, upb, sizeof(VT), dbl_words);
-    return launch_kernel(mul_outer_kernel<VT, U, FOLD, ALIGN, DBLF>, grid, tpb, smem, stream, static_cast<const VT *>(a),
+    return launch_kernel(mul_outer_kernel<VT, U, FOLD, ALIGN, DBLF, DBLA>, grid, tpb, smem, stream, static_cast<const VT *>(a),
                          static_cast<const VT *>(b), static_cast<VT *>(out), upb, T1, Q, R, (uint32_t)n_col_tiles, n_items,
                          pf_chunks, fo);
 }
@@ -448,15 +450,19 @@ cudaError_t launch_tiled_u(int fold_mode, bool align, const void *a, uint64_t T1
     }
     if constexpr (sizeof(VT) == 16 && U <= 2) {
         if (dbl_words && fold_mode == 1)
-            return launch_tiled_uf<VT, U, 1, 0, 1>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream, dbl_words);
+            return launch_tiled_uf<VT, U, 1, 0, 1, 1>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream, dbl_words);
         if (dbl_words && fold_mode == 2)
-            return launch_tiled_uf<VT, U, 2, 0, 1>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream, dbl_words);
+            return launch_tiled_uf<VT, U, 2, 0, 1, 1>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream, dbl_words);
     }
     if (dbl_words && fold_mode) return cudaErrorNotSupported;       // the launcher caps U at 2 for fused double blocks
     switch (fold_mode) {
         case 1: return launch_tiled_uf<VT, U, 1>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream);
         case 2: return launch_tiled_uf<VT, U, 2>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream);
-        default: return launch_tiled_uf<VT, U, 0>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream, dbl_words);
+        default:
+            if constexpr (sizeof(VT) == 16) {
+                if (dbl_words) return launch_tiled_uf<VT, U, 0, 0, 0, 1>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream, dbl_words);
+            }
+            return launch_tiled_uf<VT, U, 0>(a, T1, b, Q, upb, out, tpb, R, grid_cap, fold, stream);
     }
 }
 
@@ -641,11 +647,18 @@ cudaError_t launch_units(int fold_mode, const void *a, uint64_t T1, const void *
     if (fold_mode) r_max = std::min<uint32_t>(r_max, (dbl_words ? 32u : 64u) / (uint32_t)U);   // one 64-bit fail word per thread and item
     R = std::max<uint64_t>(1, std::min<uint64_t>(R, std::min<uint64_t>(r_max, T1)));
 
+    // A fused CTA ends with a global atomic and a ticket (fold.cuh): with one item per CTA every item pays that round
+    // trip.  The shared-memory-fold kernels (long blocks) therefore run as a persistent grid of 8 CTAs per SM that loop
+    // over the items (B200, tools/fused_grid_sweep.py: Context(16383,64) 300x300 fused 31.7 -> 28.6 us in a batch,
+    // 35.6 -> 33.3 us alone); the lane-aligned kernels (N = 1247) measured best with one CTA per item in a batch.
+    uint64_t grid_cap_f = grid_cap;
+    if (fold_mode && !align && dbl_words == 0 && upb >= 32 && !huge)    // (products of a GiB and more: 1.11 -> 0.98 with the cap)
+        grid_cap_f = std::min<uint64_t>(grid_cap, (uint64_t)dp.sm_count * (uint64_t)env_long("CSGN_MUL_FOLD_CTAS_PER_SM", 8));
     switch (U) {
-        case 8: return launch_tiled_u<VT, 8>(fold_mode, align, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream, dbl_words);
-        case 4: return launch_tiled_u<VT, 4>(fold_mode, align, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream, dbl_words);
-        case 2: return launch_tiled_u<VT, 2>(fold_mode, align, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream, dbl_words);
-        default: return launch_tiled_u<VT, 1>(fold_mode, align, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap, fold, stream, dbl_words);
+        case 8: return launch_tiled_u<VT, 8>(fold_mode, align, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap_f, fold, stream, dbl_words);
+        case 4: return launch_tiled_u<VT, 4>(fold_mode, align, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap_f, fold, stream, dbl_words);
+        case 2: return launch_tiled_u<VT, 2>(fold_mode, align, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap_f, fold, stream, dbl_words);
+        default: return launch_tiled_u<VT, 1>(fold_mode, align, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap_f, fold, stream, dbl_words);
     }
 }
 

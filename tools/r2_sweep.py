@@ -33,6 +33,11 @@ KNOBS = [k for k in os.environ if k.startswith("CSGN_MUL_") or k.startswith("CSG
 
 
 def setenv(**kv):
+    # R2_EXTRA="CSGN_MUL_GRID=592,CSGN_X=1": knobs applied under every measurement of a run (what-if on a whole table)
+    for item in os.environ.get("R2_EXTRA", "").split(","):
+        if "=" in item:
+            k_, v_ = item.split("=", 1)
+            kv.setdefault(k_, v_)
     for k in list(os.environ):
         if (k.startswith("CSGN_MUL_") or k.startswith("CSGN_DEC_") or k.startswith("CSGN_PERM_")) and k not in kv:
             del os.environ[k]
