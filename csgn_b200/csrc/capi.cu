@@ -937,6 +937,7 @@ int enqueue_mul(const csgn_buf *a, const csgn_buf *b, csgn_buf *out, const csgn_
     mf.host_mask = hm;
     mf.scratch = fold_scratch();
     mf.count_out = device_count;
+    mf.overlapped = folds_overlap();
     mf.peer = pp;
     cudaError_t e = launch_mul(a->d, a->n_blocks, b->d, b->n_blocks, a->L, out ? out->d : nullptr, g.stream, &mf);
     return e == cudaSuccess ? CSGN_OK : cuda_fail(e, "fused multiply-decrypt kernel");

@@ -33,6 +33,7 @@ struct MulFold {
     uint64_t *scratch;           // the launch's fold scratch word (zero between launches)
     uint64_t *count_out;         // device word for the total; may be null when `peer` is given
     const PeerPush *peer;        // optional: sharded decrypt (push / publish / collect in the same kernel)
+    bool overlapped = false;     // the caller runs this launch next to other kernels (batch lanes, automatic lanes)
 };
 // K1  out[(i*T2+j)*L+k] = a[i*L+k] & b[j*L+k]        (reference src/Ciphertext.cpp:153-163)
 // With `fold` the same launch also decrypt-folds the product (src/SecretKey.cpp:131-140) while its units are in

@@ -654,6 +654,9 @@ cudaError_t launch_units(int fold_mode, const void *a, uint64_t T1, const void *
     uint64_t grid_cap_f = grid_cap;
     if (fold_mode && !align && dbl_words == 0 && upb >= 32 && !huge)    // (products of a GiB and more: 1.11 -> 0.98 with the cap)
         grid_cap_f = std::min<uint64_t>(grid_cap, (uint64_t)dp.sm_count * (uint64_t)env_long("CSGN_MUL_FOLD_CTAS_PER_SM", 8));
+    // ... and 16 CTAs per SM when it runs alone (no other kernel fills the SMs behind its tail): 27.2 -> 25.4 us
+    if (fold_mode && align && !huge && fold && !fold->overlapped)
+        grid_cap_f = std::min<uint64_t>(grid_cap, (uint64_t)dp.sm_count * (uint64_t)env_long("CSGN_MUL_FOLD_CTAS_PER_SM_ALONE", 16));
     switch (U) {
         case 8: return launch_tiled_u<VT, 8>(fold_mode, align, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap_f, fold, stream, dbl_words);
         case 4: return launch_tiled_u<VT, 4>(fold_mode, align, a, T1, b, Q, upb, out, tpb, (uint32_t)R, grid_cap_f, fold, stream, dbl_words);
