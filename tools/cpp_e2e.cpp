@@ -137,12 +137,20 @@ int main(int argc, char **argv) {
         bool ok = true;
         // warm-up: the memory pool grows to the working set (16 products of 160 MB in flight on two lanes), the pinned
         // staging and the kernels are loaded -- on a fresh box the first dozen steps take tens of milliseconds each
-        const int warm = steps < 20 ? 20 : steps;
-        run(warm, pairs, bitlen, ctx, sk, &ok);
+        // -- blocks of 10 steps until a block is no longer faster than the one before it (at least 3, at most 40 blocks)
+        auto warm_up = [&]() {
+            double prev = 1e30;
+            for (int blk = 0; blk < 40; ++blk) {
+                const double t = run(10, pairs, bitlen, ctx, sk, &ok);
+                if (blk >= 2 && t >= 0.9 * prev) break;
+                prev = t;
+            }
+        };
+        warm_up();
         const double t_default = run(steps, pairs, bitlen, ctx, sk, &ok);
         Library::setFusedProducts(false);
         Library::setAutoLanes(false);
-        run(warm / 2, pairs, bitlen, ctx, sk, &ok);
+        warm_up();
         const double t_eager = run(steps, pairs, bitlen, ctx, sk, &ok);
         const double blocks = (double)P * T * T * steps;
         printf("{\"value\": %.6g, \"unit\": \"blocks/s\", \"ms_per_step\": %.6g, \"pairs_per_step\": %d, \"steps\": %d, "
