@@ -83,3 +83,17 @@ def test_no_gpu_means_loud_failure_not_fallback(lib):
     r = subprocess.run(["python", "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert r.returncode == 0, r.stdout
     assert "no CPU path" in r.stdout
+
+
+def test_header_is_plain_c99(tmp_path):
+    """include/csgn.h is the drop-in boundary for C callers (cgo, JNI stubs, ctypes): it must compile as C, not only C++."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi_c.c"
+    src.write_text('#include "csgn.h"\nint main(void) { return csgn_words_per_block(1247) == 20 ? 0 : 1; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-c", str(src),
+                        "-o", str(tmp_path / "abi_c.o")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
