@@ -1562,7 +1562,7 @@ int csgn_perm_create(uint64_t N, const uint64_t *perm, csgn_perm **out) {
     }
     // The plane kernel keeps slice (c, j) at word j*W + c of the tile itself: the same gather, other offsets.
     std::vector<uint32_t> planes;
-    if (permute_plane_supported(h->L) && h->L >= 32) {
+    if (permute_plane_supported(h->L)) {
         const uint32_t W = 2 * h->L;
         planes.assign((size_t)32 * W, 4u * 32u * W);      // default = the zero words behind the tile
         for (uint32_t c = 0; c < W; ++c)

@@ -399,6 +399,86 @@ permute_plane_kernel(const uint32_t *__restrict__ in, const uint64_t T, const ui
     }
 }
 
+// The plane layout for SHORT blocks (N = 1247: W = 40): a CTA works on a group of G tiles at once, one (tile, column)
+// item per thread, each tile with its own zero words behind it (the raw rows of a tile arrive by one bulk copy per
+// tile, all counted on one mbarrier).  20.5 KB of shared memory per CTA at W = 40, G = 4 instead of the 43.5 KB of the
+// padded-slice kernel above, no hoisted addresses (56 registers instead of 96): six CTAs of 160 threads per SM.
+// Measured and NOT adopted (instantiated only with -DCSGN_BUILD_VARIANTS): 55.8 us per 10^6 blocks at best against
+// 54.2 us for permute_prefetch_kernel<40,4,1,4> -- the hoisted gather addresses and the 128-bit slice stores of that
+// kernel are worth more than two extra resident CTAs (profiles/r2_perm_plane_group_sweep.log).
+template <int WC, int G, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+permute_plane_group_kernel(const uint32_t *__restrict__ in, const uint64_t T, const uint32_t *__restrict__ plane_map,
+                           uint32_t *__restrict__ out, const uint64_t n_groups) {
+    extern __shared__ __align__(128) uint32_t S[];
+    constexpr uint32_t W = WC, tile_words = 32u * W + 4u;               // a tile and its 4 zero words
+    uint64_t *bar = reinterpret_cast<uint64_t *>(S + G * tile_words);
+    for (uint32_t i = threadIdx.x; i < 4u * G; i += THREADS) S[(i >> 2) * tile_words + 32u * W + (i & 3u)] = 0u;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_init_fence();
+    }
+    __syncthreads();
+    pdl_enter();
+
+    auto issue = [&](uint64_t grp) {
+        const uint64_t first_blk = grp * (G * 32u);
+        const uint32_t blocks = (uint32_t)min((uint64_t)(G * 32u), T - first_blk);
+        mbar_expect_tx(bar, blocks * W * 4u);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const uint32_t tb = blocks > 32u * g ? min(32u, blocks - 32u * g) : 0u;
+            if (tb) bulk_g2s(S + g * tile_words, in + (first_blk + 32u * g) * W, tb * W * 4u, bar);
+        }
+    };
+    if (threadIdx.x == 0 && blockIdx.x < n_groups) issue(blockIdx.x);
+
+    uint32_t it = 0;
+    for (uint64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++it) {
+        const uint64_t first_blk = grp * (G * 32u);
+        const uint32_t blocks = (uint32_t)min((uint64_t)(G * 32u), T - first_blk);
+        mbar_wait(bar, it & 1u);
+        for (uint32_t item = threadIdx.x; item < G * W; item += THREADS) {
+            const uint32_t g = item / W, c = item - g * W;
+            uint32_t *tile = S + g * tile_words;
+            uint32_t x[32];
+#pragma unroll
+            for (int b = 0; b < 32; ++b) x[b] = tile[(uint32_t)b * W + c];
+            transpose32(x);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tile[(uint32_t)j * W + c] = x[j];
+        }
+        __syncthreads();
+        for (uint32_t item = threadIdx.x; item < G * W; item += THREADS) {
+            const uint32_t g = item / W, c = item - g * W;
+            const uint32_t tb = blocks > 32u * g ? min(32u, blocks - 32u * g) : 0u;   // rows of this tile inside the ciphertext
+            if (tb == 0) continue;
+            const uint32_t tile_addr = smem_u32(S + g * tile_words);
+            uint32_t y[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) y[j] = lds_u32(tile_addr + __ldg(plane_map + (uint32_t)j * W + c));
+            transpose32(y);
+            uint32_t *dst = out + (first_blk + 32u * g) * W + c;
+            if (tb == 32u) {
+#pragma unroll
+                for (int b = 0; b < 32; ++b) __stcs(dst + (uint32_t)b * W, y[b]);
+            } else {
+#pragma unroll
+                for (int b = 0; b < 32; ++b)
+                    if ((uint32_t)b < tb) __stcs(dst + (uint32_t)b * W, y[b]);
+            }
+        }
+        __syncthreads();   // every gather is done: the planes may be overwritten
+        if (threadIdx.x == 0) {
+            const uint64_t nxt = grp + gridDim.x;
+            if (nxt < n_groups) {
+                proxy_fence_async();
+                issue(nxt);
+            }
+        }
+    }
+}
+
 // Any W (runtime): work items (tile, column) strided over the CTA's threads.
 __global__ void __launch_bounds__(512, 2)
 permute_sliced_kernel(const uint32_t *__restrict__ in, const uint64_t T, const uint32_t W,
@@ -536,6 +616,22 @@ cudaError_t launch_plane(const uint64_t *in, uint64_t T, uint32_t W, const uint3
                          reinterpret_cast<const uint32_t *>(in), T, W, plane_map, reinterpret_cast<uint32_t *>(out), n_tiles);
 }
 
+template <int WC, int G, int THREADS, int MINB>
+cudaError_t launch_plane_group(const uint64_t *in, uint64_t T, const uint32_t *plane_map, uint64_t *out, int waves,
+                               cudaStream_t stream) {
+    constexpr size_t smem = (size_t)G * (32u * WC + 4u) * sizeof(uint32_t) + 16;
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        cudaError_t e = resident_ctas(permute_plane_group_kernel<WC, G, THREADS, MINB>, THREADS, smem, &per_sm);
+        if (e != cudaSuccess) return e;
+    }
+    const uint64_t n_groups = ((T + 31) / 32 + G - 1) / G;
+    const uint64_t cap = (uint64_t)device_props().sm_count * per_sm * (uint64_t)std::max<long>(1, env_long("CSGN_PERM_WAVES", waves));
+    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_groups, cap));
+    return launch_kernel(permute_plane_group_kernel<WC, G, THREADS, MINB>, grid, THREADS, smem, stream,
+                         reinterpret_cast<const uint32_t *>(in), T, plane_map, reinterpret_cast<uint32_t *>(out), n_groups);
+}
+
 cudaError_t launch_sliced(const uint64_t *in, uint64_t T, uint32_t W, const uint32_t *slice_map, uint64_t *out,
                           uint32_t tiles_per_cta, uint32_t tpb, size_t smem, cudaStream_t stream) {
     const DeviceProps &dp = device_props();
@@ -596,8 +692,14 @@ cudaError_t launch_permute(const uint64_t *in, uint64_t T, uint32_t L, uint32_t 
             case 12: if (W == 256 && aligned16) r = launch_plane<256, 128, 6, true>(in, T, W, plane_map, out, 4, stream); break;
             case 17: if (aligned16) r = launch_plane<0, 128, 6, true>(in, T, W, plane_map, out, 16, stream); break;
             case 18: if (aligned16) r = launch_plane<0, 192, 4, true>(in, T, W, plane_map, out, 16, stream); break;
-            case 7: if (aligned16) r = launch_plane<0, 256, 3, true>(in, T, W, plane_map, out, 16, stream); break;
 #ifdef CSGN_BUILD_VARIANTS
+            case 20: if (W == 40 && aligned16) r = launch_plane_group<40, 4, 160, 6>(in, T, plane_map, out, 2, stream); break;
+            case 21: if (W == 40 && aligned16) r = launch_plane_group<40, 4, 160, 4>(in, T, plane_map, out, 2, stream); break;
+            case 22: if (W == 40 && aligned16) r = launch_plane_group<40, 8, 320, 3>(in, T, plane_map, out, 2, stream); break;
+            case 23: if (W == 40 && aligned16) r = launch_plane_group<40, 2, 96, 10>(in, T, plane_map, out, 2, stream); break;
+            case 24: if (W == 40 && aligned16) r = launch_plane_group<40, 4, 96, 8>(in, T, plane_map, out, 2, stream); break;
+            case 25: if (W == 40 && aligned16) r = launch_plane_group<40, 6, 256, 4>(in, T, plane_map, out, 2, stream); break;
+            case 7: if (aligned16) r = launch_plane<0, 256, 3, true>(in, T, W, plane_map, out, 16, stream); break;
             case 1: if (W == 512) r = launch_plane<512, 256, 3, false>(in, T, W, plane_map, out, 1, stream); break;
             case 2: if (W == 512 && aligned16) r = launch_plane<512, 512, 1, true>(in, T, W, plane_map, out, 1, stream); break;
             case 3: if (W == 512) r = launch_plane<512, 512, 2, false>(in, T, W, plane_map, out, 1, stream); break;

@@ -336,7 +336,7 @@ def test_permute_every_kernel_variant(engine, oracle, N):
                     assert np.array_equal(ct.applyPermutation(p).getValues(), want), (N, T, variant, waves)
 
 
-@pytest.mark.parametrize("N", [16383, 8191, 4097, 33000, 2111])
+@pytest.mark.parametrize("N", [16383, 8191, 4097, 33000, 2111, 1247])
 def test_permute_plane_kernel_forms(engine, oracle, N):
     """The plane kernel (long blocks: the slices live in the tile's own 32 x W array) in every instantiation the
     launcher may pick -- bulk-copy fed and register fed, 1..4 columns per thread, compile-time and runtime W --
@@ -346,12 +346,12 @@ def test_permute_plane_kernel_forms(engine, oracle, N):
     ctx = engine.Context(N, 4)
     perm = rng.permutation(N).astype(np.uint64)
     p = engine.Permutation(ctx, perm)
-    for T in (1, 31, 32, 33, 97, 700):
+    for T in ((1, 31, 32, 33, 97, 700) if N != 1247 else (1, 31, 32, 33, 97, 127, 128, 129, 255, 257, 700, 4097, 70001)):
         v = random_blocks(rng, T, N)
         ct = engine.Ciphertext.from_host(v, ctx)
         want = oracle.permute_all(v, N, perm)
         assert np.array_equal(ct.applyPermutation(p).getValues(), want), (N, T, "default")
-        for form in range(19):
+        for form in (range(19) if N != 1247 else range(20, 26)):        # 20..25: the group form for short blocks (W = 40)
             for waves in (1, 2):
                 with _Env(CSGN_PERM_PLANE=form, CSGN_PERM_WAVES=waves):
                     assert np.array_equal(ct.applyPermutation(p).getValues(), want), (N, T, form, waves)

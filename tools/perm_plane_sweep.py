@@ -14,9 +14,10 @@ PEAK = 6533.2
 FORMS = {0: "<512,256,3,bulk>", 1: "<512,256,3,regs>", 2: "<512,512,1,bulk>", 3: "<512,512,2,regs>", 4: "<512,128,6,regs>",
          5: "<512,128,6,bulk>", 6: "<rt,256,3,regs>", 7: "<rt,256,3,bulk>", 8: "<rt,128,4,regs>", 9: "<rt,512,1,bulk>",
          10: "<512,512,2,bulk>", 11: "<512,384,2,bulk>", 12: "<256,128,6,bulk>", 13: "<256,256,3,bulk>", 14: "<256,256,4,bulk>",
-         15: "<256,128,6,regs>", 16: "<rt,1024,1,bulk>", 17: "<rt,128,6,bulk>"}
+         15: "<256,128,6,regs>", 16: "<rt,1024,1,bulk>", 17: "<rt,128,6,bulk>",
+         20: "<40,G4,160,6>", 21: "<40,G4,160,4>", 22: "<40,G8,320,3>", 23: "<40,G2,96,10>", 24: "<40,G4,96,8>", 25: "<40,G6,256,4>"}
 ONLY = [int(x) for x in os.environ.get("PLANE_FORMS", "").split(",") if x]
-SHAPES = ((16383, 90000, 6), (16383, 1000000, 2), (8191, 160000, 6), (33000, 40000, 6), (4097, 313600, 6), (2048, 640000, 6))
+SHAPES = ((1247, 1000000, 6), (1247, 10000000, 2), (16383, 90000, 6), (16383, 1000000, 2), (8191, 160000, 6), (33000, 40000, 6), (4097, 313600, 6), (2048, 640000, 6))
 if os.environ.get("PLANE_SHAPES"):
     SHAPES = SHAPES[:int(os.environ["PLANE_SHAPES"])]
 for N, T, nbuf in SHAPES:
@@ -43,7 +44,8 @@ for N, T, nbuf in SHAPES:
     for f in FORMS:
         if ONLY and f not in ONLY:
             continue
-        if (FORMS[f].startswith("<512") and 2 * L != 512) or (FORMS[f].startswith("<256") and 2 * L != 256):
+        if (FORMS[f].startswith("<512") and 2 * L != 512) or (FORMS[f].startswith("<256") and 2 * L != 256) or \
+                (FORMS[f].startswith("<40") != (2 * L == 40)):
             continue
         for w in [int(x) for x in os.environ.get('PLANE_WAVES', '1,2,4').split(',')]:
             cases.append(("plane %s waves=%d" % (FORMS[f], w), {"CSGN_PERM_PLANE": str(f), "CSGN_PERM_WAVES": str(w)}))
