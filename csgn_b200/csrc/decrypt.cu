@@ -408,6 +408,176 @@ decrypt_count_pairs_kernel(const uint4 *__restrict__ V4, const uint64_t T, const
     fold_and_publish(my_count, scratch, count_out, pp);
 }
 
+// ---------------------------------------------------------------------------------------
+// window: odd L of ANY length on full 16-byte loads.  The blocks of an odd-L ciphertext straddle 16-byte units, but the
+// stream as a whole does not care: every warp owns one contiguous run of double blocks (so the run starts on a 16-byte
+// boundary), split evenly over the grid's warps, and walks it in steps of 32 units = 64 words with every lane loading.
+// A step's verdicts are two ballots -- Flo: the low words (window words 0,2,4..), Fhi: the high words (1,3,5..) -- and
+// the block structure is laid over them afterwards: with r = words of the open block consumed before this window, the
+// blocks that END inside the window end at word offsets (L-r) + j*L <= 64; lane j checks the bits of block j in the
+// two ballots (plus, for j = 0, the carry: whether the open block failed in an earlier window), and the carry for the
+// next window is what is set behind the last end.  r repeats with period L steps, so the bit masks of every (step, end)
+// and the carry masks of every step are tabulated in shared memory once per CTA (before the PDL wait): a step is one
+// load, two mask words, two votes, one table entry per lane, one carry entry per warp and a dozen logic ops per
+// 512 bytes -- no fail strings, no idle lanes, one ragged step per warp per launch.
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t kWindowMaxWords = 999;    // tables + mask units in shared memory: 48 L + 16 bytes (L > 64) within 48 KB
+
+__device__ __forceinline__ uint4 lds128(const uint32_t addr) {                   // 16 bytes of shared memory by address
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+__host__ __device__ __forceinline__ uint32_t bits_below(const uint32_t n) {      // n in 0..32: the n low bits
+    return n >= 32u ? 0xffffffffu : (1u << n) - 1u;
+}
+
+template <int UNROLL, int MINB, int GROUP>
+__global__ void __launch_bounds__(kDecThreads, MINB)
+decrypt_count_window_kernel(const uint4 *__restrict__ V4, const uint64_t T, const uint32_t L, const uint64_t *__restrict__ M,
+                            const uint64_t per, const uint32_t extra, uint64_t *scratch, uint64_t *count_out,
+                            const __grid_constant__ PeerPush pp) {
+    // per, extra: T/2 double blocks = per * (warps of the grid) + extra, divided on the host (a 64-bit division is
+    // several hundred cycles of dependent instructions at the head of every warp)
+    extern __shared__ uint4 smem_raw[];
+    const uint32_t E = 64u / L + 1u;                                 // at most E blocks end inside one window
+    uint4 *sC = smem_raw;                                            // [L]     carry: (lo mask, hi mask, keep, ends)
+    uint4 *sE = sC + L;                                              // [L * E] end j of step s: (lo mask, hi mask, force, carry use)
+    uint4 *sM = sE + (size_t)L * E;                                  // [L]     unit t of a double block: words 2t, 2t+1 (mod L)
+    if (threadIdx.x == 0) sM[L] = make_uint4(0u, 0u, 0xffffffffu, 0u);      // [1]     the end that never counts
+    // the key mask is on its way from global memory while the tables are built (they depend on L only) ...
+    constexpr uint32_t kMaskRounds = (kWindowMaxWords + kDecThreads - 1) / kDecThreads;
+    uint64_t m0[kMaskRounds], m1[kMaskRounds];
+#pragma unroll
+    for (uint32_t k = 0; k < kMaskRounds; ++k) {
+        const uint32_t t = threadIdx.x + k * kDecThreads;
+        if (t < L) {
+            const uint32_t w0 = 2u * t < L ? 2u * t : 2u * t - L, w1 = w0 + 1u < L ? w0 + 1u : 0u;
+            m0[k] = M[w0];
+            m1[k] = M[w1];
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < L * E; i += blockDim.x) {
+        const uint32_t s = i / E, j = i - s * E;
+        const uint32_t r = (s * 64u) % L;                            // words of the open block before window s
+        const uint32_t n_ends = (64u + r) / L;
+        uint4 en = make_uint4(0u, 0u, 0xffffffffu, 0u);              // no such end in this window: never counted
+        if (j < n_ends) {
+            const uint32_t e = (L - r) + j * L, a = j * L > r ? j * L - r : 0u;      // words [a, e) of the window
+            en = make_uint4(bits_below((e + 1u) >> 1) & ~bits_below((a + 1u) >> 1), bits_below(e >> 1) & ~bits_below(a >> 1),
+                            0u, j == 0u ? 0xffffffffu : 0u);
+        }
+        sE[i] = en;
+        if (j == 0u) {
+            uint4 c = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);         // no end: the open block stays open
+            if (n_ends) {
+                const uint32_t a2 = (L - r) + (n_ends - 1u) * L;                     // the next open block starts here
+                c = make_uint4(~bits_below((a2 + 1u) >> 1), ~bits_below(a2 >> 1), 0u, n_ends);
+            }
+            sC[s] = c;
+        }
+    }
+    pdl_enter();
+
+    // ... and so are the first units of this warp's run while the mask goes to shared memory
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t pair0 = warp_global * per + min(warp_global, (uint64_t)extra);
+    const uint64_t my_pairs = per + (warp_global < extra ? 1u : 0u);
+    const uint32_t t0 = lane % L, inc32 = 32u % L;                   // this lane's unit of the double block, per step
+    const uint32_t max_sub = (1u << 30) / L;                         // unit offsets inside a run stay below 2^30
+    uint32_t cnt = 0;                                                // per lane: < 2^32 blocks per launch and lane
+    uint64_t done = 0;
+    uint32_t np = (uint32_t)min(my_pairs, (uint64_t)max_sub);
+    const uint4 *src = V4 + pair0 * L + lane;
+    uint4 v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) v[u] = u * 32u + lane < np * L ? ld_stream(src + u * 32u) : vzero<uint4>();
+#pragma unroll
+    for (uint32_t k = 0; k < kMaskRounds; ++k) {
+        const uint32_t t = threadIdx.x + k * kDecThreads;
+        if (t < L) sM[t] = make_uint4((uint32_t)m0[k], (uint32_t)(m0[k] >> 32), (uint32_t)m1[k], (uint32_t)(m1[k] >> 32));
+    }
+    __syncthreads();
+
+    // one step: v = this lane's unit of the window; CHECK: the run's last steps, where blocks past its end must not count.
+    // The three table reads go through 32-bit shared-memory addresses that are advanced (and wrapped) by byte offsets.
+#define CSGN_WINDOW_STEP(v, CHECK)                                                                                    \
+    {                                                                                                                 \
+        const uint4 m = lds128(ma);                                                                                   \
+        const uint32_t Flo = __ballot_sync(0xffffffffu, ((~(v).x & m.x) | (~(v).y & m.y)) != 0u);                     \
+        const uint32_t Fhi = __ballot_sync(0xffffffffu, ((~(v).z & m.z) | (~(v).w & m.w)) != 0u);                     \
+        const uint4 c = lds128(ca);                                                                                   \
+        const uint4 en = lds128(ea);                                                                                  \
+        const uint32_t bad = (Flo & en.x) | (Fhi & en.y) | en.z | (carry & en.w);                                     \
+        if (CHECK) {                                                                                                  \
+            cnt += (bad == 0u && cb + lane < nblk) ? 1u : 0u;                                                         \
+            cb += c.w;                                                                                                \
+        } else {                                                                                                      \
+            cnt += bad == 0u ? 1u : 0u;                                                                               \
+        }                                                                                                             \
+        carry = (carry & c.z) | (Flo & c.x) | (Fhi & c.y);                                                            \
+        ma += m_inc;                                                                                                  \
+        if (ma >= m_end) ma -= m_len;                                                                                 \
+        ca += 16u;                                                                                                    \
+        ea += e_inc;                                                                                                  \
+        if (ca == c_end) {                                                                                            \
+            ca = c_0;                                                                                                 \
+            ea = e_0;                                                                                                 \
+        }                                                                                                             \
+    }
+
+    const uint32_t m_len = 16u * L, m_inc = 16u * inc32, m_0 = (uint32_t)__cvta_generic_to_shared(sM + t0);
+    const uint32_t m_end = (uint32_t)__cvta_generic_to_shared(sM) + m_len;
+    const uint32_t c_0 = (uint32_t)__cvta_generic_to_shared(sC), c_end = c_0 + 16u * L;
+    // lanes without an end of their own (lane >= E) stay on one entry that never counts
+    const uint32_t e_0 = (uint32_t)__cvta_generic_to_shared(lane < E ? sE + lane : sM + L), e_inc = lane < E ? 16u * E : 0u;
+    while (np) {
+        const uint32_t nblk = 2u * np, n_units = np * L, steps = (n_units + 31u) >> 5, full_steps = n_units >> 5;
+        uint32_t ma = m_0, ca = c_0, ea = e_0;
+        uint32_t carry = 0, s0 = 0, cb = 0;
+        // UNROLL loads stay in flight all the time: a unit's register is refilled with the unit UNROLL steps ahead as soon
+        // as it has been folded (with loads issued in batches the memory pipe drains while a batch is being folded)
+        for (; s0 + 2u * UNROLL <= full_steps; s0 += UNROLL) {       // every step folded and every step loaded here is whole
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                CSGN_WINDOW_STEP(v[u], false)
+                v[u] = ld_stream(src + (UNROLL + u) * 32u);
+                // no thread needs this barrier; it keeps the refills HERE, GROUP of them back to back (ptxas sinks them
+                // to the end of the round, where the memory pipe has drained)
+                if (u % GROUP == GROUP - 1) __syncwarp();
+            }
+            src += UNROLL * 32u;
+        }
+        cb = (s0 * 64u) / L;                                         // blocks that ended before the remaining steps
+        for (; s0 < steps; s0 += UNROLL) {
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if (s0 + u < steps) CSGN_WINDOW_STEP(v[u], true)     // warp-uniform
+                v[u] = (s0 + UNROLL + u) * 32u + lane < n_units ? ld_stream(src + (UNROLL + u) * 32u) : vzero<uint4>();
+                if (u % GROUP == GROUP - 1) __syncwarp();            // the last refills, too, go out as early as they can
+            }
+            src += UNROLL * 32u;
+        }
+        done += np;                                                  // (a run of more than 2^30 units goes on: next piece)
+        np = (uint32_t)min(my_pairs - done, (uint64_t)max_sub);
+        src = V4 + (pair0 + done) * L + lane;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) v[u] = u * 32u + lane < np * L ? ld_stream(src + u * 32u) : vzero<uint4>();
+    }
+#undef CSGN_WINDOW_STEP
+    uint64_t my_count = cnt;
+    if ((T & 1ull) && warp_global == 0) {
+        const uint64_t *last = reinterpret_cast<const uint64_t *>(V4) + (T - 1) * L;
+        bool f = false;
+        for (uint32_t w = lane; w < L; w += 32) f |= (~__ldcs(last + w) & __ldg(M + w)) != 0ull;
+        const bool bad = __any_sync(0xffffffffu, f);
+        if (lane == 0 && !bad) ++my_count;
+    }
+    fold_and_publish(my_count, scratch, count_out, pp);
+}
+
 // Blocks longer than kDecMaxUnits units (N > 65536): one warp per block, 64-bit loads.
 __global__ void __launch_bounds__(kDecThreads)
 decrypt_count_generic_kernel(const uint64_t *__restrict__ V, const uint64_t T, const uint32_t L,
@@ -522,6 +692,23 @@ cudaError_t launch_pairs(const uint64_t *v, uint64_t T, uint32_t L, const uint64
     grid = (uint32_t)std::min<uint64_t>(work_ctas, (uint64_t)grid * fold_waves(T * (uint64_t)L * 8u, overlapped));
     return launch_kernel(decrypt_count_pairs_kernel<BPI>, grid, kDecThreads, 0, stream, reinterpret_cast<const uint4 *>(v), T, L,
                          mask, scratch, count_out, pp);
+}
+
+
+template <int UNROLL, int MINB, int GROUP>
+cudaError_t launch_window(const uint64_t *v, uint64_t T, uint32_t L, const uint64_t *mask, uint64_t *scratch,
+                          uint64_t *count_out, const PeerPush &pp, bool overlapped, cudaStream_t stream) {
+    // a warp's run is worth at least one unrolled round of steps
+    const uint64_t pairs_per_warp = std::max<uint64_t>(1, ((uint64_t)UNROLL * 32u + L - 1) / L);
+    const uint64_t work_ctas = std::max<uint64_t>(1, (T / 2 + kDecWarps * pairs_per_warp - 1) / (kDecWarps * pairs_per_warp));
+    const size_t ends = 64u / L + 1u;
+    const size_t smem = ((size_t)L * (2 + ends) + 1) * sizeof(uint4);
+    uint32_t grid = resident_grid(decrypt_count_window_kernel<UNROLL, MINB, GROUP>, smem, work_ctas);
+    grid = (uint32_t)std::min<uint64_t>(work_ctas, (uint64_t)grid * fold_waves(T * (uint64_t)L * 8u, overlapped));
+    const uint64_t n_warps = (uint64_t)grid * kDecWarps;
+    return launch_kernel(decrypt_count_window_kernel<UNROLL, MINB, GROUP>, grid, kDecThreads, smem, stream,
+                         reinterpret_cast<const uint4 *>(v), T, L, mask, (T / 2) / n_warps, (uint32_t)((T / 2) % n_warps), scratch,
+                         count_out, pp);
 }
 
 // Push and/or publish + collect without a fold (an empty local shard still owes its peers a
@@ -722,7 +909,29 @@ cudaError_t launch_decrypt_count(const uint64_t *v, uint64_t T, uint32_t L, cons
     }
 #endif
     const bool force_string = env_long("CSGN_DEC_STRING", 0) != 0;
+    // the older odd-L kernels stay reachable (tests, tools/oddl_probe.py) through their own switches
+    const bool older_odd = env_long("CSGN_DEC_PAIRS_MIN", -1) >= 0 || env_long("CSGN_DEC_STRING_PAIRS", -1) >= 0 ||
+                           env_long("CSGN_DEC_GENERIC", 0) || force_string || !env_long("CSGN_DEC_WINDOW", 1);
     if (done) {
+    } else if (L >= 3 && L <= kWindowMaxWords && !older_odd && (reinterpret_cast<uintptr_t>(v) & 15u) == 0 &&
+               (env_long("CSGN_DEC_WINDOW_ALL", 0) ||
+                ((L & 1u) ? (L == 3 || L >= 17)
+                          : (units16 && upb > 16 && upb < 129 && upb % 32 != 0 && env_long("CSGN_DEC_WINDOW_EVEN", 1))))) {
+        // the window walk over the flat stream on full 16-byte loads: every odd block length from 17 words up and 3 words
+        // (B200, tools/window_probe.py, fraction of the copy peak at 160 MB against the kernels before it: L = 3 0.90 /
+        // 0.68, 19 0.88 / 0.75, 33 0.88 / 0.73, 65 0.89 / 0.65, 97 0.88 / 0.66, 193 0.88 / 0.70; 1.6 GB at L = 65: 1.03 /
+        // 0.77; odd L of 5..15 words stay with the lane-aligned 8-byte kernel: 0.91-0.95 / 0.86-0.88), and the even
+        // lengths whose unit count fits neither the lane-aligned nor the warp-per-block kernels (17..128 units, not a
+        // multiple of 32).  Forms <loads in flight, CTAs per SM, refills per group>: tools/window_waves_probe.py.
+        const long form = env_long("CSGN_DEC_WINDOW", 1);
+        const bool big = (uint64_t)T * L * 8u >= (1ull << 30);
+        switch (form > 1 ? form : big ? 4 : 11) {
+#define CSGN_WINDOW_CASE(ID, U, B, G) \
+    case ID: err = launch_window<U, B, G>(v, T, L, mask, scratch, count_out, pp, overlapped, stream); break;
+            CSGN_WINDOW_CASE(2, 6, 4, 1) CSGN_WINDOW_CASE(4, 12, 2, 1) CSGN_WINDOW_CASE(6, 8, 3, 2) CSGN_WINDOW_CASE(11, 6, 4, 2)
+            default: err = launch_window<8, 3, 1>(v, T, L, mask, scratch, count_out, pp, overlapped, stream); break;
+#undef CSGN_WINDOW_CASE
+        }
     } else if ((L & 1u) && L >= (uint32_t)env_long("CSGN_DEC_PAIRS_MIN", 49) && !force_string &&
                !env_long("CSGN_DEC_GENERIC", 0) && (reinterpret_cast<uintptr_t>(v) & 15u) == 0) {
         // odd L of 49 words and more: double blocks of 2L words folded warp-per-double-block on 16-byte loads (B200,

@@ -217,6 +217,12 @@ def test_decrypt_every_block_shape(engine, oracle, L):
             assert key.count_satisfied(ct) == want, (L, T, "string")
         with _Env(CSGN_DEC_GENERIC=1):
             assert key.count_satisfied(ct) == want, (L, T, "generic")
+        if 3 <= L <= 999:                   # the window walk (default for odd L = 3, >= 17 and some even L): every form, any L
+            for form in (2, 3, 4, 6, 11):
+                with _Env(CSGN_DEC_WINDOW=form, CSGN_DEC_WINDOW_ALL=1):
+                    assert key.count_satisfied(ct) == want, (L, T, "window form", form)
+            with _Env(CSGN_DEC_WINDOW=0):
+                assert key.count_satisfied(ct) == want, (L, T, "without the window walk")
         if L % 2 and L >= 17:               # odd L: the double-block kernel, every blocks-per-iteration form; and without it
             for bpi in (1, 2, 4):
                 with _Env(CSGN_DEC_ROWS_BPI=bpi, CSGN_DEC_PAIRS_MIN=17):
@@ -233,6 +239,44 @@ def test_decrypt_every_block_shape(engine, oracle, L):
             t = torch.from_numpy(np.concatenate([np.zeros(1, dtype=np.uint64), v]).view(np.int64)).cuda()
             view = engine.Ciphertext.view(t.data_ptr() + 8, T, ctx, keepalive=t)
             assert key.count_satisfied(view) == want, (L, T, "misaligned view")
+
+
+@pytest.mark.parametrize("L,T,D", [(3, 400001, 5), (5, 250000, 64), (19, 90001, 300), (33, 60000, 16), (65, 40001, 1),
+                                   (97, 20000, 2000), (193, 10001, 16), (513, 4000, 7), (999, 1501, 30000),
+                                   (34, 60001, 40), (50, 40000, 3), (100, 20001, 16), (254, 8000, 500)])
+def test_decrypt_window_walk_whole_grid(engine, oracle, L, T, D):
+    """Odd L (and the even L that take the same kernel), enough blocks that every warp of the grid owns a run (and runs start at every phase of the block
+    structure), sparse and dense keys, blocks that miss the key in exactly one word -- the first, the last, or one in
+    the middle (the word a window boundary may cut)."""
+    N = 64 * L - 1
+    rng = np.random.default_rng(1000 + L)
+    ctx = engine.Context(N, D)
+    s = random_key(rng, N, D)
+    key = engine.SecretKey(ctx, s)
+    mask = key_mask(N, s)
+    v = planted(rng, T, N, s, 0.6).reshape(T, L)
+    hit = np.nonzero(mask)[0]
+    spoil = rng.random(T) < 0.3
+    which = hit[rng.integers(0, len(hit), T)]
+    which[rng.random(T) < 0.2] = hit[0]
+    which[rng.random(T) < 0.2] = hit[-1]
+    rows = np.nonzero(spoil)[0]
+    low = mask[which[rows]] & (~mask[which[rows]] + np.uint64(1))        # one key bit of that word
+    v[rows, which[rows]] &= ~low
+    v = np.ascontiguousarray(v.reshape(-1))
+    want = oracle.count_satisfied(v, N, s)
+    assert 0 < want < T
+    ct = engine.Ciphertext.from_host(v, ctx)
+    assert key.count_satisfied(ct) == want
+    for form in (2, 3, 4, 6, 11):
+        with _Env(CSGN_DEC_WINDOW=form, CSGN_DEC_WINDOW_ALL=1):
+            assert key.count_satisfied(ct) == want, form
+    with _Env(CSGN_DEC_WINDOW=0):
+        assert key.count_satisfied(ct) == want, "without the window walk"
+    with _Env(CSGN_DEC_WAVES=4):
+        assert key.count_satisfied(ct) == want, "four waves"
+    with _Env(CSGN_DEC_CTAS_PER_SM=1):
+        assert key.count_satisfied(ct) == want, "one CTA per SM"
 
 
 def test_decrypt_deferred_and_auto_lanes(engine, oracle):
