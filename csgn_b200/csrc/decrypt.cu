@@ -12,7 +12,7 @@
 //
 // The ciphertext is read as one flat stream of units -- 16 bytes (uint4) when L is even and the
 // words are 16-byte aligned, 8 bytes (uint2) otherwise (odd L: N = 191, 4097 ...) -- fully coalesced.
-// Three shapes of the same fold, chosen by units per block (UPB):
+// Shapes of the same fold, chosen by units per block (UPB):
 //   lanes  UPB <= 16          a warp step covers 32/UPB whole blocks; a lane always holds the same unit of
 //                             a block, its mask unit lives in registers, a block's verdict is UPB adjacent
 //                             bits of one ballot                                  (N=1247: UPB = 10)
@@ -21,6 +21,10 @@
 //   string any UPB <= 512     a warp owns 32 consecutive blocks and walks them in UPB coalesced steps; each
 //                             step's ballot is 32 bits of a per-chunk fail string in shared memory; block b
 //                             is satisfied iff bits [b*UPB, (b+1)*UPB) are clear -- lane b checks exactly that
+//   window odd L (3, 17..999 words) and even L with 17..128 units that fit neither of the first two: the block
+//                             structure is taken off the load pattern -- warps stream contiguous runs with every
+//                             lane loading 16 bytes, and the blocks are laid over each step's two ballots afterwards
+//   rows   long blocks whose unit count is not a multiple of 32                   (N=33000: UPB = 258)
 // plus a warp-per-block kernel for blocks longer than 512 units.  Counts fold lane -> warp -> CTA -> ONE
 // atomic per CTA (fold.cuh); the last CTA publishes the total, so a decrypt is ONE launch.
 #include "kernels.cuh"

@@ -5,7 +5,8 @@
 Touches every kernel (tiled and generic multiply; all decrypt forms incl. the lane-aligned kernel, the bulk-copy ring and
 the fused publish + collect of a sharded decrypt at world size 1; concat/append; every form of the bit-sliced permute incl.
 the bulk-copy prefetch, and the gather permute; batched encryption; the batch entry points; checksum; round 2: the fused
-multiply->decrypt in every fold form, the rows fold, the plane permute forms, deferred results, lazy sums, batched uploads)
+multiply->decrypt in every fold form, the rows fold, the window walk, the plane permute forms, deferred results, lazy sums,
+batched uploads)
 at sizes with ragged tails, and checks results against the oracle so that a silent corruption cannot pass.  compute-sanitizer is
 closed on this pool; the script runs plain in the GPU suite (tests/test_gpu_parity.py) as an oracle-checked sweep."""
 import os, sys
@@ -134,4 +135,21 @@ for i in (2, 0, 1):
     assert np.array_equal(view.getValues(), hosts[i]); n_checks += 1
     del view
 eng.sync()
+# the window walk of the decrypt fold: odd and even block lengths, whole and ragged runs, every form
+for N, T in ((191, 1001), (1215, 333), (4097, 130), (4097, 2), (3197, 77), (12351, 41)):
+    ctx = eng.Context(N, 3)
+    s = random_key(rng, N, 3)
+    key = eng.SecretKey(ctx, s)
+    v = random_blocks(rng, T, N).reshape(T, -1)
+    km = np.zeros(v.shape[1], dtype=np.uint64)
+    for pos in s:
+        km[int(pos) >> 6] |= np.uint64(1 << (63 - (int(pos) & 63)))
+    v[rng.random(T) < 0.5] |= km
+    v = np.ascontiguousarray(v.reshape(-1))
+    ct = eng.Ciphertext.from_host(v, ctx)
+    want = o.count_satisfied(v, N, s)
+    for form in ("1", "2", "4", "6", "11"):
+        os.environ["CSGN_DEC_WINDOW"] = form; os.environ["CSGN_DEC_WINDOW_ALL"] = "1"
+        assert key.count_satisfied(ct) == want; n_checks += 1
+    del os.environ["CSGN_DEC_WINDOW"], os.environ["CSGN_DEC_WINDOW_ALL"]
 print("sanitize_case OK:", n_checks, "checks,", eng.launch_count(), "launches")
