@@ -41,7 +41,7 @@ def main():
         return w.reshape(-1)
 
     checked = 0
-    for N, D, sizes in ((1247, 16, (1, 5, 1000, 40001)), (16383, 64, (3, 700)), (191, 5, (257,)), (2048, 8, (999,))):
+    for N, D, sizes in ((1247, 16, (1, 5, 1000, 40001)), (16383, 64, (3, 700)), (191, 5, (257,)), (2048, 8, (999,)), (4097, 7, (131, 4001)), (3197, 4, (77,))):
         L = words_per_block(N)
         ctx = eng.Context(N, D)
         rng = np.random.default_rng([N, 77])                 # the same stream on every rank
