@@ -28,7 +28,7 @@ $(LIBDIR)/libcsgn.so: $(CSRC) $(CHDR)
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)
 
 $(LIBDIR)/libcertFHE.so: $(FHESRC) $(FHEHDR) include/csgn.h $(LIBDIR)/libcsgn.so
-	$(CXX) -O2 -std=c++11 -fPIC -shared -Wall -Iinclude -Icsgn_b200/certfhe -o $@ $(FHESRC) -L$(LIBDIR) -lcsgn '-Wl,-rpath,$$ORIGIN'
+	$(CXX) -O3 -std=c++11 -fPIC -shared -Wall -Iinclude -Icsgn_b200/certfhe -o $@ $(FHESRC) -L$(LIBDIR) -lcsgn '-Wl,-rpath,$$ORIGIN'
 
 # the reference's demo programs say #include "../src/certFHE.h": a symlink tree makes that land on our header
 testers: all

@@ -5,6 +5,10 @@
 
 #include <atomic>
 #include <cstdarg>
+#if defined(__x86_64__) && !defined(__CUDA_ARCH__)
+#include <emmintrin.h>
+#define CSGN_HAVE_SSE2_STREAM 1
+#endif
 
 #ifdef CSGN_BUILD_VARIANTS
 #define CSGN_VERSION_STRING "csgn-b200 0.2 (sm_100a) +variants"
@@ -591,6 +595,38 @@ int csgn_buf_upload(const uint64_t *host_words, uint64_t n_blocks, uint32_t L, c
     return CSGN_OK;
 }
 
+namespace {
+// The caller's words -> pinned staging.  The destination is written once and next read by the copy engine, never by this
+// core: streaming stores skip the read-for-ownership of every destination line (an ordinary memcpy of 160 KB into a slot that
+// has left the cache reads the slot first), 20 -> 16 us per 160 KB on the build host.
+void copy_to_staging(void *dst, const void *src, size_t bytes) {
+#ifdef CSGN_HAVE_SSE2_STREAM
+    if (bytes >= (32u << 10)) {
+        char *d = static_cast<char *>(dst);
+        const char *s = static_cast<const char *>(src);
+        size_t head = (16u - (reinterpret_cast<uintptr_t>(d) & 15u)) & 15u;
+        memcpy(d, s, head);
+        d += head, s += head, bytes -= head;
+        const size_t n = bytes / 64;
+        for (size_t i = 0; i < n; ++i, s += 64, d += 64) {
+            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s));
+            const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + 16));
+            const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + 32));
+            const __m128i e = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + 48));
+            _mm_stream_si128(reinterpret_cast<__m128i *>(d), a);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(d + 16), b);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(d + 32), c);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(d + 48), e);
+        }
+        memcpy(d, s, bytes - n * 64);
+        _mm_sfence();            // the stores are globally visible before the copy engine is told about them
+        return;
+    }
+#endif
+    memcpy(dst, src, bytes);
+}
+}  // namespace
+
 int csgn_buf_upload_copy(const uint64_t *host_words, uint64_t n_blocks, uint32_t L, csgn_buf **out) {
     NEED_INIT();
     if (L == 0) return fail(CSGN_ERR_INVALID_ARGUMENT, "words per block must be > 0");
@@ -605,7 +641,7 @@ int csgn_buf_upload_copy(const uint64_t *host_words, uint64_t n_blocks, uint32_t
         note_synced(g.copy_stream);
         return CSGN_OK;
     }
-    memcpy(sl->p, host_words, bytes);
+    copy_to_staging(sl->p, host_words, bytes);
     int rc = csgn_buf_upload(static_cast<const uint64_t *>(sl->p), n_blocks, L, out);
     // whatever happened, later users of the slot wait for everything the copy stream holds so far
     cudaEventRecord(sl->done, g.copy_stream);
