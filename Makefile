@@ -48,8 +48,10 @@ cpp-tests: all
 
 tools: all
 	@mkdir -p tools/bin
-	$(CXX) -O2 -std=c++11 -Wall -Icsgn_b200/certfhe -Iinclude -o tools/bin/cpp_e2e tools/cpp_e2e.cpp -L$(LIBDIR) -lcertFHE -lcsgn \
-	    '-Wl,-rpath,$$ORIGIN/../../csgn_b200/lib'
+	for n in cpp_e2e ctor_probe; do \
+	  $(CXX) -O2 -std=c++11 -Wall -Icsgn_b200/certfhe -Iinclude -o tools/bin/$$n tools/$$n.cpp -L$(LIBDIR) -lcertFHE -lcsgn \
+	      '-Wl,-rpath,$$ORIGIN/../../csgn_b200/lib' || exit 1; \
+	done
 
 variants: $(CSRC) $(CHDR)
 	@mkdir -p $(LIBDIR)

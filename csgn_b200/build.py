@@ -154,17 +154,23 @@ def build_reference_demos(force=False, verbose=False):
 
 
 def build_tools(force=False, verbose=False):
-    """tools/bin/cpp_e2e: the bench step through the C++ drop-in API (bench.py reports it as e2e_cpp)."""
-    src = os.path.join(ROOT, "tools", "cpp_e2e.cpp")
-    if not os.path.exists(src) or not os.path.exists(libcertfhe_path()):
+    """tools/bin/cpp_e2e: the bench step through the C++ drop-in API (bench.py reports it as e2e_cpp);
+    tools/bin/ctor_probe: where the host time of the Ciphertext constructor goes."""
+    if not os.path.exists(libcertfhe_path()):
         return []
     bindir = os.path.join(ROOT, "tools", "bin")
     os.makedirs(bindir, exist_ok=True)
-    out = os.path.join(bindir, "cpp_e2e")
-    if force or _stale(out, [src, libcertfhe_path()] + glob.glob(os.path.join(CERTFHE, "*.h"))):
-        _run(["g++", "-O2", "-std=c++11", "-Wall", "-I" + CERTFHE, "-I" + INCLUDE, "-o", out, src, "-L" + LIBDIR,
-              "-lcertFHE", "-lcsgn", "-Wl,-rpath,$ORIGIN/../../csgn_b200/lib"], verbose)
-    return [out]
+    outs = []
+    for name in ("cpp_e2e", "ctor_probe"):
+        src = os.path.join(ROOT, "tools", name + ".cpp")
+        if not os.path.exists(src):
+            continue
+        out = os.path.join(bindir, name)
+        if force or _stale(out, [src, libcertfhe_path()] + glob.glob(os.path.join(CERTFHE, "*.h"))):
+            _run(["g++", "-O2", "-std=c++11", "-Wall", "-I" + CERTFHE, "-I" + INCLUDE, "-o", out, src, "-L" + LIBDIR,
+                  "-lcertFHE", "-lcsgn", "-Wl,-rpath,$ORIGIN/../../csgn_b200/lib"], verbose)
+        outs.append(out)
+    return outs
 
 
 def build_all(force=False, verbose=False):

@@ -40,13 +40,14 @@ inline uint64_t canonical_bits(uint64_t i, uint64_t L, uint64_t rem) {
 
 void require_canonical_bitlen(const uint64_t *bitlen, uint64_t len, const Context &ctx) {
     // This runs in every Ciphertext(V, Bitlen, len, ctx), over as many words as V has: the first block is compared
-    // with the canonical pattern, every later word with the word one block before it -- one long loop without a
-    // division or a branch, which the compiler vectorises (the pattern has period L).
+    // with the canonical pattern and the rest of the array with itself one block earlier (the pattern has period L) --
+    // one memcmp, which the C library runs on the widest vectors the host has (5.8 -> 3 us per 160 KB against the
+    // hand-written loop, tools/ctor_probe.cpp).
     const uint64_t L = ctx.getDefaultN(), rem = ctx.getN() % 64;
     uint64_t diff = 0;
     const uint64_t head = len < L ? len : L;
     for (uint64_t k = 0; k < head; ++k) diff |= bitlen[k] ^ canonical_bits(k, L, rem);
-    for (uint64_t i = L; i < len; ++i) diff |= bitlen[i] ^ bitlen[i - L];
+    if (len > L && memcmp(bitlen + L, bitlen, (size_t)(len - L) * sizeof(uint64_t)) != 0) diff = 1;
     if (!diff) return;
     for (uint64_t i = 0; i < len; ++i)
         if (bitlen[i] != canonical_bits(i, L, rem))
