@@ -589,6 +589,15 @@ cudaError_t launch_units(int fold_mode, const void *a, uint64_t T1, const void *
     // instead of four -- and measured slower than 2 units with more rows per item; long blocks keep 4 (63 registers)
     if (fold_mode && upb <= 16 && env_long("CSGN_MUL_U", 0) <= 0) U = std::min(U, 2);
     if (fold_mode && dbl_words) U = std::min(U, 2);                            // fused double blocks: rows x units <= 32
+    // fused, long blocks (32 units and more; the shared-memory fold): wide tiles of few rows -- 4 units per thread and
+    // 3 rows per item (B200, tools/r2_sweep.py longfused, profiles/r2_longfused.log: Context(16383,64) 300x300 0.85 -> 0.93
+    // of the copy peak, N = 8191 400x400 0.88 -> 0.97; 5 rows and no cap on the grid from 400 MB: 1000x300 0.95 -> 1.05)
+    // (unit counts that divide the 256-thread CTA -- N = 4096, 8191, 16383, 32767; for the others the rule before measured
+    // as good or better in a batch: 47 units 0.98 / 1.00, 94 units 0.93 / 1.01, 258 units 0.65 / 0.68)
+    const bool long_fold = fold_mode && upb >= 32 && 256u % upb == 0 && dbl_words == 0 && Q16 >= 8192 &&
+                           env_long("CSGN_MUL_U", 0) <= 0 && env_long("CSGN_MUL_LONGFOLD", 1) != 0;
+    const bool mid = out_units * sizeof(VT) >= (400ull << 20);    // 400 MB of output and more
+    if (long_fold) U = 4;
     U = U >= 8 ? 8 : U >= 4 ? 4 : U >= 2 ? 2 : 1;
     while (U > 1 && (uint64_t)upb * U > Q) U >>= 1;
     const uint32_t r_smem = std::max<uint32_t>(1, std::min<uint32_t>(64, kMulMaxSmem / (upb * (uint32_t)sizeof(VT))));
@@ -641,6 +650,7 @@ cudaError_t launch_units(int fold_mode, const void *a, uint64_t T1, const void *
     if (fold_mode) {
         const uint64_t row_bytes = step_units * (uint64_t)U * sizeof(VT);
         R = std::max<uint64_t>(6, (56 * 1024 + row_bytes - 1) / row_bytes);
+        if (long_fold && U == 4 && !huge) R = mid ? 5 : 3;
     }
     R = (uint64_t)env_long("CSGN_MUL_R", (long)R);
     uint32_t r_max = r_smem;
@@ -652,7 +662,7 @@ cudaError_t launch_units(int fold_mode, const void *a, uint64_t T1, const void *
     // over the items (B200, tools/fused_grid_sweep.py: Context(16383,64) 300x300 fused 31.7 -> 28.6 us in a batch,
     // 35.6 -> 33.3 us alone); the lane-aligned kernels (N = 1247) measured best with one CTA per item in a batch.
     uint64_t grid_cap_f = grid_cap;
-    if (fold_mode && !align && dbl_words == 0 && upb >= 32 && !huge)    // (products of a GiB and more: 1.11 -> 0.98 with the cap)
+    if (fold_mode && !align && dbl_words == 0 && upb >= 32 && !huge && !(long_fold && mid))    // (a GiB and more: 1.11 -> 0.98 with the cap)
         grid_cap_f = std::min<uint64_t>(grid_cap, (uint64_t)dp.sm_count * (uint64_t)env_long("CSGN_MUL_FOLD_CTAS_PER_SM", 8));
     // ... and 16 CTAs per SM when it runs alone (no other kernel fills the SMs behind its tail): 27.2 -> 25.4 us
     if (fold_mode && align && !huge && fold && !fold->overlapped)

@@ -224,6 +224,31 @@ def sec_rsel():
         torch.cuda.empty_cache()
 
 
+def sec_longfused():
+    """fused multiply->decrypt of long blocks (shared-memory fold, persistent grid): rows per item x units per thread x
+    CTAs per SM of the persistent grid, single stream (the way bench.py's other_workloads times it)"""
+    shapes = [("cfg5 300x300", 16383, 64, 300, 300, 12), ("N=8191 400x400", 8191, 32, 400, 400, 12),
+              ("N=4097 560x560", 4097, 16, 560, 560, 12), ("cfg5 1000x300", 16383, 64, 1000, 300, 4)]
+    for name, N, D, T1, T2, P in shapes:
+        ctx, L, va, vb, vo, key, cnt, keep = setup(N, D, T1, T2, P)
+        nb = T1 * T2 * L * 8
+        print("# %s: %.1f MB per product, %d buffers" % (name, nb / 1e6, P))
+        setenv()
+        f = timed(lambda i: key.mul_count_async(va[i], vb[i], cnt.data_ptr() + 8 * i, out=vo[i]), P)
+        print("  default                      fused %9.2f us %.3f" % (f[0], nb / f[0] / 1e3 / PEAK), flush=True)
+        for U in (2, 4):
+            for R in (2, 3, 4, 5, 6, 7, 8, 10):
+                row = "  U=%d R=%-2d |" % (U, R)
+                for cps in (4, 8, 16, 1000):
+                    setenv(CSGN_MUL_R=R, CSGN_MUL_U=U, CSGN_MUL_FOLD_CTAS_PER_SM=cps)
+                    f = timed(lambda i: key.mul_count_async(va[i], vb[i], cnt.data_ptr() + 8 * i, out=vo[i]), P)
+                    row += " %4d/SM %7.2f us %.3f |" % (cps, f[0], nb / f[0] / 1e3 / PEAK)
+                print(row, flush=True)
+        setenv()
+        del va, vb, vo, keep
+        torch.cuda.empty_cache()
+
+
 if __name__ == "__main__" and len(sys.argv) >= 1 and os.path.basename(sys.argv[0]) == "r2_sweep.py":
     for which in (sys.argv[1:] or ["fused", "chain", "shapes"]):
-        {"fused": sec_fused, "chain": sec_chain, "shapes": sec_shapes, "rsel": sec_rsel}[which]()
+        {"fused": sec_fused, "chain": sec_chain, "shapes": sec_shapes, "rsel": sec_rsel, "longfused": sec_longfused}[which]()
