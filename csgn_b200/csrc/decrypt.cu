@@ -928,7 +928,9 @@ cudaError_t launch_decrypt_count(const uint64_t *v, uint64_t T, uint32_t L, cons
         // lengths whose unit count fits neither the lane-aligned nor the warp-per-block kernels (17..128 units, not a
         // multiple of 32).  Forms <loads in flight, CTAs per SM, refills per group>: tools/window_waves_probe.py.
         const long form = env_long("CSGN_DEC_WINDOW", 1);
-        const bool big = (uint64_t)T * L * 8u >= (1ull << 30);
+        // fewer, deeper warps (<12,2,1>) from half a GiB on and for long blocks, whose runs are few double blocks per warp
+        // (160 MB: L = 641 0.84 / 0.80, L = 999 0.80 / 0.75; 640 MB: 1.00 / 0.96 over L = 129 .. 999)
+        const bool big = (uint64_t)T * L * 8u >= (1ull << 29) || L >= 300;
         switch (form > 1 ? form : big ? 4 : 11) {
 #define CSGN_WINDOW_CASE(ID, U, B, G) \
     case ID: err = launch_window<U, B, G>(v, T, L, mask, scratch, count_out, pp, overlapped, stream); break;
