@@ -413,17 +413,19 @@ decrypt_count_pairs_kernel(const uint4 *__restrict__ V4, const uint64_t T, const
 }
 
 // ---------------------------------------------------------------------------------------
-// window: odd L of ANY length on full 16-byte loads.  The blocks of an odd-L ciphertext straddle 16-byte units, but the
-// stream as a whole does not care: every warp owns one contiguous run of double blocks (so the run starts on a 16-byte
-// boundary), split evenly over the grid's warps, and walks it in steps of 32 units = 64 words with every lane loading.
+// window: blocks of ANY length (odd L above all, and the even L the kernels above serve badly) on full 16-byte loads.
+// The blocks of an odd-L ciphertext straddle 16-byte units, but the stream as a whole does not care: every warp owns one
+// contiguous run of double blocks (so the run starts on a 16-byte boundary), split evenly over the grid's warps, and walks
+// it in steps of 32 units = 64 words with every lane loading.
 // A step's verdicts are two ballots -- Flo: the low words (window words 0,2,4..), Fhi: the high words (1,3,5..) -- and
 // the block structure is laid over them afterwards: with r = words of the open block consumed before this window, the
 // blocks that END inside the window end at word offsets (L-r) + j*L <= 64; lane j checks the bits of block j in the
 // two ballots (plus, for j = 0, the carry: whether the open block failed in an earlier window), and the carry for the
 // next window is what is set behind the last end.  r repeats with period L steps, so the bit masks of every (step, end)
 // and the carry masks of every step are tabulated in shared memory once per CTA (before the PDL wait): a step is one
-// load, two mask words, two votes, one table entry per lane, one carry entry per warp and a dozen logic ops per
-// 512 bytes -- no fail strings, no idle lanes, one ragged step per warp per launch.
+// load, one 16-byte mask unit, two votes, one table entry per lane, one carry entry per warp and a dozen logic ops per
+// 512 bytes (31 SASS instructions) -- no fail strings, no idle lanes, one ragged step per warp per launch.  The loads
+// form a software pipeline (UNROLL in flight per lane, refilled GROUP at a time as registers free up).
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t kWindowMaxWords = 999;    // tables + mask units in shared memory: 48 L + 16 bytes (L > 64) within 48 KB
 
